@@ -1,0 +1,268 @@
+#!/usr/bin/env python
+"""Headline benchmark: QAT-step images/sec on synthetic CIFAR-10-shaped batches.
+
+    python bench.py --gpus 1 --steps 20 --warmup 5            # this repo's CUDA engine
+    python bench.py --impl reference --gpus 1 --steps 3 --warmup 2   # CPU reference path (oracle port)
+
+Workload (BASELINE.json configs[1]): NIN-GC, wbwtab W-ternary / A-binary, batch 256 per GPU,
+3x32x32 inputs, CrossEntropy + Adam(lr 0.01) - the reference's training step
+(wbwtab/main.py:70-98).  N > 1: one process per GPU under torchrun, batch sharded (256 per
+rank, weak scaling), one NCCL all-reduce of the flat gradient bucket per step.
+
+One JSON line on stdout (rank 0).  `value` is timed with inputs resident in HBM; `e2e` is the
+same step fed from pinned HOST buffers (H2D of the batch + D2H of the loss inside the timed
+region); `roofline` is for the dominant engine kernel, timed live with CUDA events on the
+launching stream; `cpu_baseline` is the oracle port of the reference timed on the host cores."""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+from harness import train as H  # noqa: E402
+
+WORKLOAD = "nin_gc_wbwtab_w3a2"
+BATCH_PER_GPU = 256
+CPU_SAMPLE_BATCH = 32
+METRIC = "qat_step_images_per_sec"
+
+
+def _peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d["hbm_gbs"], d["bf16_tflops"], "measured"
+    return 6650.0, 1590.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index=0):
+        self.rows, self.proc, self.gpu = [], None, gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.gpu)], stdout=subprocess.PIPE, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            if len(r) < 9:
+                continue
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def conv_algorithmic(shape, kind):
+    """F = 2*B*K*P*Q*(C/g)*R*S ; Bytes = 4(B*C*H*W + B*K*P*Q) + 4|W| (fp32 module surface)."""
+    B, C, Hh, W, K, R, S, sh, sw, ph, pw, dh, dw, G = shape
+    P = (Hh + 2 * ph - dh * (R - 1) - 1) // sh + 1
+    Q = (W + 2 * pw - dw * (S - 1) - 1) // sw + 1
+    flops = 2.0 * B * K * P * Q * (C // G) * R * S
+    nbytes = 4.0 * (B * C * Hh * W + B * K * P * Q) + 4.0 * K * (C // G) * R * S
+    return flops, nbytes
+
+
+def run_cpu_baseline(steps=3, warmup=2):
+    """the reference's own CPU path (oracle port), all host threads, bounded sample (B=32)."""
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    w = H.WORKLOADS[WORKLOAD]
+    model = H.prepare_oracle(H.build_float_model(w["model"]), w["scheme"], **w["prepare"])
+    stepper = H.QatStepper(model, lr=0.01, wd=w["wd"])
+    x, t = H.synthetic_batch(CPU_SAMPLE_BATCH, w["hw"], seed=1)
+    for _ in range(warmup):
+        stepper.step(x, t)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        stepper.step(x, t)
+    dt = (time.perf_counter() - t0) / steps
+    return {"value": CPU_SAMPLE_BATCH / dt, "unit": "img/s", "cores": cores, "kind": "port",
+            "sample": f"{steps} QAT steps of the same model at batch {CPU_SAMPLE_BATCH} (oracle/reference_port.py, "
+                      f"torch CPU, {cores} threads), {dt * 1e3:.0f} ms/step"}, dt
+
+
+def config_dict(n_gpus):
+    return {"workload": f"NIN-GC wbwtab W-ternary/A-binary QAT step, synthetic 3x32x32, batch {BATCH_PER_GPU}/GPU "
+                        f"(BASELINE.json configs[1])",
+            "global_batch": BATCH_PER_GPU * n_gpus, "per_gpu_batch": BATCH_PER_GPU, "optimizer": "Adam lr=0.01",
+            "parallelism": f"dp{n_gpus}", "l2": "per-step working set ~2.4 GB of activations >> 126 MB L2 (no flush needed)"}
+
+
+def main_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    base, dt = run_cpu_baseline(steps=max(1, args.steps), warmup=max(0, args.warmup))
+    line = {"impl": "reference", "metric": METRIC, "value": base["value"], "unit": "img/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
+            "config": config_dict(args.gpus), "cpu_baseline": base,
+            "e2e": {"value": base["value"], "unit": "img/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="engine", choices=["engine", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return main_reference(args)
+    args.warmup = max(args.warmup, 3)
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device - the engine has no CPU path (use --impl reference for the CPU baseline)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+
+    from micronet_b200 import _lib as L, functional as F_
+    from micronet_b200.parallel import FlatGradBucket
+
+    w = H.WORKLOADS[WORKLOAD]
+    model = H.prepare_engine(H.build_float_model(w["model"]), w["scheme"], **w["prepare"]).to(dev)
+    bucket = FlatGradBucket(model.parameters()) if world > 1 else None
+    stepper = H.QatStepper(model, lr=0.01, wd=w["wd"], bucket=bucket)
+    # distinct batches, pre-staged on the device for `value`, pinned on the host for `e2e`
+    nbuf = 4
+    host = [H.synthetic_batch(BATCH_PER_GPU, w["hw"], seed=100 + rank * 17 + i, pin=True) for i in range(nbuf)]
+    devb = [(x.to(dev), t.to(dev)) for x, t in host]
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(step_fn, steps):
+        barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for i in range(steps):
+            step_fn(i)
+        b.record()
+        barrier()
+        ms = torch.tensor([a.elapsed_time(b)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return ms.item()
+
+    def step_resident(i):
+        x, t = devb[i % nbuf]
+        stepper.step(x, t)
+
+    loss_host = torch.empty((), dtype=torch.float32).pin_memory()
+
+    def step_e2e(i):
+        hx, ht = host[i % nbuf]
+        x = hx.to(dev, non_blocking=True)
+        t = ht.to(dev, non_blocking=True)
+        loss = stepper.step(x, t)
+        loss_host.copy_(loss.detach(), non_blocking=False)  # D2H read of the step's result
+
+    for i in range(args.warmup):
+        step_resident(i)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    launches0 = L.launch_count()
+    F_.TIMER = F_.KernelTimer()
+    ms_total = timed(step_resident, args.steps)
+    torch.cuda.synchronize()
+    timer, F_.TIMER = F_.TIMER, None
+    launches = L.launch_count() - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    for i in range(2):
+        step_e2e(i)
+    ms_e2e = timed(step_e2e, args.steps)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    imgs = BATCH_PER_GPU * world * args.steps
+    value = imgs / (ms_total / 1e3)
+    e2e_value = imgs / (ms_e2e / 1e3)
+    hbm, tfl, peak_src = _peaks()
+    # dominant engine kernel by total device time
+    agg = {}
+    for (kind, shape), times in timer.summary().items():
+        agg[(kind, shape)] = (sum(times), len(times))
+    (dk, dshape), (dtot, dn) = max(agg.items(), key=lambda kv: kv[1][0])
+    flops, nbytes = conv_algorithmic(dshape, dk)
+    avg_s = dtot / dn / 1e3
+    t_hbm, t_tc = nbytes / (hbm * 1e9), flops / (tfl * 1e12)
+    if t_hbm >= t_tc:
+        roof = {"bound": "hbm", "achieved": nbytes / avg_s / 1e9, "peak": hbm, "unit": "GB/s"}
+    else:
+        roof = {"bound": "tensor", "achieved": flops / avg_s / 1e12, "peak": tfl, "unit": "TFLOP/s"}
+    roof["frac"] = roof["achieved"] / roof["peak"]
+    roof.update({"traffic": None, "peak_source": peak_src,
+                 "kernel": f"conv2d_{dk} shape(B,C,H,W,K,R,S,sh,sw,ph,pw,dh,dw,G)={list(dshape)}",
+                 "avg_launch_us": avg_s * 1e6, "launches_timed": dn,
+                 "share_of_step": dtot / ms_total,
+                 "engine_conv_share_of_step": sum(v[0] for v in agg.values()) / ms_total})
+    line = {"metric": METRIC, "value": value, "unit": "img/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "fp32 (s32 accumulate on integer levels)", "data": "synthetic",
+            "config": config_dict(world), "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": "img/s", "ms_per_step": ms_e2e / args.steps,
+                    "h2d_bytes_per_step": (BATCH_PER_GPU * 3 * w["hw"] * w["hw"] * 4 + BATCH_PER_GPU * 8) * world,
+                    "d2h_bytes_per_step": 4 * world},
+            "gpu_launches": int(launches), "roofline": roof}
+    if not args.no_cpu_baseline and world == 1:
+        line["cpu_baseline"], _ = run_cpu_baseline()
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,79 @@
+"""QAT step harness shared by bench.py, smoke() and the tests.
+
+Re-creates the reference's training step (wbwtab/main.py:70-98: forward, CrossEntropy, zero_grad,
+backward, Adam step; init wbwtab/main.py:309-317; one Adam param-group per tensor :331-339) on
+synthetic CIFAR-10-shaped data - there is no dataset / network in this environment."""
+from __future__ import annotations
+
+import torch
+import torch.nn as nn
+
+from . import models as zoo
+
+# the BASELINE.json configs, as (model factory, scheme, prepare kwargs, weight decay)
+WORKLOADS = {
+    # configs[1]: the configuration the headline metric is quoted on
+    "nin_gc_wbwtab_w3a2": dict(model="nin_gc", scheme="wbwtab", prepare=dict(W=3, A=2), wd=0.0, hw=32),
+    "nin_dorefa_w8a8": dict(model="nin", scheme="dorefa", prepare=dict(a_bits=8, w_bits=8), wd=1e-5, hw=32),
+    "resnet18_iao_w8a8_bnfuse": dict(model="resnet18", scheme="iao",
+                                     prepare=dict(a_bits=8, w_bits=8, q_type=0, q_level=0, weight_observer=0,
+                                                  bn_fuse=True), wd=1e-5, hw=32),
+    "nin_gc_dorefa_w4a4": dict(model="nin_gc", scheme="dorefa", prepare=dict(a_bits=4, w_bits=4), wd=1e-5, hw=32),
+}
+
+
+def build_float_model(name, seed=1):
+    torch.manual_seed(seed)
+    m = {"nin": zoo.NIN, "nin_gc": zoo.NINGC, "resnet18": zoo.resnet18}[name]()
+    return zoo.init_like_reference(m)
+
+
+def prepare_engine(model, scheme, **kw):
+    import micronet_b200 as E
+    return {"wbwtab": E.wbwtab, "dorefa": E.dorefa, "iao": E.iao}[scheme].prepare(model, inplace=True, **kw)
+
+
+def prepare_oracle(model, scheme, **kw):
+    from oracle import reference_port as O  # CPU checker / baseline only
+    if scheme == "wbwtab":
+        return O.prepare_wbwtab(model, inplace=True, **kw)
+    if scheme == "dorefa":
+        return O.prepare_dorefa(model, inplace=True, **kw)
+    return O.prepare_iao(model, inplace=True, add_type=zoo.Add, **kw)
+
+
+def make_optimizer(model, lr=0.01, wd=0.0):
+    groups = [{"params": [p], "lr": lr, "weight_decay": wd} for p in model.parameters()]
+    return torch.optim.Adam(groups, lr=lr, weight_decay=wd)
+
+
+def synthetic_batch(batch, hw, seed, device="cpu", pin=False):
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randn(batch, 3, hw, hw, generator=g)
+    t = torch.randint(0, 10, (batch,), generator=g)
+    if pin:
+        x, t = x.pin_memory(), t.pin_memory()
+    return x.to(device), t.to(device)
+
+
+class QatStepper:
+    """one QAT step = forward + CE loss + zero_grad + backward (+ grad all-reduce) + Adam."""
+
+    def __init__(self, model, lr=0.01, wd=0.0, bucket=None):
+        self.model, self.bucket = model, bucket
+        self.opt = make_optimizer(model, lr, wd)
+        self.crit = nn.CrossEntropyLoss()
+
+    def step(self, x, t):
+        self.model.train()
+        out = self.model(x)
+        loss = self.crit(out, t)
+        if self.bucket is not None:
+            self.bucket.zero()
+        else:
+            self.opt.zero_grad()
+        loss.backward()
+        if self.bucket is not None:
+            self.bucket.all_reduce()
+        self.opt.step()
+        return loss

@@ -1,0 +1,171 @@
+/*
+ * micronet_b200 — C-ABI of the B200 (sm_100a) fake-quant conv/linear engine.
+ *
+ * The reference (666DZY666/micronet) has no FFI: its hot path is Python
+ * nn.Module code that composes ATen ops.  This header is the boundary a
+ * maintainer binds instead (ctypes stub in INTEGRATION.md): plain device
+ * pointers, sizes and a cudaStream_t — no torch types.  Every entry point
+ * cites the reference lines it replaces; aliases:
+ *   DF  = micronet/compression/quantization/wqaq/dorefa/quantize.py
+ *   WB  = micronet/compression/quantization/wbwtab/quantize.py
+ *   IAO = micronet/compression/quantization/wqaq/iao/quantize.py
+ *
+ * Conventions
+ *   - all pointers are DEVICE pointers unless the name ends in _host;
+ *   - tensors are contiguous fp32 NCHW (weights KCRS) as at the reference's
+ *     module surface; "codes" are u8 integer levels (level - qmin);
+ *   - every call is asynchronous on `stream`, allocates nothing and keeps no
+ *     pointer after returning; scratch is passed in by the caller;
+ *   - return value: 0 = ok, <0 = invalid argument (MNB_E_*), >0 = cudaError_t;
+ *     mnb_last_error() gives a thread-local message.
+ */
+#ifndef MICRONET_B200_H
+#define MICRONET_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* mnb_stream_t; /* cudaStream_t */
+
+#define MNB_E_ARG (-1)         /* bad shape / null pointer / unsupported bits */
+#define MNB_E_UNSUPPORTED (-2) /* valid request this build has no kernel for  */
+
+int mnb_version(void);
+const char* mnb_last_error(void);
+/* number of kernel launches issued through this library since load (bench.py's gpu_launches) */
+int64_t mnb_launch_count(void);
+
+/* ------------------------------------------------------------------------
+ * Convolution geometry (F.conv2d arguments: WB:186-194, DF:113-121, IAO:498-506)
+ * ---------------------------------------------------------------------- */
+typedef struct {
+  int32_t batch, in_c, in_h, in_w;
+  int32_t out_c, ker_h, ker_w;
+  int32_t stride_h, stride_w, pad_h, pad_w, dil_h, dil_w, groups;
+} mnb_conv_shape;
+
+/* ------------------------------------------------------------------------
+ * Activation fake-quantizers
+ * ---------------------------------------------------------------------- */
+#define MNB_ACT_DOREFA 1 /* DF:36-46   clamp(0.1x,0,1) -> round(./s), s = 1/(2^a-1)      */
+#define MNB_ACT_IAO 2    /* IAO:214-240 clamp(round(x/s - zp), qmin, qmax)              */
+#define MNB_ACT_SIGN 3   /* WB:11-36   sign(x) with 0 -> +1, saturate-STE               */
+
+typedef struct {
+  int32_t mode;        /* MNB_ACT_*                                                    */
+  int32_t bits;        /* DoReFa a_bits (2..8)                                         */
+  int32_t qmin, qmax;  /* IAO level range (IAO:243-288)                                */
+  int32_t q_type;      /* IAO: 0 symmetric / 1 asymmetric STE range (IAO:148-157)      */
+  const float* scale;  /* IAO: device scalar `scale`                                   */
+  const float* zero_point; /* IAO: device scalar `zero_point`                          */
+  const float* obs_min;    /* IAO: device scalar observer.min_val                      */
+  const float* obs_max;    /* IAO: device scalar observer.max_val                      */
+} mnb_act_qparams;
+
+/* Forward.  Any of the three outputs may be NULL.
+ *   codes    u8[n]      level - level_min   (DoReFa/IAO; SIGN: 0 or 2 so that e = code-1)
+ *   pass_bits u32[ceil(n/32)]  bit i set  <=>  the STE passes the gradient at element i
+ *   xq       f32[n]     the fake-quantized tensor the reference module returns           */
+int mnb_act_quant_fwd(const float* x, int64_t n, const mnb_act_qparams* qp, uint8_t* codes,
+                      uint32_t* pass_bits, float* xq, mnb_stream_t stream);
+/* Backward of the same op (autograd of DF:43-45 / IAO:227-239 / WB:22-36):
+ *   DoReFa dx = (((g*s)/s) * pass) * 0.1 ; IAO dx = ((g*s) * pass) / s ; SIGN dx = g * pass   */
+int mnb_act_quant_bwd(const float* g, const uint32_t* pass_bits, int64_t n, const mnb_act_qparams* qp,
+                      float* dx, mnb_stream_t stream);
+
+/* ------------------------------------------------------------------------
+ * IAO observers + update_qparams (IAO:15-139, 292-321), all on device, no host sync.
+ *   observer kinds: 0 = MinMaxObserver (running extremum), 1 = MovingAverageMinMaxObserver,
+ *                   2 = HistogramObserver (EMA of the k-th smallest |x|, k=int(p*n))
+ *   `first` = 1 on the observer's first call (the reference's num_flag == 0 branch).
+ *   `rows`  = 1 for q_level "L"; = out_channels for "C"/"FC" (x viewed as [rows, n/rows]).
+ *   min_val/max_val/scale/zero_point: the module's registered buffers (rows floats each).
+ *   symmetric: 1 -> SymmetricQuantizer, 0 -> AsymmetricQuantizer.  update_qparams=0 only observes.
+ *   scratch: >= mnb_observe_scratch_bytes(n, rows) bytes, zero-initialised once by the caller
+ *   (the kernels leave it zeroed again).                                                   */
+int64_t mnb_observe_scratch_bytes(int64_t n, int32_t rows);
+int mnb_iao_observe(const float* x, int64_t n, int32_t rows, int32_t observer_kind, int32_t first,
+                    double momentum, double percentile, float* min_val, float* max_val,
+                    int32_t update_qparams, int32_t symmetric, int32_t qmin, int32_t qmax,
+                    float* scale, float* zero_point, void* scratch, mnb_stream_t stream);
+/* update_qparams only (QuantAdd's union range, IAO:1487-1494). */
+int mnb_iao_update_qparams(const float* min_val, const float* max_val, int32_t rows, int32_t symmetric,
+                           int32_t qmin, int32_t qmax, float* scale, float* zero_point,
+                           mnb_stream_t stream);
+
+/* ------------------------------------------------------------------------
+ * Weight quantizers.  Forward writes
+ *   w_int   i16[numel]  effective integer e with  wq = e * w_scale[k]   (exact)
+ *   w_scale f32[K]      per-output-channel dequantization scale
+ *   wq      f32[numel]  the fake-quantized weight the reference feeds F.conv2d
+ * and whatever the closed-form backward needs in `aux`.
+ * ---------------------------------------------------------------------- */
+/* DF:61-73.  aux: f32[numel + 4] (tanh values, then {max|t|, #ties, s, -}).  scratch as above. */
+int mnb_dorefa_weight_fwd(const float* w, int64_t numel, int32_t out_c, int32_t w_bits, int16_t* w_int,
+                          float* w_scale, float* wq, float* aux, void* scratch, mnb_stream_t stream);
+int mnb_dorefa_weight_bwd(const float* g_wq, const float* aux, int64_t numel, int32_t w_bits, float* dw,
+                          void* scratch, mnb_stream_t stream);
+/* WB:98-149.  W = 2 (binary; MUTATES w in place: mean-centre over dim 1 + clamp, WB:98-102)
+ *             W = 3 (ternary).  w is [out_c, in_c_per_group, kh*kw].
+ * aux: f32[3*out_c] = {alpha_k, threshold_k, count_k}.                                          */
+int mnb_wb_weight_fwd(float* w, int32_t out_c, int32_t in_c_per_group, int32_t ker_hw, int32_t W,
+                      int16_t* w_int, float* w_scale, float* wq, float* aux, mnb_stream_t stream);
+int mnb_wb_weight_bwd(const float* g_wq, const float* w, const float* aux, int32_t out_c,
+                      int32_t in_c_per_group, int32_t ker_hw, int32_t W, float* dw, mnb_stream_t stream);
+/* IAO:214-240 on a weight tensor with per-row (rows = out_c) or per-layer (rows = 1) qparams that
+ * were just refreshed by mnb_iao_observe.  pass: u8[numel] STE mask.                           */
+int mnb_iao_weight_fwd(const float* w, int64_t numel, int32_t out_c, int32_t rows, const float* scale,
+                       const float* zero_point, const float* obs_min, const float* obs_max,
+                       int32_t q_type, int32_t qmin, int32_t qmax, int16_t* w_int, float* w_scale,
+                       float* wq, uint8_t* pass, mnb_stream_t stream);
+int mnb_iao_weight_bwd(const float* g_wq, const uint8_t* pass, const float* scale, int64_t numel,
+                       int32_t out_c, int32_t rows, float* dw, mnb_stream_t stream);
+
+/* ------------------------------------------------------------------------
+ * Fake-quantized convolution (WB:186, DF:113, IAO:498/947) and its autograd (ATen
+ * convolution_backward).  F.linear (DF:198, IAO:1156) is the 1x1 case on a [B, C, 1, 1] view.
+ *
+ * Activation operand:  a_codes != NULL : u8 codes, effective integer e_a = code + a_offset,
+ *                                        value = e_a * a_scale[0]; a_offset_zp (device scalar,
+ *                                        may be NULL) is added to a_offset (IAO zero_point);
+ *                      else            : a_f32 raw fp32 activations.
+ * Weight operand:      w_int != NULL && a_codes != NULL : exact integer path, s32 accumulate,
+ *                                        y = bias + acc * a_scale * w_scale[k];
+ *                      else            : w_f32 fp32 weights, fp32 accumulate.
+ * ---------------------------------------------------------------------- */
+typedef struct {
+  const uint8_t* a_codes;
+  const float* a_f32;
+  int32_t a_offset;
+  const float* a_offset_zp;
+  const float* a_scale; /* device scalar or NULL (= 1) */
+  const int16_t* w_int;
+  const float* w_scale; /* f32[out_c] */
+  const float* w_f32;
+  const float* bias; /* f32[out_c] or NULL */
+} mnb_conv_operands;
+
+int mnb_conv2d_fwd(const mnb_conv_shape* s, const mnb_conv_operands* op, float* y, mnb_stream_t stream);
+/* dX = conv_transpose(dY, Wq) fused with the activation STE:  pass_bits/qp may be NULL (plain dgrad). */
+int mnb_conv2d_dgrad(const mnb_conv_shape* s, const float* dy, const float* wq, const uint32_t* pass_bits,
+                     const mnb_act_qparams* qp, float* dx, mnb_stream_t stream);
+/* dWq = corr(Xq, dY); Xq given as codes (+offset, *a_scale) or fp32.  scratch >= mnb_wgrad_scratch_bytes. */
+int64_t mnb_wgrad_scratch_bytes(const mnb_conv_shape* s);
+int mnb_conv2d_wgrad(const mnb_conv_shape* s, const float* dy, const mnb_conv_operands* op, float* dwq,
+                     void* scratch, mnb_stream_t stream);
+/* per-channel sums over (B, H, W) of a [B, C, HW] tensor:
+ *   stats[0..C) = sum, stats[C..2C) = sum of squares (both accumulated in fp64, stored fp32 as
+ *   mean and UNBIASED variance when `as_mean_var` != 0 — torch.mean / torch.var of IAO:854-855). */
+int mnb_channel_stats(const float* x, int32_t batch, int32_t channels, int32_t hw, int32_t as_mean_var,
+                      float* stats, void* scratch, mnb_stream_t stream);
+/* backward of (mean, var):  dx = dmean/N + dvar * 2 (x - mean)/(N-1) */
+int mnb_channel_stats_bwd(const float* x, const float* mean, const float* dmean, const float* dvar,
+                          int32_t batch, int32_t channels, int32_t hw, float* dx, mnb_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MICRONET_B200_H */

@@ -1,0 +1,122 @@
+"""ctypes binding of ``libmicronet_b200.so`` (the C-ABI in ``include/micronet_b200.h``).
+
+There is no CPU fallback: if the shared library is missing, or a tensor is not on
+a CUDA device, the call raises."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libmicronet_b200.so")
+
+ACT_DOREFA, ACT_IAO, ACT_SIGN = 1, 2, 3
+
+
+class ConvShape(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in (
+        "batch", "in_c", "in_h", "in_w", "out_c", "ker_h", "ker_w", "stride_h", "stride_w",
+        "pad_h", "pad_w", "dil_h", "dil_w", "groups")]
+
+
+class ActQParams(C.Structure):
+    _fields_ = [("mode", C.c_int32), ("bits", C.c_int32), ("qmin", C.c_int32), ("qmax", C.c_int32),
+                ("q_type", C.c_int32), ("scale", C.c_void_p), ("zero_point", C.c_void_p),
+                ("obs_min", C.c_void_p), ("obs_max", C.c_void_p)]
+
+
+class ConvOperands(C.Structure):
+    _fields_ = [("a_codes", C.c_void_p), ("a_f32", C.c_void_p), ("a_offset", C.c_int32),
+                ("a_offset_zp", C.c_void_p), ("a_scale", C.c_void_p), ("w_int", C.c_void_p),
+                ("w_scale", C.c_void_p), ("w_f32", C.c_void_p), ("bias", C.c_void_p)]
+
+
+_P, _I, _L, _D = C.c_void_p, C.c_int32, C.c_int64, C.c_double
+_SHAPE, _ACTQ, _OPS = C.POINTER(ConvShape), C.POINTER(ActQParams), C.POINTER(ConvOperands)
+
+# name -> (restype, argtypes); mirrors include/micronet_b200.h one to one
+PROTOTYPES = {
+    "mnb_version": (C.c_int, []),
+    "mnb_last_error": (C.c_char_p, []),
+    "mnb_launch_count": (_L, []),
+    "mnb_act_quant_fwd": (C.c_int, [_P, _L, _ACTQ, _P, _P, _P, _P]),
+    "mnb_act_quant_bwd": (C.c_int, [_P, _P, _L, _ACTQ, _P, _P]),
+    "mnb_observe_scratch_bytes": (_L, [_L, _I]),
+    "mnb_iao_observe": (C.c_int, [_P, _L, _I, _I, _I, _D, _D, _P, _P, _I, _I, _I, _I, _P, _P, _P, _P]),
+    "mnb_iao_update_qparams": (C.c_int, [_P, _P, _I, _I, _I, _I, _P, _P, _P]),
+    "mnb_dorefa_weight_fwd": (C.c_int, [_P, _L, _I, _I, _P, _P, _P, _P, _P, _P]),
+    "mnb_dorefa_weight_bwd": (C.c_int, [_P, _P, _L, _I, _P, _P, _P]),
+    "mnb_wb_weight_fwd": (C.c_int, [_P, _I, _I, _I, _I, _P, _P, _P, _P, _P]),
+    "mnb_wb_weight_bwd": (C.c_int, [_P, _P, _P, _I, _I, _I, _I, _P, _P]),
+    "mnb_iao_weight_fwd": (C.c_int, [_P, _L, _I, _I, _P, _P, _P, _P, _I, _I, _I, _P, _P, _P, _P, _P]),
+    "mnb_iao_weight_bwd": (C.c_int, [_P, _P, _P, _L, _I, _I, _P, _P]),
+    "mnb_conv2d_fwd": (C.c_int, [_SHAPE, _OPS, _P, _P]),
+    "mnb_conv2d_dgrad": (C.c_int, [_SHAPE, _P, _P, _P, _ACTQ, _P, _P]),
+    "mnb_wgrad_scratch_bytes": (_L, [_SHAPE]),
+    "mnb_conv2d_wgrad": (C.c_int, [_SHAPE, _P, _OPS, _P, _P, _P]),
+    "mnb_channel_stats": (C.c_int, [_P, _I, _I, _I, _I, _P, _P, _P]),
+    "mnb_channel_stats_bwd": (C.c_int, [_P, _P, _P, _P, _I, _I, _I, _P, _P]),
+}
+
+_lib = None
+
+
+def load():
+    """Load the shared library (once).  Raises if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            f"micronet_b200: {LIB_PATH} is missing - build it with `python -m micronet_b200.build` "
+            "(there is no CPU / PyTorch fallback for the fake-quant hot path)")
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in PROTOTYPES.items():
+        fn = getattr(lib, name)  # AttributeError if the .so does not export a declared symbol
+        fn.restype, fn.argtypes = res, args
+    _lib = lib
+    return lib
+
+
+def check(rc: int, what: str):
+    if rc != 0:
+        msg = load().mnb_last_error().decode(errors="replace")
+        kind = ValueError if rc < 0 else RuntimeError
+        raise kind(f"micronet_b200.{what} failed (code {rc}): {msg}")
+
+
+def ptr(t):
+    return None if t is None else t.data_ptr()
+
+
+def stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def require_cuda(*tensors):
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError(
+                "micronet_b200: the fake-quant engine runs on CUDA (sm_100a) tensors only; "
+                "got a CPU tensor - there is deliberately no CPU fallback")
+
+
+def launch_count() -> int:
+    return int(load().mnb_launch_count())
+
+
+_scratch = {}
+
+
+def scratch(device, rows=1):
+    """persistent zero-initialised scratch (block counters / histograms); kernels re-zero it."""
+    lib = load()
+    need = int(lib.mnb_observe_scratch_bytes(0, int(rows)))
+    key = (device.type, device.index)
+    buf = _scratch.get(key)
+    if buf is None or buf.numel() < need:
+        buf = torch.zeros(max(need, 1 << 20), dtype=torch.uint8, device=device)
+        _scratch[key] = buf
+    return buf

@@ -1,0 +1,123 @@
+// Shared helpers for the micronet_b200 sm_100a kernels.
+#pragma once
+#include <cuda_runtime.h>
+#include <float.h>
+#include <stdint.h>
+
+#include "../../include/micronet_b200.h"
+
+int mnb_fail(int code, const char* fmt, ...);
+void mnb_count_launches(int n);
+
+#define MNB_REQUIRE(cond, ...)                            \
+  do {                                                    \
+    if (!(cond)) return mnb_fail(MNB_E_ARG, __VA_ARGS__); \
+  } while (0)
+
+// call after every launch: surfaces launch-configuration errors as return codes
+#define MNB_LAUNCHED(nlaunch)                                                        \
+  do {                                                                               \
+    mnb_count_launches(nlaunch);                                                     \
+    cudaError_t e__ = cudaGetLastError();                                            \
+    if (e__ != cudaSuccess) return mnb_fail((int)e__, "%s:%d launch failed: %s", __FILE__, __LINE__, \
+                                            cudaGetErrorString(e__));                \
+  } while (0)
+
+static inline int mnb_ceil_div(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
+constexpr int MNB_NUM_SMS = 148;  // B200: 2 dies x 74 SMs
+
+// ---- exact-rounding primitives (never contracted into FMA, never fast-math) ----
+
+// sign(v) * floor(|v| + 0.5) in fp32 — DF:13-16 / IAO:158-159, including the
+// fp32 double-rounding quirk (0.49999997 -> 1).  rintf/roundf are both wrong here.
+__device__ __forceinline__ float mnb_round_half_away(float v) {
+  float r = floorf(__fadd_rn(fabsf(v), 0.5f));
+  return v > 0.f ? r : (v < 0.f ? -r : 0.f);
+}
+// torch.sign: -1 / 0 / +1
+__device__ __forceinline__ float mnb_sign0(float v) { return v > 0.f ? 1.f : (v < 0.f ? -1.f : 0.f); }
+
+// order-preserving float <-> uint32 (for atomic / integer min-max)
+__device__ __forceinline__ uint32_t mnb_f2ord(float f) {
+  uint32_t u = __float_as_uint(f);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float mnb_ord2f(uint32_t u) {
+  return __uint_as_float((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u);
+}
+
+template <typename T, typename Op>
+__device__ __forceinline__ T mnb_warp_reduce(T v, Op op) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = op(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+// block-wide reduction; result valid in every thread.  `smem` holds >= 32 T.
+template <typename T, typename Op>
+__device__ __forceinline__ T mnb_block_reduce(T v, Op op, T identity, T* smem) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  v = mnb_warp_reduce(v, op);
+  __syncthreads();
+  if (lane == 0) smem[wid] = v;
+  __syncthreads();
+  const int nw = (blockDim.x + 31) >> 5;
+  T r = (lane < nw) ? smem[lane] : identity;
+  r = mnb_warp_reduce(r, op);
+  return r;
+}
+struct MnbMin { template <typename T> __device__ T operator()(T a, T b) const { return a < b ? a : b; } };
+struct MnbMax { template <typename T> __device__ T operator()(T a, T b) const { return a > b ? a : b; } };
+struct MnbSum { template <typename T> __device__ T operator()(T a, T b) const { return a + b; } };
+
+// ---- the activation quantizer, shared by the standalone kernel and the fused conv loaders ----
+struct MnbActQ {
+  int mode, qmin, qmax;
+  float s, zp, lo, hi;
+};
+
+__device__ __forceinline__ MnbActQ mnb_load_actq(const mnb_act_qparams& p) {
+  MnbActQ q;
+  q.mode = p.mode; q.qmin = p.qmin; q.qmax = p.qmax;
+  q.s = 1.f; q.zp = 0.f; q.lo = 0.f; q.hi = 0.f;
+  if (p.mode == MNB_ACT_DOREFA) {
+    q.s = (float)(1.0 / (double)((1 << p.bits) - 1));  // Python: 1 / float(2**a - 1), cast to fp32 by ATen
+  } else if (p.mode == MNB_ACT_IAO) {
+    q.s = __ldg(p.scale);
+    q.zp = __ldg(p.zero_point);
+    float a = __fsub_rn(__fdiv_rn(__ldg(p.obs_min), q.s), q.zp);
+    float b = __fsub_rn(__fdiv_rn(__ldg(p.obs_max), q.s), q.zp);
+    if (p.q_type == 0) { q.hi = fmaxf(fabsf(a), fabsf(b)); q.lo = -q.hi; }
+    else { q.lo = a; q.hi = b; }
+  }
+  return q;
+}
+
+// returns the clamped level; sets pass (STE gradient mask) and xq (dequantized value)
+__device__ __forceinline__ int mnb_act_quantize_one(const MnbActQ& q, float x, bool& pass, float& xq) {
+  if (q.mode == MNB_ACT_DOREFA) {
+    float t = __fmul_rn(x, 0.1f);
+    pass = (t >= 0.f) && (t <= 1.f);
+    float c = fminf(fmaxf(t, 0.f), 1.f);
+    float r = floorf(__fadd_rn(__fdiv_rn(c, q.s), 0.5f));  // c >= 0: sign*floor(|.|+0.5)
+    xq = __fmul_rn(r, q.s);
+    return (int)r;
+  } else if (q.mode == MNB_ACT_IAO) {
+    float v = __fsub_rn(__fdiv_rn(x, q.s), q.zp);
+    float r = mnb_round_half_away(v);
+    float c = fminf(fmaxf(r, (float)q.qmin), (float)q.qmax);
+    pass = !(v > q.hi) && !(v < q.lo) && (r >= (float)q.qmin) && (r <= (float)q.qmax);
+    xq = __fmul_rn(__fadd_rn(c, q.zp), q.s);
+    return (int)c - q.qmin;
+  } else {  // SIGN
+    bool pos = !(x < 0.f);
+    pass = !(x >= 1.0f) && !(x <= -1.0f);
+    xq = pos ? 1.f : -1.f;
+    return pos ? 2 : 0;
+  }
+}
+
+__device__ __forceinline__ float mnb_act_ste_one(const MnbActQ& q, float g, bool pass) {
+  if (q.mode == MNB_ACT_DOREFA) return __fmul_rn(pass ? __fdiv_rn(__fmul_rn(g, q.s), q.s) : 0.f, 0.1f);
+  if (q.mode == MNB_ACT_IAO) return pass ? __fdiv_rn(__fmul_rn(g, q.s), q.s) : 0.f;
+  return pass ? g : 0.f;
+}

@@ -1,0 +1,367 @@
+"""autograd.Function wrappers around the C-ABI kernels.
+
+Each Function mirrors one autograd node (or a fused chain of nodes) of the
+reference's forward path; the math each kernel implements is documented in
+``include/micronet_b200.h`` with the reference file:line it replaces."""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+from torch.autograd import Function
+
+from . import _lib as L
+
+
+# --------------------------------------------------------------------------
+# optional per-launch device timing of the conv kernels (bench.py's roofline leg)
+# --------------------------------------------------------------------------
+class KernelTimer:
+    """records a CUDA-event pair on the launching (current) stream around each conv kernel call"""
+
+    def __init__(self):
+        self.records = []  # (kind, shape tuple, start event, end event)
+
+    def run(self, kind, sh, fn):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        rc = fn()
+        b.record()
+        self.records.append((kind, tuple(getattr(sh, f) for f, _ in sh._fields_), a, b))
+        return rc
+
+    def summary(self):
+        """{(kind, shape): [ms, ...]} — call after torch.cuda.synchronize()"""
+        out = {}
+        for kind, shape, a, b in self.records:
+            out.setdefault((kind, shape), []).append(a.elapsed_time(b))
+        return out
+
+
+TIMER = None  # set to a KernelTimer to enable
+
+
+def _timed(kind, sh, fn):
+    return fn() if TIMER is None else TIMER.run(kind, sh, fn)
+
+
+# --------------------------------------------------------------------------
+# activation quantizer description
+# --------------------------------------------------------------------------
+class ActSpec:
+    """Which activation fake-quantizer to run and where its device-resident
+    parameters live (tensors are the module's registered buffers)."""
+
+    __slots__ = ("mode", "bits", "qmin", "qmax", "q_type", "scale", "zero_point", "obs_min", "obs_max")
+
+    def __init__(self, mode, bits=8, qmin=0, qmax=255, q_type=0, scale=None, zero_point=None,
+                 obs_min=None, obs_max=None):
+        self.mode, self.bits, self.qmin, self.qmax, self.q_type = mode, bits, qmin, qmax, q_type
+        self.scale, self.zero_point, self.obs_min, self.obs_max = scale, zero_point, obs_min, obs_max
+
+    def struct(self):
+        return L.ActQParams(self.mode, self.bits, self.qmin, self.qmax, self.q_type, L.ptr(self.scale),
+                            L.ptr(self.zero_point), L.ptr(self.obs_min), L.ptr(self.obs_max))
+
+    # decoding of the u8 codes: effective integer e = code + offset (+ zero_point), value = e * scale
+    @property
+    def code_offset(self):
+        if self.mode == L.ACT_IAO:
+            return self.qmin
+        if self.mode == L.ACT_SIGN:
+            return -1
+        return 0
+
+
+def _dorefa_scale_tensor(bits, device, _cache={}):
+    key = (bits, device.type, device.index)
+    if key not in _cache:
+        # Python double 1/(2^a-1), cast to fp32 exactly as ATen does for `tensor / python_float`
+        _cache[key] = torch.tensor([1.0 / float(2 ** bits - 1)], dtype=torch.float32, device=device)
+    return _cache[key]
+
+
+def act_quant_raw(x, spec: ActSpec, want_codes, want_bits, want_xq):
+    """run the activation quantizer kernel; returns (codes, pass_bits, xq)"""
+    L.require_cuda(x)
+    lib = L.load()
+    x = x.contiguous()
+    n = x.numel()
+    codes = torch.empty(x.shape, dtype=torch.uint8, device=x.device) if want_codes else None
+    bits = torch.empty((n + 31) // 32, dtype=torch.int32, device=x.device) if want_bits else None
+    xq = torch.empty_like(x) if want_xq else None
+    qp = spec.struct()
+    L.check(lib.mnb_act_quant_fwd(x.data_ptr(), n, C.byref(qp), L.ptr(codes), L.ptr(bits), L.ptr(xq),
+                                  L.stream()), "act_quant_fwd")
+    return codes, bits, xq
+
+
+class ActQuantFn(Function):
+    """standalone fake-quant of an activation tensor (reference: ActivationQuantizer /
+    Quantizer.forward returning the dequantized tensor)."""
+
+    @staticmethod
+    def forward(ctx, x, spec: ActSpec):
+        _, bits, xq = act_quant_raw(x, spec, False, ctx.needs_input_grad[0], True)
+        ctx.spec, ctx.bits = spec, bits
+        return xq
+
+    @staticmethod
+    def backward(ctx, g):
+        lib = L.load()
+        g = g.contiguous()
+        dx = torch.empty_like(g)
+        qp = ctx.spec.struct()
+        L.check(lib.mnb_act_quant_bwd(g.data_ptr(), ctx.bits.data_ptr(), g.numel(), C.byref(qp),
+                                      dx.data_ptr(), L.stream()), "act_quant_bwd")
+        return dx, None
+
+
+# --------------------------------------------------------------------------
+# weight quantizers: return (wq fp32, w_int i16, w_scale f32[K])
+# --------------------------------------------------------------------------
+class DorefaWeightFn(Function):
+    @staticmethod
+    def forward(ctx, w, w_bits):
+        L.require_cuda(w)
+        lib = L.load()
+        w = w.contiguous()
+        n, k = w.numel(), w.shape[0]
+        wq = torch.empty_like(w)
+        w_int = torch.empty(w.shape, dtype=torch.int16, device=w.device)
+        w_scale = torch.empty(k, dtype=torch.float32, device=w.device)
+        aux = torch.empty(n + 4, dtype=torch.float32, device=w.device)
+        L.check(lib.mnb_dorefa_weight_fwd(w.data_ptr(), n, k, w_bits, w_int.data_ptr(), w_scale.data_ptr(),
+                                          wq.data_ptr(), aux.data_ptr(), L.scratch(w.device).data_ptr(),
+                                          L.stream()), "dorefa_weight_fwd")
+        ctx.aux, ctx.w_bits = aux, w_bits
+        ctx.mark_non_differentiable(w_int, w_scale)
+        return wq, w_int, w_scale
+
+    @staticmethod
+    def backward(ctx, g, _gi, _gs):
+        lib = L.load()
+        g = g.contiguous()
+        dw = torch.empty_like(g)
+        L.check(lib.mnb_dorefa_weight_bwd(g.data_ptr(), ctx.aux.data_ptr(), g.numel(), ctx.w_bits,
+                                          dw.data_ptr(), L.scratch(g.device).data_ptr(), L.stream()),
+                "dorefa_weight_bwd")
+        return dw, None
+
+
+class WbWeightFn(Function):
+    """wbwtab binary / ternary weights.  W == 2 mutates ``w`` in place (WB:98-102)."""
+
+    @staticmethod
+    def forward(ctx, w, W):
+        L.require_cuda(w)
+        lib = L.load()
+        assert w.is_contiguous() and w.dim() == 4
+        k, cpg, khw = w.shape[0], w.shape[1], w.shape[2] * w.shape[3]
+        wq = torch.empty_like(w)
+        w_int = torch.empty(w.shape, dtype=torch.int16, device=w.device)
+        w_scale = torch.empty(k, dtype=torch.float32, device=w.device)
+        aux = torch.empty(3 * k, dtype=torch.float32, device=w.device)
+        L.check(lib.mnb_wb_weight_fwd(w.data_ptr(), k, cpg, khw, W, w_int.data_ptr(), w_scale.data_ptr(),
+                                      wq.data_ptr(), aux.data_ptr(), L.stream()), "wb_weight_fwd")
+        ctx.w, ctx.aux, ctx.W = w.detach(), aux, W  # gradient is taken at the (mutated) parameter values
+        ctx.mark_non_differentiable(w_int, w_scale)
+        return wq, w_int, w_scale
+
+    @staticmethod
+    def backward(ctx, g, _gi, _gs):
+        lib = L.load()
+        g = g.contiguous()
+        w = ctx.w
+        dw = torch.empty_like(g)
+        L.check(lib.mnb_wb_weight_bwd(g.data_ptr(), w.data_ptr(), ctx.aux.data_ptr(), w.shape[0], w.shape[1],
+                                      w.shape[2] * w.shape[3], ctx.W, dw.data_ptr(), L.stream()),
+                "wb_weight_bwd")
+        return dw, None
+
+
+class IaoWeightFn(Function):
+    """IAO fake-quant of a weight tensor with (already refreshed) per-row or per-layer qparams."""
+
+    @staticmethod
+    def forward(ctx, w, scale, zero_point, obs_min, obs_max, q_type, qmin, qmax):
+        L.require_cuda(w)
+        lib = L.load()
+        w = w.contiguous()
+        n, k, rows = w.numel(), w.shape[0], scale.numel()
+        wq = torch.empty_like(w)
+        w_int = torch.empty(w.shape, dtype=torch.int16, device=w.device)
+        w_scale = torch.empty(k, dtype=torch.float32, device=w.device)
+        keep = torch.empty(w.shape, dtype=torch.uint8, device=w.device)
+        L.check(lib.mnb_iao_weight_fwd(w.data_ptr(), n, k, rows, scale.data_ptr(), zero_point.data_ptr(),
+                                       obs_min.data_ptr(), obs_max.data_ptr(), q_type, qmin, qmax,
+                                       w_int.data_ptr(), w_scale.data_ptr(), wq.data_ptr(), keep.data_ptr(),
+                                       L.stream()), "iao_weight_fwd")
+        ctx.keep, ctx.scale, ctx.k, ctx.rows = keep, scale, k, rows
+        ctx.mark_non_differentiable(w_int, w_scale)
+        return wq, w_int, w_scale
+
+    @staticmethod
+    def backward(ctx, g, _gi, _gs):
+        lib = L.load()
+        g = g.contiguous()
+        dw = torch.empty_like(g)
+        L.check(lib.mnb_iao_weight_bwd(g.data_ptr(), ctx.keep.data_ptr(), ctx.scale.data_ptr(), g.numel(),
+                                       ctx.k, ctx.rows, dw.data_ptr(), L.stream()), "iao_weight_bwd")
+        return (dw,) + (None,) * 7
+
+
+# --------------------------------------------------------------------------
+# the fake-quantized convolution
+# --------------------------------------------------------------------------
+def _shape_struct(x_shape, w_shape, stride, padding, dilation, groups):
+    b, c, h, w = x_shape
+    k, _, r, s = w_shape
+    return L.ConvShape(b, c, h, w, k, r, s, stride[0], stride[1], padding[0], padding[1],
+                       dilation[0], dilation[1], groups)
+
+
+def _out_hw(sh: L.ConvShape):
+    p = (sh.in_h + 2 * sh.pad_h - sh.dil_h * (sh.ker_h - 1) - 1) // sh.stride_h + 1
+    q = (sh.in_w + 2 * sh.pad_w - sh.dil_w * (sh.ker_w - 1) - 1) // sh.stride_w + 1
+    return p, q
+
+
+def channel_sums(x4):
+    """sum over (B, H, W) of a [B, C, H, W] tensor -> [C] (bias gradient)."""
+    lib = L.load()
+    b, c = x4.shape[0], x4.shape[1]
+    hw = x4.numel() // (b * c)
+    out = torch.empty(2 * c, dtype=torch.float32, device=x4.device)
+    L.check(lib.mnb_channel_stats(x4.data_ptr(), b, c, hw, 0, out.data_ptr(),
+                                  L.scratch(x4.device, c).data_ptr(), L.stream()), "channel_stats")
+    return out[:c]
+
+
+class QuantConv2dFn(Function):
+    """y = conv2d(Q_a(x), wq, bias) with the activation quantizer fused on the input side
+    and the clip-STE fused into dgrad.  ``spec`` None => x is used as fp32 (wbwtab, a_bits=32)."""
+
+    @staticmethod
+    def forward(ctx, x, wq, bias, w_int, w_scale, spec, stride, padding, dilation, groups):
+        L.require_cuda(x, wq)
+        lib = L.load()
+        x = x.contiguous()
+        wq = wq.contiguous()
+        sh = _shape_struct(x.shape, wq.shape, stride, padding, dilation, groups)
+        p, q = _out_hw(sh)
+        y = torch.empty((x.shape[0], wq.shape[0], p, q), dtype=torch.float32, device=x.device)
+        codes = bits = None
+        ops = L.ConvOperands()
+        if spec is not None:
+            codes, bits, _ = act_quant_raw(x, spec, True, ctx.needs_input_grad[0], False)
+            ops.a_codes = codes.data_ptr()
+            ops.a_offset = spec.code_offset
+            ops.a_offset_zp = L.ptr(spec.zero_point) if spec.mode == L.ACT_IAO else None
+            a_scale = spec.scale if spec.mode == L.ACT_IAO else (
+                _dorefa_scale_tensor(spec.bits, x.device) if spec.mode == L.ACT_DOREFA else None)
+            ops.a_scale = L.ptr(a_scale)
+        else:
+            a_scale = None
+            ops.a_f32 = x.data_ptr()
+        if codes is not None and w_int is not None:
+            ops.w_int, ops.w_scale = w_int.data_ptr(), w_scale.data_ptr()
+        else:
+            ops.w_f32 = wq.data_ptr()
+        ops.bias = L.ptr(bias)
+        L.check(_timed("fwd", sh, lambda: lib.mnb_conv2d_fwd(C.byref(sh), C.byref(ops), y.data_ptr(), L.stream())),
+                "conv2d_fwd")
+        ctx.sh, ctx.spec, ctx.a_scale = sh, spec, a_scale
+        ctx.codes, ctx.bits = codes, bits
+        ctx.x = x if codes is None else None
+        ctx.wq = wq
+        ctx.has_bias = bias is not None
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        lib = L.load()
+        dy = dy.contiguous()
+        sh, spec = ctx.sh, ctx.spec
+        dx = dwq = db = None
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            db = channel_sums(dy)
+        if ctx.needs_input_grad[0]:
+            dx = torch.empty((sh.batch, sh.in_c, sh.in_h, sh.in_w), dtype=torch.float32, device=dy.device)
+            if spec is not None:
+                qp = spec.struct()
+                rc = _timed("dgrad", sh, lambda: lib.mnb_conv2d_dgrad(
+                    C.byref(sh), dy.data_ptr(), ctx.wq.data_ptr(), ctx.bits.data_ptr(), C.byref(qp),
+                    dx.data_ptr(), L.stream()))
+            else:
+                rc = _timed("dgrad", sh, lambda: lib.mnb_conv2d_dgrad(
+                    C.byref(sh), dy.data_ptr(), ctx.wq.data_ptr(), None, None, dx.data_ptr(), L.stream()))
+            L.check(rc, "conv2d_dgrad")
+        if ctx.needs_input_grad[1]:
+            dwq = torch.empty_like(ctx.wq)
+            ops = L.ConvOperands()
+            if ctx.codes is not None:
+                ops.a_codes = ctx.codes.data_ptr()
+                ops.a_offset = spec.code_offset
+                ops.a_offset_zp = L.ptr(spec.zero_point) if spec.mode == L.ACT_IAO else None
+                ops.a_scale = L.ptr(ctx.a_scale)
+            else:
+                ops.a_f32 = ctx.x.data_ptr()
+            nbytes = int(lib.mnb_wgrad_scratch_bytes(C.byref(sh)))
+            ws = torch.empty(max(nbytes, 4), dtype=torch.uint8, device=dy.device)
+            L.check(_timed("wgrad", sh, lambda: lib.mnb_conv2d_wgrad(
+                C.byref(sh), dy.data_ptr(), C.byref(ops), dwq.data_ptr(), ws.data_ptr(), L.stream())),
+                "conv2d_wgrad")
+        return dx, dwq, db, None, None, None, None, None, None, None
+
+
+def quant_conv2d(x, wq, bias, w_int, w_scale, spec, stride, padding, dilation, groups):
+    return QuantConv2dFn.apply(x, wq, bias, w_int, w_scale, spec, tuple(stride), tuple(padding),
+                               tuple(dilation), groups)
+
+
+def quant_linear(x, wq, bias, w_int, w_scale, spec):
+    """F.linear on the same kernels: [*, C] -> 1x1 conv on a [N, C, 1, 1] view."""
+    lead = x.shape[:-1]
+    x4 = x.reshape(-1, x.shape[-1], 1, 1)
+    w4 = wq.reshape(wq.shape[0], wq.shape[1], 1, 1)
+    wi4 = None if w_int is None else w_int.reshape(w4.shape)
+    y = QuantConv2dFn.apply(x4, w4, bias, wi4, w_scale, spec, (1, 1), (0, 0), (1, 1), 1)
+    return y.reshape(*lead, wq.shape[0])
+
+
+# --------------------------------------------------------------------------
+# per-channel batch statistics (BN-fuse training path, IAO:853-855)
+# --------------------------------------------------------------------------
+class ChannelMeanVarFn(Function):
+    @staticmethod
+    def forward(ctx, x):
+        L.require_cuda(x)
+        lib = L.load()
+        x = x.contiguous()
+        b, c = x.shape[0], x.shape[1]
+        hw = x.numel() // (b * c)
+        out = torch.empty(2 * c, dtype=torch.float32, device=x.device)
+        L.check(lib.mnb_channel_stats(x.data_ptr(), b, c, hw, 1, out.data_ptr(),
+                                      L.scratch(x.device, c).data_ptr(), L.stream()), "channel_stats")
+        mean, var = out[:c], out[c:]
+        ctx.save_for_backward(x, mean)
+        return mean, var
+
+    @staticmethod
+    def backward(ctx, dmean, dvar):
+        lib = L.load()
+        x, mean = ctx.saved_tensors
+        b, c = x.shape[0], x.shape[1]
+        hw = x.numel() // (b * c)
+        dmean = torch.zeros_like(mean) if dmean is None else dmean.contiguous()
+        dvar = torch.zeros_like(mean) if dvar is None else dvar.contiguous()
+        dx = torch.empty_like(x)
+        L.check(lib.mnb_channel_stats_bwd(x.data_ptr(), mean.contiguous().data_ptr(), dmean.data_ptr(),
+                                          dvar.data_ptr(), b, c, hw, dx.data_ptr(), L.stream()),
+                "channel_stats_bwd")
+        return dx
+
+
+def channel_mean_var(x):
+    return ChannelMeanVarFn.apply(x)

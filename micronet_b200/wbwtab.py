@@ -1,0 +1,101 @@
+"""Binary / ternary weight, binary activation QAT modules on the B200 engine.
+
+Drop-in for the reference's ``micronet/compression/quantization/wbwtab/quantize.py``
+(constructor signatures WB:80, WB:106, WB:153-166; ``prepare`` rules WB:247-347)."""
+from __future__ import annotations
+
+import copy
+
+import torch.nn as nn
+
+from . import _lib as L
+from . import functional as F_
+
+
+class ActivationQuantizer(nn.Module):
+    """WB:79-94: A == 2 -> sign(x) (0 -> +1) with the saturate-STE; otherwise ReLU."""
+
+    def __init__(self, A=2):
+        super().__init__()
+        self.A = A
+        self.relu = nn.ReLU(inplace=True)
+
+    def binary(self, input):
+        return F_.ActQuantFn.apply(input, F_.ActSpec(L.ACT_SIGN))
+
+    def forward(self, input):
+        return self.binary(input) if self.A == 2 else self.relu(input)
+
+
+class WeightQuantizer(nn.Module):
+    """WB:105-149: W == 2 binary (in-place mean-centre + clamp of the parameter, then
+    sign * E|w|), W == 3 ternary (threshold 0.7 E|w|, scaled by the mean surviving |w|)."""
+
+    def __init__(self, W=2):
+        super().__init__()
+        self.W = W
+
+    def quantize(self, weight):
+        if self.W == 2 or self.W == 3:
+            return F_.WbWeightFn.apply(weight, self.W)
+        return weight, None, None
+
+    def forward(self, input):
+        return self.quantize(input)[0]
+
+
+class QuantConv2d(nn.Conv2d):
+    def __init__(self, in_channels, out_channels, kernel_size, stride=1, padding=0, dilation=1, groups=1,
+                 bias=True, padding_mode="zeros", W=2, quant_inference=False):
+        super().__init__(in_channels, out_channels, kernel_size, stride, padding, dilation, groups, bias,
+                         padding_mode)
+        self.quant_inference = quant_inference
+        self.weight_quantizer = WeightQuantizer(W=W)
+
+    def forward(self, input):
+        if not self.quant_inference:
+            wq, w_int, w_scale = self.weight_quantizer.quantize(self.weight)
+        else:
+            wq, w_int, w_scale = self.weight, None, None
+        # the input is NOT quantized here (WB:181-195): it is whatever the previous block produced
+        # (+-1 after an ActivationQuantizer(A=2), plain fp32 when A == 32)
+        return F_.quant_conv2d(input, wq, self.bias, w_int, w_scale, None, self.stride, self.padding,
+                               self.dilation, self.groups)
+
+
+def _adopt(dst, src):
+    dst.weight.data = src.weight
+    if src.bias is not None:
+        dst.bias.data = src.bias
+    return dst
+
+
+def add_quant_op(module, layer_counter, layer_num, A=2, W=2, quant_inference=False):
+    """WB:247-331: all convs but the first and the last are quantized; every ReLU that
+    follows conv 1 .. L-1 becomes an ActivationQuantizer."""
+    for name, child in module.named_children():
+        if isinstance(child, nn.Conv2d):
+            layer_counter[0] += 1
+            if 1 < layer_counter[0] < layer_num:
+                module._modules[name] = _adopt(QuantConv2d(
+                    child.in_channels, child.out_channels, child.kernel_size, stride=child.stride,
+                    padding=child.padding, dilation=child.dilation, groups=child.groups,
+                    bias=child.bias is not None, padding_mode=child.padding_mode, W=W,
+                    quant_inference=quant_inference), child)
+        elif isinstance(child, nn.ConvTranspose2d):
+            layer_counter[0] += 1
+            if 1 < layer_counter[0] < layer_num:
+                raise NotImplementedError("QuantConvTranspose2d is out of scope of the B200 engine (SURVEY §8 f4)")
+        elif isinstance(child, nn.ReLU):
+            if 0 < layer_counter[0] < layer_num:
+                module._modules[name] = ActivationQuantizer(A=A)
+        else:
+            add_quant_op(child, layer_counter, layer_num, A=A, W=W, quant_inference=quant_inference)
+
+
+def prepare(model, inplace=False, A=2, W=2, quant_inference=False):
+    if not inplace:
+        model = copy.deepcopy(model)
+    layer_num = sum(isinstance(m, (nn.Conv2d, nn.ConvTranspose2d)) for m in model.modules())
+    add_quant_op(model, [0], layer_num, A=A, W=W, quant_inference=quant_inference)
+    return model

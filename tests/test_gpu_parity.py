@@ -1,0 +1,337 @@
+"""GPU parity suite (run on the B200 box): the CUDA engine, called through the C-ABI, against
+ (a) the committed golden fixtures generated from the reference itself, and
+ (b) the CPU oracle on seeded inputs.
+Bar (BASELINE.json north_star): integer quantized levels bit-exact, fp32 results within 1e-5
+relative (per tensor, |a-b| <= 1e-5 * max|b|)."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as TF
+
+from tests.golden.cases import LAYER_CASES, MODEL_CASES
+from tests.oracle_util import ORACLE_CLASSES, build_from_golden, load_golden, rel_err, run_layer_steps
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-5
+DEV = "cuda:0"
+
+
+def engine_classes():
+    import micronet_b200 as E
+    return {
+        ("dorefa", "conv"): E.dorefa.QuantConv2d, ("dorefa", "linear"): E.dorefa.QuantLinear,
+        ("wbwtab", "conv"): E.wbwtab.QuantConv2d, ("iao", "conv"): E.iao.QuantConv2d,
+        ("iao", "bnfuse"): E.iao.QuantBNFuseConv2d, ("iao", "linear"): E.iao.QuantLinear,
+    }
+
+
+def _state_tol(case, key):
+    """bit-exact for everything that depends only on min/max/EMA arithmetic; the BN-fuse weight
+    range depends on batch statistics of an fp32 conv, which is not bit-reproducible even
+    CPU<->CPU."""
+    if case["kind"] == "bnfuse" and ("weight_quantizer" in key or "running_" in key):
+        return 2e-6
+    if case["scheme"] == "wbwtab" and key == "state.weight":
+        return 1e-6  # binary: in-place mean-centring, fp32 reduction order
+    return 0.0
+
+
+@pytest.mark.parametrize("case", LAYER_CASES, ids=[c["name"] for c in LAYER_CASES])
+def test_layer_case_matches_golden(case):
+    gold = load_golden("layer", case["name"])
+    mod = build_from_golden(engine_classes()[(case["scheme"], case["kind"])], case, gold, device=DEV)
+    for i, res in run_layer_steps(mod, case, gold, device=DEV):
+        for key, val in res.items():
+            ref = gold[f"s{i}.{key}"]
+            val = val.cpu()
+            if key.startswith("state."):
+                tol = _state_tol(case, key)
+                if tol == 0.0:
+                    assert np.array_equal(val.numpy(), ref), f"step {i} {key}: {val.flatten()[:4]} vs {ref.flatten()[:4]}"
+                else:
+                    assert rel_err(val, ref) <= tol, f"step {i} {key}: {rel_err(val, ref)}"
+            elif case["kind"] == "bnfuse" and key == "d.bias":
+                assert val.abs().max() <= 1e-4
+            else:
+                e = rel_err(val, ref)
+                assert e <= TOL, f"step {i} {key}: rel err {e}"
+
+
+def _tie_excused(pre, got, want):
+    """a level mismatch is excused only if the pre-round value sits within 2 ulp of k + 0.5"""
+    bad = got != want
+    if not bad.any():
+        return 0, 0
+    frac = np.abs(np.abs(pre[bad]) % 1.0 - 0.5)
+    ulp = np.spacing(np.abs(pre[bad]).astype(np.float32))
+    return int(bad.sum()), int((frac > 2 * ulp).sum())
+
+
+@pytest.mark.parametrize("case", [c for c in LAYER_CASES if c["scheme"] == "dorefa" and c["kind"] == "conv"],
+                         ids=lambda c: c["name"])
+def test_dorefa_levels_bit_exact(case):
+    from micronet_b200 import _lib as L, functional as F_
+    from oracle import reference_port as O
+    gold = load_golden("layer", case["name"])
+    ab, wb = case["kwargs"].get("a_bits", 8), case["kwargs"].get("w_bits", 8)
+    x = torch.from_numpy(gold["s0.x"]).to(DEV)
+    if ab != 32:
+        codes, _, _ = F_.act_quant_raw(x, F_.ActSpec(L.ACT_DOREFA, bits=ab), True, False, False)
+        assert np.array_equal(codes.cpu().numpy().astype(np.float32), gold["s0.lvl_a"])
+    w = torch.from_numpy(gold["init.weight"]).to(DEV)
+    _, w_int, _ = F_.DorefaWeightFn.apply(w, wb)
+    k = (w_int.cpu().numpy().astype(np.int32) + (2 ** wb - 1)) // 2
+    _, pre = O.dorefa_weight_levels(torch.from_numpy(gold["init.weight"]), wb)
+    nbad, unexcused = _tie_excused(pre.numpy(), k.astype(np.float32), gold["s0.lvl_w"])
+    assert unexcused == 0, f"{nbad} weight-level mismatches, {unexcused} not tie-excused"
+
+
+@pytest.mark.parametrize("case", [c for c in LAYER_CASES if c["scheme"] == "iao" and c["kind"] == "conv"],
+                         ids=lambda c: c["name"])
+def test_iao_activation_levels_bit_exact(case):
+    from micronet_b200 import functional as F_
+    gold = load_golden("layer", case["name"])
+    mod = build_from_golden(engine_classes()[("iao", "conv")], case, gold, device=DEV)
+    mod.train()
+    for i in range(case["train_steps"]):
+        x = torch.from_numpy(gold[f"s{i}.x"]).to(DEV)
+        aq = mod.activation_quantizer
+        spec = aq.prepare_activation(x)
+        codes, _, _ = F_.act_quant_raw(x, spec, True, False, False)
+        lv = codes.cpu().numpy().astype(np.float32) + aq.qmin
+        assert np.array_equal(lv, gold[f"s{i}.lvl_a"]), f"step {i}"
+        mod.weight_quantizer.quantize_weight(mod.weight)  # keep the weight observer in step
+
+
+# ---------------------------------------------------------------- kernels vs oracle at larger sizes
+def test_act_quant_large_vs_oracle():
+    from micronet_b200 import _lib as L, functional as F_
+    from oracle import reference_port as O
+    torch.manual_seed(0)
+    x = (torch.randn(7, 33, 29, 31) * 4)
+    xg = x.to(DEV).requires_grad_(True)
+    for bits in (2, 4, 8):
+        y = F_.ActQuantFn.apply(xg, F_.ActSpec(L.ACT_DOREFA, bits=bits))
+        xr = x.clone().requires_grad_(True)
+        yr = O.dorefa_quantize_activation(xr, bits)
+        assert torch.equal(y.detach().cpu(), yr.detach())
+        g = torch.randn_like(x)
+        y.backward(g.to(DEV)); yr.backward(g)
+        assert torch.equal(xg.grad.cpu(), xr.grad)
+        xg.grad = None
+    # sign + saturate STE (WB:11-36)
+    xs = torch.randn(5, 17, 13, 11) * 1.2
+    xs[0, 0, 0, :4] = torch.tensor([0.0, 1.0, -1.0, -0.0])
+    a = xs.to(DEV).requires_grad_(True)
+    b = xs.clone().requires_grad_(True)
+    ya, yb = F_.ActQuantFn.apply(a, F_.ActSpec(L.ACT_SIGN)), O.wb_binarize_activation(b)
+    assert torch.equal(ya.detach().cpu(), yb.detach())
+    g = torch.randn_like(xs)
+    ya.backward(g.to(DEV)); yb.backward(g)
+    assert torch.equal(a.grad.cpu(), b.grad)
+
+
+@pytest.mark.parametrize("n", [1, 31, 1000, 1 << 20, (1 << 22) + 77])
+def test_percentile_observer_matches_kthvalue(n):
+    import micronet_b200 as E
+    torch.manual_seed(n)
+    obs = E.iao.HistogramObserver("L", percentile=0.999 if n > 1 else 1.0).to(DEV)
+    ref_prev = None
+    for step in range(2):
+        x = torch.randn(n) * (1 + step)
+        obs(x.to(DEV))
+        k = int(obs.percentile * n)
+        cur = torch.kthvalue(x.abs(), k)[0]
+        ref_prev = cur if ref_prev is None else (1 - 0.1) * ref_prev + 0.1 * cur
+        assert torch.equal(obs.max_val.cpu(), ref_prev.reshape(1)), (step, obs.max_val, ref_prev)
+        assert obs.min_val.item() == 0.0
+
+
+def test_channel_stats_vs_torch():
+    from micronet_b200 import functional as F_
+    torch.manual_seed(3)
+    x = torch.randn(9, 20, 13, 7) * 2 + 0.5
+    xg = x.to(DEV).requires_grad_(True)
+    m, v = F_.channel_mean_var(xg)
+    xr = x.double().requires_grad_(True)
+    mr, vr = xr.mean(dim=[0, 2, 3]), xr.var(dim=[0, 2, 3])
+    assert rel_err(m.detach(), mr.detach()) < 1e-6 and rel_err(v.detach(), vr.detach()) < 1e-6
+    gm, gv = torch.randn(20), torch.randn(20)
+    (m * gm.to(DEV) + v * gv.to(DEV)).sum().backward()
+    (mr * gm.double() + vr * gv.double()).sum().backward()
+    assert rel_err(xg.grad, xr.grad) < 1e-5
+
+
+CONV_SWEEP = [
+    # B, C, H, W, K, R, S, stride, pad, dil, groups
+    (2, 3, 32, 32, 16, 5, 5, 1, 2, 1, 1),
+    (3, 16, 17, 19, 24, 3, 3, 2, 1, 1, 1),
+    (2, 32, 16, 16, 64, 3, 3, 1, 1, 1, 16),
+    (2, 64, 9, 9, 64, 1, 1, 1, 0, 1, 4),
+    (2, 8, 15, 15, 12, 3, 3, 1, 2, 2, 2),
+    (4, 40, 8, 8, 10, 1, 1, 1, 0, 1, 1),
+    (2, 6, 11, 13, 4, 3, 5, 2, 1, 1, 1),
+    (5, 130, 1, 1, 70, 1, 1, 1, 0, 1, 1),
+]
+
+
+@pytest.mark.parametrize("cfg", CONV_SWEEP, ids=[str(c) for c in CONV_SWEEP])
+def test_conv_kernels_vs_torch_cpu(cfg):
+    """fp32 path and exact-integer path of fwd / dgrad / wgrad against ATen-CPU conv2d."""
+    from micronet_b200 import _lib as L, functional as F_
+    B, C, H, W, K, R, S, st, pd, dl, G = cfg
+    torch.manual_seed(sum(cfg))
+    x = torch.randn(B, C, H, W)
+    w = torch.randn(K, C // G, R, S) * 0.2
+    b = torch.randn(K)
+    # fp32 x fp32
+    xg, wg, bg = (t.to(DEV).requires_grad_(True) for t in (x, w, b))
+    y = F_.quant_conv2d(xg, wg, bg, None, None, None, (st, st), (pd, pd), (dl, dl), G)
+    xr, wr, br = (t.clone().requires_grad_(True) for t in (x, w, b))
+    yr = TF.conv2d(xr, wr, br, st, pd, dl, G)
+    go = torch.randn_like(yr)
+    y.backward(go.to(DEV)); yr.backward(go)
+    assert rel_err(y.detach(), yr.detach()) <= TOL
+    assert rel_err(xg.grad, xr.grad) <= TOL and rel_err(wg.grad, wr.grad) <= TOL and rel_err(bg.grad, br.grad) <= TOL
+    # DoReFa codes x integer weights: exact integer accumulation, compare against fp64 conv of the levels
+    spec = F_.ActSpec(L.ACT_DOREFA, bits=8)
+    w_int = torch.randint(-255, 256, w.shape, dtype=torch.int16)
+    w_scale = torch.rand(K) * 0.01 + 0.001
+    wq = w_int.float() * w_scale.view(-1, 1, 1, 1)
+    xg = (x * 4).to(DEV).requires_grad_(True)
+    wqg = wq.to(DEV).requires_grad_(True)
+    y = F_.quant_conv2d(xg, wqg, None, w_int.to(DEV), w_scale.to(DEV), spec, (st, st), (pd, pd), (dl, dl), G)
+    from oracle import reference_port as O
+    lv = O.dorefa_activation_levels(x * 4, 8).double()
+    acc = TF.conv2d(lv, w_int.double(), None, st, pd, dl, G)
+    s = np.float32(1.0 / 255.0)
+    want = (acc.float() * (torch.tensor(s) * w_scale).view(1, -1, 1, 1))
+    assert rel_err(y.detach(), want) <= 2e-7, "integer path must be exact up to the final fp32 scale"
+    y.backward(go.to(DEV))
+    xr = (x * 4).clone().requires_grad_(True)
+    wqr = wq.clone().requires_grad_(True)
+    yr = TF.conv2d(O.dorefa_quantize_activation(xr, 8), wqr, None, st, pd, dl, G)
+    yr.backward(go)
+    assert rel_err(xg.grad, xr.grad) <= TOL and rel_err(wqg.grad, wqr.grad) <= TOL
+
+
+# ---------------------------------------------------------------- model level
+def _zoo_model(case):
+    from harness import models as zoo
+    if case["model"] == "nin_gc":
+        return zoo.NINGC(case["cfg"])
+    if case["model"] == "nin":
+        return zoo.NIN(case["cfg"])
+    return zoo.ResNet(widths=tuple(case["cfg"]))
+
+
+def _prepare_engine(model, case):
+    import micronet_b200 as E
+    mod = {"wbwtab": E.wbwtab, "dorefa": E.dorefa, "iao": E.iao}[case["scheme"]]
+    return mod.prepare(model, inplace=True, **case["prepare"])
+
+
+@pytest.mark.parametrize("case", MODEL_CASES, ids=[c["name"] for c in MODEL_CASES])
+def test_model_first_step_matches_golden(case):
+    """whole prepared model, one QAT step, against the reference's own numbers.  Sign / round
+    discontinuities make deep-net parity chaotic at the 1e-7 level, so the bar here is looser
+    than the per-layer one; the strict check is the teacher-forced test below."""
+    gold = load_golden("model", case["name"])
+    m = _zoo_model(case)
+    m.load_state_dict({k[5:]: torch.from_numpy(v) for k, v in gold.items() if k.startswith("init.")})
+    m = _prepare_engine(m, case).to(DEV)
+    m.train()
+    x, t = torch.from_numpy(gold["s0.x"]).to(DEV), torch.from_numpy(gold["s0.t"]).to(DEV)
+    y = m(x)
+    loss = torch.nn.functional.cross_entropy(y, t)
+    loss.backward()
+    assert rel_err(y.detach(), gold["s0.logits"]) <= 2e-3
+    assert abs(loss.item() - float(gold["s0.loss"])) <= 1e-3 * max(1.0, abs(float(gold["s0.loss"])))
+    worst = 0.0
+    for n, p in m.named_parameters():
+        k = f"s0.gradnorm.{n}"
+        if k in gold and float(gold[k]) > 1e-6:
+            worst = max(worst, abs(p.grad.norm().item() - float(gold[k])) / float(gold[k]))
+    assert worst <= 2e-2, worst
+
+
+@pytest.mark.parametrize("case", MODEL_CASES, ids=[c["name"] for c in MODEL_CASES])
+def test_model_layers_teacher_forced(case):
+    """every quantized conv/linear of the prepared model, fed the ORACLE's own layer input and
+    output-gradient (captured with hooks), must match the oracle's layer output / gradients to 1e-5."""
+    from tests.test_oracle_golden import prepare_oracle
+    gold = load_golden("model", case["name"])
+    init = {k[5:]: torch.from_numpy(v) for k, v in gold.items() if k.startswith("init.")}
+    om = _zoo_model(case); om.load_state_dict(init); om = prepare_oracle(om, case); om.train()
+    em = _zoo_model(case); em.load_state_dict(init); em = _prepare_engine(em, case).to(DEV); em.train()
+    names = [n for n, mod in em.named_modules() if type(mod).__name__ in ("QuantConv2d", "QuantBNFuseConv2d", "QuantLinear")]
+    cap = {}
+
+    def fwd_hook(name):
+        def h(mod, inp, out):
+            cap[name] = {"x": inp[0].detach().clone(), "y": out.detach().clone()}
+            out.register_hook(lambda g: cap[name].__setitem__("go", g.detach().clone()))
+        return h
+
+    omods = dict(om.named_modules())
+    hooks = [omods[n].register_forward_hook(fwd_hook(n)) for n in names]
+    # snapshot oracle weights BEFORE the step (binary quantizer mutates them in place)
+    x, t = torch.from_numpy(gold["s0.x"]), torch.from_numpy(gold["s0.t"])
+    torch.nn.functional.cross_entropy(om(x), t).backward()
+    for h in hooks:
+        h.remove()
+    emods = dict(em.named_modules())
+    assert names, "no quantized layers found"
+    for n in names:
+        e, o, c = emods[n], omods[n], cap[n]
+        xin = c["x"].to(DEV).requires_grad_(True)
+        y = e(xin)
+        assert rel_err(y.detach(), c["y"]) <= TOL, f"{n}: fwd {rel_err(y.detach(), c['y'])}"
+        e.zero_grad()
+        y.backward(c["go"].to(DEV))
+        ograds = {k: p.grad for k, p in o.named_parameters()}
+        for k, p in e.named_parameters():
+            if ograds[k] is None:
+                continue
+            if k == "bias" and type(e).__name__ == "QuantBNFuseConv2d":
+                continue
+            assert rel_err(p.grad, ograds[k]) <= 2e-5, f"{n}.{k}: {rel_err(p.grad, ograds[k])}"
+
+
+# ---------------------------------------------------------------- BASELINE-size layers vs the CPU oracle
+FULL_LAYERS = [
+    # scheme, ctor args, kwargs, input shape, input kind
+    ("wbwtab", (256, 256, 1), dict(groups=2, W=3), (256, 256, 32, 32), "pm1"),
+    ("wbwtab", (256, 512, 3), dict(padding=1, groups=16, W=3), (64, 256, 16, 16), "pm1"),
+    ("dorefa", (512, 512, 1), dict(groups=4, a_bits=4, w_bits=4), (64, 512, 16, 16), "relu"),
+    ("iao", (64, 64, 3), dict(padding=1, bias=False), (32, 64, 32, 32), "relu"),
+]
+
+
+@pytest.mark.parametrize("spec", FULL_LAYERS, ids=[f"{s[0]}-{s[1]}" for s in FULL_LAYERS])
+def test_full_size_layer_vs_oracle(spec):
+    scheme, args, kwargs, shape, kind = spec
+    ecls = engine_classes()[(scheme, "conv")]
+    ocls = ORACLE_CLASSES[(scheme, "conv")]
+    torch.manual_seed(7)
+    o = ocls(*args, **kwargs)
+    with torch.no_grad():
+        o.weight.mul_(3.0)
+    e = ecls(*args, **kwargs)
+    e.load_state_dict(o.state_dict())
+    e = e.to(DEV)
+    g = torch.Generator().manual_seed(11)
+    if kind == "pm1":
+        x = torch.randint(0, 2, shape, generator=g).float() * 2 - 1
+    else:
+        x = torch.relu(torch.randn(shape, generator=g) * 3)
+    xo = x.clone().requires_grad_(True)
+    xe = x.to(DEV).requires_grad_(True)
+    o.train(); e.train()
+    yo, ye = o(xo), e(xe)
+    assert rel_err(ye.detach(), yo.detach()) <= TOL
+    go = torch.randn(yo.shape, generator=g)
+    yo.backward(go); ye.backward(go.to(DEV))
+    assert rel_err(xe.grad, xo.grad) <= TOL
+    assert rel_err(e.weight.grad, o.weight.grad) <= 2e-5
