@@ -165,6 +165,19 @@ int mnb_channel_stats(const float* x, int32_t batch, int32_t channels, int32_t h
 int mnb_channel_stats_bwd(const float* x, const float* mean, const float* dmean, const float* dvar,
                           int32_t batch, int32_t channels, int32_t hw, float* dx, mnb_stream_t stream);
 
+/* ------------------------------------------------------------------------
+ * Hardware self-tests of the sm_100a building blocks (run by tests/test_gpu_tc_selftest.py).
+ * Bounded waits: a wrong descriptor sets *err_flag (device int) instead of hanging the GPU.
+ * ---------------------------------------------------------------------- */
+/* D[128 x N] = A[128 x K] * B[N x K]^T through tcgen05.mma (kind::f16 on bf16, or kind::i8) with
+ * thread-written K-major no-swizzle operands; A/B/D are fp32 row-major device arrays.            */
+int mnb_selftest_umma(const float* A, const float* B, float* D, int32_t N, int32_t K, int32_t int8,
+                      int32_t* err_flag, mnb_stream_t stream);
+/* one cp.async.bulk.tensor.3d box (dims/box/coord innermost-first, fp32) copied to `out`;
+ * elements outside the tensor must read back as 0.                                              */
+int mnb_selftest_tma3d(const float* src, const int64_t* dims3_host, const int32_t* box3_host,
+                       const int32_t* coord3_host, float* out, int32_t* err_flag, mnb_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

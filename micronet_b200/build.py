@@ -40,7 +40,8 @@ def build(force=False, verbose=False):
         cmd = [NVCC, *FLAGS, "-c", path, "-o", obj] + (["-Xptxas", "-v"] if verbose else [])
         subprocess.run(cmd, check=True)
         objs.append(obj)
-    subprocess.run([NVCC, "-shared", "-cudart", "static", "-o", LIB_PATH, *objs], check=True)
+    subprocess.run([NVCC, "-shared", "-cudart", "static", "-gencode", "arch=compute_100a,code=sm_100a",
+                    "-o", LIB_PATH, *objs], check=True)
     return LIB_PATH
 
 

@@ -257,8 +257,11 @@ __global__ void radix_finalize_kernel(uint64_t k, ObsCfg c, float* min_val, floa
 
 extern "C" int64_t mnb_observe_scratch_bytes(int64_t n, int32_t rows) {
   (void)n;
-  // 64 B header + 2*OBS_MAXB floats + 4x256 histograms; channel_stats: rows counters + rows*32*2 doubles
-  return 16384 + (int64_t)rows * (8 + 32 * 16);
+  // [0,16K): block counter, min/max partials, 4x256 radix histograms
+  // [16K,48K): per-channel completion counters of channel_stats (fixed size: the layout must not
+  //            depend on the channel count, or one call's partial sums alias another call's counters)
+  // [48K,...): channel_stats partial sums, rows * 32 splits * 2 doubles
+  return 49152 + (int64_t)rows * (32 * 16);
 }
 
 extern "C" int mnb_iao_observe(const float* x, int64_t n, int32_t rows, int32_t observer_kind, int32_t first,
@@ -669,10 +672,11 @@ __global__ void __launch_bounds__(256) channel_stats_bwd_kernel(const float* __r
 extern "C" int mnb_channel_stats(const float* x, int32_t batch, int32_t channels, int32_t hw,
                                  int32_t as_mean_var, float* stats, void* scratch, mnb_stream_t stream) {
   MNB_REQUIRE(x && stats && scratch && batch > 0 && channels > 0 && hw > 0, "bad channel_stats arguments");
+  MNB_REQUIRE(channels <= 8192, "channel_stats supports at most 8192 channels, got %d", channels);
   int64_t per = (int64_t)batch * hw;
   int splits = (int)std::max<int64_t>(1, std::min<int64_t>(STATS_SPLITS, per / 2048));
   uint32_t* counters = reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(scratch) + 16384);
-  double* partial = reinterpret_cast<double*>(reinterpret_cast<char*>(scratch) + 16384 + (int64_t)channels * 8);
+  double* partial = reinterpret_cast<double*>(reinterpret_cast<char*>(scratch) + 49152);
   channel_stats_kernel<<<dim3(channels, splits), 256, 0, S(stream)>>>(x, batch, channels, hw, as_mean_var, stats,
                                                                        counters, partial);
   MNB_LAUNCHED(1);

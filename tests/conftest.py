@@ -8,7 +8,19 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 
+def _no_tf32():
+    # the float layers that stay stock PyTorch (first / last conv, BN) must run true fp32 on the GPU,
+    # otherwise cuDNN's TF32 default (1e-3 error) flips quantization levels downstream
+    try:
+        import torch
+        torch.backends.cudnn.allow_tf32 = False
+        torch.backends.cuda.matmul.allow_tf32 = False
+    except Exception:
+        pass
+
+
 def pytest_configure(config):
+    _no_tf32()
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
 
 
