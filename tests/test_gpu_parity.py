@@ -233,10 +233,11 @@ def _prepare_engine(model, case):
 
 
 @pytest.mark.parametrize("case", MODEL_CASES, ids=[c["name"] for c in MODEL_CASES])
-def test_model_first_step_matches_golden(case):
-    """whole prepared model, one QAT step, against the reference's own numbers.  Sign / round
-    discontinuities make deep-net parity chaotic at the 1e-7 level, so the bar here is looser
-    than the per-layer one; the strict check is the teacher-forced test below."""
+def test_model_first_step_sanity(case):
+    """whole prepared model, one QAT step, against the reference's own numbers.  sign() / round()
+    discontinuities make deep-net parity chaotic at the 1e-7 level (one flipped +-1 activation in
+    these narrow test nets moves the logits by percents), so this is only a sanity bound; the
+    strict 1e-5 check is the teacher-forced test below."""
     gold = load_golden("model", case["name"])
     m = _zoo_model(case)
     m.load_state_dict({k[5:]: torch.from_numpy(v) for k, v in gold.items() if k.startswith("init.")})
@@ -246,37 +247,44 @@ def test_model_first_step_matches_golden(case):
     y = m(x)
     loss = torch.nn.functional.cross_entropy(y, t)
     loss.backward()
-    assert rel_err(y.detach(), gold["s0.logits"]) <= 2e-3
-    assert abs(loss.item() - float(gold["s0.loss"])) <= 1e-3 * max(1.0, abs(float(gold["s0.loss"])))
-    worst = 0.0
+    assert torch.isfinite(y).all()
+    assert rel_err(y.detach(), gold["s0.logits"]) <= 0.3
+    assert abs(loss.item() - float(gold["s0.loss"])) <= 0.05 * max(1.0, abs(float(gold["s0.loss"])))
     for n, p in m.named_parameters():
-        k = f"s0.gradnorm.{n}"
-        if k in gold and float(gold[k]) > 1e-6:
-            worst = max(worst, abs(p.grad.norm().item() - float(gold[k])) / float(gold[k]))
-    assert worst <= 2e-2, worst
+        assert p.grad is not None and torch.isfinite(p.grad).all(), n
+
+
+QUANT_TYPES = ("QuantConv2d", "QuantBNFuseConv2d", "QuantLinear", "QuantAdd", "QuantAdaptiveAvgPool2d",
+               "QuantMaxPool2d", "QuantAvgPool2d", "ActivationQuantizer")
 
 
 @pytest.mark.parametrize("case", MODEL_CASES, ids=[c["name"] for c in MODEL_CASES])
 def test_model_layers_teacher_forced(case):
-    """every quantized conv/linear of the prepared model, fed the ORACLE's own layer input and
-    output-gradient (captured with hooks), must match the oracle's layer output / gradients to 1e-5."""
+    """every engine module of the prepared model (quant conv / linear / bn-fuse conv, binarizer,
+    quantized add / pool), fed the ORACLE's own inputs and output-gradient at that layer (captured
+    with hooks during one oracle QAT step), must reproduce the oracle's output, input gradients and
+    parameter gradients to 1e-5 / 2e-5."""
     from tests.test_oracle_golden import prepare_oracle
     gold = load_golden("model", case["name"])
     init = {k[5:]: torch.from_numpy(v) for k, v in gold.items() if k.startswith("init.")}
     om = _zoo_model(case); om.load_state_dict(init); om = prepare_oracle(om, case); om.train()
     em = _zoo_model(case); em.load_state_dict(init); em = _prepare_engine(em, case).to(DEV); em.train()
-    names = [n for n, mod in em.named_modules() if type(mod).__name__ in ("QuantConv2d", "QuantBNFuseConv2d", "QuantLinear")]
+    names = [n for n, mod in em.named_modules() if type(mod).__name__ in QUANT_TYPES
+             and not n.endswith("activation_quantizer")]
     cap = {}
 
     def fwd_hook(name):
         def h(mod, inp, out):
-            cap[name] = {"x": inp[0].detach().clone(), "y": out.detach().clone()}
-            out.register_hook(lambda g: cap[name].__setitem__("go", g.detach().clone()))
+            rec = {"x": [t.detach().clone() for t in inp], "y": out.detach().clone(), "gx": [None] * len(inp)}
+            cap[name] = rec
+            out.register_hook(lambda g: rec.__setitem__("go", g.detach().clone()))
+            for i, t in enumerate(inp):
+                if t.requires_grad:
+                    t.register_hook(lambda g, i=i: rec["gx"].__setitem__(i, g.detach().clone()))
         return h
 
     omods = dict(om.named_modules())
     hooks = [omods[n].register_forward_hook(fwd_hook(n)) for n in names]
-    # snapshot oracle weights BEFORE the step (binary quantizer mutates them in place)
     x, t = torch.from_numpy(gold["s0.x"]), torch.from_numpy(gold["s0.t"])
     torch.nn.functional.cross_entropy(om(x), t).backward()
     for h in hooks:
@@ -285,16 +293,23 @@ def test_model_layers_teacher_forced(case):
     assert names, "no quantized layers found"
     for n in names:
         e, o, c = emods[n], omods[n], cap[n]
-        xin = c["x"].to(DEV).requires_grad_(True)
-        y = e(xin)
+        xin = [t.to(DEV).requires_grad_(c["gx"][i] is not None) for i, t in enumerate(c["x"])]
+        y = e(*xin)
         assert rel_err(y.detach(), c["y"]) <= TOL, f"{n}: fwd {rel_err(y.detach(), c['y'])}"
         e.zero_grad()
         y.backward(c["go"].to(DEV))
+        for i, g in enumerate(c["gx"]):
+            if g is not None:
+                assert rel_err(xin[i].grad, g) <= TOL, f"{n}: dx[{i}] {rel_err(xin[i].grad, g)}"
         ograds = {k: p.grad for k, p in o.named_parameters()}
+        wscale = max((g.abs().max().item() for k, g in ograds.items() if g is not None and k != "bias"), default=1.0)
         for k, p in e.named_parameters():
-            if ograds[k] is None:
+            if ograds.get(k) is None:
                 continue
-            if k == "bias" and type(e).__name__ == "QuantBNFuseConv2d":
+            if k == "bias":
+                # a conv bias in front of a BatchNorm has a mathematically zero gradient: both sides
+                # hold round-off noise, compare on the scale of the layer's weight gradient instead
+                assert (p.grad.cpu() - ograds[k]).abs().max().item() <= 2e-5 * max(wscale, ograds[k].abs().max().item()), f"{n}.bias"
                 continue
             assert rel_err(p.grad, ograds[k]) <= 2e-5, f"{n}.{k}: {rel_err(p.grad, ograds[k])}"
 
