@@ -166,6 +166,21 @@ int mnb_channel_stats_bwd(const float* x, const float* mean, const float* dmean,
                           int32_t batch, int32_t channels, int32_t hw, float* dx, mnb_stream_t stream);
 
 /* ------------------------------------------------------------------------
+ * Fused tensor-core forward (tcgen05 + TMA): fake-quantize the fp32 NCHW input on the fly while
+ * it is staged for the MMA, convolve exact integer levels, scale + bias in the epilogue.
+ *   qp == NULL : x is used as it is (wbwtab: +-1 or plain fp32 activations, exact 3-term bf16 split)
+ *   qp != NULL : DoReFa / IAO quantizer; `codes` (u8, same shape as x) and `pass_bits`
+ *                (u32[ceil(numel/32)], ZERO-INITIALISED by the caller) receive what backward needs.
+ * Replaces activation_quantizer(input) + F.conv2d of DF:108-121 / IAO:493-506 / WB:186-194.
+ * Returns MNB_E_UNSUPPORTED (and launches nothing) for geometries outside the kernel's cover
+ * (see mnb_conv_tc.cu); the caller then composes mnb_act_quant_fwd + mnb_conv2d_fwd.
+ * err_flag: device int, stays 0 unless a bounded pipeline wait timed out (a bug, never expected).
+ * ---------------------------------------------------------------------- */
+int mnb_fq_conv2d_fwd_tc(const mnb_conv_shape* s, const float* x, const mnb_act_qparams* qp,
+                         const int16_t* w_int, const float* w_scale, const float* bias, float* y,
+                         uint8_t* codes, uint32_t* pass_bits, int32_t* err_flag, mnb_stream_t stream);
+
+/* ------------------------------------------------------------------------
  * Hardware self-tests of the sm_100a building blocks (run by tests/test_gpu_tc_selftest.py).
  * Bounded waits: a wrong descriptor sets *err_flag (device int) instead of hanging the GPU.
  * ---------------------------------------------------------------------- */

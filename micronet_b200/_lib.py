@@ -58,6 +58,7 @@ PROTOTYPES = {
     "mnb_conv2d_wgrad": (C.c_int, [_SHAPE, _P, _OPS, _P, _P, _P]),
     "mnb_channel_stats": (C.c_int, [_P, _I, _I, _I, _I, _P, _P, _P]),
     "mnb_channel_stats_bwd": (C.c_int, [_P, _P, _P, _P, _I, _I, _I, _P, _P]),
+    "mnb_fq_conv2d_fwd_tc": (C.c_int, [_SHAPE, _P, _ACTQ, _P, _P, _P, _P, _P, _P, _P, _P]),
     "mnb_selftest_umma": (C.c_int, [_P, _P, _P, _I, _I, _I, _P, _P]),
     "mnb_selftest_tma3d": (C.c_int, [_P, C.POINTER(C.c_int64), C.POINTER(C.c_int32), C.POINTER(C.c_int32), _P, _P, _P]),
 }
@@ -108,6 +109,28 @@ def require_cuda(*tensors):
 def launch_count() -> int:
     return int(load().mnb_launch_count())
 
+
+_errflags = {}
+
+
+def tc_err_flag(device):
+    """device int the tensor-core kernels set if a bounded pipeline wait ever times out"""
+    key = (device.type, device.index)
+    if key not in _errflags:
+        _errflags[key] = torch.zeros(1, dtype=torch.int32, device=device)
+    return _errflags[key]
+
+
+def tc_check(device=None):
+    """synchronising check of the tensor-core error flag(s); raises if any kernel reported a timeout"""
+    for key, flag in _errflags.items():
+        code = int(flag.item())
+        if code:
+            raise RuntimeError(f"micronet_b200: tensor-core pipeline wait timed out (code {code}) on {key}")
+
+
+E_UNSUPPORTED = -2
+USE_TC = os.environ.get("MNB_DISABLE_TC", "0") != "1"
 
 _scratch = {}
 

@@ -252,25 +252,45 @@ class QuantConv2dFn(Function):
         p, q = _out_hw(sh)
         y = torch.empty((x.shape[0], wq.shape[0], p, q), dtype=torch.float32, device=x.device)
         codes = bits = None
-        ops = L.ConvOperands()
-        if spec is not None:
-            codes, bits, _ = act_quant_raw(x, spec, True, ctx.needs_input_grad[0], False)
-            ops.a_codes = codes.data_ptr()
-            ops.a_offset = spec.code_offset
-            ops.a_offset_zp = L.ptr(spec.zero_point) if spec.mode == L.ACT_IAO else None
-            a_scale = spec.scale if spec.mode == L.ACT_IAO else (
-                _dorefa_scale_tensor(spec.bits, x.device) if spec.mode == L.ACT_DOREFA else None)
-            ops.a_scale = L.ptr(a_scale)
-        else:
-            a_scale = None
-            ops.a_f32 = x.data_ptr()
-        if codes is not None and w_int is not None:
-            ops.w_int, ops.w_scale = w_int.data_ptr(), w_scale.data_ptr()
-        else:
-            ops.w_f32 = wq.data_ptr()
-        ops.bias = L.ptr(bias)
-        L.check(_timed("fwd", sh, lambda: lib.mnb_conv2d_fwd(C.byref(sh), C.byref(ops), y.data_ptr(), L.stream())),
-                "conv2d_fwd")
+        a_scale = None
+        if spec is not None and spec.mode != L.ACT_SIGN:
+            a_scale = spec.scale if spec.mode == L.ACT_IAO else _dorefa_scale_tensor(spec.bits, x.device)
+        done = False
+        if L.USE_TC and w_int is not None and x.dtype == torch.float32:
+            # fused tcgen05 path: quantize inside the operand staging of the tensor-core conv
+            qp = None
+            if spec is not None:
+                qp = spec.struct()
+                codes = torch.empty(x.shape, dtype=torch.uint8, device=x.device)
+                if ctx.needs_input_grad[0]:
+                    bits = torch.zeros((x.numel() + 31) // 32, dtype=torch.int32, device=x.device)
+            rc = _timed("fwd_tc", sh, lambda: lib.mnb_fq_conv2d_fwd_tc(
+                C.byref(sh), x.data_ptr(), None if qp is None else C.byref(qp), w_int.data_ptr(),
+                w_scale.data_ptr(), L.ptr(bias), y.data_ptr(), L.ptr(codes), L.ptr(bits),
+                L.tc_err_flag(x.device).data_ptr(), L.stream()))
+            if rc == 0:
+                done = True
+            elif rc == L.E_UNSUPPORTED:
+                codes = bits = None
+            else:
+                L.check(rc, "fq_conv2d_fwd_tc")
+        if not done:
+            ops = L.ConvOperands()
+            if spec is not None:
+                codes, bits, _ = act_quant_raw(x, spec, True, ctx.needs_input_grad[0], False)
+                ops.a_codes = codes.data_ptr()
+                ops.a_offset = spec.code_offset
+                ops.a_offset_zp = L.ptr(spec.zero_point) if spec.mode == L.ACT_IAO else None
+                ops.a_scale = L.ptr(a_scale)
+            else:
+                ops.a_f32 = x.data_ptr()
+            if codes is not None and w_int is not None:
+                ops.w_int, ops.w_scale = w_int.data_ptr(), w_scale.data_ptr()
+            else:
+                ops.w_f32 = wq.data_ptr()
+            ops.bias = L.ptr(bias)
+            L.check(_timed("fwd", sh, lambda: lib.mnb_conv2d_fwd(C.byref(sh), C.byref(ops), y.data_ptr(), L.stream())),
+                    "conv2d_fwd")
         ctx.sh, ctx.spec, ctx.a_scale = sh, spec, a_scale
         ctx.codes, ctx.bits = codes, bits
         ctx.x = x if codes is None else None

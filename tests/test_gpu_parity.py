@@ -267,7 +267,9 @@ def test_model_layers_teacher_forced(case):
     from tests.test_oracle_golden import prepare_oracle
     gold = load_golden("model", case["name"])
     init = {k[5:]: torch.from_numpy(v) for k, v in gold.items() if k.startswith("init.")}
+    import copy
     om = _zoo_model(case); om.load_state_dict(init); om = prepare_oracle(om, case); om.train()
+    pristine = copy.deepcopy(om)  # per-layer replay needs first-call observer state
     em = _zoo_model(case); em.load_state_dict(init); em = _prepare_engine(em, case).to(DEV); em.train()
     names = [n for n, mod in em.named_modules() if type(mod).__name__ in QUANT_TYPES
              and not n.endswith("activation_quantizer")]
@@ -275,12 +277,9 @@ def test_model_layers_teacher_forced(case):
 
     def fwd_hook(name):
         def h(mod, inp, out):
-            rec = {"x": [t.detach().clone() for t in inp], "y": out.detach().clone(), "gx": [None] * len(inp)}
+            rec = {"x": [t.detach().clone() for t in inp], "y": out.detach().clone()}
             cap[name] = rec
             out.register_hook(lambda g: rec.__setitem__("go", g.detach().clone()))
-            for i, t in enumerate(inp):
-                if t.requires_grad:
-                    t.register_hook(lambda g, i=i: rec["gx"].__setitem__(i, g.detach().clone()))
         return h
 
     omods = dict(om.named_modules())
@@ -289,18 +288,23 @@ def test_model_layers_teacher_forced(case):
     torch.nn.functional.cross_entropy(om(x), t).backward()
     for h in hooks:
         h.remove()
-    emods = dict(em.named_modules())
+    emods, pmods = dict(em.named_modules()), dict(pristine.named_modules())
     assert names, "no quantized layers found"
     for n in names:
-        e, o, c = emods[n], omods[n], cap[n]
-        xin = [t.to(DEV).requires_grad_(c["gx"][i] is not None) for i, t in enumerate(c["x"])]
+        e, o, c = emods[n], pmods[n], cap[n]
+        # oracle layer replayed stand-alone on the captured inputs (a tensor hook on the model's
+        # activation would also collect the gradient of its other consumers, e.g. the residual add)
+        xo = [t.clone().requires_grad_(True) for t in c["x"]]
+        yo = o(*xo)
+        assert torch.equal(yo.detach(), c["y"]) or rel_err(yo.detach(), c["y"]) <= 1e-6
+        yo.backward(c["go"])
+        xin = [t.to(DEV).requires_grad_(True) for t in c["x"]]
         y = e(*xin)
         assert rel_err(y.detach(), c["y"]) <= TOL, f"{n}: fwd {rel_err(y.detach(), c['y'])}"
         e.zero_grad()
         y.backward(c["go"].to(DEV))
-        for i, g in enumerate(c["gx"]):
-            if g is not None:
-                assert rel_err(xin[i].grad, g) <= TOL, f"{n}: dx[{i}] {rel_err(xin[i].grad, g)}"
+        for i in range(len(xin)):
+            assert rel_err(xin[i].grad, xo[i].grad) <= TOL, f"{n}: dx[{i}] {rel_err(xin[i].grad, xo[i].grad)}"
         ograds = {k: p.grad for k, p in o.named_parameters()}
         wscale = max((g.abs().max().item() for k, g in ograds.items() if g is not None and k != "bias"), default=1.0)
         for k, p in e.named_parameters():
@@ -309,7 +313,8 @@ def test_model_layers_teacher_forced(case):
             if k == "bias":
                 # a conv bias in front of a BatchNorm has a mathematically zero gradient: both sides
                 # hold round-off noise, compare on the scale of the layer's weight gradient instead
-                assert (p.grad.cpu() - ograds[k]).abs().max().item() <= 2e-5 * max(wscale, ograds[k].abs().max().item()), f"{n}.bias"
+                tol = max(1e-6, 2e-5 * max(wscale, ograds[k].abs().max().item()))
+                assert (p.grad.cpu() - ograds[k]).abs().max().item() <= tol, f"{n}.bias"
                 continue
             assert rel_err(p.grad, ograds[k]) <= 2e-5, f"{n}.{k}: {rel_err(p.grad, ograds[k])}"
 

@@ -43,7 +43,8 @@ box = (8, 4, 2)
 src = torch.arange(Wd * Hd * Cd, dtype=torch.float32).reshape(Cd, Hd, Wd) + 1.0
 pad = torch.zeros(Cd + 8, Hd + 16, Wd + 32)
 pad[:Cd, 8:8 + Hd, 16:16 + Wd] = src
-want = pad[coord[2]:coord[2] + box[2], 8 + coord[1]:8 + coord[1] + box[1], 16 + coord[0]:16 + coord[0] + box[0]]
+pad = torch.nn.functional.pad(pad, (0, 0, 0, 0, 4, 0))  # room for negative channel coordinates
+want = pad[4 + coord[2]:4 + coord[2] + box[2], 8 + coord[1]:8 + coord[1] + box[1], 16 + coord[0]:16 + coord[0] + box[0]]
 out = torch.full((box[2], box[1], box[0]), float("nan"), device="cuda:0")
 err = torch.zeros(1, dtype=torch.int32, device="cuda:0")
 sd = src.to("cuda:0")
