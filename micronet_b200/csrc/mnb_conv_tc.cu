@@ -204,6 +204,7 @@ constexpr int NTHREADS = 512;
 constexpr int NCONV = 256;  // converter threads (warps 8..15)
 constexpr int NEPI = 128;   // epilogue threads (warps 4..7)
 constexpr int NST = 3, NOP = 2, NACC = 2;
+constexpr int kMaxDynSmem = 227 * 1024 - 2048;  // 227 KB per CTA minus the static barrier block
 
 struct FwdParams {
   int B, C, H, W, K, R, S, pad, G, Cg, Ng;
@@ -543,7 +544,7 @@ extern "C" int mnb_fq_conv2d_fwd_tc(const mnb_conv_shape* s, const float* x, con
   p.op_buf_bytes = p.op_term_bytes * (p.mode == 0 ? 3 : 1);
   p.b_group_bytes = p.R * p.S * p.Cg * p.Ng * 2;
   const int fixed = NST * p.stage_bytes + NOP * p.op_buf_bytes + 2048;
-  const int budget = 225 * 1024 - fixed;
+  const int budget = kMaxDynSmem - 2048 - fixed;
   if (budget < p.b_group_bytes) return unsupported("weights of one group do not fit in shared memory");
   int max_groups = std::max(1, std::min(p.G, std::min(budget / p.b_group_bytes, std::max(1, 64 * 1024 / p.b_group_bytes))));
   while (p.G % max_groups) --max_groups;  // equal slabs: every CTA does the same work per tile
@@ -553,7 +554,7 @@ extern "C" int mnb_fq_conv2d_fwd_tc(const mnb_conv_shape* s, const float* x, con
   p.off_op = (NST * p.stage_bytes + 1023) / 1024 * 1024;
   p.off_b = p.off_op + (NOP * p.op_buf_bytes + 1023) / 1024 * 1024;
   const int smem_bytes = p.off_b + p.slab_groups * p.b_group_bytes;
-  if (smem_bytes > 227 * 1024) return unsupported("shared memory budget");
+  if (smem_bytes > kMaxDynSmem) return unsupported("shared memory budget");
   int cols = 32;
   while (cols < NACC * p.Ng) cols <<= 1;
   p.tmem_cols = cols;
@@ -566,7 +567,7 @@ extern "C" int mnb_fq_conv2d_fwd_tc(const mnb_conv_shape* s, const float* x, con
   if (int e = mnb_make_tmap(&tmap, x, 4, 4, dims, box)) return e;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t ce = cudaFuncSetAttribute(fq_conv_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaError_t ce = cudaFuncSetAttribute(fq_conv_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem);
     if (ce != cudaSuccess) return mnb_fail((int)ce, "cudaFuncSetAttribute: %s", cudaGetErrorString(ce));
     attr_set = true;
   }

@@ -76,7 +76,8 @@ def test_tc_forward_matches_generic_and_cpu(shape, mode):
     assert err.item() == 0, f"tensor-core pipeline timed out, code {err.item()}"
     y_gen = _run(xd, wqd, bd, wid, wsd, spec, R, G, False)
     assert torch.isfinite(y_tc).all()
-    assert rel_err(y_tc, y_gen) <= 1e-6, f"tc vs generic {rel_err(y_tc, y_gen)}"
+    # both paths are exact on integer levels; on raw fp32 they differ only by fp32 summation order
+    assert rel_err(y_tc, y_gen) <= (5e-6 if mode == "raw_fp32" else 1e-6), f"tc vs generic {rel_err(y_tc, y_gen)}"
     # CPU reference: conv2d of the dequantized operands
     if spec is None:
         xq = x
