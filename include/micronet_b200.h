@@ -180,6 +180,14 @@ int mnb_fq_conv2d_fwd_tc(const mnb_conv_shape* s, const float* x, const mnb_act_
                          const int16_t* w_int, const float* w_scale, const float* bias, float* y,
                          uint8_t* codes, uint32_t* pass_bits, int32_t* err_flag, mnb_stream_t stream);
 
+/* Data gradient of the same convolution on the tensor-core path (ATen convolution_backward's
+ * grad_input): dx = STE( conv_transpose(dy, w_scale[k] * w_int) ), the per-channel weight scale folded
+ * into dy while it is staged (exact 3-term bf16 split of the fp32 product).  pass_bits / qp NULL:
+ * plain dgrad (wbwtab).  Same geometry cover and error conventions as mnb_fq_conv2d_fwd_tc.   */
+int mnb_conv2d_dgrad_tc(const mnb_conv_shape* s, const float* dy, const int16_t* w_int, const float* w_scale,
+                        const uint32_t* pass_bits, const mnb_act_qparams* qp, float* dx, int32_t* err_flag,
+                        mnb_stream_t stream);
+
 /* ------------------------------------------------------------------------
  * Hardware self-tests of the sm_100a building blocks (run by tests/test_gpu_tc_selftest.py).
  * Bounded waits: a wrong descriptor sets *err_flag (device int) instead of hanging the GPU.

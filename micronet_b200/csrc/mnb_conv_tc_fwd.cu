@@ -1,0 +1,523 @@
+// Fused fake-quant convolution on tcgen05 tensor cores: forward and data-gradient.
+//
+// Both are "same"-padded stride-1 correlations of an fp32 NCHW tensor with small-integer weights:
+//
+//   forward : y[b, gNg+n, h, w] = bias[n] + (s_a * s_w[n]) * sum_{c,r,s} e_a[b, gCg+c, h+r-p, w+s-p] * e_w[gNg+n, c, r, s]
+//   dgrad   : dx[b, gCg+c, h, w] = STE( sum_{k,r,s} (dy * s_w[k])[b, gNg+k, h+r-p, w+s-p] * e_w[gNg+k, c, R-1-r, S-1-s] )
+//
+// Data flow per CTA (persistent, one CTA per SM, bound to a slab of groups whose integer weights
+// stay resident in shared memory as bf16):
+//
+//   TMA warp    : cp.async.bulk.tensor.4d box (W, TH+2p, CC, TB) of the fp32 input -> staging ring;
+//                 rows above / below the image are zero-filled by the TMA unit
+//   8 converter : staging fp32 -> integer level (DoReFa / IAO fake-quant) or exact 3-way bf16 split
+//     warps       of a raw / pre-scaled fp32 value -> "position-major" bf16 operand
+//                 op[c/8][position][8 ch], position = row*(W+2p) + col of the zero-padded tile.
+//                 This IS the UMMA K-major no-swizzle canonical layout with positions as GEMM rows,
+//                 so filter tap (r, s) is the same buffer with the descriptor start address moved by
+//                 (r*BW + s)*16 bytes: implicit GEMM without any im2col copy.  Side outputs of the
+//                 fused quantizer: u8 level codes + STE pass bits for the backward pass.
+//   MMA warp    : one thread issues tcgen05.mma kind::f16 (bf16 x bf16 -> fp32 accumulators in TMEM);
+//                 every operand is an exact small integer or an exact bf16 piece of an fp32 value,
+//                 M = 128 positions, N = output channels of the group, K = 16 channels per MMA
+//   4 epilogue  : tcgen05.ld accumulator rows -> scale + bias (fwd) or STE mask (dgrad) -> coalesced
+//     warps       fp32 NCHW stores
+#include <cuda.h>
+#include <cuda_bf16.h>
+
+#include "mnb_common.cuh"
+#include "mnb_tc.cuh"
+
+namespace tcconv {
+
+constexpr int NTHREADS = 512;
+constexpr int NCONV = 256;  // converter threads (warps 8..15)
+constexpr int NEPI = 128;   // epilogue threads (warps 4..7)
+constexpr int MAXST = 4, NOP = 2, NACC = 2;
+constexpr int KMAX = 6;     // operand entries per converter thread and chunk
+constexpr int kMaxDynSmem = 227 * 1024 - 6144;  // 227 KB per CTA minus the static block below (5 KB)
+
+struct Params {
+  // tensors: input [B, Cin, H, W], output [B, Cout, H, W]
+  int B, Cin, Cout, H, W, R, S, pad, G, cin_g, cout_g;
+  int BW, TH, THH, TB, CC, nchunk, nst;
+  int npos_in, row_tiles, n_tiles, slab_groups, n_slabs;
+  int quant_mode;   // 0: raw fp32 input (exact 3-term split); else MNB_ACT_DOREFA / MNB_ACT_IAO
+  int dgrad;        // 1: weights transposed + flipped, per-input-channel pre-scale, STE epilogue
+  int a_offset, tmem_cols;
+  int stage_bytes, op_term_bytes, op_buf_bytes, b_group_bytes, off_stage, off_op, off_b;
+  float a_scale_const;
+  mnb_act_qparams qp;
+  const int16_t* w_int;     // [K, Cg, R, S] integer weights (K = fwd output channels)
+  const float* w_scale;     // [K]
+  const float* a_scale;     // device scalar (IAO) or NULL
+  const float* bias;        // fwd only
+  const uint32_t* ste_bits; // dgrad only (may be NULL: plain dgrad)
+  float* out;
+  uint8_t* codes; uint32_t* pass_bits;  // fwd side outputs of the fused quantizer
+  int* err;
+};
+
+struct alignas(16) Shared {
+  uint64_t stage_full[MAXST], stage_empty[MAXST], op_full[NOP], op_empty[NOP], acc_full[NACC], acc_empty[NACC];
+  uint32_t tmem_slot;
+  uint32_t op_flags[NOP][8];
+  float epi_scale[NACC][256];
+  float epi_bias[NACC][256];
+};
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+__device__ __forceinline__ float bf16_round(float v) { return __bfloat162float(__float2bfloat16_rn(v)); }
+
+__global__ void __launch_bounds__(NTHREADS, 1)
+conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const Params p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ Shared sh;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  uint8_t* stage_base = smem + p.off_stage;
+  uint8_t* op_base = smem + p.off_op;
+  uint8_t* b_base = smem + p.off_b;
+  const int RS = p.R * p.S, c8_per_group = p.cin_g / 8;
+
+  // ---- work assignment: CTA -> slab of groups; the slab's tiles are dealt round-robin
+  const int slab = blockIdx.x % p.n_slabs;
+  const int rank_in_slab = blockIdx.x / p.n_slabs;
+  const int ctas_in_slab = (gridDim.x - slab + p.n_slabs - 1) / p.n_slabs;
+  const int g_first = slab * p.slab_groups;
+  const int g_count = min(p.slab_groups, p.G - g_first);
+
+  // ---- one-time setup
+  if (tid == 0) {
+    for (int i = 0; i < p.nst; ++i) { tc::mbar_init(&sh.stage_full[i], 1); tc::mbar_init(&sh.stage_empty[i], NCONV); }
+    for (int i = 0; i < NOP; ++i) { tc::mbar_init(&sh.op_full[i], NCONV); tc::mbar_init(&sh.op_empty[i], 1); }
+    for (int i = 0; i < NACC; ++i) { tc::mbar_init(&sh.acc_full[i], 1); tc::mbar_init(&sh.acc_empty[i], NEPI); }
+    tc::fence_barrier_init();
+    tc::prefetch_tmap(&tmap_in);
+  }
+  if (tid < NOP * 8) sh.op_flags[tid / 8][tid % 8] = 0;
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tc::smem_u32(&sh.tmem_slot)),
+                 "r"((uint32_t)p.tmem_cols));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  // zero the operand buffers once: the mid / lo planes are only rewritten when a chunk needs them
+  for (int i = tid; i < NOP * p.op_buf_bytes / 16; i += NTHREADS)
+    reinterpret_cast<uint4*>(op_base)[i] = make_uint4(0, 0, 0, 0);
+  // resident integer weights of this slab as the B operand: B[gi][tap][k/8][n][8] bf16
+  {
+    const int per_group = RS * p.cin_g * p.cout_g;
+    for (int idx = tid; idx < g_count * per_group; idx += NTHREADS) {
+      const int gi = idx / per_group;
+      int r = idx - gi * per_group;
+      const int n = r / (p.cin_g * RS);   // output channel of this GEMM within the group
+      r -= n * (p.cin_g * RS);
+      const int c = r / RS, tap = r - c * RS;  // input channel within the group, tap of this GEMM
+      const int g = g_first + gi;
+      int64_t src;
+      if (!p.dgrad) src = ((int64_t)(g * p.cout_g + n) * p.cin_g + c) * RS + tap;              // W[k=n][c][tap]
+      else src = ((int64_t)(g * p.cin_g + c) * p.cout_g + n) * RS + (RS - 1 - tap);              // W[k=c][c'=n][flipped tap]
+      const int16_t v = __ldg(p.w_int + src);
+      uint8_t* dst = b_base + (size_t)gi * p.b_group_bytes +
+                     ((size_t)((tap * c8_per_group + (c >> 3)) * p.cout_g + n)) * 16 + (c & 7) * 2;
+      *reinterpret_cast<__nv_bfloat16*>(dst) = __float2bfloat16_rn((float)v);
+    }
+  }
+  tc::fence_proxy_async_smem();
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tmem = sh.tmem_slot;
+
+  if (warp == 0) {
+    // ================================================================= TMA producer
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int tile = rank_in_slab; tile < p.n_tiles; tile += ctas_in_slab) {
+        const int bt = tile / p.row_tiles, rt = tile - bt * p.row_tiles;
+        const int b0 = bt * p.TB, h0 = rt * p.TH;
+        for (int gi = 0; gi < g_count; ++gi) {
+          for (int ch = 0; ch < p.nchunk; ++ch, ++it) {
+            const int st = it % p.nst;
+            const uint32_t ph = (it / p.nst) & 1;
+            if (!tc::mbar_wait(&sh.stage_empty[st], ph ^ 1, p.err, 301)) goto done;
+            tc::mbar_arrive_expect_tx(&sh.stage_full[st], (uint32_t)p.stage_bytes);
+            tc::tma_load_4d(stage_base + (size_t)st * p.stage_bytes, &tmap_in, &sh.stage_full[st], 0, h0 - p.pad,
+                            (g_first + gi) * p.cin_g + ch * p.CC, b0);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================================================================= MMA issuer
+    if (lane == 0) {
+      const uint32_t idesc = tc::make_idesc(1, 1, 1, 128, (uint32_t)p.cout_g);
+      const uint32_t a_lbo = (uint32_t)p.npos_in * 16u, b_lbo = (uint32_t)p.cout_g * 16u;
+      uint32_t it = 0, item = 0;
+      for (int tile = rank_in_slab; tile < p.n_tiles; tile += ctas_in_slab) {
+        for (int gi = 0; gi < g_count; ++gi, ++item) {
+          const int acc = item % NACC;
+          const uint32_t aph = (item / NACC) & 1;
+          if (!tc::mbar_wait(&sh.acc_empty[acc], aph ^ 1, p.err, 302)) goto done;
+          tc::tc_fence_after();
+          const uint32_t d_tmem = tmem + (uint32_t)(acc * p.cout_g);
+          uint32_t accumulate = 0;
+          for (int ch = 0; ch < p.nchunk; ++ch, ++it) {
+            const int ob = it % NOP;
+            const uint32_t oph = (it / NOP) & 1;
+            if (!tc::mbar_wait(&sh.op_full[ob], oph, p.err, 303)) goto done;
+            tc::tc_fence_after();
+            int nterms = 1;
+            if (p.quant_mode == 0) {
+              uint32_t any = 0;
+#pragma unroll
+              for (int w8 = 0; w8 < 8; ++w8) any |= sh.op_flags[ob][w8];
+              nterms = any ? 3 : 1;
+            }
+            const uint32_t op_addr = tc::smem_u32(op_base + (size_t)ob * p.op_buf_bytes);
+            const uint32_t b_addr = tc::smem_u32(b_base + (size_t)gi * p.b_group_bytes);
+            for (int tap = 0; tap < RS; ++tap) {
+              const int r = tap / p.S, s = tap - r * p.S;
+              const uint32_t tap_off = (uint32_t)(r * p.BW + s) * 16u;
+              for (int j = 0; j < p.CC / 16; ++j) {
+                const uint32_t b_start = b_addr + (uint32_t)((tap * c8_per_group + ch * (p.CC / 8) + 2 * j) * p.cout_g) * 16u;
+                const uint64_t bd = tc::smem_desc_kmajor_noswz(b_start, b_lbo, 128);
+                for (int t = 0; t < nterms; ++t) {
+                  const uint32_t a_start = op_addr + (uint32_t)t * p.op_term_bytes + (uint32_t)(2 * j) * a_lbo + tap_off;
+                  const uint64_t ad = tc::smem_desc_kmajor_noswz(a_start, a_lbo, 128);
+                  tc::mma_f16(d_tmem, ad, bd, idesc, accumulate);
+                  accumulate = 1;
+                }
+              }
+            }
+            tc::mma_commit(&sh.op_empty[ob]);  // operand buffer is free once these MMAs retire
+          }
+          tc::mma_commit(&sh.acc_full[acc]);
+        }
+      }
+    }
+  } else if (warp >= 4 && warp < 8) {
+    // ================================================================= epilogue
+    const int q = warp - 4;            // TMEM lane quarter of this warp (warp % 4)
+    const int et = tid - 128;
+    const int pos = q * 32 + lane;     // GEMM row = padded-tile position
+    const int tb = pos / (p.THH * p.BW);
+    const int rem = pos - tb * (p.THH * p.BW);
+    const int th = rem / p.BW, wc = rem - th * p.BW;
+    const float a_sc = p.a_scale ? __ldg(p.a_scale) : p.a_scale_const;
+    MnbActQ ste;
+    if (p.dgrad && p.ste_bits) ste = mnb_load_actq(p.qp);
+    const int64_t plane = (int64_t)p.H * p.W;
+    uint32_t item = 0;
+    for (int tile = rank_in_slab; tile < p.n_tiles; tile += ctas_in_slab) {
+      const int bt = tile / p.row_tiles, rt = tile - bt * p.row_tiles;
+      const int b = bt * p.TB + tb, h = rt * p.TH + th;
+      const bool valid = tb < p.TB && th < p.TH && wc < p.W && b < p.B && h < p.H;
+      for (int gi = 0; gi < g_count; ++gi, ++item) {
+        const int acc = item % NACC;
+        const uint32_t aph = (item / NACC) & 1;
+        const int ch0 = (g_first + gi) * p.cout_g;
+        if (!p.dgrad) {
+          // per-channel scale / bias of this group -> smem (slot `acc` was released two items ago)
+          for (int n = et; n < p.cout_g; n += NEPI) {
+            sh.epi_scale[acc][n] = __fmul_rn(a_sc, __ldg(p.w_scale + ch0 + n));
+            sh.epi_bias[acc][n] = p.bias ? __ldg(p.bias + ch0 + n) : 0.f;
+          }
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+        }
+        if (!tc::mbar_wait(&sh.acc_full[acc], aph, p.err, 304)) goto done;
+        tc::tc_fence_after();
+        const int64_t obase = (((int64_t)b * p.Cout + ch0) * p.H + h) * p.W + wc;
+        for (int n0 = 0; n0 < p.cout_g; n0 += 32) {
+          uint32_t r[32];
+          tc::tmem_ld_32x32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.cout_g + n0), r);
+          tc::tmem_ld_wait();
+          if (valid) {
+            if (!p.dgrad) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (n0 + j < p.cout_g)
+                  p.out[obase + (int64_t)(n0 + j) * plane] =
+                      __fadd_rn(__fmul_rn(__uint_as_float(r[j]), sh.epi_scale[acc][n0 + j]), sh.epi_bias[acc][n0 + j]);
+            } else if (p.ste_bits) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (n0 + j < p.cout_g) {
+                  const int64_t fi = obase + (int64_t)(n0 + j) * plane;
+                  const bool pass = (__ldg(p.ste_bits + (fi >> 5)) >> (fi & 31)) & 1u;
+                  p.out[fi] = mnb_act_ste_one(ste, __uint_as_float(r[j]), pass);
+                }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (n0 + j < p.cout_g) p.out[obase + (int64_t)(n0 + j) * plane] = __uint_as_float(r[j]);
+            }
+          }
+        }
+        tc::tc_fence_before();
+        tc::mbar_arrive(&sh.acc_empty[acc]);
+      }
+    }
+  } else if (warp >= 8) {
+    // ================================================================= converters
+    const int ct = tid - 256;
+    const int cw = ct >> 5;
+    MnbActQ q;
+    if (p.quant_mode != 0) q = mnb_load_actq(p.qp);
+    const int a_off = p.a_offset + ((p.quant_mode == MNB_ACT_IAO && p.qp.zero_point) ? (int)__ldg(p.qp.zero_point) : 0);
+    const int per_img = p.THH * p.BW;
+    const int total = p.npos_in * (p.CC / 8);
+    const int chstride = p.THH * p.W;  // floats between consecutive channels in the staging box
+    // per-thread operand entries: fixed for the whole kernel (depend on the tile geometry only)
+    int soff[KMAX];   // staging float offset of channel 0 of the entry's 8-channel group, -1: halo / dead
+    int meta[KMAX];   // hr | tb << 8 | c8 << 16 | w << 20
+#pragma unroll
+    for (int k = 0; k < KMAX; ++k) {
+      const int idx = ct + k * NCONV;
+      soff[k] = -1; meta[k] = 0;
+      if (idx < total) {
+        const int c8 = idx / p.npos_in, ip = idx - c8 * p.npos_in;
+        const int tb = ip / per_img;
+        const int rem = ip - tb * per_img;
+        const int hr = rem / p.BW, wc = rem - hr * p.BW;
+        const int w = wc - p.pad;
+        if (tb < p.TB && w >= 0 && w < p.W) {
+          soff[k] = ((tb * p.CC + c8 * 8) * p.THH + hr) * p.W + w;
+          meta[k] = hr | (tb << 8) | (c8 << 16) | (w << 20);
+        }
+      }
+    }
+    uint32_t dirty_mask[NOP] = {0, 0};
+    uint32_t it = 0;
+    for (int tile = rank_in_slab; tile < p.n_tiles; tile += ctas_in_slab) {
+      const int bt = tile / p.row_tiles, rt = tile - bt * p.row_tiles;
+      const int b0 = bt * p.TB, h0 = rt * p.TH;
+      for (int gi = 0; gi < g_count; ++gi) {
+        for (int ch = 0; ch < p.nchunk; ++ch, ++it) {
+          const int st = it % p.nst, ob = it % NOP;
+          const uint32_t ph = (it / p.nst) & 1, oph = (it / NOP) & 1;
+          if (!tc::mbar_wait(&sh.op_empty[ob], oph ^ 1, p.err, 306)) goto done;
+          if (!tc::mbar_wait(&sh.stage_full[st], ph, p.err, 305)) goto done;
+          // did THIS thread leave non-zero mid / lo pieces in its entries of this buffer last time?
+          // (entries are owned by fixed threads, so dirtiness is thread-private state)
+          const uint32_t dirty = dirty_mask[ob];
+          uint32_t now_dirty = 0;
+          const float* stg = reinterpret_cast<const float*>(stage_base + (size_t)st * p.stage_bytes);
+          uint8_t* opb = op_base + (size_t)ob * p.op_buf_bytes;
+          const int cbase = (g_first + gi) * p.cin_g + ch * p.CC;
+          uint32_t any_low = 0;
+#pragma unroll
+          for (int k = 0; k < KMAX; ++k) {
+            if ((ct & ~31) + k * NCONV >= total) break;  // warp-uniform
+            const int idx = ct + k * NCONV;
+            const bool live = idx < total;
+            const int so = soff[k];
+            uint32_t u[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) u[j] = so >= 0 ? __float_as_uint(stg[so + j * chstride]) : 0u;
+            uint4 hi;
+            if (p.quant_mode == 0) {
+              if (p.dgrad) {  // fold the per-input-channel weight scale into the gradient operand
+                const int c0 = cbase + ((meta[k] >> 16) & 15) * 8;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) u[j] = __float_as_uint(__fmul_rn(__uint_as_float(u[j]), __ldg(p.w_scale + c0 + j)));
+              }
+              uint32_t low = 0;
+#pragma unroll
+              for (int j = 0; j < 8; ++j) low |= u[j] & 0xffffu;
+              if (low == 0) {
+                // already bf16-exact (e.g. +-1 activations): the high halves ARE the operand
+                hi = make_uint4(__byte_perm(u[0], u[1], 0x7632), __byte_perm(u[2], u[3], 0x7632),
+                                __byte_perm(u[4], u[5], 0x7632), __byte_perm(u[6], u[7], 0x7632));
+                if (((dirty >> k) & 1u) && live) {
+                  *reinterpret_cast<uint4*>(opb + (size_t)p.op_term_bytes + (size_t)idx * 16) = make_uint4(0, 0, 0, 0);
+                  *reinterpret_cast<uint4*>(opb + (size_t)2 * p.op_term_bytes + (size_t)idx * 16) = make_uint4(0, 0, 0, 0);
+                }
+              } else {
+                // exact 3-way split x = hi + mid + lo (8 + 8 + 8 significand bits)
+                float h1[8], m1[8], l1[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                  const float v = __uint_as_float(u[j]);
+                  h1[j] = bf16_round(v);
+                  const float r1 = v - h1[j];
+                  m1[j] = bf16_round(r1);
+                  l1[j] = r1 - m1[j];
+                }
+                any_low = 1;
+                now_dirty |= 1u << k;
+                hi = make_uint4(pack_bf16x2(h1[0], h1[1]), pack_bf16x2(h1[2], h1[3]), pack_bf16x2(h1[4], h1[5]), pack_bf16x2(h1[6], h1[7]));
+                if (live) {
+                  *reinterpret_cast<uint4*>(opb + (size_t)p.op_term_bytes + (size_t)idx * 16) =
+                      make_uint4(pack_bf16x2(m1[0], m1[1]), pack_bf16x2(m1[2], m1[3]), pack_bf16x2(m1[4], m1[5]), pack_bf16x2(m1[6], m1[7]));
+                  *reinterpret_cast<uint4*>(opb + (size_t)2 * p.op_term_bytes + (size_t)idx * 16) =
+                      make_uint4(pack_bf16x2(l1[0], l1[1]), pack_bf16x2(l1[2], l1[3]), pack_bf16x2(l1[4], l1[5]), pack_bf16x2(l1[6], l1[7]));
+                }
+              }
+            } else {
+              // fused fake-quant: integer level (exact in bf16), plus the saved codes / STE bits
+              const int hr = meta[k] & 255, tb = (meta[k] >> 8) & 255, c8 = (meta[k] >> 16) & 15, w = meta[k] >> 20;
+              const int h = h0 - p.pad + hr, b = b0 + tb;
+              const bool inside = so >= 0 && h >= 0 && h < p.H && b < p.B;
+              const bool owned = inside && hr >= p.pad && hr < p.pad + p.TH;
+              float e[8];
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                bool pass; float xq;
+                const int code = mnb_act_quantize_one(q, __uint_as_float(u[j]), pass, xq);
+                e[j] = inside ? (float)(code + a_off) : 0.f;
+                const int64_t fi = (((int64_t)b * p.Cin + cbase + c8 * 8 + j) * p.H + h) * p.W + w;
+                if (p.codes && owned) p.codes[fi] = (uint8_t)code;
+                if (p.pass_bits) {
+                  // lanes that fall into the same 32-bit word combine their bits: one atomic per word
+                  const uint32_t word = owned ? (uint32_t)(fi >> 5) : 0xffffffffu;
+                  const uint32_t peers = __match_any_sync(0xffffffffu, word);
+                  const uint32_t mine = (owned && pass) ? (1u << (fi & 31)) : 0u;
+                  const uint32_t val = __reduce_or_sync(peers, mine);
+                  if (owned && val && (__ffs(peers) - 1) == lane) atomicOr(p.pass_bits + word, val);
+                }
+              }
+              hi = make_uint4(pack_bf16x2(e[0], e[1]), pack_bf16x2(e[2], e[3]), pack_bf16x2(e[4], e[5]), pack_bf16x2(e[6], e[7]));
+            }
+            if (live) *reinterpret_cast<uint4*>(opb + (size_t)idx * 16) = hi;
+          }
+          dirty_mask[ob] = now_dirty;
+          if (p.quant_mode == 0) {
+            any_low = __reduce_or_sync(0xffffffffu, any_low);
+            if (lane == 0) sh.op_flags[ob][cw] = any_low;
+          }
+          tc::fence_proxy_async_smem();
+          tc::mbar_arrive(&sh.op_full[ob]);
+          tc::mbar_arrive(&sh.stage_empty[st]);
+        }
+      }
+    }
+  }
+done:
+  tc::tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc::tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"((uint32_t)p.tmem_cols));
+  }
+}
+
+// geometry + shared-memory plan shared by forward and dgrad; returns 0 / MNB_E_UNSUPPORTED / error
+static int plan(const mnb_conv_shape* s, bool dgrad, int quant_mode, Params& p, int& smem_bytes) {
+  MNB_REQUIRE(s != nullptr, "conv shape is NULL");
+  const int C = s->in_c, K = s->out_c, G = s->groups;
+  MNB_REQUIRE(s->batch > 0 && C > 0 && K > 0 && s->in_h > 0 && s->in_w > 0 && G > 0 && C % G == 0 && K % G == 0,
+              "bad conv shape");
+  auto unsupported = [](const char* why) { return mnb_fail(MNB_E_UNSUPPORTED, "tc conv: %s", why); };
+  if (s->stride_h != 1 || s->stride_w != 1 || s->dil_h != 1 || s->dil_w != 1) return unsupported("stride/dilation != 1");
+  p.R = s->ker_h; p.S = s->ker_w;
+  if (p.R != p.S || (p.R & 1) == 0 || s->pad_h != p.R / 2 || s->pad_w != p.R / 2) return unsupported("not a 'same' odd square filter");
+  p.B = s->batch; p.H = s->in_h; p.W = s->in_w; p.G = G; p.pad = p.R / 2;
+  p.dgrad = dgrad ? 1 : 0;
+  p.Cin = dgrad ? K : C; p.Cout = dgrad ? C : K;
+  p.cin_g = p.Cin / G; p.cout_g = p.Cout / G;
+  if (p.cin_g % 16 || p.cout_g % 16 || p.cout_g > 256) return unsupported("channels per group");
+  if ((p.W * 4) % 16 || p.W > 64 || p.H > 255) return unsupported("image size");
+  p.BW = p.W + 2 * p.pad;
+  p.TH = std::min(p.H, 128 / p.BW);
+  if (p.TH < 1) return unsupported("padded row wider than 128 positions");
+  p.THH = p.TH + 2 * p.pad;
+  p.TB = 1;
+  if (p.pad == 0 && p.TH == p.H) p.TB = std::max(1, std::min(p.B, 128 / (p.H * p.W)));  // small images: several per tile
+  p.CC = (p.cin_g % 32 == 0) ? 32 : 16;
+  p.nchunk = p.cin_g / p.CC;
+  const int halo = (p.R - 1) * p.BW + (p.S - 1);
+  const int npos = std::max(p.TB * p.THH * p.BW, 128) + halo;  // MMA rows read [tap_off, tap_off + 128)
+  p.npos_in = (npos + 7) / 8 * 8;
+  if (p.npos_in * (p.CC / 8) > KMAX * NCONV) {
+    p.CC = 16; p.nchunk = p.cin_g / 16;
+    if (p.npos_in * 2 > KMAX * NCONV) return unsupported("tile too large for the converter");
+  }
+  p.row_tiles = (p.H + p.TH - 1) / p.TH;
+  p.n_tiles = ((p.B + p.TB - 1) / p.TB) * p.row_tiles;
+  p.quant_mode = quant_mode;
+  p.stage_bytes = p.W * p.THH * p.CC * p.TB * 4;
+  p.op_term_bytes = p.npos_in * (p.CC / 8) * 16;
+  p.op_buf_bytes = p.op_term_bytes * (quant_mode == 0 ? 3 : 1);
+  p.b_group_bytes = p.R * p.S * p.cin_g * p.cout_g * 2;
+  p.nst = MAXST;
+  int fixed = 0, budget = 0;
+  for (;; --p.nst) {
+    fixed = (p.nst * p.stage_bytes + 1023) / 1024 * 1024 + (NOP * p.op_buf_bytes + 1023) / 1024 * 1024;
+    budget = kMaxDynSmem - fixed;
+    if (budget >= p.b_group_bytes || p.nst == 2) break;
+  }
+  if (budget < p.b_group_bytes) return unsupported("weights of one group do not fit in shared memory");
+  int max_groups = std::max(1, std::min(p.G, std::min(budget / p.b_group_bytes, std::max(1, 64 * 1024 / p.b_group_bytes))));
+  while (p.G % max_groups) --max_groups;  // equal slabs: every CTA does the same work per tile
+  p.slab_groups = max_groups;
+  p.n_slabs = p.G / p.slab_groups;
+  p.off_stage = 0;
+  p.off_op = (p.nst * p.stage_bytes + 1023) / 1024 * 1024;
+  p.off_b = p.off_op + (NOP * p.op_buf_bytes + 1023) / 1024 * 1024;
+  smem_bytes = p.off_b + p.slab_groups * p.b_group_bytes;
+  if (smem_bytes > kMaxDynSmem) return unsupported("shared memory budget");
+  int cols = 32;
+  while (cols < NACC * p.cout_g) cols <<= 1;
+  p.tmem_cols = cols;
+  return 0;
+}
+
+static int launch(const Params& p, const void* in, int smem_bytes, cudaStream_t st) {
+  CUtensorMap tmap;
+  uint64_t dims[4] = {(uint64_t)p.W, (uint64_t)p.H, (uint64_t)p.Cin, (uint64_t)p.B};
+  uint32_t box[4] = {(uint32_t)p.W, (uint32_t)p.THH, (uint32_t)p.CC, (uint32_t)p.TB};
+  if (int e = mnb_make_tmap(&tmap, in, 4, 4, dims, box)) return e;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t ce = cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem);
+    if (ce != cudaSuccess) return mnb_fail((int)ce, "cudaFuncSetAttribute: %s", cudaGetErrorString(ce));
+    attr_set = true;
+  }
+  const int64_t items = (int64_t)p.n_tiles * p.n_slabs;
+  int grid = (int)std::min<int64_t>(items, MNB_NUM_SMS);
+  grid = std::max(grid, p.n_slabs);
+  conv_tc_kernel<<<grid, NTHREADS, smem_bytes, st>>>(tmap, p);
+  MNB_LAUNCHED(1);
+  return 0;
+}
+
+}  // namespace tcconv
+
+extern "C" int mnb_fq_conv2d_fwd_tc(const mnb_conv_shape* s, const float* x, const mnb_act_qparams* qp,
+                                    const int16_t* w_int, const float* w_scale, const float* bias, float* y,
+                                    uint8_t* codes, uint32_t* pass_bits, int32_t* err_flag, mnb_stream_t stream) {
+  using namespace tcconv;
+  MNB_REQUIRE(s && x && w_int && w_scale && y && err_flag, "NULL pointer");
+  if (qp) MNB_REQUIRE(qp->mode == MNB_ACT_DOREFA || qp->mode == MNB_ACT_IAO, "fused quantizer must be DoReFa or IAO");
+  Params p{};
+  int smem_bytes = 0;
+  if (int e = plan(s, false, qp ? qp->mode : 0, p, smem_bytes)) return e;
+  if (qp) {
+    if (qp->mode == MNB_ACT_DOREFA) MNB_REQUIRE(qp->bits >= 2 && qp->bits <= 8, "DoReFa a_bits must be in [2,8]");
+    p.qp = *qp;
+    p.a_offset = qp->mode == MNB_ACT_IAO ? qp->qmin : 0;
+  }
+  p.a_scale = (qp && qp->mode == MNB_ACT_IAO) ? qp->scale : nullptr;
+  p.a_scale_const = (qp && qp->mode == MNB_ACT_DOREFA) ? (float)(1.0 / (double)((1 << qp->bits) - 1)) : 1.f;
+  p.w_int = w_int; p.w_scale = w_scale; p.bias = bias; p.out = y; p.codes = codes; p.pass_bits = pass_bits;
+  p.err = err_flag;
+  return launch(p, x, smem_bytes, (cudaStream_t)stream);
+}
+
+extern "C" int mnb_conv2d_dgrad_tc(const mnb_conv_shape* s, const float* dy, const int16_t* w_int,
+                                   const float* w_scale, const uint32_t* pass_bits, const mnb_act_qparams* qp,
+                                   float* dx, int32_t* err_flag, mnb_stream_t stream) {
+  using namespace tcconv;
+  MNB_REQUIRE(s && dy && w_int && w_scale && dx && err_flag, "NULL pointer");
+  MNB_REQUIRE((pass_bits == nullptr) == (qp == nullptr), "pass_bits and qp go together");
+  Params p{};
+  int smem_bytes = 0;
+  if (int e = plan(s, true, 0, p, smem_bytes)) return e;
+  if (qp) p.qp = *qp;
+  p.a_scale_const = 1.f;
+  p.w_int = w_int; p.w_scale = w_scale; p.ste_bits = pass_bits; p.out = dx; p.err = err_flag;
+  return launch(p, dy, smem_bytes, (cudaStream_t)stream);
+}

@@ -150,3 +150,7 @@ __host__ __device__ constexpr uint32_t make_idesc(uint32_t cfmt, uint32_t afmt, 
 }
 
 }  // namespace tc
+
+// host: rank-`rank` tiled tensor map over a dense tensor (dims / box innermost-first)
+int mnb_make_tmap(CUtensorMap* out, const void* base, int elem_bytes, int rank, const uint64_t* dims,
+                  const uint32_t* box);

@@ -295,6 +295,7 @@ class QuantConv2dFn(Function):
         ctx.codes, ctx.bits = codes, bits
         ctx.x = x if codes is None else None
         ctx.wq = wq
+        ctx.w_int, ctx.w_scale = (w_int, w_scale) if w_int is not None else (None, None)
         ctx.has_bias = bias is not None
         return y
 
@@ -308,14 +309,18 @@ class QuantConv2dFn(Function):
             db = channel_sums(dy)
         if ctx.needs_input_grad[0]:
             dx = torch.empty((sh.batch, sh.in_c, sh.in_h, sh.in_w), dtype=torch.float32, device=dy.device)
-            if spec is not None:
-                qp = spec.struct()
+            qp = spec.struct() if spec is not None else None
+            bits_ptr = ctx.bits.data_ptr() if spec is not None else None
+            rc = L.E_UNSUPPORTED
+            if L.USE_TC and ctx.w_int is not None:
+                rc = _timed("dgrad_tc", sh, lambda: lib.mnb_conv2d_dgrad_tc(
+                    C.byref(sh), dy.data_ptr(), ctx.w_int.data_ptr(), ctx.w_scale.data_ptr(), bits_ptr,
+                    None if qp is None else C.byref(qp), dx.data_ptr(), L.tc_err_flag(dy.device).data_ptr(),
+                    L.stream()))
+            if rc == L.E_UNSUPPORTED:
                 rc = _timed("dgrad", sh, lambda: lib.mnb_conv2d_dgrad(
-                    C.byref(sh), dy.data_ptr(), ctx.wq.data_ptr(), ctx.bits.data_ptr(), C.byref(qp),
+                    C.byref(sh), dy.data_ptr(), ctx.wq.data_ptr(), bits_ptr, None if qp is None else C.byref(qp),
                     dx.data_ptr(), L.stream()))
-            else:
-                rc = _timed("dgrad", sh, lambda: lib.mnb_conv2d_dgrad(
-                    C.byref(sh), dy.data_ptr(), ctx.wq.data_ptr(), None, None, dx.data_ptr(), L.stream()))
             L.check(rc, "conv2d_dgrad")
         if ctx.needs_input_grad[1]:
             dwq = torch.empty_like(ctx.wq)

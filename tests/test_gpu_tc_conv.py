@@ -121,3 +121,53 @@ def test_tc_forward_emits_identical_codes_and_bits(shape, mode):
     assert err.item() == 0
     assert torch.equal(codes, codes_ref)
     assert torch.equal(bits, bits_ref)
+
+
+@pytest.mark.parametrize("shape", SHAPES, ids=[str(s) for s in SHAPES])
+@pytest.mark.parametrize("mode", ["raw", "dorefa8", "iao_sym"])
+def test_tc_dgrad_matches_generic_and_cpu(shape, mode):
+    """dx through the tensor-core dgrad (weight scale folded into dy, exact 3-term split, fused STE)."""
+    from micronet_b200 import _lib as L, functional as F_
+    B, C, H, W, K, R, G = shape
+    g = torch.Generator().manual_seed(hash((shape, mode, "dgrad")) % (1 << 31))
+    x = torch.randn(B, C, H, W, generator=g) * 4
+    lim = 1 if mode == "raw" else 127
+    w_int = torch.randint(-lim, lim + 1, (K, C // G, R, R), generator=g, dtype=torch.int16)
+    w_scale = torch.rand(K, generator=g) * 0.02 + 0.001
+    wq = w_int.float() * w_scale.view(-1, 1, 1, 1)
+    spec = None
+    if mode == "dorefa8":
+        spec = F_.ActSpec(L.ACT_DOREFA, bits=8)
+    elif mode == "iao_sym":
+        bufs = dict(scale=torch.tensor([9.0 / 127.5]), zero_point=torch.zeros(1), obs_min=torch.tensor([-9.0]),
+                    obs_max=torch.tensor([7.0]))
+        spec = F_.ActSpec(L.ACT_IAO, qmin=-128, qmax=127, q_type=0, **{k: v.to(DEV) for k, v in bufs.items()})
+    go = torch.randn(B, K, H, W, generator=g)
+    err = L.tc_err_flag(torch.device(DEV)); err.zero_()
+    grads = {}
+    for use_tc in (True, False):
+        L.USE_TC = use_tc
+        try:
+            xg = x.to(DEV).requires_grad_(True)
+            y = F_.quant_conv2d(xg, wq.to(DEV), None, w_int.to(DEV), w_scale.to(DEV), spec, (1, 1), (R // 2, R // 2), (1, 1), G)
+            y.backward(go.to(DEV))
+            torch.cuda.synchronize()
+            grads[use_tc] = xg.grad.clone()
+        finally:
+            L.USE_TC = True
+    assert err.item() == 0, f"tensor-core pipeline timed out, code {err.item()}"
+    assert rel_err(grads[True], grads[False]) <= 2e-6, rel_err(grads[True], grads[False])
+    # CPU: autograd of conv2d on the dequantized input
+    from oracle import reference_port as O
+    xr = x.clone().requires_grad_(True)
+    if mode == "raw":
+        xq = xr
+    elif mode == "dorefa8":
+        xq = O.dorefa_quantize_activation(xr, 8)
+    else:
+        s = torch.tensor([9.0 / 127.5])
+        v = xr / s
+        r = O._RoundRangeSTE.apply(v, torch.tensor([-9.0]) / s, torch.tensor([7.0]) / s, 0)
+        xq = torch.clamp(r, -128, 127) * s
+    TF.conv2d(xq, wq, None, 1, R // 2, 1, G).backward(go)
+    assert rel_err(grads[True], xr.grad) <= 1e-5, rel_err(grads[True], xr.grad)
