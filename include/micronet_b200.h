@@ -188,12 +188,24 @@ int mnb_conv2d_dgrad_tc(const mnb_conv_shape* s, const float* dy, const int16_t*
                         const uint32_t* pass_bits, const mnb_act_qparams* qp, float* dx, int32_t* err_flag,
                         mnb_stream_t stream);
 
+/* Weight gradient on the tensor-core path: dWq = s_a * corr(e_a, dy) with e_a re-quantized from the
+ * fp32 input x on the fly (qp as in the forward; NULL = raw x, which must be bf16-exact such as the
+ * +-1 activations of wbwtab - otherwise *inexact_flag is set on the device and the result is to be
+ * replaced by mnb_conv2d_wgrad_cond(..., inexact_flag), which runs only when the flag is non-zero,
+ * so no host synchronisation is needed).  scratch >= mnb_wgrad_tc_scratch_bytes(s) (-1: unsupported). */
+int64_t mnb_wgrad_tc_scratch_bytes(const mnb_conv_shape* s);
+int mnb_conv2d_wgrad_tc(const mnb_conv_shape* s, const float* dy, const float* x, const mnb_act_qparams* qp,
+                        float* dwq, void* scratch, int32_t* inexact_flag, int32_t* err_flag, mnb_stream_t stream);
+int mnb_conv2d_wgrad_cond(const mnb_conv_shape* s, const float* dy, const mnb_conv_operands* op, float* dwq,
+                          void* scratch, const int32_t* run_if_nonzero, mnb_stream_t stream);
+
 /* ------------------------------------------------------------------------
  * Hardware self-tests of the sm_100a building blocks (run by tests/test_gpu_tc_selftest.py).
  * Bounded waits: a wrong descriptor sets *err_flag (device int) instead of hanging the GPU.
  * ---------------------------------------------------------------------- */
 /* D[128 x N] = A[128 x K] * B[N x K]^T through tcgen05.mma (kind::f16 on bf16, or kind::i8) with
- * thread-written K-major no-swizzle operands; A/B/D are fp32 row-major device arrays.            */
+ * thread-written no-swizzle operands; A/B/D are fp32 row-major device arrays.
+ * int8: 0 = bf16 K-major operands, 1 = int8 K-major, 2 = bf16 MN-major (the wgrad kernel's form).    */
 int mnb_selftest_umma(const float* A, const float* B, float* D, int32_t N, int32_t K, int32_t int8,
                       int32_t* err_flag, mnb_stream_t stream);
 /* one cp.async.bulk.tensor.3d box (dims/box/coord innermost-first, fp32) copied to `out`;

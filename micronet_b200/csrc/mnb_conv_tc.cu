@@ -39,6 +39,8 @@ int mnb_make_tmap(CUtensorMap* out, const void* base, int elem_bytes, int rank, 
                   const uint32_t* box) {
   EncodeTiledFn enc = get_encode_tiled();
   if (!enc) return mnb_fail(MNB_E_UNSUPPORTED, "cuTensorMapEncodeTiled is not available from this driver");
+  // driver-API call: make sure this host thread (e.g. an autograd worker) has the primary context bound
+  cudaFree(nullptr);
   cuuint64_t gdim[5], gstr[5];
   cuuint32_t bdim[5], estr[5];
   uint64_t stride = (uint64_t)elem_bytes;
@@ -129,12 +131,66 @@ __global__ void __launch_bounds__(160) selftest_umma_kernel(const float* __restr
   if (warp == 4) tc::tmem_dealloc<128>(tmem);
 }
 
+// MN-major variant (the wgrad kernel's operand form): operands stored as buf[m/8][k][8 elements],
+// i.e. D[128 x N] = sum_k At[k][m] * Bt[k][n] with both operands "transposed" in shared memory.
+__global__ void __launch_bounds__(160) selftest_umma_mn_kernel(const float* __restrict__ A, const float* __restrict__ B,
+                                                               float* __restrict__ D, int N, int K, int* err) {
+  __shared__ __align__(128) uint8_t a_s[128 * 64 * 2];
+  __shared__ __align__(128) uint8_t b_s[128 * 64 * 2];
+  __shared__ __align__(8) uint64_t done_bar;
+  __shared__ uint32_t tmem_slot;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (tid < 128) {
+    for (int k = 0; k < K; ++k) {
+      reinterpret_cast<__nv_bfloat16*>(a_s)[((size_t)(tid >> 3) * K + k) * 8 + (tid & 7)] = __float2bfloat16_rn(A[(size_t)tid * K + k]);
+      if (tid < N)
+        reinterpret_cast<__nv_bfloat16*>(b_s)[((size_t)(tid >> 3) * K + k) * 8 + (tid & 7)] = __float2bfloat16_rn(B[(size_t)tid * K + k]);
+    }
+    tc::fence_proxy_async_smem();
+  }
+  if (warp == 4) {
+    tc::tmem_alloc<128>(&tmem_slot);
+    if (lane == 0) { tc::mbar_init(&done_bar, 1); tc::fence_barrier_init(); }
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tmem = tmem_slot;
+  if (warp == 4 && lane == 0) {
+    const uint32_t idesc = tc::make_idesc_major(1, 1, 1, 128, N, 1, 1);
+    for (int ks = 0; ks < K / 16; ++ks) {
+      uint64_t ad = tc::smem_desc_mnmajor_noswz(tc::smem_u32(a_s) + ks * 256, 128, K * 16);
+      uint64_t bd = tc::smem_desc_mnmajor_noswz(tc::smem_u32(b_s) + ks * 256, 128, K * 16);
+      tc::mma_f16(tmem, ad, bd, idesc, ks > 0);
+    }
+    tc::mma_commit(&done_bar);
+  }
+  if (warp < 4) {
+    bool ok = tc::mbar_wait(&done_bar, 0, err, 102);
+    tc::tc_fence_after();
+    if (ok) {
+      for (int n0 = 0; n0 < N; n0 += 32) {
+        uint32_t r[32];
+        tc::tmem_ld_32x32(tmem + ((uint32_t)(warp * 32) << 16) + n0, r);
+        tc::tmem_ld_wait();
+        for (int j = 0; j < 32 && n0 + j < N; ++j) D[(size_t)(warp * 32 + lane) * N + n0 + j] = __uint_as_float(r[j]);
+      }
+    }
+    tc::tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 4) tc::tmem_dealloc<128>(tmem);
+}
+
 extern "C" int mnb_selftest_umma(const float* A, const float* B, float* D, int32_t N, int32_t K, int32_t int8,
                                  int32_t* err_flag, mnb_stream_t stream) {
   MNB_REQUIRE(A && B && D && err_flag, "NULL self-test pointers");
   MNB_REQUIRE(N >= 16 && N <= 128 && N % 16 == 0, "self-test N must be a multiple of 16 in [16,128]");
-  MNB_REQUIRE(K >= 32 && K <= (int8 ? 128 : 64) && K % 32 == 0, "self-test K out of range");
-  if (int8) selftest_umma_kernel<true><<<1, 160, 0, (cudaStream_t)stream>>>(A, B, D, N, K, err_flag);
+  MNB_REQUIRE(K >= 32 && K <= (int8 == 1 ? 128 : 64) && K % 32 == 0, "self-test K out of range");
+  if (int8 == 2) {
+    MNB_REQUIRE(K <= 64, "MN-major self-test K <= 64");
+    selftest_umma_mn_kernel<<<1, 160, 0, (cudaStream_t)stream>>>(A, B, D, N, K, err_flag);
+  } else if (int8) selftest_umma_kernel<true><<<1, 160, 0, (cudaStream_t)stream>>>(A, B, D, N, K, err_flag);
   else selftest_umma_kernel<false><<<1, 160, 0, (cudaStream_t)stream>>>(A, B, D, N, K, err_flag);
   MNB_LAUNCHED(1);
   return 0;

@@ -149,6 +149,20 @@ __host__ __device__ constexpr uint32_t make_idesc(uint32_t cfmt, uint32_t afmt, 
   return (cfmt << 4) | (afmt << 7) | (bfmt << 10) | ((N >> 3) << 17) | ((M >> 4) << 24);
 }
 
+// same, with explicit operand majors (0 = K-major, 1 = MN-major)
+__host__ __device__ constexpr uint32_t make_idesc_major(uint32_t cfmt, uint32_t afmt, uint32_t bfmt, uint32_t M,
+                                                        uint32_t N, uint32_t a_mn, uint32_t b_mn) {
+  return make_idesc(cfmt, afmt, bfmt, M, N) | (a_mn << 15) | (b_mn << 16);
+}
+// MN-major no-swizzle canonical layout: 16-byte vectors hold 8 consecutive M (or N) elements,
+// 8 consecutive K rows are 16 bytes apart (128-byte core matrix);
+//   LBO = byte distance between consecutive 8-row K groups,
+//   SBO = byte distance between consecutive 8-element M/N groups.
+// The bit layout of the descriptor is the same as the K-major one.
+__device__ __forceinline__ uint64_t smem_desc_mnmajor_noswz(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  return smem_desc_kmajor_noswz(saddr, lbo_bytes, sbo_bytes);
+}
+
 }  // namespace tc
 
 // host: rank-`rank` tiled tensor map over a dense tensor (dims / box innermost-first)

@@ -293,7 +293,7 @@ class QuantConv2dFn(Function):
                     "conv2d_fwd")
         ctx.sh, ctx.spec, ctx.a_scale = sh, spec, a_scale
         ctx.codes, ctx.bits = codes, bits
-        ctx.x = x if codes is None else None
+        ctx.x = x if (codes is None or (L.USE_TC and w_int is not None)) else None
         ctx.wq = wq
         ctx.w_int, ctx.w_scale = (w_int, w_scale) if w_int is not None else (None, None)
         ctx.has_bias = bias is not None
@@ -333,10 +333,31 @@ class QuantConv2dFn(Function):
             else:
                 ops.a_f32 = ctx.x.data_ptr()
             nbytes = int(lib.mnb_wgrad_scratch_bytes(C.byref(sh)))
-            ws = torch.empty(max(nbytes, 4), dtype=torch.uint8, device=dy.device)
-            L.check(_timed("wgrad", sh, lambda: lib.mnb_conv2d_wgrad(
-                C.byref(sh), dy.data_ptr(), C.byref(ops), dwq.data_ptr(), ws.data_ptr(), L.stream())),
-                "conv2d_wgrad")
+            done = False
+            if L.USE_TC and ctx.w_int is not None and ctx.x is not None:
+                tbytes = int(lib.mnb_wgrad_tc_scratch_bytes(C.byref(sh)))
+                if tbytes > 0:
+                    qp = spec.struct() if spec is not None else None
+                    ws = torch.empty(max(tbytes, nbytes, 4), dtype=torch.uint8, device=dy.device)
+                    inexact = torch.zeros(1, dtype=torch.int32, device=dy.device)
+                    rc = _timed("wgrad_tc", sh, lambda: lib.mnb_conv2d_wgrad_tc(
+                        C.byref(sh), dy.data_ptr(), ctx.x.data_ptr(), None if qp is None else C.byref(qp),
+                        dwq.data_ptr(), ws.data_ptr(), inexact.data_ptr(), L.tc_err_flag(dy.device).data_ptr(),
+                        L.stream()))
+                    if rc == 0:
+                        done = True
+                        if spec is None:
+                            # raw fp32 activations that are not bf16-exact: device-side fallback, no host sync
+                            L.check(lib.mnb_conv2d_wgrad_cond(C.byref(sh), dy.data_ptr(), C.byref(ops), dwq.data_ptr(),
+                                                              ws.data_ptr(), inexact.data_ptr(), L.stream()),
+                                    "conv2d_wgrad_cond")
+                    elif rc != L.E_UNSUPPORTED:
+                        L.check(rc, "conv2d_wgrad_tc")
+            if not done:
+                ws = torch.empty(max(nbytes, 4), dtype=torch.uint8, device=dy.device)
+                L.check(_timed("wgrad", sh, lambda: lib.mnb_conv2d_wgrad(
+                    C.byref(sh), dy.data_ptr(), C.byref(ops), dwq.data_ptr(), ws.data_ptr(), L.stream())),
+                    "conv2d_wgrad")
         return dx, dwq, db, None, None, None, None, None, None, None
 
 

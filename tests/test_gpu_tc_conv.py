@@ -156,7 +156,7 @@ def test_tc_dgrad_matches_generic_and_cpu(shape, mode):
         finally:
             L.USE_TC = True
     assert err.item() == 0, f"tensor-core pipeline timed out, code {err.item()}"
-    assert rel_err(grads[True], grads[False]) <= 2e-6, rel_err(grads[True], grads[False])
+    assert rel_err(grads[True], grads[False]) <= 5e-6, rel_err(grads[True], grads[False])  # fp32 summation order
     # CPU: autograd of conv2d on the dequantized input
     from oracle import reference_port as O
     xr = x.clone().requires_grad_(True)
@@ -171,3 +171,55 @@ def test_tc_dgrad_matches_generic_and_cpu(shape, mode):
         xq = torch.clamp(r, -128, 127) * s
     TF.conv2d(xq, wq, None, 1, R // 2, 1, G).backward(go)
     assert rel_err(grads[True], xr.grad) <= 1e-5, rel_err(grads[True], xr.grad)
+
+
+@pytest.mark.parametrize("shape", SHAPES, ids=[str(s) for s in SHAPES])
+@pytest.mark.parametrize("mode", ["raw_pm1", "raw_fp32", "dorefa8", "iao_sym"])
+def test_tc_wgrad_matches_generic_and_cpu(shape, mode):
+    """dWq through the tensor-core wgrad (MN-major operands, TMEM-resident accumulators, deterministic
+    two-stage reduction); raw fp32 inputs that are not bf16-exact take the device-side fallback."""
+    from micronet_b200 import _lib as L, functional as F_
+    from oracle import reference_port as O
+    B, C, H, W, K, R, G = shape
+    g = torch.Generator().manual_seed(hash((shape, mode, "wgrad")) % (1 << 31))
+    if mode == "raw_pm1":
+        x = torch.randint(0, 2, (B, C, H, W), generator=g).float() * 2 - 1
+    else:
+        x = torch.randn(B, C, H, W, generator=g) * 4
+    lim = 1 if mode.startswith("raw") else 127
+    w_int = torch.randint(-lim, lim + 1, (K, C // G, R, R), generator=g, dtype=torch.int16)
+    w_scale = torch.rand(K, generator=g) * 0.02 + 0.001
+    wq = w_int.float() * w_scale.view(-1, 1, 1, 1)
+    spec = None
+    if mode == "dorefa8":
+        spec = F_.ActSpec(L.ACT_DOREFA, bits=8)
+    elif mode == "iao_sym":
+        bufs = dict(scale=torch.tensor([9.0 / 127.5]), zero_point=torch.zeros(1), obs_min=torch.tensor([-9.0]),
+                    obs_max=torch.tensor([7.0]))
+        spec = F_.ActSpec(L.ACT_IAO, qmin=-128, qmax=127, q_type=0, **{k: v.to(DEV) for k, v in bufs.items()})
+    go = torch.randn(B, K, H, W, generator=g)
+    err = L.tc_err_flag(torch.device(DEV)); err.zero_()
+    grads = {}
+    for use_tc in (True, False):
+        L.USE_TC = use_tc
+        try:
+            wg = wq.to(DEV).requires_grad_(True)
+            y = F_.quant_conv2d(x.to(DEV), wg, None, w_int.to(DEV), w_scale.to(DEV), spec, (1, 1), (R // 2, R // 2), (1, 1), G)
+            y.backward(go.to(DEV))
+            torch.cuda.synchronize()
+            grads[use_tc] = wg.grad.clone()
+        finally:
+            L.USE_TC = True
+    assert err.item() == 0, f"tensor-core pipeline timed out, code {err.item()}"
+    assert torch.isfinite(grads[True]).all()
+    assert rel_err(grads[True], grads[False]) <= 1e-5, rel_err(grads[True], grads[False])
+    if mode.startswith("raw"):
+        xq = x
+    elif mode == "dorefa8":
+        xq = O.dorefa_quantize_activation(x, 8)
+    else:
+        s = torch.tensor([9.0 / 127.5])
+        xq = torch.clamp(O.round_half_away(x / s), -128, 127) * s
+    wr = wq.clone().double().requires_grad_(True)
+    TF.conv2d(xq.double(), wr, None, 1, R // 2, 1, G).backward(go.double())
+    assert rel_err(grads[True], wr.grad) <= 1e-5, rel_err(grads[True], wr.grad)

@@ -12,13 +12,13 @@ def _err_flag():
     return torch.zeros(1, dtype=torch.int32, device=DEV)
 
 
-@pytest.mark.parametrize("int8", [0, 1])
+@pytest.mark.parametrize("int8", [0, 1, 2])  # 0: bf16 K-major, 1: int8 K-major, 2: bf16 MN-major operands
 @pytest.mark.parametrize("N,K", [(16, 32), (32, 64), (64, 32), (128, 64), (48, 64)])
 def test_umma_descriptor_selftest(N, K, int8):
     from micronet_b200 import _lib as L
     lib = L.load()
     g = torch.Generator().manual_seed(N * 1000 + K + int8)
-    lo, hi = (-128, 128) if int8 else (-16, 17)
+    lo, hi = (-128, 128) if int8 == 1 else (-16, 17)
     A = torch.randint(lo, hi, (128, K), generator=g).float()
     B = torch.randint(lo, hi, (N, K), generator=g).float()
     want = A.double() @ B.double().t()
