@@ -158,6 +158,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="engine", choices=["engine", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--kernels-json", default=None, help="dump the per-kernel CUDA-event timings of the timed region")
     args = ap.parse_args()
     if args.impl == "reference":
         return main_reference(args)
@@ -248,6 +249,14 @@ def main():
     agg = {}
     for (kind, shape), times in timer.summary().items():
         agg[(kind, shape)] = (sum(times), len(times))
+    if args.kernels_json:
+        rows = []
+        for (kind, shape), (tot, n) in sorted(agg.items(), key=lambda kv: -kv[1][0]):
+            fl, nb = conv_algorithmic(shape, kind)
+            rows.append({"kind": kind, "shape": list(shape), "launches": n, "avg_us": tot / n * 1e3,
+                         "algo_GBps": nb / (tot / n / 1e3) / 1e9, "algo_TFLOPs": fl / (tot / n / 1e3) / 1e12,
+                         "hbm_roof_us": nb / (hbm * 1e9) * 1e6})
+        json.dump({"ms_per_step": ms_total / args.steps, "kernels": rows}, open(args.kernels_json, "w"), indent=1)
     (dk, dshape), (dtot, dn) = max(agg.items(), key=lambda kv: kv[1][0])
     flops, nbytes = conv_algorithmic(dshape, dk)
     avg_s = dtot / dn / 1e3
