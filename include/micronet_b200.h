@@ -178,15 +178,17 @@ int mnb_channel_stats_bwd(const float* x, const float* mean, const float* dmean,
  * ---------------------------------------------------------------------- */
 int mnb_fq_conv2d_fwd_tc(const mnb_conv_shape* s, const float* x, const mnb_act_qparams* qp,
                          const int16_t* w_int, const float* w_scale, const float* bias, float* y,
-                         uint8_t* codes, uint32_t* pass_bits, int32_t* err_flag, mnb_stream_t stream);
+                         uint8_t* codes, uint32_t* pass_bits, void* wpack_scratch, int32_t* err_flag,
+                         mnb_stream_t stream);
+/* wpack_scratch: >= 2 * numel(w_int) bytes, 16-byte aligned (bf16 operand image of the weights). */
 
 /* Data gradient of the same convolution on the tensor-core path (ATen convolution_backward's
  * grad_input): dx = STE( conv_transpose(dy, w_scale[k] * w_int) ), the per-channel weight scale folded
  * into dy while it is staged (exact 3-term bf16 split of the fp32 product).  pass_bits / qp NULL:
  * plain dgrad (wbwtab).  Same geometry cover and error conventions as mnb_fq_conv2d_fwd_tc.   */
 int mnb_conv2d_dgrad_tc(const mnb_conv_shape* s, const float* dy, const int16_t* w_int, const float* w_scale,
-                        const uint32_t* pass_bits, const mnb_act_qparams* qp, float* dx, int32_t* err_flag,
-                        mnb_stream_t stream);
+                        const uint32_t* pass_bits, const mnb_act_qparams* qp, float* dx, void* wpack_scratch,
+                        int32_t* err_flag, mnb_stream_t stream);
 
 /* Weight gradient on the tensor-core path: dWq = s_a * corr(e_a, dy) with e_a re-quantized from the
  * fp32 input x on the fly (qp as in the forward; NULL = raw x, which must be bf16-exact such as the

@@ -49,6 +49,7 @@ struct Params {
   float a_scale_const;
   mnb_act_qparams qp;
   const int16_t* w_int;     // [K, Cg, R, S] integer weights (K = fwd output channels)
+  const uint8_t* w_pack;    // bf16 B-operand image [g][tap][k/8][n][8], written by pack_b_kernel
   const float* w_scale;     // [K]
   const float* a_scale;     // device scalar (IAO) or NULL
   const float* bias;        // fwd only
@@ -59,11 +60,11 @@ struct Params {
 };
 
 struct alignas(16) Shared {
-  uint64_t stage_full[MAXST], stage_empty[MAXST], op_full[NOP], op_empty[NOP], acc_full[NACC], acc_empty[NACC];
+  uint64_t stage_full[MAXST], stage_empty[MAXST], op_full[NOP], op_empty[NOP], acc_full[NACC], acc_empty[NACC], b_full;
   uint32_t tmem_slot;
   uint32_t op_flags[NOP][8];
-  float epi_scale[NACC][256];
-  float epi_bias[NACC][256];
+  float epi_scale[256];   // per output channel of the slab (fixed for the whole kernel)
+  float epi_bias[256];
 };
 
 __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
@@ -94,6 +95,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const Params p) {
     for (int i = 0; i < p.nst; ++i) { tc::mbar_init(&sh.stage_full[i], 1); tc::mbar_init(&sh.stage_empty[i], NCONV); }
     for (int i = 0; i < NOP; ++i) { tc::mbar_init(&sh.op_full[i], NCONV); tc::mbar_init(&sh.op_empty[i], 1); }
     for (int i = 0; i < NACC; ++i) { tc::mbar_init(&sh.acc_full[i], 1); tc::mbar_init(&sh.acc_empty[i], NEPI); }
+    tc::mbar_init(&sh.b_full, 1);
     tc::fence_barrier_init();
     tc::prefetch_tmap(&tmap_in);
   }
@@ -106,23 +108,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const Params p) {
   // zero the operand buffers once: the mid / lo planes are only rewritten when a chunk needs them
   for (int i = tid; i < NOP * p.op_buf_bytes / 16; i += NTHREADS)
     reinterpret_cast<uint4*>(op_base)[i] = make_uint4(0, 0, 0, 0);
-  // resident integer weights of this slab as the B operand: B[gi][tap][k/8][n][8] bf16
-  {
-    const int per_group = RS * p.cin_g * p.cout_g;
-    for (int idx = tid; idx < g_count * per_group; idx += NTHREADS) {
-      const int gi = idx / per_group;
-      int r = idx - gi * per_group;
-      const int n = r / (p.cin_g * RS);   // output channel of this GEMM within the group
-      r -= n * (p.cin_g * RS);
-      const int c = r / RS, tap = r - c * RS;  // input channel within the group, tap of this GEMM
-      const int g = g_first + gi;
-      int64_t src;
-      if (!p.dgrad) src = ((int64_t)(g * p.cout_g + n) * p.cin_g + c) * RS + tap;              // W[k=n][c][tap]
-      else src = ((int64_t)(g * p.cin_g + c) * p.cout_g + n) * RS + (RS - 1 - tap);              // W[k=c][c'=n][flipped tap]
-      const int16_t v = __ldg(p.w_int + src);
-      uint8_t* dst = b_base + (size_t)gi * p.b_group_bytes +
-                     ((size_t)((tap * c8_per_group + (c >> 3)) * p.cout_g + n)) * 16 + (c & 7) * 2;
-      *reinterpret_cast<__nv_bfloat16*>(dst) = __float2bfloat16_rn((float)v);
+  // per-channel epilogue constants of this slab (forward): loaded once
+  if (!p.dgrad) {
+    const float a_sc0 = p.a_scale ? __ldg(p.a_scale) : p.a_scale_const;
+    const int ch_first = g_first * p.cout_g;
+    for (int n = tid; n < g_count * p.cout_g; n += NTHREADS) {
+      sh.epi_scale[n] = __fmul_rn(a_sc0, __ldg(p.w_scale + ch_first + n));
+      sh.epi_bias[n] = p.bias ? __ldg(p.bias + ch_first + n) : 0.f;
     }
   }
   tc::fence_proxy_async_smem();
@@ -134,6 +126,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const Params p) {
   if (warp == 0) {
     // ================================================================= TMA producer
     if (lane == 0) {
+      // resident B operand of this slab: one bulk copy of the pre-packed bf16 image (L2 -> smem)
+      {
+        const uint32_t bytes = (uint32_t)(g_count * p.b_group_bytes);
+        tc::mbar_arrive_expect_tx(&sh.b_full, bytes);
+        tc::bulk_load_1d(b_base, p.w_pack + (size_t)g_first * p.b_group_bytes, bytes, &sh.b_full);
+      }
       uint32_t it = 0;
       for (int tile = rank_in_slab; tile < p.n_tiles; tile += ctas_in_slab) {
         const int bt = tile / p.row_tiles, rt = tile - bt * p.row_tiles;
@@ -155,14 +153,22 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const Params p) {
     if (lane == 0) {
       const uint32_t idesc = tc::make_idesc(1, 1, 1, 128, (uint32_t)p.cout_g);
       const uint32_t a_lbo = (uint32_t)p.npos_in * 16u, b_lbo = (uint32_t)p.cout_g * 16u;
+      // descriptors differ only in the 14-bit start-address field: build once, then add (bytes >> 4)
+      const uint64_t a_desc0 = tc::smem_desc_kmajor_noswz(tc::smem_u32(op_base), a_lbo, 128);
+      const uint64_t b_desc0 = tc::smem_desc_kmajor_noswz(tc::smem_u32(b_base), b_lbo, 128);
+      const uint32_t a_kstep = (2u * a_lbo) >> 4, a_term = (uint32_t)p.op_term_bytes >> 4, a_buf = (uint32_t)p.op_buf_bytes >> 4;
+      const uint32_t b_kstep = (2u * b_lbo) >> 4, b_tap = (uint32_t)(c8_per_group * p.cout_g * 16) >> 4;
+      const uint32_t b_chunk = (uint32_t)((p.CC / 8) * p.cout_g * 16) >> 4, b_group = (uint32_t)p.b_group_bytes >> 4;
+      const int ksteps = p.CC / 16, slab_cols = g_count * p.cout_g;
+      if (!tc::mbar_wait(&sh.b_full, 0, p.err, 307)) goto done;
       uint32_t it = 0, item = 0;
-      for (int tile = rank_in_slab; tile < p.n_tiles; tile += ctas_in_slab) {
-        for (int gi = 0; gi < g_count; ++gi, ++item) {
-          const int acc = item % NACC;
-          const uint32_t aph = (item / NACC) & 1;
-          if (!tc::mbar_wait(&sh.acc_empty[acc], aph ^ 1, p.err, 302)) goto done;
-          tc::tc_fence_after();
-          const uint32_t d_tmem = tmem + (uint32_t)(acc * p.cout_g);
+      for (int tile = rank_in_slab; tile < p.n_tiles; tile += ctas_in_slab, ++item) {
+        const int acc = item % NACC;
+        const uint32_t aph = (item / NACC) & 1;
+        if (!tc::mbar_wait(&sh.acc_empty[acc], aph ^ 1, p.err, 302)) goto done;
+        tc::tc_fence_after();
+        for (int gi = 0; gi < g_count; ++gi) {
+          const uint32_t d_tmem = tmem + (uint32_t)(acc * slab_cols + gi * p.cout_g);
           uint32_t accumulate = 0;
           for (int ch = 0; ch < p.nchunk; ++ch, ++it) {
             const int ob = it % NOP;
@@ -176,89 +182,78 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const Params p) {
               for (int w8 = 0; w8 < 8; ++w8) any |= sh.op_flags[ob][w8];
               nterms = any ? 3 : 1;
             }
-            const uint32_t op_addr = tc::smem_u32(op_base + (size_t)ob * p.op_buf_bytes);
-            const uint32_t b_addr = tc::smem_u32(b_base + (size_t)gi * p.b_group_bytes);
-            for (int tap = 0; tap < RS; ++tap) {
-              const int r = tap / p.S, s = tap - r * p.S;
-              const uint32_t tap_off = (uint32_t)(r * p.BW + s) * 16u;
-              for (int j = 0; j < p.CC / 16; ++j) {
-                const uint32_t b_start = b_addr + (uint32_t)((tap * c8_per_group + ch * (p.CC / 8) + 2 * j) * p.cout_g) * 16u;
-                const uint64_t bd = tc::smem_desc_kmajor_noswz(b_start, b_lbo, 128);
-                for (int t = 0; t < nterms; ++t) {
-                  const uint32_t a_start = op_addr + (uint32_t)t * p.op_term_bytes + (uint32_t)(2 * j) * a_lbo + tap_off;
-                  const uint64_t ad = tc::smem_desc_kmajor_noswz(a_start, a_lbo, 128);
-                  tc::mma_f16(d_tmem, ad, bd, idesc, accumulate);
-                  accumulate = 1;
+            const uint64_t a_chunk = a_desc0 + (uint64_t)((uint32_t)ob * a_buf);
+            const uint64_t b_chunk_d = b_desc0 + (uint64_t)((uint32_t)gi * b_group + (uint32_t)ch * b_chunk);
+            uint32_t row_off = 0, b_t = 0;  // (r * BW) positions == 16-byte units; tap stride in B
+            for (int r = 0; r < p.R; ++r, row_off += (uint32_t)p.BW) {
+              for (int s2 = 0; s2 < p.S; ++s2, b_t += b_tap) {
+                const uint64_t a_tap = a_chunk + (uint64_t)(row_off + (uint32_t)s2);
+                const uint64_t b_tapd = b_chunk_d + (uint64_t)b_t;
+                for (int j = 0; j < ksteps; ++j) {
+                  const uint64_t bd = b_tapd + (uint64_t)((uint32_t)j * b_kstep);
+                  uint64_t ad = a_tap + (uint64_t)((uint32_t)j * a_kstep);
+                  for (int t = 0; t < nterms; ++t, ad += a_term) {
+                    tc::mma_f16(d_tmem, ad, bd, idesc, accumulate);
+                    accumulate = 1;
+                  }
                 }
               }
             }
             tc::mma_commit(&sh.op_empty[ob]);  // operand buffer is free once these MMAs retire
           }
-          tc::mma_commit(&sh.acc_full[acc]);
         }
+        tc::mma_commit(&sh.acc_full[acc]);
       }
     }
   } else if (warp >= 4 && warp < 8) {
     // ================================================================= epilogue
     const int q = warp - 4;            // TMEM lane quarter of this warp (warp % 4)
-    const int et = tid - 128;
     const int pos = q * 32 + lane;     // GEMM row = padded-tile position
     const int tb = pos / (p.THH * p.BW);
     const int rem = pos - tb * (p.THH * p.BW);
     const int th = rem / p.BW, wc = rem - th * p.BW;
-    const float a_sc = p.a_scale ? __ldg(p.a_scale) : p.a_scale_const;
     MnbActQ ste;
     if (p.dgrad && p.ste_bits) ste = mnb_load_actq(p.qp);
     const int64_t plane = (int64_t)p.H * p.W;
+    const int slab_cols = g_count * p.cout_g, ch_first = g_first * p.cout_g;
     uint32_t item = 0;
-    for (int tile = rank_in_slab; tile < p.n_tiles; tile += ctas_in_slab) {
+    for (int tile = rank_in_slab; tile < p.n_tiles; tile += ctas_in_slab, ++item) {
       const int bt = tile / p.row_tiles, rt = tile - bt * p.row_tiles;
       const int b = bt * p.TB + tb, h = rt * p.TH + th;
       const bool valid = tb < p.TB && th < p.TH && wc < p.W && b < p.B && h < p.H;
-      for (int gi = 0; gi < g_count; ++gi, ++item) {
-        const int acc = item % NACC;
-        const uint32_t aph = (item / NACC) & 1;
-        const int ch0 = (g_first + gi) * p.cout_g;
-        if (!p.dgrad) {
-          // per-channel scale / bias of this group -> smem (slot `acc` was released two items ago)
-          for (int n = et; n < p.cout_g; n += NEPI) {
-            sh.epi_scale[acc][n] = __fmul_rn(a_sc, __ldg(p.w_scale + ch0 + n));
-            sh.epi_bias[acc][n] = p.bias ? __ldg(p.bias + ch0 + n) : 0.f;
-          }
-          asm volatile("bar.sync 1, 128;" ::: "memory");
-        }
-        if (!tc::mbar_wait(&sh.acc_full[acc], aph, p.err, 304)) goto done;
-        tc::tc_fence_after();
-        const int64_t obase = (((int64_t)b * p.Cout + ch0) * p.H + h) * p.W + wc;
-        for (int n0 = 0; n0 < p.cout_g; n0 += 32) {
-          uint32_t r[32];
-          tc::tmem_ld_32x32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.cout_g + n0), r);
-          tc::tmem_ld_wait();
-          if (valid) {
-            if (!p.dgrad) {
+      const int acc = item % NACC;
+      const uint32_t aph = (item / NACC) & 1;
+      if (!tc::mbar_wait(&sh.acc_full[acc], aph, p.err, 304)) goto done;
+      tc::tc_fence_after();
+      float* orow = p.out + (((int64_t)b * p.Cout + ch_first) * p.H + h) * p.W + wc;
+      const int64_t obase = (((int64_t)b * p.Cout + ch_first) * p.H + h) * p.W + wc;
+      for (int n0 = 0; n0 < slab_cols; n0 += 32) {
+        uint32_t r[32];
+        tc::tmem_ld_32x32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * slab_cols + n0), r);
+        tc::tmem_ld_wait();
+        if (valid) {
+          if (!p.dgrad) {
 #pragma unroll
-              for (int j = 0; j < 32; ++j)
-                if (n0 + j < p.cout_g)
-                  p.out[obase + (int64_t)(n0 + j) * plane] =
-                      __fadd_rn(__fmul_rn(__uint_as_float(r[j]), sh.epi_scale[acc][n0 + j]), sh.epi_bias[acc][n0 + j]);
-            } else if (p.ste_bits) {
+            for (int j = 0; j < 32; ++j)
+              if (n0 + j < slab_cols)
+                orow[(int64_t)(n0 + j) * plane] = fmaf(__uint_as_float(r[j]), sh.epi_scale[n0 + j], sh.epi_bias[n0 + j]);
+          } else if (p.ste_bits) {
 #pragma unroll
-              for (int j = 0; j < 32; ++j)
-                if (n0 + j < p.cout_g) {
-                  const int64_t fi = obase + (int64_t)(n0 + j) * plane;
-                  const bool pass = (__ldg(p.ste_bits + (fi >> 5)) >> (fi & 31)) & 1u;
-                  p.out[fi] = mnb_act_ste_one(ste, __uint_as_float(r[j]), pass);
-                }
-            } else {
+            for (int j = 0; j < 32; ++j)
+              if (n0 + j < slab_cols) {
+                const int64_t fi = obase + (int64_t)(n0 + j) * plane;
+                const bool pass = (__ldg(p.ste_bits + (fi >> 5)) >> (fi & 31)) & 1u;
+                p.out[fi] = mnb_act_ste_one(ste, __uint_as_float(r[j]), pass);
+              }
+          } else {
 #pragma unroll
-              for (int j = 0; j < 32; ++j)
-                if (n0 + j < p.cout_g) p.out[obase + (int64_t)(n0 + j) * plane] = __uint_as_float(r[j]);
-            }
+            for (int j = 0; j < 32; ++j)
+              if (n0 + j < slab_cols) orow[(int64_t)(n0 + j) * plane] = __uint_as_float(r[j]);
           }
         }
-        tc::tc_fence_before();
-        tc::mbar_arrive(&sh.acc_empty[acc]);
       }
+      tc::tc_fence_before();
+      tc::mbar_arrive(&sh.acc_empty[acc]);
     }
   } else if (warp >= 8) {
     // ================================================================= converters
@@ -404,6 +399,28 @@ done:
   }
 }
 
+// bf16 B-operand image of the integer weights: out[g][tap][k/8][n][8] (K-major no-swizzle, rows = n);
+// forward: n = output channel, k = input channel; dgrad: n = input channel, k = output channel, taps flipped
+__global__ void __launch_bounds__(256) pack_b_kernel(const int16_t* __restrict__ w_int, __nv_bfloat16* __restrict__ out,
+                                                     int G, int cin_g, int cout_g, int RS, int dgrad) {
+  const int per_group = RS * cin_g * cout_g;
+  const int total = G * per_group;
+  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+    // idx enumerates the destination: [g][tap][c8][n][e]
+    const int g = idx / per_group;
+    int r = idx - g * per_group;
+    const int tap = r / (cin_g * cout_g);
+    r -= tap * (cin_g * cout_g);
+    const int c8 = r / (cout_g * 8);
+    r -= c8 * (cout_g * 8);
+    const int n = r >> 3, c = c8 * 8 + (r & 7);
+    int64_t src;
+    if (!dgrad) src = ((int64_t)(g * cout_g + n) * cin_g + c) * RS + tap;
+    else src = ((int64_t)(g * cin_g + c) * cout_g + n) * RS + (RS - 1 - tap);
+    out[idx] = __float2bfloat16_rn((float)__ldg(w_int + src));
+  }
+}
+
 // geometry + shared-memory plan shared by forward and dgrad; returns 0 / MNB_E_UNSUPPORTED / error
 static int plan(const mnb_conv_shape* s, bool dgrad, int quant_mode, Params& p, int& smem_bytes) {
   MNB_REQUIRE(s != nullptr, "conv shape is NULL");
@@ -451,6 +468,7 @@ static int plan(const mnb_conv_shape* s, bool dgrad, int quant_mode, Params& p, 
   }
   if (budget < p.b_group_bytes) return unsupported("weights of one group do not fit in shared memory");
   int max_groups = std::max(1, std::min(p.G, std::min(budget / p.b_group_bytes, std::max(1, 64 * 1024 / p.b_group_bytes))));
+  max_groups = std::max(1, std::min(max_groups, 256 / p.cout_g));  // one accumulator row block per tile: <= 256 columns
   while (p.G % max_groups) --max_groups;  // equal slabs: every CTA does the same work per tile
   p.slab_groups = max_groups;
   p.n_slabs = p.G / p.slab_groups;
@@ -460,12 +478,17 @@ static int plan(const mnb_conv_shape* s, bool dgrad, int quant_mode, Params& p, 
   smem_bytes = p.off_b + p.slab_groups * p.b_group_bytes;
   if (smem_bytes > kMaxDynSmem) return unsupported("shared memory budget");
   int cols = 32;
-  while (cols < NACC * p.cout_g) cols <<= 1;
+  while (cols < NACC * p.slab_groups * p.cout_g) cols <<= 1;
   p.tmem_cols = cols;
   return 0;
 }
 
 static int launch(const Params& p, const void* in, int smem_bytes, cudaStream_t st) {
+  {
+    const int total = p.G * p.b_group_bytes / 2;
+    pack_b_kernel<<<std::min(mnb_ceil_div(total, 256), MNB_NUM_SMS * 4), 256, 0, st>>>(
+        p.w_int, reinterpret_cast<__nv_bfloat16*>(const_cast<uint8_t*>(p.w_pack)), p.G, p.cin_g, p.cout_g, p.R * p.S, p.dgrad);
+  }
   CUtensorMap tmap;
   uint64_t dims[4] = {(uint64_t)p.W, (uint64_t)p.H, (uint64_t)p.Cin, (uint64_t)p.B};
   uint32_t box[4] = {(uint32_t)p.W, (uint32_t)p.THH, (uint32_t)p.CC, (uint32_t)p.TB};
@@ -480,7 +503,7 @@ static int launch(const Params& p, const void* in, int smem_bytes, cudaStream_t 
   int grid = (int)std::min<int64_t>(items, MNB_NUM_SMS);
   grid = std::max(grid, p.n_slabs);
   conv_tc_kernel<<<grid, NTHREADS, smem_bytes, st>>>(tmap, p);
-  MNB_LAUNCHED(1);
+  MNB_LAUNCHED(2);
   return 0;
 }
 
@@ -488,9 +511,10 @@ static int launch(const Params& p, const void* in, int smem_bytes, cudaStream_t 
 
 extern "C" int mnb_fq_conv2d_fwd_tc(const mnb_conv_shape* s, const float* x, const mnb_act_qparams* qp,
                                     const int16_t* w_int, const float* w_scale, const float* bias, float* y,
-                                    uint8_t* codes, uint32_t* pass_bits, int32_t* err_flag, mnb_stream_t stream) {
+                                    uint8_t* codes, uint32_t* pass_bits, void* wpack_scratch, int32_t* err_flag,
+                                    mnb_stream_t stream) {
   using namespace tcconv;
-  MNB_REQUIRE(s && x && w_int && w_scale && y && err_flag, "NULL pointer");
+  MNB_REQUIRE(s && x && w_int && w_scale && y && err_flag && wpack_scratch, "NULL pointer");
   if (qp) MNB_REQUIRE(qp->mode == MNB_ACT_DOREFA || qp->mode == MNB_ACT_IAO, "fused quantizer must be DoReFa or IAO");
   Params p{};
   int smem_bytes = 0;
@@ -503,15 +527,15 @@ extern "C" int mnb_fq_conv2d_fwd_tc(const mnb_conv_shape* s, const float* x, con
   p.a_scale = (qp && qp->mode == MNB_ACT_IAO) ? qp->scale : nullptr;
   p.a_scale_const = (qp && qp->mode == MNB_ACT_DOREFA) ? (float)(1.0 / (double)((1 << qp->bits) - 1)) : 1.f;
   p.w_int = w_int; p.w_scale = w_scale; p.bias = bias; p.out = y; p.codes = codes; p.pass_bits = pass_bits;
-  p.err = err_flag;
+  p.err = err_flag; p.w_pack = reinterpret_cast<const uint8_t*>(wpack_scratch);
   return launch(p, x, smem_bytes, (cudaStream_t)stream);
 }
 
 extern "C" int mnb_conv2d_dgrad_tc(const mnb_conv_shape* s, const float* dy, const int16_t* w_int,
                                    const float* w_scale, const uint32_t* pass_bits, const mnb_act_qparams* qp,
-                                   float* dx, int32_t* err_flag, mnb_stream_t stream) {
+                                   float* dx, void* wpack_scratch, int32_t* err_flag, mnb_stream_t stream) {
   using namespace tcconv;
-  MNB_REQUIRE(s && dy && w_int && w_scale && dx && err_flag, "NULL pointer");
+  MNB_REQUIRE(s && dy && w_int && w_scale && dx && err_flag && wpack_scratch, "NULL pointer");
   MNB_REQUIRE((pass_bits == nullptr) == (qp == nullptr), "pass_bits and qp go together");
   Params p{};
   int smem_bytes = 0;
@@ -519,5 +543,6 @@ extern "C" int mnb_conv2d_dgrad_tc(const mnb_conv_shape* s, const float* dy, con
   if (qp) p.qp = *qp;
   p.a_scale_const = 1.f;
   p.w_int = w_int; p.w_scale = w_scale; p.ste_bits = pass_bits; p.out = dx; p.err = err_flag;
+  p.w_pack = reinterpret_cast<const uint8_t*>(wpack_scratch);
   return launch(p, dy, smem_bytes, (cudaStream_t)stream);
 }

@@ -116,22 +116,26 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
     // ================================================================= MMA issuer
     if (lane == 0) {
       const uint32_t idesc = tc::make_idesc_major(1, 1, 1, 128, (uint32_t)p.n_block, 1, 1);
-      const uint32_t x_sbo = (uint32_t)p.npos_x * 16u, d_sbo = 128u * 16u;
-      const uint32_t xa = tc::smem_u32(xop), da = tc::smem_u32(dop);
+      // descriptors differ only in the 14-bit start-address field: build once, then add (bytes >> 4)
+      const uint64_t b_desc0 = tc::smem_desc_mnmajor_noswz(tc::smem_u32(xop), 128, (uint32_t)p.npos_x * 16u);
+      const uint64_t a_desc0 = tc::smem_desc_mnmajor_noswz(tc::smem_u32(dop), 128, 128u * 16u);
+      const uint32_t a_term = (uint32_t)p.dop_term_bytes >> 4;
       uint32_t t = 0;
       for (int tile = rank; tile < p.n_tiles; tile += p.ranks, ++t) {
         if (!tc::mbar_wait(&sh.op_full, t & 1, p.err, 402)) goto done;
         tc::tc_fence_after();
-        for (int tap = 0; tap < RS; ++tap) {
-          const int r = tap / p.S, s = tap - r * p.S;
-          const uint32_t tap_off = (uint32_t)(r * p.BW + s) * 16u;
-          const uint32_t d_tmem = tmem + (uint32_t)(tap * p.n_block);
-          for (int ps = 0; ps < 8; ++ps) {
-            const uint64_t bd = tc::smem_desc_mnmajor_noswz(xa + tap_off + (uint32_t)ps * 256u, 128, x_sbo);
+        uint32_t row_off = 0, d_col = 0;
+        for (int r = 0; r < p.R; ++r, row_off += (uint32_t)p.BW) {
+          for (int s2 = 0; s2 < p.S; ++s2, d_col += (uint32_t)p.n_block) {
+            const uint64_t b_tap = b_desc0 + (uint64_t)(row_off + (uint32_t)s2);
+            const uint32_t d_tmem = tmem + d_col;
 #pragma unroll
-            for (int term = 0; term < 3; ++term) {
-              const uint64_t ad = tc::smem_desc_mnmajor_noswz(da + (uint32_t)term * p.dop_term_bytes + (uint32_t)ps * 256u, 128, d_sbo);
-              tc::mma_f16(d_tmem, ad, bd, idesc, (t | (uint32_t)ps | (uint32_t)term) != 0);
+            for (int ps = 0; ps < 8; ++ps) {
+              const uint64_t bd = b_tap + (uint64_t)(ps * 16);   // 16 positions x 16 bytes = 256 B
+              const uint64_t ad = a_desc0 + (uint64_t)(ps * 16);
+              tc::mma_f16(d_tmem, ad, bd, idesc, (t | (uint32_t)ps) != 0);
+              tc::mma_f16(d_tmem, ad + a_term, bd, idesc, 1);
+              tc::mma_f16(d_tmem, ad + 2 * a_term, bd, idesc, 1);
             }
           }
         }

@@ -264,9 +264,10 @@ class QuantConv2dFn(Function):
                 codes = torch.empty(x.shape, dtype=torch.uint8, device=x.device)
                 if ctx.needs_input_grad[0]:
                     bits = torch.zeros((x.numel() + 31) // 32, dtype=torch.int32, device=x.device)
+            wpack = torch.empty(w_int.numel(), dtype=torch.int16, device=x.device)
             rc = _timed("fwd_tc", sh, lambda: lib.mnb_fq_conv2d_fwd_tc(
                 C.byref(sh), x.data_ptr(), None if qp is None else C.byref(qp), w_int.data_ptr(),
-                w_scale.data_ptr(), L.ptr(bias), y.data_ptr(), L.ptr(codes), L.ptr(bits),
+                w_scale.data_ptr(), L.ptr(bias), y.data_ptr(), L.ptr(codes), L.ptr(bits), wpack.data_ptr(),
                 L.tc_err_flag(x.device).data_ptr(), L.stream()))
             if rc == 0:
                 done = True
@@ -313,10 +314,11 @@ class QuantConv2dFn(Function):
             bits_ptr = ctx.bits.data_ptr() if spec is not None else None
             rc = L.E_UNSUPPORTED
             if L.USE_TC and ctx.w_int is not None:
+                wpack = torch.empty(ctx.w_int.numel(), dtype=torch.int16, device=dy.device)
                 rc = _timed("dgrad_tc", sh, lambda: lib.mnb_conv2d_dgrad_tc(
                     C.byref(sh), dy.data_ptr(), ctx.w_int.data_ptr(), ctx.w_scale.data_ptr(), bits_ptr,
-                    None if qp is None else C.byref(qp), dx.data_ptr(), L.tc_err_flag(dy.device).data_ptr(),
-                    L.stream()))
+                    None if qp is None else C.byref(qp), dx.data_ptr(), wpack.data_ptr(),
+                    L.tc_err_flag(dy.device).data_ptr(), L.stream()))
             if rc == L.E_UNSUPPORTED:
                 rc = _timed("dgrad", sh, lambda: lib.mnb_conv2d_dgrad(
                     C.byref(sh), dy.data_ptr(), ctx.wq.data_ptr(), bits_ptr, None if qp is None else C.byref(qp),

@@ -112,8 +112,10 @@ def test_tc_forward_emits_identical_codes_and_bits(shape, mode):
     bits = torch.zeros_like(bits_ref)
     err = L.tc_err_flag(torch.device(DEV)); err.zero_()
     qp = spec.struct()
+    wpack = torch.empty(w_int.numel(), dtype=torch.int16, device=DEV)
     rc = lib.mnb_fq_conv2d_fwd_tc(C.byref(sh), x.data_ptr(), C.byref(qp), w_int.data_ptr(), w_scale.data_ptr(), None,
-                                  y.data_ptr(), codes.data_ptr(), bits.data_ptr(), err.data_ptr(), L.stream())
+                                  y.data_ptr(), codes.data_ptr(), bits.data_ptr(), wpack.data_ptr(), err.data_ptr(),
+                                  L.stream())
     if rc == L.E_UNSUPPORTED:
         pytest.skip("geometry not covered by the tensor-core kernel")
     L.check(rc, "fq_conv2d_fwd_tc")
