@@ -201,6 +201,10 @@ int mnb_conv2d_wgrad_tc(const mnb_conv_shape* s, const float* dy, const float* x
 int mnb_conv2d_wgrad_cond(const mnb_conv_shape* s, const float* dy, const mnb_conv_operands* op, float* dwq,
                           void* scratch, const int32_t* run_if_nonzero, mnb_stream_t stream);
 
+/* Debug hook: 16 int64 device counters [role: tma, mma, epilogue, converter][wait a, wait b, wait c,
+ * total cycles], accumulated by the fwd/dgrad tensor-core kernel while the pointer is non-NULL.  */
+void mnb_set_tc_profile_buffer(void* dev_int64x16);
+
 /* ------------------------------------------------------------------------
  * Hardware self-tests of the sm_100a building blocks (run by tests/test_gpu_tc_selftest.py).
  * Bounded waits: a wrong descriptor sets *err_flag (device int) instead of hanging the GPU.

@@ -57,6 +57,7 @@ struct Params {
   float* out;
   uint8_t* codes; uint32_t* pass_bits;  // fwd side outputs of the fused quantizer
   int* err;
+  long long* prof;  // optional debug counters (cycles): see mnb_set_tc_profile_buffer
 };
 
 struct alignas(16) Shared {
@@ -73,6 +74,15 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
 }
 __device__ __forceinline__ float bf16_round(float v) { return __bfloat162float(__float2bfloat16_rn(v)); }
 
+// debug instrumentation: time spent inside a bounded wait, accumulated per role
+#define PROF_WAIT(slot, call)                                   \
+  do {                                                          \
+    long long t0__ = p.prof ? clock64() : 0;                    \
+    const bool ok__ = (call);                                   \
+    if (p.prof) prof_acc[slot] += clock64() - t0__;             \
+    if (!ok__) goto done;                                       \
+  } while (0)
+
 __global__ void __launch_bounds__(NTHREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const Params p) {
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -82,6 +92,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const Params p) {
   uint8_t* op_base = smem + p.off_op;
   uint8_t* b_base = smem + p.off_b;
   const int RS = p.R * p.S, c8_per_group = p.cin_g / 8;
+  long long prof_acc[3] = {0, 0, 0};
+  const long long prof_t0 = p.prof ? clock64() : 0;
 
   // ---- work assignment: CTA -> slab of groups; the slab's tiles are dealt round-robin
   const int slab = blockIdx.x % p.n_slabs;
@@ -140,7 +152,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const Params p) {
           for (int ch = 0; ch < p.nchunk; ++ch, ++it) {
             const int st = it % p.nst;
             const uint32_t ph = (it / p.nst) & 1;
-            if (!tc::mbar_wait(&sh.stage_empty[st], ph ^ 1, p.err, 301)) goto done;
+            PROF_WAIT(0, tc::mbar_wait(&sh.stage_empty[st], ph ^ 1, p.err, 301));
             tc::mbar_arrive_expect_tx(&sh.stage_full[st], (uint32_t)p.stage_bytes);
             tc::tma_load_4d(stage_base + (size_t)st * p.stage_bytes, &tmap_in, &sh.stage_full[st], 0, h0 - p.pad,
                             (g_first + gi) * p.cin_g + ch * p.CC, b0);
@@ -160,12 +172,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const Params p) {
       const uint32_t b_kstep = (2u * b_lbo) >> 4, b_tap = (uint32_t)(c8_per_group * p.cout_g * 16) >> 4;
       const uint32_t b_chunk = (uint32_t)((p.CC / 8) * p.cout_g * 16) >> 4, b_group = (uint32_t)p.b_group_bytes >> 4;
       const int ksteps = p.CC / 16, slab_cols = g_count * p.cout_g;
-      if (!tc::mbar_wait(&sh.b_full, 0, p.err, 307)) goto done;
+      PROF_WAIT(2, tc::mbar_wait(&sh.b_full, 0, p.err, 307));
       uint32_t it = 0, item = 0;
       for (int tile = rank_in_slab; tile < p.n_tiles; tile += ctas_in_slab, ++item) {
         const int acc = item % NACC;
         const uint32_t aph = (item / NACC) & 1;
-        if (!tc::mbar_wait(&sh.acc_empty[acc], aph ^ 1, p.err, 302)) goto done;
+        PROF_WAIT(0, tc::mbar_wait(&sh.acc_empty[acc], aph ^ 1, p.err, 302));
         tc::tc_fence_after();
         for (int gi = 0; gi < g_count; ++gi) {
           const uint32_t d_tmem = tmem + (uint32_t)(acc * slab_cols + gi * p.cout_g);
@@ -173,7 +185,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const Params p) {
           for (int ch = 0; ch < p.nchunk; ++ch, ++it) {
             const int ob = it % NOP;
             const uint32_t oph = (it / NOP) & 1;
-            if (!tc::mbar_wait(&sh.op_full[ob], oph, p.err, 303)) goto done;
+            PROF_WAIT(1, tc::mbar_wait(&sh.op_full[ob], oph, p.err, 303));
             tc::tc_fence_after();
             int nterms = 1;
             if (p.quant_mode == 0) {
@@ -223,7 +235,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const Params p) {
       const bool valid = tb < p.TB && th < p.TH && wc < p.W && b < p.B && h < p.H;
       const int acc = item % NACC;
       const uint32_t aph = (item / NACC) & 1;
-      if (!tc::mbar_wait(&sh.acc_full[acc], aph, p.err, 304)) goto done;
+      PROF_WAIT(0, tc::mbar_wait(&sh.acc_full[acc], aph, p.err, 304));
       tc::tc_fence_after();
       float* orow = p.out + (((int64_t)b * p.Cout + ch_first) * p.H + h) * p.W + wc;
       const int64_t obase = (((int64_t)b * p.Cout + ch_first) * p.H + h) * p.W + wc;
@@ -293,8 +305,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const Params p) {
         for (int ch = 0; ch < p.nchunk; ++ch, ++it) {
           const int st = it % p.nst, ob = it % NOP;
           const uint32_t ph = (it / p.nst) & 1, oph = (it / NOP) & 1;
-          if (!tc::mbar_wait(&sh.op_empty[ob], oph ^ 1, p.err, 306)) goto done;
-          if (!tc::mbar_wait(&sh.stage_full[st], ph, p.err, 305)) goto done;
+          PROF_WAIT(0, tc::mbar_wait(&sh.op_empty[ob], oph ^ 1, p.err, 306));
+          PROF_WAIT(1, tc::mbar_wait(&sh.stage_full[st], ph, p.err, 305));
           // did THIS thread leave non-zero mid / lo pieces in its entries of this buffer last time?
           // (entries are owned by fixed threads, so dirtiness is thread-private state)
           const uint32_t dirty = dirty_mask[ob];
@@ -391,6 +403,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const Params p) {
     }
   }
 done:
+  if (p.prof && lane == 0 && (warp == 0 || warp == 1 || warp == 4 || warp == 8)) {
+    // slots: [role 0..3 = tma, mma, epilogue, converter][wait a, wait b, wait c, total]
+    const int role = warp == 0 ? 0 : (warp == 1 ? 1 : (warp == 4 ? 2 : 3));
+    atomicAdd(reinterpret_cast<unsigned long long*>(p.prof + role * 4 + 0), (unsigned long long)prof_acc[0]);
+    atomicAdd(reinterpret_cast<unsigned long long*>(p.prof + role * 4 + 1), (unsigned long long)prof_acc[1]);
+    atomicAdd(reinterpret_cast<unsigned long long*>(p.prof + role * 4 + 2), (unsigned long long)prof_acc[2]);
+    atomicAdd(reinterpret_cast<unsigned long long*>(p.prof + role * 4 + 3), (unsigned long long)(clock64() - prof_t0));
+  }
   tc::tc_fence_before();
   __syncthreads();
   if (warp == 2) {
@@ -398,6 +418,8 @@ done:
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"((uint32_t)p.tmem_cols));
   }
 }
+
+static long long* g_prof_buffer = nullptr;
 
 // bf16 B-operand image of the integer weights: out[g][tap][k/8][n][8] (K-major no-swizzle, rows = n);
 // forward: n = output channel, k = input channel; dgrad: n = input channel, k = output channel, taps flipped
@@ -502,12 +524,17 @@ static int launch(const Params& p, const void* in, int smem_bytes, cudaStream_t 
   const int64_t items = (int64_t)p.n_tiles * p.n_slabs;
   int grid = (int)std::min<int64_t>(items, MNB_NUM_SMS);
   grid = std::max(grid, p.n_slabs);
-  conv_tc_kernel<<<grid, NTHREADS, smem_bytes, st>>>(tmap, p);
+  Params pp = p;
+  pp.prof = g_prof_buffer;
+  conv_tc_kernel<<<grid, NTHREADS, smem_bytes, st>>>(tmap, pp);
   MNB_LAUNCHED(2);
   return 0;
 }
 
 }  // namespace tcconv
+
+// debug hook: device buffer of 16 int64 cycle counters (NULL disables); see PROF_WAIT above
+extern "C" void mnb_set_tc_profile_buffer(void* dev_ptr) { tcconv::g_prof_buffer = reinterpret_cast<long long*>(dev_ptr); }
 
 extern "C" int mnb_fq_conv2d_fwd_tc(const mnb_conv_shape* s, const float* x, const mnb_act_qparams* qp,
                                     const int16_t* w_int, const float* w_scale, const float* bias, float* y,
