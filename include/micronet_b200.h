@@ -219,6 +219,11 @@ int mnb_selftest_umma(const float* A, const float* B, float* D, int32_t N, int32
 int mnb_selftest_tma3d(const float* src, const int64_t* dims3_host, const int32_t* box3_host,
                        const int32_t* coord3_host, float* out, int32_t* err_flag, mnb_stream_t stream);
 
+/* micro-benchmark: `iters` back-to-back M128 x N x K16 bf16 MMAs from one thread over n_acc accumulators;
+ * out2[0] = cycles until all have retired, out2[1] = cycles spent issuing.                         */
+int mnb_selftest_mma_rate(int32_t N, int32_t n_acc, int32_t a_shift16, int32_t iters, int32_t mn_major,
+                          int64_t* out2, int32_t* err_flag, mnb_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -231,3 +231,50 @@ extern "C" int mnb_selftest_tma3d(const float* src, const int64_t* dims3, const 
   return 0;
 }
 
+
+// ------------------------------------------------------------------ micro-benchmark: MMA issue / execution rate
+// `iters` back-to-back tcgen05.mma (M=128, N, K=16, bf16, K-major no-swizzle operands of zeros) from one
+// thread, cycling over `n_acc` accumulators; A start address shifted by `a_shift16` 16-byte units.
+// out[0] = SM cycles from first issue until the final commit arrives.
+__global__ void __launch_bounds__(64) mma_rate_kernel(int N, int n_acc, int a_shift16, int iters, int mn_major,
+                                                      long long* out, int* err) {
+  __shared__ __align__(1024) uint8_t ab[48 * 1024 - 1024];
+  __shared__ __align__(8) uint64_t bar;
+  __shared__ uint32_t tmem_slot;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  for (int i = tid; i < (int)sizeof(ab) / 16; i += 64) reinterpret_cast<uint4*>(ab)[i] = make_uint4(0, 0, 0, 0);
+  tc::fence_proxy_async_smem();
+  if (warp == 1) {
+    tc::tmem_alloc<512>(&tmem_slot);
+    if (lane == 0) { tc::mbar_init(&bar, 1); tc::fence_barrier_init(); }
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tmem = tmem_slot;
+  if (tid == 0) {
+    const uint32_t idesc = mn_major ? tc::make_idesc_major(1, 1, 1, 128, N, 1, 1) : tc::make_idesc(1, 1, 1, 128, N);
+    const uint32_t a_addr = tc::smem_u32(ab) + (uint32_t)a_shift16 * 16u, b_addr = tc::smem_u32(ab) + 24 * 1024;
+    const uint64_t ad = mn_major ? tc::smem_desc_mnmajor_noswz(a_addr, 128, 136 * 16) : tc::smem_desc_kmajor_noswz(a_addr, 136 * 16, 128);
+    const uint64_t bd = mn_major ? tc::smem_desc_mnmajor_noswz(b_addr, 128, 136 * 16) : tc::smem_desc_kmajor_noswz(b_addr, (uint32_t)N * 16, 128);
+    const long long t0 = clock64();
+    for (int i = 0; i < iters; ++i) tc::mma_f16(tmem + (uint32_t)((i % n_acc) * N), ad, bd, idesc, 1);
+    const long long t1 = clock64();
+    tc::mma_commit(&bar);
+    bool ok = tc::mbar_wait(&bar, 0, err, 501);
+    const long long t2 = clock64();
+    out[0] = ok ? (t2 - t0) : -1;
+    out[1] = t1 - t0;
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tc::tmem_dealloc<512>(tmem);
+}
+
+extern "C" int mnb_selftest_mma_rate(int32_t N, int32_t n_acc, int32_t a_shift16, int32_t iters, int32_t mn_major,
+                                     int64_t* out2, int32_t* err_flag, mnb_stream_t stream) {
+  MNB_REQUIRE(out2 && err_flag && N >= 16 && N <= 256 && N % 16 == 0 && n_acc >= 1 && n_acc * N <= 512, "bad mma_rate arguments");
+  mma_rate_kernel<<<1, 64, 0, (cudaStream_t)stream>>>(N, n_acc, a_shift16, iters, mn_major, reinterpret_cast<long long*>(out2), err_flag);
+  MNB_LAUNCHED(1);
+  return 0;
+}

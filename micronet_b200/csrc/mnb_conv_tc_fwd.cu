@@ -64,8 +64,8 @@ struct alignas(16) Shared {
   uint64_t stage_full[MAXST], stage_empty[MAXST], op_full[NOP], op_empty[NOP], acc_full[NACC], acc_empty[NACC], b_full;
   uint32_t tmem_slot;
   uint32_t op_flags[NOP][8];
-  float epi_scale[256];   // per output channel of the slab (fixed for the whole kernel)
-  float epi_bias[256];
+  alignas(16) float epi_scale[288];   // per output channel of the slab (fixed for the whole kernel)
+  alignas(16) float epi_bias[288];
 };
 
 __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
@@ -104,8 +104,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const Params p) {
 
   // ---- one-time setup
   if (tid == 0) {
-    for (int i = 0; i < p.nst; ++i) { tc::mbar_init(&sh.stage_full[i], 1); tc::mbar_init(&sh.stage_empty[i], NCONV); }
-    for (int i = 0; i < NOP; ++i) { tc::mbar_init(&sh.op_full[i], NCONV); tc::mbar_init(&sh.op_empty[i], 1); }
+    for (int i = 0; i < p.nst; ++i) { tc::mbar_init(&sh.stage_full[i], 1); tc::mbar_init(&sh.stage_empty[i], NCONV / 32); }
+    for (int i = 0; i < NOP; ++i) { tc::mbar_init(&sh.op_full[i], NCONV / 32); tc::mbar_init(&sh.op_empty[i], 1); }
     for (int i = 0; i < NACC; ++i) { tc::mbar_init(&sh.acc_full[i], 1); tc::mbar_init(&sh.acc_empty[i], NEPI); }
     tc::mbar_init(&sh.b_full, 1);
     tc::fence_barrier_init();
@@ -245,10 +245,20 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const Params p) {
         tc::tmem_ld_wait();
         if (valid) {
           if (!p.dgrad) {
+            // scale / bias of the 32 columns as 16 vector loads up front (the per-element LDS latency
+            // chain was the kernel's bottleneck), then a pure FFMA + STG stream
+            float sc[32], bs[32];
 #pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (n0 + j < slab_cols)
-                orow[(int64_t)(n0 + j) * plane] = fmaf(__uint_as_float(r[j]), sh.epi_scale[n0 + j], sh.epi_bias[n0 + j]);
+            for (int v = 0; v < 8; ++v) {
+              const float4 a = *reinterpret_cast<const float4*>(&sh.epi_scale[n0 + 4 * v]);
+              const float4 c = *reinterpret_cast<const float4*>(&sh.epi_bias[n0 + 4 * v]);
+              sc[4 * v] = a.x; sc[4 * v + 1] = a.y; sc[4 * v + 2] = a.z; sc[4 * v + 3] = a.w;
+              bs[4 * v] = c.x; bs[4 * v + 1] = c.y; bs[4 * v + 2] = c.z; bs[4 * v + 3] = c.w;
+            }
+            float* op = orow + (int64_t)n0 * plane;
+#pragma unroll
+            for (int j = 0; j < 32; ++j, op += plane)
+              if (n0 + j < slab_cols) *op = fmaf(__uint_as_float(r[j]), sc[j], bs[j]);
           } else if (p.ste_bits) {
 #pragma unroll
             for (int j = 0; j < 32; ++j)
@@ -258,9 +268,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const Params p) {
                 p.out[fi] = mnb_act_ste_one(ste, __uint_as_float(r[j]), pass);
               }
           } else {
+            float* op = orow + (int64_t)n0 * plane;
 #pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (n0 + j < slab_cols) orow[(int64_t)(n0 + j) * plane] = __uint_as_float(r[j]);
+            for (int j = 0; j < 32; ++j, op += plane)
+              if (n0 + j < slab_cols) *op = __uint_as_float(r[j]);
           }
         }
       }
@@ -395,9 +406,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const Params p) {
             any_low = __reduce_or_sync(0xffffffffu, any_low);
             if (lane == 0) sh.op_flags[ob][cw] = any_low;
           }
-          tc::fence_proxy_async_smem();
-          tc::mbar_arrive(&sh.op_full[ob]);
-          tc::mbar_arrive(&sh.stage_empty[st]);
+          tc::fence_proxy_async_smem();   // every writer publishes its smem stores to the async proxy
+          __syncwarp();
+          if (lane == 0) {                // one arrival per warp: 16 instead of 512 smem atomics per chunk
+            tc::mbar_arrive(&sh.op_full[ob]);
+            tc::mbar_arrive(&sh.stage_empty[st]);
+          }
         }
       }
     }
