@@ -252,19 +252,24 @@ __global__ void __launch_bounds__(64) mma_rate_kernel(int N, int n_acc, int a_sh
   __syncthreads();
   tc::tc_fence_after();
   const uint32_t tmem = tmem_slot;
-  if (tid == 0) {
+  if (warp == 0) {
     const uint32_t idesc = mn_major ? tc::make_idesc_major(1, 1, 1, 128, N, 1, 1) : tc::make_idesc(1, 1, 1, 128, N);
     const uint32_t a_addr = tc::smem_u32(ab) + (uint32_t)a_shift16 * 16u, b_addr = tc::smem_u32(ab) + 24 * 1024;
     const uint64_t ad = mn_major ? tc::smem_desc_mnmajor_noswz(a_addr, 128, 136 * 16) : tc::smem_desc_kmajor_noswz(a_addr, 136 * 16, 128);
     const uint64_t bd = mn_major ? tc::smem_desc_mnmajor_noswz(b_addr, 128, 136 * 16) : tc::smem_desc_kmajor_noswz(b_addr, (uint32_t)N * 16, 128);
+    const uint32_t guard = lane == 0;
+    const uint32_t mask = (uint32_t)n_acc - 1;  // n_acc is a power of two
     const long long t0 = clock64();
-    for (int i = 0; i < iters; ++i) tc::mma_f16(tmem + (uint32_t)((i % n_acc) * N), ad, bd, idesc, 1);
+    if (a_shift16 >= 100) {
+      if (lane == 0) for (int i = 0; i < iters; ++i) tc::mma_f16(tmem + (uint32_t)((i & mask) * N), ad + (i & 3), bd, idesc, 1);
+    } else {
+      for (int i = 0; i < iters; ++i) tc::mma_f16_guarded(tmem + (uint32_t)((i & mask) * N), ad + (i & 3), bd, idesc, 1, guard);
+    }
     const long long t1 = clock64();
-    tc::mma_commit(&bar);
+    if (lane == 0) tc::mma_commit(&bar);
     bool ok = tc::mbar_wait(&bar, 0, err, 501);
     const long long t2 = clock64();
-    out[0] = ok ? (t2 - t0) : -1;
-    out[1] = t1 - t0;
+    if (lane == 0) { out[0] = ok ? (t2 - t0) : -1; out[1] = t1 - t0; }
   }
   tc::tc_fence_before();
   __syncthreads();

@@ -105,6 +105,18 @@ __device__ __forceinline__ void mma_f16(uint32_t d_tmem, uint64_t adesc, uint64_
       ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// Same instruction for warp-converged issue loops: every lane executes the (uniform) address
+// arithmetic so that ptxas keeps descriptors in uniform registers, and only the lane whose `guard`
+// is non-zero issues.  (Guarding the whole loop with `if (lane == 0)` instead makes every operand a
+// per-thread value: each MMA then pays an ELECT loop plus five R2UR broadcasts, ~150+ cycles.)
+__device__ __forceinline__ void mma_f16_guarded(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                                uint32_t accumulate, uint32_t guard) {
+  asm volatile(
+      "{\n\t.reg .pred p, q;\n\tsetp.ne.b32 p, %4, 0;\n\tsetp.ne.b32 q, %5, 0;\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(guard)
+      : "memory");
+}
 __device__ __forceinline__ void mma_i8(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
                                        uint32_t accumulate) {
   asm volatile(
