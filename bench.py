@@ -178,12 +178,10 @@ def main():
     torch.backends.cuda.matmul.allow_tf32 = False
 
     from micronet_b200 import _lib as L, functional as F_
-    from micronet_b200.parallel import FlatGradBucket
 
     w = H.WORKLOADS[WORKLOAD]
     model = H.prepare_engine(H.build_float_model(w["model"]), w["scheme"], **w["prepare"]).to(dev)
-    bucket = FlatGradBucket(model.parameters()) if world > 1 else None
-    stepper = H.QatStepper(model, lr=0.01, wd=w["wd"], bucket=bucket)
+    stepper = H.QatStepper(model, lr=0.01, wd=w["wd"], flat=True)
     # distinct batches, pre-staged on the device for `value`, pinned on the host for `e2e`
     nbuf = 4
     host = [H.synthetic_batch(BATCH_PER_GPU, w["hw"], seed=100 + rank * 17 + i, pin=True) for i in range(nbuf)]

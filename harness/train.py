@@ -57,23 +57,29 @@ def synthetic_batch(batch, hw, seed, device="cpu", pin=False):
 
 
 class QatStepper:
-    """one QAT step = forward + CE loss + zero_grad + backward (+ grad all-reduce) + Adam."""
+    """one QAT step = forward + CE loss + zero_grad + backward (+ grad all-reduce) + Adam.
 
-    def __init__(self, model, lr=0.01, wd=0.0, bucket=None):
-        self.model, self.bucket = model, bucket
-        self.opt = make_optimizer(model, lr, wd)
+    ``flat=True`` (engine on CUDA): parameters / gradients live in flat buckets, the gradient
+    all-reduce is one NCCL call and Adam is one fused launch (micronet_b200.FlatAdam); otherwise the
+    reference's own ``torch.optim.Adam`` with one param group per tensor."""
+
+    def __init__(self, model, lr=0.01, wd=0.0, flat=False):
+        self.model = model
         self.crit = nn.CrossEntropyLoss()
+        if flat:
+            from micronet_b200 import FlatAdam
+            self.opt = FlatAdam(model.parameters(), lr=lr, weight_decay=wd)
+        else:
+            self.opt = make_optimizer(model, lr, wd)
+        self.flat = flat
 
     def step(self, x, t):
         self.model.train()
         out = self.model(x)
         loss = self.crit(out, t)
-        if self.bucket is not None:
-            self.bucket.zero()
-        else:
-            self.opt.zero_grad()
+        self.opt.zero_grad()
         loss.backward()
-        if self.bucket is not None:
-            self.bucket.all_reduce()
+        if self.flat:
+            self.opt.all_reduce()
         self.opt.step()
         return loss

@@ -201,6 +201,11 @@ int mnb_conv2d_wgrad_tc(const mnb_conv_shape* s, const float* dy, const float* x
 int mnb_conv2d_wgrad_cond(const mnb_conv_shape* s, const float* dy, const mnb_conv_operands* op, float* dwq,
                           void* scratch, const int32_t* run_if_nonzero, mnb_stream_t stream);
 
+/* Optimizer step of the QAT loop (torch.optim.Adam semantics, L2 weight decay, no amsgrad;
+ * wbwtab/main.py:84,331-339) over one flat fp32 parameter / gradient bucket: a single launch. */
+int mnb_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n, float lr,
+                  float beta1, float beta2, float eps, float weight_decay, int32_t step, mnb_stream_t stream);
+
 /* Debug hook: 16 int64 device counters [role: tma, mma, epilogue, converter][wait a, wait b, wait c,
  * total cycles], accumulated by the fwd/dgrad tensor-core kernel while the pointer is non-NULL.  */
 void mnb_set_tc_profile_buffer(void* dev_int64x16);

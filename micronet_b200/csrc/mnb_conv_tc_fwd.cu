@@ -172,7 +172,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const Params p) {
       const uint32_t b_kstep = (2u * b_lbo) >> 4, b_tap = (uint32_t)(c8_per_group * p.cout_g * 16) >> 4;
       const uint32_t b_chunk = (uint32_t)((p.CC / 8) * p.cout_g * 16) >> 4, b_group = (uint32_t)p.b_group_bytes >> 4;
       const int ksteps = p.CC / 16, slab_cols = g_count * p.cout_g;
-      PROF_WAIT(2, tc::mbar_wait(&sh.b_full, 0, p.err, 307));
+      PROF_WAIT(0, tc::mbar_wait(&sh.b_full, 0, p.err, 307));
       uint32_t it = 0, item = 0;
       for (int tile = rank_in_slab; tile < p.n_tiles; tile += ctas_in_slab, ++item) {
         const int acc = item % NACC;
@@ -197,6 +197,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const Params p) {
             const uint64_t a_chunk = a_desc0 + (uint64_t)((uint32_t)ob * a_buf);
             const uint64_t b_chunk_d = b_desc0 + (uint64_t)((uint32_t)gi * b_group + (uint32_t)ch * b_chunk);
             uint32_t row_off = 0, b_t = 0;  // (r * BW) positions == 16-byte units; tap stride in B
+            const long long tmma0 = p.prof ? clock64() : 0;
             for (int r = 0; r < p.R; ++r, row_off += (uint32_t)p.BW) {
               for (int s2 = 0; s2 < p.S; ++s2, b_t += b_tap) {
                 const uint64_t a_tap = a_chunk + (uint64_t)(row_off + (uint32_t)s2);
@@ -211,6 +212,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const Params p) {
                 }
               }
             }
+            if (p.prof) prof_acc[2] += clock64() - tmma0;
             tc::mma_commit(&sh.op_empty[ob]);  // operand buffer is free once these MMAs retire
           }
         }

@@ -1,5 +1,6 @@
 // Quantizer / observer kernels of the fake-quant hot path (HBM-bound elementwise + reductions).
 // Reference semantics: DF:11-73, WB:11-149, IAO:15-321 (see include/micronet_b200.h).
+#include <math.h>
 #include <stdarg.h>
 #include <stdio.h>
 
@@ -613,7 +614,7 @@ extern "C" int mnb_iao_weight_bwd(const float* g_wq, const uint8_t* pass, const 
 // grid (channels, splits): fp64 partial sums, last split-block of a channel finalises.
 constexpr int STATS_SPLITS = 32;
 
-__global__ void __launch_bounds__(256) channel_stats_kernel(const float* __restrict__ x, int batch, int channels,
+__global__ void __launch_bounds__(128) channel_stats_kernel(const float* __restrict__ x, int batch, int channels,
                                                             int hw, int as_mean_var, float* __restrict__ stats,
                                                             uint32_t* counters, double* partial) {
   __shared__ double red[32];
@@ -621,11 +622,28 @@ __global__ void __launch_bounds__(256) channel_stats_kernel(const float* __restr
   const int c = blockIdx.x, sp = blockIdx.y, nsp = gridDim.y;
   const int64_t per = (int64_t)batch * hw;
   double s1 = 0.0, s2 = 0.0;
-  for (int64_t i = (int64_t)sp * blockDim.x + threadIdx.x; i < per; i += (int64_t)nsp * blockDim.x) {
-    int b = (int)(i / hw), p = (int)(i - (int64_t)b * hw);
-    float v = __ldg(x + ((int64_t)b * channels + c) * hw + p);
-    s1 += (double)v;
-    s2 += (double)v * (double)v;
+  // images [b_lo, b_hi) of this split; within an image the channel plane is contiguous: no per-element
+  // index division, float4 loads when the plane allows it, fp32 partials per image row folded into fp64
+  const int b_lo = (int)((int64_t)batch * sp / nsp), b_hi = (int)((int64_t)batch * (sp + 1) / nsp);
+  const bool vec = (hw & 3) == 0 && ((reinterpret_cast<uintptr_t>(x) & 15) == 0);
+  for (int b = b_lo; b < b_hi; ++b) {
+    const float* plane = x + ((int64_t)b * channels + c) * hw;
+    float f1 = 0.f, f2 = 0.f;
+    if (vec) {
+      const float4* p4 = reinterpret_cast<const float4*>(plane);
+      for (int i = threadIdx.x; i < (hw >> 2); i += blockDim.x) {
+        const float4 v = __ldg(p4 + i);
+        f1 += (v.x + v.y) + (v.z + v.w);
+        f2 += (v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w);
+      }
+    } else {
+      for (int i = threadIdx.x; i < hw; i += blockDim.x) {
+        const float v = __ldg(plane + i);
+        f1 += v; f2 += v * v;
+      }
+    }
+    s1 += (double)f1;
+    s2 += (double)f2;
   }
   s1 = mnb_block_reduce(s1, MnbSum(), 0.0, red);
   s2 = mnb_block_reduce(s2, MnbSum(), 0.0, red);
@@ -674,10 +692,10 @@ extern "C" int mnb_channel_stats(const float* x, int32_t batch, int32_t channels
   MNB_REQUIRE(x && stats && scratch && batch > 0 && channels > 0 && hw > 0, "bad channel_stats arguments");
   MNB_REQUIRE(channels <= 8192, "channel_stats supports at most 8192 channels, got %d", channels);
   int64_t per = (int64_t)batch * hw;
-  int splits = (int)std::max<int64_t>(1, std::min<int64_t>(STATS_SPLITS, per / 2048));
+  int splits = (int)std::max<int64_t>(1, std::min<int64_t>(std::min<int64_t>(STATS_SPLITS, batch), per / 2048));
   uint32_t* counters = reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(scratch) + 16384);
   double* partial = reinterpret_cast<double*>(reinterpret_cast<char*>(scratch) + 49152);
-  channel_stats_kernel<<<dim3(channels, splits), 256, 0, S(stream)>>>(x, batch, channels, hw, as_mean_var, stats,
+  channel_stats_kernel<<<dim3(channels, splits), 128, 0, S(stream)>>>(x, batch, channels, hw, as_mean_var, stats,
                                                                        counters, partial);
   MNB_LAUNCHED(1);
   return 0;
@@ -690,6 +708,41 @@ extern "C" int mnb_channel_stats_bwd(const float* x, const float* mean, const fl
   int64_t n = (int64_t)batch * channels * hw;
   int blocks = (int)std::min<int64_t>(mnb_ceil_div(n, 256 * 4), MNB_NUM_SMS * 8);
   channel_stats_bwd_kernel<<<blocks, 256, 0, S(stream)>>>(x, mean, dmean, dvar, batch, channels, hw, dx);
+  MNB_LAUNCHED(1);
+  return 0;
+}
+
+// ------------------------------------------------------------------ fused Adam over a flat parameter bucket
+// torch.optim.Adam (no amsgrad, L2 weight decay folded into the gradient) on one contiguous fp32 buffer:
+// the optimizer step of the QAT loop (wbwtab/main.py:84, one param group per tensor with identical
+// hyper-parameters) as a single HBM-bound launch instead of ~5 launches per parameter tensor.
+__global__ void __launch_bounds__(256) adam_step_kernel(float* __restrict__ p, const float* __restrict__ g,
+                                                        float* __restrict__ m, float* __restrict__ v, int64_t n,
+                                                        float lr, float b1, float b2, float eps, float wd,
+                                                        float bc1, float sqrt_bc2) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const float step_size = lr / bc1;
+  for (; i < n; i += stride) {
+    float gi = g[i];
+    const float pi = p[i];
+    if (wd != 0.f) gi = fmaf(wd, pi, gi);
+    const float mi = m[i] + (gi - m[i]) * (1.f - b1);          // exp_avg.lerp_(grad, 1 - beta1)
+    const float vi = fmaf(1.f - b2, gi * gi, v[i] * b2);       // exp_avg_sq.mul_(beta2).addcmul_(grad, grad, 1 - beta2)
+    const float denom = sqrtf(vi) / sqrt_bc2 + eps;
+    m[i] = mi; v[i] = vi;
+    p[i] = pi - step_size * (mi / denom);
+  }
+}
+
+extern "C" int mnb_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1,
+                             float beta2, float eps, float weight_decay, int32_t step, mnb_stream_t stream) {
+  MNB_REQUIRE(p && g && m && v && n >= 0 && step >= 1, "bad Adam arguments");
+  if (n == 0) return 0;
+  const float bc1 = (float)(1.0 - pow((double)beta1, (double)step));
+  const float sqrt_bc2 = (float)sqrt(1.0 - pow((double)beta2, (double)step));
+  int blocks = (int)std::min<int64_t>(mnb_ceil_div(n, 256), MNB_NUM_SMS * 8);
+  adam_step_kernel<<<blocks, 256, 0, S(stream)>>>(p, g, m, v, n, lr, beta1, beta2, eps, weight_decay, bc1, sqrt_bc2);
   MNB_LAUNCHED(1);
   return 0;
 }

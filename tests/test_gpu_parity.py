@@ -355,3 +355,25 @@ def test_full_size_layer_vs_oracle(spec):
     yo.backward(go); ye.backward(go.to(DEV))
     assert rel_err(xe.grad, xo.grad) <= TOL
     assert rel_err(e.weight.grad, o.weight.grad) <= 2e-5
+
+
+def test_flat_adam_matches_torch_adam():
+    """micronet_b200.FlatAdam (one fused launch over flat buckets) == torch.optim.Adam with one param
+    group per tensor (the optimizer the reference constructs, wbwtab/main.py:331-339)."""
+    import copy
+    import micronet_b200 as E
+    torch.manual_seed(5)
+    net = torch.nn.Sequential(torch.nn.Conv2d(3, 8, 3, padding=1), torch.nn.ReLU(), torch.nn.Conv2d(8, 4, 1)).to(DEV)
+    ref = copy.deepcopy(net)
+    for wd in (0.0, 1e-5):
+        a = E.FlatAdam(net.parameters(), lr=0.01, weight_decay=wd)
+        groups = [{"params": [p], "lr": 0.01, "weight_decay": wd} for p in ref.parameters()]
+        b = torch.optim.Adam(groups, lr=0.01, weight_decay=wd)
+        for step in range(4):
+            x = torch.randn(5, 3, 9, 9, device=DEV)
+            for m, o in ((net, a), (ref, b)):
+                o.zero_grad()
+                m(x).square().mean().backward()
+                o.step()
+            for p, q in zip(net.parameters(), ref.parameters()):
+                assert rel_err(p.detach(), q.detach()) <= 2e-6, (wd, step)
