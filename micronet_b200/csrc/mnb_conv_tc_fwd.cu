@@ -63,6 +63,7 @@ struct Params {
 struct alignas(16) Shared {
   uint64_t stage_full[MAXST], stage_empty[MAXST], op_full[NOP], op_empty[NOP], acc_full[NACC], acc_empty[NACC], b_full;
   uint32_t tmem_slot;
+  uint32_t abort;
   uint32_t op_flags[NOP][8];
   alignas(16) float epi_scale[288];   // per output channel of the slab (fixed for the whole kernel)
   alignas(16) float epi_bias[288];
@@ -81,6 +82,13 @@ __device__ __forceinline__ float bf16_round(float v) { return __bfloat162float(_
     const bool ok__ = (call);                                   \
     if (p.prof) prof_acc[slot] += clock64() - t0__;             \
     if (!ok__) goto done;                                       \
+  } while (0)
+
+#define PROF_SOFT(slot, call)                                   \
+  do {                                                          \
+    long long t0__ = p.prof ? clock64() : 0;                    \
+    call;                                                       \
+    if (p.prof) prof_acc[slot] += clock64() - t0__;             \
   } while (0)
 
 __global__ void __launch_bounds__(NTHREADS, 1)
@@ -112,6 +120,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const Params p) {
     tc::prefetch_tmap(&tmap_in);
   }
   if (tid < NOP * 8) sh.op_flags[tid / 8][tid % 8] = 0;
+  if (tid == 0) sh.abort = 0;
   if (warp == 2) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tc::smem_u32(&sh.tmem_slot)),
                  "r"((uint32_t)p.tmem_cols));
@@ -162,7 +171,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const Params p) {
     }
   } else if (warp == 1) {
     // ================================================================= MMA issuer
-    if (lane == 0) {
+    // The whole warp runs the (warp-uniform) loops and address arithmetic; only lane 0's guard lets the
+    // tcgen05.mma through.  Terms that a chunk does not need are predicated off instead of shortening
+    // the loop, so every trip count stays uniform.
+    {
+      const uint32_t lead = lane == 0;
       const uint32_t idesc = tc::make_idesc(1, 1, 1, 128, (uint32_t)p.cout_g);
       const uint32_t a_lbo = (uint32_t)p.npos_in * 16u, b_lbo = (uint32_t)p.cout_g * 16u;
       // descriptors differ only in the 14-bit start-address field: build once, then add (bytes >> 4)
@@ -172,12 +185,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const Params p) {
       const uint32_t b_kstep = (2u * b_lbo) >> 4, b_tap = (uint32_t)(c8_per_group * p.cout_g * 16) >> 4;
       const uint32_t b_chunk = (uint32_t)((p.CC / 8) * p.cout_g * 16) >> 4, b_group = (uint32_t)p.b_group_bytes >> 4;
       const int ksteps = p.CC / 16, slab_cols = g_count * p.cout_g;
-      PROF_WAIT(0, tc::mbar_wait(&sh.b_full, 0, p.err, 307));
+      const int max_terms = p.quant_mode == 0 ? 3 : 1;
+      PROF_SOFT(0, tc::mbar_wait_soft(&sh.b_full, 0, p.err, 307, &sh.abort));
       uint32_t it = 0, item = 0;
       for (int tile = rank_in_slab; tile < p.n_tiles; tile += ctas_in_slab, ++item) {
         const int acc = item % NACC;
         const uint32_t aph = (item / NACC) & 1;
-        PROF_WAIT(0, tc::mbar_wait(&sh.acc_empty[acc], aph ^ 1, p.err, 302));
+        PROF_SOFT(0, tc::mbar_wait_soft(&sh.acc_empty[acc], aph ^ 1, p.err, 302, &sh.abort));
         tc::tc_fence_after();
         for (int gi = 0; gi < g_count; ++gi) {
           const uint32_t d_tmem = tmem + (uint32_t)(acc * slab_cols + gi * p.cout_g);
@@ -185,14 +199,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const Params p) {
           for (int ch = 0; ch < p.nchunk; ++ch, ++it) {
             const int ob = it % NOP;
             const uint32_t oph = (it / NOP) & 1;
-            PROF_WAIT(1, tc::mbar_wait(&sh.op_full[ob], oph, p.err, 303));
+            PROF_SOFT(1, tc::mbar_wait_soft(&sh.op_full[ob], oph, p.err, 303, &sh.abort));
             tc::tc_fence_after();
-            int nterms = 1;
+            uint32_t low_guard = 0;  // mid / lo planes needed for this chunk?
             if (p.quant_mode == 0) {
               uint32_t any = 0;
 #pragma unroll
               for (int w8 = 0; w8 < 8; ++w8) any |= sh.op_flags[ob][w8];
-              nterms = any ? 3 : 1;
+              low_guard = (any != 0) & lead;
             }
             const uint64_t a_chunk = a_desc0 + (uint64_t)((uint32_t)ob * a_buf);
             const uint64_t b_chunk_d = b_desc0 + (uint64_t)((uint32_t)gi * b_group + (uint32_t)ch * b_chunk);
@@ -204,19 +218,23 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const Params p) {
                 const uint64_t b_tapd = b_chunk_d + (uint64_t)b_t;
                 for (int j = 0; j < ksteps; ++j) {
                   const uint64_t bd = b_tapd + (uint64_t)((uint32_t)j * b_kstep);
-                  uint64_t ad = a_tap + (uint64_t)((uint32_t)j * a_kstep);
-                  for (int t = 0; t < nterms; ++t, ad += a_term) {
-                    tc::mma_f16(d_tmem, ad, bd, idesc, accumulate);
-                    accumulate = 1;
+                  const uint64_t ad = a_tap + (uint64_t)((uint32_t)j * a_kstep);
+                  tc::mma_f16_guarded(d_tmem, ad, bd, idesc, accumulate, lead);
+                  accumulate = 1;
+                  if (max_terms == 3) {
+                    tc::mma_f16_guarded(d_tmem, ad + a_term, bd, idesc, 1, low_guard);
+                    tc::mma_f16_guarded(d_tmem, ad + 2 * a_term, bd, idesc, 1, low_guard);
                   }
                 }
               }
             }
             if (p.prof) prof_acc[2] += clock64() - tmma0;
-            tc::mma_commit(&sh.op_empty[ob]);  // operand buffer is free once these MMAs retire
+            if (lead) tc::mma_commit(&sh.op_empty[ob]);  // operand buffer is free once these MMAs retire
+            __syncwarp();
           }
         }
-        tc::mma_commit(&sh.acc_full[acc]);
+        if (lead) tc::mma_commit(&sh.acc_full[acc]);
+        __syncwarp();
       }
     }
   } else if (warp >= 4 && warp < 8) {

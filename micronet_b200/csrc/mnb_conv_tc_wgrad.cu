@@ -39,6 +39,7 @@ struct Params {
 struct alignas(16) Shared {
   uint64_t stage_full[MAXST], stage_empty[MAXST], op_full, op_empty, done;
   uint32_t tmem_slot;
+  uint32_t abort;
 };
 
 __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
@@ -68,10 +69,11 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
   const int my_tiles = (p.n_tiles > rank) ? (p.n_tiles - rank + p.ranks - 1) / p.ranks : 0;
 
   if (tid == 0) {
-    for (int i = 0; i < p.nst; ++i) { tc::mbar_init(&sh.stage_full[i], 1); tc::mbar_init(&sh.stage_empty[i], NCONV); }
-    tc::mbar_init(&sh.op_full, NCONV);
+    for (int i = 0; i < p.nst; ++i) { tc::mbar_init(&sh.stage_full[i], 1); tc::mbar_init(&sh.stage_empty[i], NCONV / 32); }
+    tc::mbar_init(&sh.op_full, NCONV / 32);
     tc::mbar_init(&sh.op_empty, 1);
     tc::mbar_init(&sh.done, 1);
+    sh.abort = 0;
     tc::fence_barrier_init();
     tc::prefetch_tmap(&tmap_x);
     tc::prefetch_tmap(&tmap_dy);
@@ -113,8 +115,9 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
       }
     }
   } else if (warp == 1) {
-    // ================================================================= MMA issuer
-    if (lane == 0) {
+    // ================================================================= MMA issuer (warp-converged, lane 0 issues)
+    {
+      const uint32_t lead = lane == 0;
       const uint32_t idesc = tc::make_idesc_major(1, 1, 1, 128, (uint32_t)p.n_block, 1, 1);
       // descriptors differ only in the 14-bit start-address field: build once, then add (bytes >> 4)
       const uint64_t b_desc0 = tc::smem_desc_mnmajor_noswz(tc::smem_u32(xop), 128, (uint32_t)p.npos_x * 16u);
@@ -122,7 +125,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
       const uint32_t a_term = (uint32_t)p.dop_term_bytes >> 4;
       uint32_t t = 0;
       for (int tile = rank; tile < p.n_tiles; tile += p.ranks, ++t) {
-        if (!tc::mbar_wait(&sh.op_full, t & 1, p.err, 402)) goto done;
+        tc::mbar_wait_soft(&sh.op_full, t & 1, p.err, 402, &sh.abort);
         tc::tc_fence_after();
         uint32_t row_off = 0, d_col = 0;
         for (int r = 0; r < p.R; ++r, row_off += (uint32_t)p.BW) {
@@ -133,15 +136,17 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
             for (int ps = 0; ps < 8; ++ps) {
               const uint64_t bd = b_tap + (uint64_t)(ps * 16);   // 16 positions x 16 bytes = 256 B
               const uint64_t ad = a_desc0 + (uint64_t)(ps * 16);
-              tc::mma_f16(d_tmem, ad, bd, idesc, (t | (uint32_t)ps) != 0);
-              tc::mma_f16(d_tmem, ad + a_term, bd, idesc, 1);
-              tc::mma_f16(d_tmem, ad + 2 * a_term, bd, idesc, 1);
+              tc::mma_f16_guarded(d_tmem, ad, bd, idesc, (t | (uint32_t)ps) != 0, lead);
+              tc::mma_f16_guarded(d_tmem, ad + a_term, bd, idesc, 1, lead);
+              tc::mma_f16_guarded(d_tmem, ad + 2 * a_term, bd, idesc, 1, lead);
             }
           }
         }
-        tc::mma_commit(&sh.op_empty);
+        if (lead) tc::mma_commit(&sh.op_empty);
+        __syncwarp();
       }
-      tc::mma_commit(&sh.done);
+      if (lead) tc::mma_commit(&sh.done);
+      __syncwarp();
     }
   } else if (warp >= 4 && warp < 8) {
     // ================================================================= final epilogue: TMEM -> partial dW
@@ -289,10 +294,12 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
             *reinterpret_cast<uint4*>(d0 + 2 * p.dop_term_bytes) = make_uint4(pack_bf16x2(l1[0], l1[1]), pack_bf16x2(l1[2], l1[3]), pack_bf16x2(l1[4], l1[5]), pack_bf16x2(l1[6], l1[7]));
           }
         }
-        tc::mbar_arrive(&sh.stage_empty[st]);
+        __syncwarp();
+        if (lane == 0) tc::mbar_arrive(&sh.stage_empty[st]);
       }
       tc::fence_proxy_async_smem();
-      tc::mbar_arrive(&sh.op_full);
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(&sh.op_full);
     }
   }
 done:

@@ -50,6 +50,26 @@ __device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity, int* e
   return false;
 }
 
+// Bounded wait WITHOUT an early-exit branch: on timeout it records the error and simply returns, so the
+// caller's loops keep warp-uniform control flow (ptxas can then keep loop-carried address arithmetic in
+// uniform registers, which the single-thread tcgen05.mma issue path depends on).  After a timeout every
+// later wait of the CTA returns after a short spin (shared `abort` flag): wrong results, but no hang.
+__device__ __forceinline__ void mbar_wait_soft(uint64_t* bar, uint32_t parity, int* err_flag, int code,
+                                               volatile uint32_t* abort_flag) {
+  for (uint32_t it = 0;; ++it) {
+    if (mbar_try_wait(bar, parity)) return;
+    if ((it & 0xfffu) == 0xfffu) {
+      if (*abort_flag) return;
+      if (it >= (1u << 24)) {
+        *abort_flag = 1u;
+        if (err_flag) atomicCAS(err_flag, 0, code);
+        return;
+      }
+      __nanosleep(64);
+    }
+  }
+}
+
 // generic-proxy smem writes -> visible to the async proxy (TMA / tcgen05.mma operand reads)
 __device__ __forceinline__ void fence_proxy_async_smem() {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
