@@ -264,14 +264,19 @@ def main():
     else:
         roof = {"bound": "tensor", "achieved": flops / avg_s / 1e12, "peak": tfl, "unit": "TFLOP/s"}
     roof["frac"] = roof["achieved"] / roof["peak"]
-    roof.update({"traffic": None, "peak_source": peak_src,
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "kernel_traffic.json")
+    if os.path.exists(tpath):  # measured dram__bytes_{read,write}.sum per launch from the committed ncu capture
+        rec = json.load(open(tpath))["kernels"].get(f"{dk}:{list(dshape)}")
+        traffic = rec["dram_bytes"] if rec else None
+    roof.update({"traffic": traffic, "algorithmic_bytes": nbytes, "algorithmic_flops": flops, "peak_source": peak_src,
                  "kernel": f"conv2d_{dk} shape(B,C,H,W,K,R,S,sh,sw,ph,pw,dh,dw,G)={list(dshape)}",
                  "avg_launch_us": avg_s * 1e6, "launches_timed": dn,
                  "share_of_step": dtot / ms_total,
                  "engine_conv_share_of_step": sum(v[0] for v in agg.values()) / ms_total})
     line = {"metric": METRIC, "value": value, "unit": "img/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "fp32 (s32 accumulate on integer levels)", "data": "synthetic",
+            "vs_baseline": None, "dtype": "f32 (bf16 tensor-core products of exact integer levels, fp32 accumulate)", "data": "synthetic",
             "config": config_dict(world), "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "img/s", "ms_per_step": ms_e2e / args.steps,
                     "h2d_bytes_per_step": (BATCH_PER_GPU * 3 * w["hw"] * w["hw"] * 4 + BATCH_PER_GPU * 8) * world,

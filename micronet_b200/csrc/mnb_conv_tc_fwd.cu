@@ -201,12 +201,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const Params p) {
             const uint32_t oph = (it / NOP) & 1;
             PROF_SOFT(1, tc::mbar_wait_soft(&sh.op_full[ob], oph, p.err, 303, &sh.abort));
             tc::tc_fence_after();
-            uint32_t low_guard = 0;  // mid / lo planes needed for this chunk?
+            bool need_low = false;  // mid / lo planes needed for this chunk?
             if (p.quant_mode == 0) {
               uint32_t any = 0;
 #pragma unroll
               for (int w8 = 0; w8 < 8; ++w8) any |= sh.op_flags[ob][w8];
-              low_guard = (any != 0) & lead;
+              need_low = any != 0;
             }
             const uint64_t a_chunk = a_desc0 + (uint64_t)((uint32_t)ob * a_buf);
             const uint64_t b_chunk_d = b_desc0 + (uint64_t)((uint32_t)gi * b_group + (uint32_t)ch * b_chunk);
@@ -221,9 +221,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const Params p) {
                   const uint64_t ad = a_tap + (uint64_t)((uint32_t)j * a_kstep);
                   tc::mma_f16_guarded(d_tmem, ad, bd, idesc, accumulate, lead);
                   accumulate = 1;
-                  if (max_terms == 3) {
-                    tc::mma_f16_guarded(d_tmem, ad + a_term, bd, idesc, 1, low_guard);
-                    tc::mma_f16_guarded(d_tmem, ad + 2 * a_term, bd, idesc, 1, low_guard);
+                  if (max_terms == 3 && need_low) {  // (warp-uniform in practice: same flags for every lane)
+                    tc::mma_f16_guarded(d_tmem, ad + a_term, bd, idesc, 1, lead);
+                    tc::mma_f16_guarded(d_tmem, ad + 2 * a_term, bd, idesc, 1, lead);
                   }
                 }
               }
