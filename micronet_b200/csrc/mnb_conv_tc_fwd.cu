@@ -65,6 +65,7 @@ struct alignas(16) Shared {
   uint32_t tmem_slot;
   uint32_t abort;
   uint32_t op_flags[NOP][8];
+  uint2 mma_off[64];   // per (tap, k-step): start-address offsets (16-byte units) of the A and B operands
   alignas(16) float epi_scale[288];   // per output channel of the slab (fixed for the whole kernel)
   alignas(16) float epi_bias[288];
 };
@@ -121,6 +122,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const Params p) {
   }
   if (tid < NOP * 8) sh.op_flags[tid / 8][tid % 8] = 0;
   if (tid == 0) sh.abort = 0;
+  if (tid < RS * (p.CC / 16)) {
+    const int ks = p.CC / 16, tap = tid / ks, j = tid - tap * ks;
+    const int r = tap / p.S, s2 = tap - r * p.S;
+    sh.mma_off[tid] = make_uint2((uint32_t)(r * p.BW + s2) + (uint32_t)j * (uint32_t)(2 * p.npos_in),
+                                 (uint32_t)tap * (uint32_t)(c8_per_group * p.cout_g) + (uint32_t)j * (uint32_t)(2 * p.cout_g));
+  }
   if (warp == 2) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tc::smem_u32(&sh.tmem_slot)),
                  "r"((uint32_t)p.tmem_cols));
@@ -210,22 +217,24 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const Params p) {
             }
             const uint64_t a_chunk = a_desc0 + (uint64_t)((uint32_t)ob * a_buf);
             const uint64_t b_chunk_d = b_desc0 + (uint64_t)((uint32_t)gi * b_group + (uint32_t)ch * b_chunk);
-            uint32_t row_off = 0, b_t = 0;  // (r * BW) positions == 16-byte units; tap stride in B
             const long long tmma0 = p.prof ? clock64() : 0;
-            for (int r = 0; r < p.R; ++r, row_off += (uint32_t)p.BW) {
-              for (int s2 = 0; s2 < p.S; ++s2, b_t += b_tap) {
-                const uint64_t a_tap = a_chunk + (uint64_t)(row_off + (uint32_t)s2);
-                const uint64_t b_tapd = b_chunk_d + (uint64_t)b_t;
-                for (int j = 0; j < ksteps; ++j) {
-                  const uint64_t bd = b_tapd + (uint64_t)((uint32_t)j * b_kstep);
-                  const uint64_t ad = a_tap + (uint64_t)((uint32_t)j * a_kstep);
-                  tc::mma_f16_guarded(d_tmem, ad, bd, idesc, accumulate, lead);
-                  accumulate = 1;
-                  if (max_terms == 3 && need_low) {  // (warp-uniform in practice: same flags for every lane)
-                    tc::mma_f16_guarded(d_tmem, ad + a_term, bd, idesc, 1, lead);
-                    tc::mma_f16_guarded(d_tmem, ad + 2 * a_term, bd, idesc, 1, lead);
-                  }
-                }
+            // one flat loop over (tap, k-step): the offsets come from a small shared-memory table so the
+            // single issuing thread spends a handful of instructions per MMA
+            const int n_off = RS * ksteps;
+            if (max_terms == 3 && need_low) {
+              for (int e = 0; e < n_off; ++e) {
+                const uint2 off = sh.mma_off[e];
+                const uint64_t ad = a_chunk + (uint64_t)off.x, bd = b_chunk_d + (uint64_t)off.y;
+                tc::mma_f16_guarded(d_tmem, ad, bd, idesc, accumulate, lead);
+                tc::mma_f16_guarded(d_tmem, ad + a_term, bd, idesc, 1, lead);
+                tc::mma_f16_guarded(d_tmem, ad + 2 * a_term, bd, idesc, 1, lead);
+                accumulate = 1;
+              }
+            } else {
+              for (int e = 0; e < n_off; ++e) {
+                const uint2 off = sh.mma_off[e];
+                tc::mma_f16_guarded(d_tmem, a_chunk + (uint64_t)off.x, b_chunk_d + (uint64_t)off.y, idesc, accumulate, lead);
+                accumulate = 1;
               }
             }
             if (p.prof) prof_acc[2] += clock64() - tmma0;

@@ -28,6 +28,7 @@ struct Params {
   int BW, TH, THH, TB, CC, nst;
   int npos_x, row_tiles, n_tiles;
   int Gb, nsplit, n_block, n_slabs, ranks;
+  int tap_groups, tpc;   // filter taps are split over `tap_groups` CTA sets of `tpc` taps (TMEM holds tpc * n_block columns)
   int quant_mode, a_offset, tmem_cols;
   int slot_bytes, stage_x_bytes, stage_d_bytes, xop_bytes, dop_term_bytes, off_stage, off_xop, off_dop;
   mnb_act_qparams qp;
@@ -61,7 +62,9 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
 
   // ---- block of gradient channels owned by this CTA
   const int slab = blockIdx.x % p.n_slabs, rank = blockIdx.x / p.n_slabs;
-  const int gbi = slab / p.nsplit, ms = slab - gbi * p.nsplit;
+  const int tg = slab % p.tap_groups, cb = slab / p.tap_groups;   // tap group, channel block
+  const int gbi = cb / p.nsplit, ms = cb - gbi * p.nsplit;
+  const int tap0 = tg * p.tpc, tap1 = min(RS, tap0 + p.tpc);
   const int dy_ch0 = gbi * p.Gb * p.Ng + ms * 128;
   const int m_real = min(128, p.Gb * p.Ng - ms * 128);
   const int x_ch0 = gbi * p.Gb * p.Cg;
@@ -127,19 +130,18 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
       for (int tile = rank; tile < p.n_tiles; tile += p.ranks, ++t) {
         tc::mbar_wait_soft(&sh.op_full, t & 1, p.err, 402, &sh.abort);
         tc::tc_fence_after();
-        uint32_t row_off = 0, d_col = 0;
-        for (int r = 0; r < p.R; ++r, row_off += (uint32_t)p.BW) {
-          for (int s2 = 0; s2 < p.S; ++s2, d_col += (uint32_t)p.n_block) {
-            const uint64_t b_tap = b_desc0 + (uint64_t)(row_off + (uint32_t)s2);
-            const uint32_t d_tmem = tmem + d_col;
+        uint32_t d_col = 0;
+        for (int tap = tap0; tap < tap1; ++tap, d_col += (uint32_t)p.n_block) {
+          const int r = tap / p.S, s2 = tap - r * p.S;
+          const uint64_t b_tap = b_desc0 + (uint64_t)((uint32_t)(r * p.BW + s2));
+          const uint32_t d_tmem = tmem + d_col;
 #pragma unroll
-            for (int ps = 0; ps < 8; ++ps) {
-              const uint64_t bd = b_tap + (uint64_t)(ps * 16);   // 16 positions x 16 bytes = 256 B
-              const uint64_t ad = a_desc0 + (uint64_t)(ps * 16);
-              tc::mma_f16_guarded(d_tmem, ad, bd, idesc, (t | (uint32_t)ps) != 0, lead);
-              tc::mma_f16_guarded(d_tmem, ad + a_term, bd, idesc, 1, lead);
-              tc::mma_f16_guarded(d_tmem, ad + 2 * a_term, bd, idesc, 1, lead);
-            }
+          for (int ps = 0; ps < 8; ++ps) {
+            const uint64_t bd = b_tap + (uint64_t)(ps * 16);   // 16 positions x 16 bytes = 256 B
+            const uint64_t ad = a_desc0 + (uint64_t)(ps * 16);
+            tc::mma_f16_guarded(d_tmem, ad, bd, idesc, (t | (uint32_t)ps) != 0, lead);
+            tc::mma_f16_guarded(d_tmem, ad + a_term, bd, idesc, 1, lead);
+            tc::mma_f16_guarded(d_tmem, ad + 2 * a_term, bd, idesc, 1, lead);
           }
         }
         if (lead) tc::mma_commit(&sh.op_empty);
@@ -160,11 +162,11 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
     }
     const int k_abs = dy_ch0 + m;
     const int k_group = k_abs / p.Ng;
-    for (int tap = 0; tap < RS; ++tap) {
+    for (int tap = tap0; tap < tap1; ++tap) {
       for (int n0 = 0; n0 < p.n_block; n0 += 32) {
         uint32_t r[32];
         if (have) {
-          tc::tmem_ld_32x32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(tap * p.n_block + n0), r);
+          tc::tmem_ld_32x32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)((tap - tap0) * p.n_block + n0), r);
           tc::tmem_ld_wait();
         } else {
 #pragma unroll
@@ -335,20 +337,37 @@ static int plan(const mnb_conv_shape* s, int quant_mode, Params& p, int& smem_by
   const int RS = p.R * p.S;
   if (p.Cg % 16 || p.Ng % 16) return unsupported("channels per group");
   if ((p.W * 4) % 16 || p.W > 64 || p.H > 255) return unsupported("image size");
-  // block of gradient channels: Gb whole groups (Gb*Ng <= 128) or a 128-slice of one big group
-  p.Gb = 1; p.nsplit = 1;
+  // block of gradient channels: Gb whole groups (Gb*Ng <= 128) or a 128-slice of one big group.  An MMA
+  // costs ~61 cycles whatever its N (<= 128), so wide blocks are cheaper per channel even if their taps no
+  // longer fit TMEM at once and must be split over `tap_groups` CTA sets (each re-reading the inputs).
+  p.Gb = 1; p.nsplit = 1; p.tap_groups = 1; p.tpc = RS;
   if (p.Ng >= 128) {
     p.nsplit = (p.Ng + 127) / 128;
+    if (p.Cg > 256) return unsupported("more than 256 activation channels per group");
+    p.tpc = std::min(RS, 512 / p.Cg);
+    if (p.tpc < 1) return unsupported("accumulators exceed tensor memory");
+    p.tap_groups = (RS + p.tpc - 1) / p.tpc;
+    p.tpc = (RS + p.tap_groups - 1) / p.tap_groups;
   } else {
-    for (int gb = p.G; gb >= 1; --gb)
-      if (p.G % gb == 0 && gb * p.Ng <= 128 && RS * gb * p.Cg <= 512 && gb * p.Cg <= 256) { p.Gb = gb; break; }
+    double best = 1e30;
+    for (int gb = 1; gb <= p.G; ++gb) {
+      if (p.G % gb || gb * p.Ng > 128 || gb * p.Cg > 256) continue;
+      int tpc = std::min(RS, 512 / (gb * p.Cg));
+      if (tpc < 1) continue;
+      const int tgs = (RS + tpc - 1) / tpc;
+      tpc = (RS + tgs - 1) / tgs;
+      const double mma = tpc * 24.0 * 61.0;
+      const double bytes = 4.0 * 128.0 * gb * (p.Cg * 1.3 + p.Ng);   // rough bytes per tile (activation halo ~1.3x)
+      const double cost = tgs * std::max(mma, bytes / 23.0) / gb;
+      if (cost < best) { best = cost; p.Gb = gb; p.tpc = tpc; p.tap_groups = tgs; }
+    }
   }
   p.n_block = p.Gb * p.Cg;
-  if (p.n_block > 256 || RS * p.n_block > 512) return unsupported("accumulators exceed tensor memory");
+  if (p.n_block > 256 || p.tpc * p.n_block > 512) return unsupported("accumulators exceed tensor memory");
   p.CC = 32;
   if (p.n_block % 32 || (p.Gb * p.Ng) % 32 || (p.nsplit > 1 && p.Ng % 32)) p.CC = 16;
   if (p.nsplit > 1 && (p.Ng % 128) % p.CC) return unsupported("ragged channel split");
-  p.n_slabs = (p.G / p.Gb) * p.nsplit;
+  p.n_slabs = (p.G / p.Gb) * p.nsplit * p.tap_groups;
   p.BW = p.W + 2 * p.pad;
   p.TH = std::min(p.H, 128 / p.BW);
   if (p.TH < 1) return unsupported("padded row wider than 128 positions");
@@ -379,7 +398,7 @@ static int plan(const mnb_conv_shape* s, int quant_mode, Params& p, int& smem_by
   smem_bytes = ops + p.nst * p.slot_bytes;
   if (smem_bytes > kMaxDynSmem) return unsupported("shared memory budget");
   int cols = 32;
-  while (cols < RS * p.n_block) cols <<= 1;
+  while (cols < p.tpc * p.n_block) cols <<= 1;
   p.tmem_cols = cols;
   return 0;
 }
