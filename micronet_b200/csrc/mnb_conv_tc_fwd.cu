@@ -31,7 +31,8 @@
 namespace tcconv {
 
 constexpr int NTHREADS = 512;
-constexpr int NCONV = 256;  // converter threads (warps 8..15)
+constexpr int NCONV = 320;  // converter threads (warps 2, 3 and 8..15)
+constexpr int NCW = NCONV / 32;
 constexpr int NEPI = 128;   // epilogue threads (warps 4..7)
 constexpr int MAXST = 4, NOP = 2, NACC = 2;
 constexpr int KMAX = 6;     // operand entries per converter thread and chunk
@@ -64,7 +65,7 @@ struct alignas(16) Shared {
   uint64_t stage_full[MAXST], stage_empty[MAXST], op_full[NOP], op_empty[NOP], acc_full[NACC], acc_empty[NACC], b_full;
   uint32_t tmem_slot;
   uint32_t abort;
-  uint32_t op_flags[NOP][8];
+  uint32_t op_flags[NOP][NCW];
   uint2 mma_off[64];   // per (tap, k-step): start-address offsets (16-byte units) of the A and B operands
   alignas(16) float epi_scale[288];   // per output channel of the slab (fixed for the whole kernel)
   alignas(16) float epi_bias[288];
@@ -120,7 +121,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const Params p) {
     tc::fence_barrier_init();
     tc::prefetch_tmap(&tmap_in);
   }
-  if (tid < NOP * 8) sh.op_flags[tid / 8][tid % 8] = 0;
+  if (tid < NOP * NCW) sh.op_flags[tid / NCW][tid % NCW] = 0;
   if (tid == 0) sh.abort = 0;
   if (tid < RS * (p.CC / 16)) {
     const int ks = p.CC / 16, tap = tid / ks, j = tid - tap * ks;
@@ -212,7 +213,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const Params p) {
             if (p.quant_mode == 0) {
               uint32_t any = 0;
 #pragma unroll
-              for (int w8 = 0; w8 < 8; ++w8) any |= sh.op_flags[ob][w8];
+              for (int w8 = 0; w8 < NCW; ++w8) any |= sh.op_flags[ob][w8];
               need_low = any != 0;
             }
             const uint64_t a_chunk = a_desc0 + (uint64_t)((uint32_t)ob * a_buf);
@@ -307,9 +308,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const Params p) {
       tc::tc_fence_before();
       tc::mbar_arrive(&sh.acc_empty[acc]);
     }
-  } else if (warp >= 8) {
+  } else if (warp >= 8 || warp == 2 || warp == 3) {
     // ================================================================= converters
-    const int ct = tid - 256;
+    const int ct = warp >= 8 ? tid - 256 + 64 : tid - 64;
     const int cw = ct >> 5;
     MnbActQ q;
     if (p.quant_mode != 0) q = mnb_load_actq(p.qp);

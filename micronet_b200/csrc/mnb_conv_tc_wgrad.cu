@@ -19,8 +19,8 @@
 
 namespace tcwgrad {
 
-constexpr int NTHREADS = 512, NCONV = 256, NEPI = 128, MAXST = 4;
-constexpr int KX = 6, KD = 4;  // operand entries per converter thread: activation / gradient chunks
+constexpr int NTHREADS = 512, NCONV = 448, NEPI = 128, MAXST = 4;  // converters: warps 2..15 (4..7 also run the final epilogue)
+constexpr int KX = 4, KD = 3;  // operand entries per converter thread: activation / gradient chunks
 constexpr int kMaxDynSmem = 227 * 1024 - 2048;
 
 struct Params {
@@ -150,47 +150,9 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
       if (lead) tc::mma_commit(&sh.done);
       __syncwarp();
     }
-  } else if (warp >= 4 && warp < 8) {
-    // ================================================================= final epilogue: TMEM -> partial dW
-    const int q = warp - 4, m = q * 32 + lane;
-    const int64_t wsize = (int64_t)p.K * p.Cg * RS;
-    float* mine = p.partial + (int64_t)rank * wsize;
-    bool have = my_tiles > 0;
-    if (have) {
-      if (!tc::mbar_wait(&sh.done, 0, p.err, 403)) goto done;
-      tc::tc_fence_after();
-    }
-    const int k_abs = dy_ch0 + m;
-    const int k_group = k_abs / p.Ng;
-    for (int tap = tap0; tap < tap1; ++tap) {
-      for (int n0 = 0; n0 < p.n_block; n0 += 32) {
-        uint32_t r[32];
-        if (have) {
-          tc::tmem_ld_32x32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)((tap - tap0) * p.n_block + n0), r);
-          tc::tmem_ld_wait();
-        } else {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) r[j] = 0u;
-        }
-        if (m < m_real) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const int n = n0 + j;
-            if (n < p.n_block) {
-              const int xg = (x_ch0 + n) / p.Cg;           // group of this activation channel
-              if (xg == k_group) {
-                const int c = (x_ch0 + n) - xg * p.Cg;
-                mine[((int64_t)k_abs * p.Cg + c) * RS + tap] = __uint_as_float(r[j]);
-              }
-            }
-          }
-        }
-      }
-    }
-    tc::tc_fence_before();
-  } else if (warp >= 8) {
-    // ================================================================= converters
-    const int ct = tid - 256;
+  } else {
+    // ================================================================= converters (warps 2..15)
+    const int ct = tid - 64;
     MnbActQ q;
     if (p.quant_mode != 0) q = mnb_load_actq(p.qp);
     const int a_off = p.a_offset + ((p.quant_mode == MNB_ACT_IAO && p.qp.zero_point) ? (int)__ldg(p.qp.zero_point) : 0);
@@ -303,6 +265,45 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
       __syncwarp();
       if (lane == 0) tc::mbar_arrive(&sh.op_full);
     }
+  }
+  if (warp >= 4 && warp < 8) {
+    // ================================================================= final epilogue: TMEM -> partial dW
+    const int q = warp - 4, m = q * 32 + lane;
+    const int64_t wsize = (int64_t)p.K * p.Cg * RS;
+    float* mine = p.partial + (int64_t)rank * wsize;
+    bool have = my_tiles > 0;
+    if (have) {
+      if (!tc::mbar_wait(&sh.done, 0, p.err, 403)) goto done;
+      tc::tc_fence_after();
+    }
+    const int k_abs = dy_ch0 + m;
+    const int k_group = k_abs / p.Ng;
+    for (int tap = tap0; tap < tap1; ++tap) {
+      for (int n0 = 0; n0 < p.n_block; n0 += 32) {
+        uint32_t r[32];
+        if (have) {
+          tc::tmem_ld_32x32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)((tap - tap0) * p.n_block + n0), r);
+          tc::tmem_ld_wait();
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) r[j] = 0u;
+        }
+        if (m < m_real) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const int n = n0 + j;
+            if (n < p.n_block) {
+              const int xg = (x_ch0 + n) / p.Cg;           // group of this activation channel
+              if (xg == k_group) {
+                const int c = (x_ch0 + n) - xg * p.Cg;
+                mine[((int64_t)k_abs * p.Cg + c) * RS + tap] = __uint_as_float(r[j]);
+              }
+            }
+          }
+        }
+      }
+    }
+    tc::tc_fence_before();
   }
 done:
   tc::tc_fence_before();
