@@ -76,6 +76,14 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
   return *reinterpret_cast<uint32_t*>(&v);
 }
 __device__ __forceinline__ float bf16_round(float v) { return __bfloat162float(__float2bfloat16_rn(v)); }
+// (a, b) -> packed bf16 pairs of the exact pieces hi, mid, lo with a = hi_a + mid_a + lo_a (same for b)
+__device__ __forceinline__ void split3_pair(float a, float b, uint32_t& hp, uint32_t& mp, uint32_t& lp) {
+  hp = pack_bf16x2(a, b);
+  const float ra = a - __uint_as_float(hp << 16), rb = b - __uint_as_float(hp & 0xffff0000u);
+  mp = pack_bf16x2(ra, rb);
+  const float la = ra - __uint_as_float(mp << 16), lb = rb - __uint_as_float(mp & 0xffff0000u);
+  lp = pack_bf16x2(la, lb);
+}
 
 // debug instrumentation: time spent inside a bounded wait, accumulated per role
 #define PROF_WAIT(slot, call)                                   \
@@ -137,8 +145,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const Params p) {
   // zero the operand buffers once: the mid / lo planes are only rewritten when a chunk needs them
   for (int i = tid; i < NOP * p.op_buf_bytes / 16; i += NTHREADS)
     reinterpret_cast<uint4*>(op_base)[i] = make_uint4(0, 0, 0, 0);
-  // per-channel epilogue constants of this slab (forward): loaded once
-  if (!p.dgrad) {
+  // per-channel constants of this slab, loaded once: forward = epilogue scale / bias per output channel,
+  // dgrad = weight scale per INPUT channel (folded into dy while it is converted)
+  if (p.dgrad) {
+    const int ch_first = g_first * p.cin_g;
+    for (int n = tid; n < g_count * p.cin_g && n < 288; n += NTHREADS) sh.epi_scale[n] = __ldg(p.w_scale + ch_first + n);
+  } else {
     const float a_sc0 = p.a_scale ? __ldg(p.a_scale) : p.a_scale_const;
     const int ch_first = g_first * p.cout_g;
     for (int n = tid; n < g_count * p.cout_g; n += NTHREADS) {
@@ -368,9 +380,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const Params p) {
             uint4 hi;
             if (p.quant_mode == 0) {
               if (p.dgrad) {  // fold the per-input-channel weight scale into the gradient operand
-                const int c0 = cbase + ((meta[k] >> 16) & 15) * 8;
-#pragma unroll
-                for (int j = 0; j < 8; ++j) u[j] = __float_as_uint(__fmul_rn(__uint_as_float(u[j]), __ldg(p.w_scale + c0 + j)));
+                const float* sc = &sh.epi_scale[gi * p.cin_g + ch * p.CC + ((meta[k] >> 16) & 15) * 8];
+                const float4 s0 = *reinterpret_cast<const float4*>(sc), s1 = *reinterpret_cast<const float4*>(sc + 4);
+                u[0] = __float_as_uint(__fmul_rn(__uint_as_float(u[0]), s0.x)); u[1] = __float_as_uint(__fmul_rn(__uint_as_float(u[1]), s0.y));
+                u[2] = __float_as_uint(__fmul_rn(__uint_as_float(u[2]), s0.z)); u[3] = __float_as_uint(__fmul_rn(__uint_as_float(u[3]), s0.w));
+                u[4] = __float_as_uint(__fmul_rn(__uint_as_float(u[4]), s1.x)); u[5] = __float_as_uint(__fmul_rn(__uint_as_float(u[5]), s1.y));
+                u[6] = __float_as_uint(__fmul_rn(__uint_as_float(u[6]), s1.z)); u[7] = __float_as_uint(__fmul_rn(__uint_as_float(u[7]), s1.w));
               }
               uint32_t low = 0;
 #pragma unroll
@@ -384,24 +399,17 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const Params p) {
                   *reinterpret_cast<uint4*>(opb + (size_t)2 * p.op_term_bytes + (size_t)idx * 16) = make_uint4(0, 0, 0, 0);
                 }
               } else {
-                // exact 3-way split x = hi + mid + lo (8 + 8 + 8 significand bits)
-                float h1[8], m1[8], l1[8];
+                // exact 3-way split x = hi + mid + lo (8 + 8 + 8 significand bits), two values per
+                // cvt.rn.bf16x2 so that the three planes cost ~13 instructions per pair
+                uint32_t hp[4], mp[4], lp[4];
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                  const float v = __uint_as_float(u[j]);
-                  h1[j] = bf16_round(v);
-                  const float r1 = v - h1[j];
-                  m1[j] = bf16_round(r1);
-                  l1[j] = r1 - m1[j];
-                }
+                for (int j = 0; j < 4; ++j) split3_pair(__uint_as_float(u[2 * j]), __uint_as_float(u[2 * j + 1]), hp[j], mp[j], lp[j]);
                 any_low = 1;
                 now_dirty |= 1u << k;
-                hi = make_uint4(pack_bf16x2(h1[0], h1[1]), pack_bf16x2(h1[2], h1[3]), pack_bf16x2(h1[4], h1[5]), pack_bf16x2(h1[6], h1[7]));
+                hi = make_uint4(hp[0], hp[1], hp[2], hp[3]);
                 if (live) {
-                  *reinterpret_cast<uint4*>(opb + (size_t)p.op_term_bytes + (size_t)idx * 16) =
-                      make_uint4(pack_bf16x2(m1[0], m1[1]), pack_bf16x2(m1[2], m1[3]), pack_bf16x2(m1[4], m1[5]), pack_bf16x2(m1[6], m1[7]));
-                  *reinterpret_cast<uint4*>(opb + (size_t)2 * p.op_term_bytes + (size_t)idx * 16) =
-                      make_uint4(pack_bf16x2(l1[0], l1[1]), pack_bf16x2(l1[2], l1[3]), pack_bf16x2(l1[4], l1[5]), pack_bf16x2(l1[6], l1[7]));
+                  *reinterpret_cast<uint4*>(opb + (size_t)p.op_term_bytes + (size_t)idx * 16) = make_uint4(mp[0], mp[1], mp[2], mp[3]);
+                  *reinterpret_cast<uint4*>(opb + (size_t)2 * p.op_term_bytes + (size_t)idx * 16) = make_uint4(lp[0], lp[1], lp[2], lp[3]);
                 }
               }
             } else {
@@ -535,6 +543,10 @@ static int plan(const mnb_conv_shape* s, bool dgrad, int quant_mode, Params& p, 
   if (budget < p.b_group_bytes) return unsupported("weights of one group do not fit in shared memory");
   int max_groups = std::max(1, std::min(p.G, std::min(budget / p.b_group_bytes, std::max(1, 64 * 1024 / p.b_group_bytes))));
   max_groups = std::max(1, std::min(max_groups, 256 / p.cout_g));  // one accumulator row block per tile: <= 256 columns
+  if (dgrad) {  // per-input-channel scales of the slab are staged in a 288-float shared array
+    if (p.cin_g > 288) return unsupported("more than 288 gradient channels per group");
+    max_groups = std::max(1, std::min(max_groups, 288 / p.cin_g));
+  }
   while (p.G % max_groups) --max_groups;  // equal slabs: every CTA does the same work per tile
   p.slab_groups = max_groups;
   p.n_slabs = p.G / p.slab_groups;

@@ -47,7 +47,14 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
   __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&v);
 }
-__device__ __forceinline__ float bf16_round(float v) { return __bfloat162float(__float2bfloat16_rn(v)); }
+// (a, b) -> packed bf16 pairs of the exact pieces hi, mid, lo with a = hi_a + mid_a + lo_a (same for b)
+__device__ __forceinline__ void split3_pair(float a, float b, uint32_t& hp, uint32_t& mp, uint32_t& lp) {
+  hp = pack_bf16x2(a, b);
+  const float ra = a - __uint_as_float(hp << 16), rb = b - __uint_as_float(hp & 0xffff0000u);
+  mp = pack_bf16x2(ra, rb);
+  const float la = ra - __uint_as_float(mp << 16), lb = rb - __uint_as_float(mp & 0xffff0000u);
+  lp = pack_bf16x2(la, lb);
+}
 
 __global__ void __launch_bounds__(NTHREADS, 1)
 wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_dy,
@@ -243,19 +250,14 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
           for (int k = 0; k < KD; ++k) {
             if (ct + k * NCONV >= total_d) break;
             const int so = dso[k];
-            float h1[8], m1[8], l1[8];
+            uint32_t hp[4], mp[4], lp[4];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const float v = stg[so + j * d_chstride];
-              h1[j] = bf16_round(v);
-              const float r1 = v - h1[j];
-              m1[j] = bf16_round(r1);
-              l1[j] = r1 - m1[j];
-            }
+            for (int j = 0; j < 4; ++j)
+              split3_pair(stg[so + (2 * j) * d_chstride], stg[so + (2 * j + 1) * d_chstride], hp[j], mp[j], lp[j]);
             uint8_t* d0 = dstb + ddst[k];
-            *reinterpret_cast<uint4*>(d0) = make_uint4(pack_bf16x2(h1[0], h1[1]), pack_bf16x2(h1[2], h1[3]), pack_bf16x2(h1[4], h1[5]), pack_bf16x2(h1[6], h1[7]));
-            *reinterpret_cast<uint4*>(d0 + p.dop_term_bytes) = make_uint4(pack_bf16x2(m1[0], m1[1]), pack_bf16x2(m1[2], m1[3]), pack_bf16x2(m1[4], m1[5]), pack_bf16x2(m1[6], m1[7]));
-            *reinterpret_cast<uint4*>(d0 + 2 * p.dop_term_bytes) = make_uint4(pack_bf16x2(l1[0], l1[1]), pack_bf16x2(l1[2], l1[3]), pack_bf16x2(l1[4], l1[5]), pack_bf16x2(l1[6], l1[7]));
+            *reinterpret_cast<uint4*>(d0) = make_uint4(hp[0], hp[1], hp[2], hp[3]);
+            *reinterpret_cast<uint4*>(d0 + p.dop_term_bytes) = make_uint4(mp[0], mp[1], mp[2], mp[3]);
+            *reinterpret_cast<uint4*>(d0 + 2 * p.dop_term_bytes) = make_uint4(lp[0], lp[1], lp[2], lp[3]);
           }
         }
         __syncwarp();
