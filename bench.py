@@ -29,7 +29,7 @@ sys.path.insert(0, ROOT)
 
 from harness import train as H  # noqa: E402
 
-WORKLOAD = "nin_gc_wbwtab_w3a2"
+WORKLOAD = "nin_gc_wbwtab_w3a2"   # BASELINE.json configs[1]; --workload picks another config for side measurements
 BATCH_PER_GPU = 256
 CPU_SAMPLE_BATCH = 32
 METRIC = "qat_step_images_per_sec"
@@ -132,8 +132,11 @@ def run_cpu_baseline(steps=3, warmup=2):
 
 
 def config_dict(n_gpus):
-    return {"workload": f"NIN-GC wbwtab W-ternary/A-binary QAT step, synthetic 3x32x32, batch {BATCH_PER_GPU}/GPU "
-                        f"(BASELINE.json configs[1])",
+    names = {"nin_gc_wbwtab_w3a2": "NIN-GC wbwtab W-ternary/A-binary QAT step (BASELINE.json configs[1])",
+             "nin_dorefa_w8a8": "NIN DoReFa W8A8 QAT step (configs[0] model)",
+             "resnet18_iao_w8a8_bnfuse": "ResNet-18 IAO W8A8 per-channel + BN-fuse QAT step (configs[2])",
+             "nin_gc_dorefa_w4a4": "NIN-GC DoReFa W4A4 QAT step (configs[3] model)"}
+    return {"workload": f"{names[WORKLOAD]}, synthetic 3x32x32, batch {BATCH_PER_GPU}/GPU",
             "global_batch": BATCH_PER_GPU * n_gpus, "per_gpu_batch": BATCH_PER_GPU, "optimizer": "Adam lr=0.01",
             "parallelism": f"dp{n_gpus}", "l2": "per-step working set ~2.4 GB of activations >> 126 MB L2 (no flush needed)"}
 
@@ -159,7 +162,10 @@ def main():
     ap.add_argument("--impl", default="engine", choices=["engine", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--kernels-json", default=None, help="dump the per-kernel CUDA-event timings of the timed region")
+    ap.add_argument("--workload", default=WORKLOAD, choices=sorted(H.WORKLOADS),
+                    help="default: the headline configuration (BASELINE.json configs[1])")
     args = ap.parse_args()
+    globals()["WORKLOAD"] = args.workload
     if args.impl == "reference":
         return main_reference(args)
     args.warmup = max(args.warmup, 3)
