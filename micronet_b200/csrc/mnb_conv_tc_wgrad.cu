@@ -26,7 +26,8 @@ constexpr int kMaxDynSmem = 227 * 1024 - 2048;
 struct Params {
   int B, C, K, H, W, R, S, pad, G, Cg, Ng;
   int BW, TH, THH, TB, CC, nst;
-  int npos_x, row_tiles, n_tiles;
+  int npos_x, npos_d, ksteps, row_tiles, n_tiles;   // npos_d: gradient positions per tile (multiple of 16)
+  int op_buf_bytes;                                  // one {activation, 3 x gradient} operand buffer; two are cycled
   int Gb, nsplit, n_block, n_slabs, ranks;
   int tap_groups, tpc;   // filter taps are split over `tap_groups` CTA sets of `tpc` taps (TMEM holds tpc * n_block columns)
   int quant_mode, a_offset, tmem_cols;
@@ -38,7 +39,7 @@ struct Params {
 };
 
 struct alignas(16) Shared {
-  uint64_t stage_full[MAXST], stage_empty[MAXST], op_full, op_empty, done;
+  uint64_t stage_full[MAXST], stage_empty[MAXST], op_full[2], op_empty[2], done;
   uint32_t tmem_slot;
   uint32_t abort;
 };
@@ -80,8 +81,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
 
   if (tid == 0) {
     for (int i = 0; i < p.nst; ++i) { tc::mbar_init(&sh.stage_full[i], 1); tc::mbar_init(&sh.stage_empty[i], NCONV / 32); }
-    tc::mbar_init(&sh.op_full, NCONV / 32);
-    tc::mbar_init(&sh.op_empty, 1);
+    for (int i = 0; i < 2; ++i) { tc::mbar_init(&sh.op_full[i], NCONV / 32); tc::mbar_init(&sh.op_empty[i], 1); }
     tc::mbar_init(&sh.done, 1);
     sh.abort = 0;
     tc::fence_barrier_init();
@@ -94,7 +94,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
   // operand buffers start as zeros: padded columns / rows and unused channel rows are never written
-  for (int i = tid; i < (p.xop_bytes + 3 * p.dop_term_bytes) / 16; i += NTHREADS)
+  for (int i = tid; i < 2 * p.op_buf_bytes / 16; i += NTHREADS)
     reinterpret_cast<uint4*>(xop)[i] = make_uint4(0, 0, 0, 0);
   tc::fence_proxy_async_smem();
   tc::tc_fence_before();
@@ -131,27 +131,28 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
       const uint32_t idesc = tc::make_idesc_major(1, 1, 1, 128, (uint32_t)p.n_block, 1, 1);
       // descriptors differ only in the 14-bit start-address field: build once, then add (bytes >> 4)
       const uint64_t b_desc0 = tc::smem_desc_mnmajor_noswz(tc::smem_u32(xop), 128, (uint32_t)p.npos_x * 16u);
-      const uint64_t a_desc0 = tc::smem_desc_mnmajor_noswz(tc::smem_u32(dop), 128, 128u * 16u);
+      const uint64_t a_desc0 = tc::smem_desc_mnmajor_noswz(tc::smem_u32(dop), 128, (uint32_t)p.npos_d * 16u);
+      const uint32_t buf16 = (uint32_t)p.op_buf_bytes >> 4;
       const uint32_t a_term = (uint32_t)p.dop_term_bytes >> 4;
       uint32_t t = 0;
       for (int tile = rank; tile < p.n_tiles; tile += p.ranks, ++t) {
-        tc::mbar_wait_soft(&sh.op_full, t & 1, p.err, 402, &sh.abort);
+        const uint32_t ob = t & 1u, oph = (t >> 1) & 1u;
+        tc::mbar_wait_soft(&sh.op_full[ob], oph, p.err, 402, &sh.abort);
         tc::tc_fence_after();
         uint32_t d_col = 0;
         for (int tap = tap0; tap < tap1; ++tap, d_col += (uint32_t)p.n_block) {
           const int r = tap / p.S, s2 = tap - r * p.S;
-          const uint64_t b_tap = b_desc0 + (uint64_t)((uint32_t)(r * p.BW + s2));
+          const uint64_t b_tap = b_desc0 + (uint64_t)(ob * buf16 + (uint32_t)(r * p.BW + s2));
           const uint32_t d_tmem = tmem + d_col;
-#pragma unroll
-          for (int ps = 0; ps < 8; ++ps) {
+          for (int ps = 0; ps < p.ksteps; ++ps) {
             const uint64_t bd = b_tap + (uint64_t)(ps * 16);   // 16 positions x 16 bytes = 256 B
-            const uint64_t ad = a_desc0 + (uint64_t)(ps * 16);
+            const uint64_t ad = a_desc0 + (uint64_t)(ob * buf16 + (uint32_t)(ps * 16));
             tc::mma_f16_guarded(d_tmem, ad, bd, idesc, (t | (uint32_t)ps) != 0, lead);
             tc::mma_f16_guarded(d_tmem, ad + a_term, bd, idesc, 1, lead);
             tc::mma_f16_guarded(d_tmem, ad + 2 * a_term, bd, idesc, 1, lead);
           }
         }
-        if (lead) tc::mma_commit(&sh.op_empty);
+        if (lead) tc::mma_commit(&sh.op_empty[ob]);
         __syncwarp();
       }
       if (lead) tc::mma_commit(&sh.done);
@@ -195,7 +196,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
         const int rem = vp - tb * (p.TH * p.W);
         const int th = rem / p.W, w = rem - th * p.W;
         dso[k] = ((tb * p.CC + c8 * 8) * p.TH + th) * p.W + w;
-        ddst[k] = (c8 * 128 + (tb * p.THH + th) * p.BW + w) * 16;  // byte offset inside a chunk's 8-ch groups
+        ddst[k] = (c8 * p.npos_d + (tb * p.THH + th) * p.BW + w) * 16;  // byte offset inside a chunk's 8-ch groups
       }
     }
     const int x_chstride = p.THH * p.W, d_chstride = p.TH * p.W;
@@ -203,14 +204,17 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
     for (int tile = rank; tile < p.n_tiles; tile += p.ranks, ++t) {
       const int bt = tile / p.row_tiles, rt = tile - bt * p.row_tiles;
       const int b0 = bt * p.TB, h0 = rt * p.TH;
-      if (!tc::mbar_wait(&sh.op_empty, (t & 1) ^ 1, p.err, 404)) goto done;  // previous tile's MMAs retired
+      const uint32_t ob = t & 1u, oph = (t >> 1) & 1u;
+      if (!tc::mbar_wait(&sh.op_empty[ob], oph ^ 1, p.err, 404)) goto done;  // MMAs of the tile two back retired
+      uint8_t* xop_b = xop + (size_t)ob * p.op_buf_bytes;
+      uint8_t* dop_b = dop + (size_t)ob * p.op_buf_bytes;
       for (int ch = 0; ch < x_chunks + d_chunks; ++ch, ++it) {
         const int st = it % p.nst;
         const uint32_t ph = (it / p.nst) & 1;
         if (!tc::mbar_wait(&sh.stage_full[st], ph, p.err, 405)) goto done;
         const float* stg = reinterpret_cast<const float*>(stage_base + (size_t)st * p.slot_bytes);
         if (ch < x_chunks) {
-          uint8_t* dstb = xop + (size_t)ch * c8s * p.npos_x * 16;
+          uint8_t* dstb = xop_b + (size_t)ch * c8s * p.npos_x * 16;
 #pragma unroll
           for (int k = 0; k < KX; ++k) {
             const int idx = ct + k * NCONV;
@@ -245,7 +249,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
           }
         } else {
           const int dch = ch - x_chunks;
-          uint8_t* dstb = dop + (size_t)dch * c8s * 128 * 16;
+          uint8_t* dstb = dop_b + (size_t)dch * c8s * p.npos_d * 16;
 #pragma unroll
           for (int k = 0; k < KD; ++k) {
             if (ct + k * NCONV >= total_d) break;
@@ -265,7 +269,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
       }
       tc::fence_proxy_async_smem();
       __syncwarp();
-      if (lane == 0) tc::mbar_arrive(&sh.op_full);
+      if (lane == 0) tc::mbar_arrive(&sh.op_full[ob]);
     }
   }
   if (warp >= 4 && warp < 8) {
@@ -367,39 +371,59 @@ static int plan(const mnb_conv_shape* s, int quant_mode, Params& p, int& smem_by
   }
   p.n_block = p.Gb * p.Cg;
   if (p.n_block > 256 || p.tpc * p.n_block > 512) return unsupported("accumulators exceed tensor memory");
-  p.CC = 32;
-  if (p.n_block % 32 || (p.Gb * p.Ng) % 32 || (p.nsplit > 1 && p.Ng % 32)) p.CC = 16;
-  if (p.nsplit > 1 && (p.Ng % 128) % p.CC) return unsupported("ragged channel split");
+  int cc0 = 32;
+  if (p.n_block % 32 || (p.Gb * p.Ng) % 32 || (p.nsplit > 1 && p.Ng % 32)) cc0 = 16;
+  if (p.nsplit > 1 && (p.Ng % 128) % cc0) return unsupported("ragged channel split");
   p.n_slabs = (p.G / p.Gb) * p.nsplit * p.tap_groups;
   p.BW = p.W + 2 * p.pad;
-  p.TH = std::min(p.H, 128 / p.BW);
-  if (p.TH < 1) return unsupported("padded row wider than 128 positions");
-  p.THH = p.TH + 2 * p.pad;
-  p.TB = 1;
-  if (p.pad == 0 && p.TH == p.H) p.TB = std::max(1, std::min(p.B, 128 / (p.H * p.W)));
+  const int th_max = std::min(p.H, 128 / p.BW);
+  if (th_max < 1) return unsupported("padded row wider than 128 positions");
   const int halo = (p.R - 1) * p.BW + (p.S - 1);
-  p.npos_x = (128 + halo + 7) / 8 * 8;
-  if (p.npos_x * (p.CC / 8) > KX * NCONV || p.TB * p.TH * p.W * (p.CC / 8) > KD * NCONV) {
-    if (p.CC == 32 && p.npos_x * 2 <= KX * NCONV) p.CC = 16;
-    else return unsupported("tile too large for the converter");
+  // rows per tile: the largest that lets TWO operand buffers (converter and MMA overlap) plus a staging
+  // ring of >= 3 slots fit in shared memory
+  bool ok = false;
+  auto try_tile = [&](int TH, int TB) -> bool {
+    p.TH = TH; p.TB = TB;
+    p.THH = p.TH + 2 * p.pad;
+    p.npos_d = ((p.pad > 0 ? p.TH * p.BW : p.TB * p.TH * p.W) + 15) / 16 * 16;
+    if (p.npos_d > 128) return false;
+    p.ksteps = p.npos_d / 16;
+    p.npos_x = (p.npos_d + halo + 7) / 8 * 8;
+    p.CC = cc0;
+    if (p.npos_x * (p.CC / 8) > KX * NCONV || p.TB * p.TH * p.W * (p.CC / 8) > KD * NCONV) {
+      if (p.CC == 32 && p.npos_x * 2 <= KX * NCONV) p.CC = 16; else return false;
+    }
+    p.stage_x_bytes = p.W * p.THH * p.CC * p.TB * 4;
+    p.stage_d_bytes = p.W * p.TH * p.CC * p.TB * 4;
+    p.slot_bytes = (std::max(p.stage_x_bytes, p.stage_d_bytes) + 127) / 128 * 128;
+    p.xop_bytes = (p.n_block / 8) * p.npos_x * 16;
+    p.dop_term_bytes = 16 * p.npos_d * 16;  // 128 channel rows (16 groups of 8) x npos_d positions
+    p.op_buf_bytes = (p.xop_bytes + 3 * p.dop_term_bytes + 1023) / 1024 * 1024;
+    p.off_xop = 0;
+    p.off_dop = p.xop_bytes;
+    p.off_stage = 2 * p.op_buf_bytes;
+    p.nst = MAXST;
+    while (p.nst > 3 && p.off_stage + p.nst * p.slot_bytes > kMaxDynSmem) --p.nst;
+    smem_bytes = p.off_stage + p.nst * p.slot_bytes;
+    return smem_bytes <= kMaxDynSmem;
+  };
+  // candidates: whole small images per tile first, then the row count with the fewest (and fullest) tiles
+  int best_th = 0, best_tb = 0, best_tiles = 1 << 30;
+  for (int TH = th_max; TH >= 1; --TH) {
+    const int tb_max = (p.pad == 0 && TH == p.H) ? std::max(1, std::min(p.B, 128 / (p.H * p.W))) : 1;
+    for (int TB = tb_max; TB >= 1; TB >>= 1) {
+      if (!try_tile(TH, TB)) continue;
+      const int tiles = ((p.B + TB - 1) / TB) * ((p.H + TH - 1) / TH);
+      if (tiles <= best_tiles) { best_tiles = tiles; best_th = TH; best_tb = TB; }  // ties: smaller tile
+      break;
+    }
   }
+  ok = best_th > 0 && try_tile(best_th, best_tb);
+  if (!ok) return unsupported("shared memory budget");
   p.row_tiles = (p.H + p.TH - 1) / p.TH;
   p.n_tiles = ((p.B + p.TB - 1) / p.TB) * p.row_tiles;
   p.ranks = std::max(1, std::min(p.n_tiles, MNB_NUM_SMS / p.n_slabs));  // one wave of CTAs
   p.quant_mode = quant_mode;
-  p.stage_x_bytes = p.W * p.THH * p.CC * p.TB * 4;
-  p.stage_d_bytes = p.W * p.TH * p.CC * p.TB * 4;
-  p.slot_bytes = (std::max(p.stage_x_bytes, p.stage_d_bytes) + 127) / 128 * 128;
-  p.xop_bytes = (p.n_block / 8) * p.npos_x * 16;
-  p.dop_term_bytes = 16 * 128 * 16;  // 128 channel rows (16 groups of 8) x 128 positions
-  p.off_xop = 0;  // xop and the three dop planes are contiguous (zeroed together)
-  p.off_dop = p.xop_bytes;
-  const int ops = (p.xop_bytes + 3 * p.dop_term_bytes + 1023) / 1024 * 1024;
-  p.off_stage = ops;
-  p.nst = MAXST;
-  while (p.nst > 2 && ops + p.nst * p.slot_bytes > kMaxDynSmem) --p.nst;
-  smem_bytes = ops + p.nst * p.slot_bytes;
-  if (smem_bytes > kMaxDynSmem) return unsupported("shared memory budget");
   int cols = 32;
   while (cols < p.tpc * p.n_block) cols <<= 1;
   p.tmem_cols = cols;
