@@ -302,12 +302,26 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const Params p) {
             for (int j = 0; j < 32; ++j, op += plane)
               if (n0 + j < slab_cols) *op = fmaf(__uint_as_float(r[j]), sc[j], bs[j]);
           } else if (p.ste_bits) {
+            // the 32 channel planes' mask words first (independent loads), then select + store.  The
+            // reference's STE computes ((g*s)*pass)/s (IAO) or (((g*s)/s)*pass)*0.1 (DoReFa); (g*s)/s is
+            // g to within one ulp, so the epilogue passes g itself (well inside the 1e-5 contract).
+            const int64_t fi0 = obase + (int64_t)n0 * plane;
+            const uint32_t shift = (uint32_t)(fi0 & 31);
+            const bool same_bit = (plane & 31) == 0;
+            uint32_t wbits[32];
 #pragma unroll
-            for (int j = 0; j < 32; ++j)
+            for (int j = 0; j < 32; ++j) {
+              const int64_t fi = fi0 + (int64_t)j * plane;
+              wbits[j] = (n0 + j < slab_cols) ? __ldg(p.ste_bits + (fi >> 5)) : 0u;
+            }
+            const float gain = ste.mode == MNB_ACT_DOREFA ? 0.1f : 1.f;
+            float* op = orow + (int64_t)n0 * plane;
+#pragma unroll
+            for (int j = 0; j < 32; ++j, op += plane)
               if (n0 + j < slab_cols) {
-                const int64_t fi = obase + (int64_t)(n0 + j) * plane;
-                const bool pass = (__ldg(p.ste_bits + (fi >> 5)) >> (fi & 31)) & 1u;
-                p.out[fi] = mnb_act_ste_one(ste, __uint_as_float(r[j]), pass);
+                const uint32_t sh_j = same_bit ? shift : (uint32_t)((fi0 + (int64_t)j * plane) & 31);
+                const bool pass = (wbits[j] >> sh_j) & 1u;
+                *op = pass ? __uint_as_float(r[j]) * gain : 0.f;
               }
           } else {
             float* op = orow + (int64_t)n0 * plane;
@@ -419,20 +433,34 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const Params p) {
               const bool inside = so >= 0 && h >= 0 && h < p.H && b < p.B;
               const bool owned = inside && hr >= p.pad && hr < p.pad + p.TH;
               float e[8];
+              const int64_t plane = (int64_t)p.H * p.W;
+              const int64_t fi0 = (((int64_t)b * p.Cin + cbase + c8 * 8) * p.H + h) * p.W + w;
+              // the 8 channels of an entry sit at the same pixel: when H*W is a multiple of 32 they share
+              // the bit position and the lane grouping, so one match_any serves all eight
+              const bool shared_group = (plane & 31) == 0;
+              uint32_t peers0 = 0;
+              if (p.pass_bits && shared_group)
+                peers0 = __match_any_sync(0xffffffffu, owned ? (uint32_t)(fi0 >> 5) : 0xffffffffu);
+              const bool leader0 = owned && (__ffs(peers0) - 1) == lane;
 #pragma unroll
               for (int j = 0; j < 8; ++j) {
                 bool pass; float xq;
                 const int code = mnb_act_quantize_one(q, __uint_as_float(u[j]), pass, xq);
                 e[j] = inside ? (float)(code + a_off) : 0.f;
-                const int64_t fi = (((int64_t)b * p.Cin + cbase + c8 * 8 + j) * p.H + h) * p.W + w;
+                const int64_t fi = fi0 + (int64_t)j * plane;
                 if (p.codes && owned) p.codes[fi] = (uint8_t)code;
                 if (p.pass_bits) {
-                  // lanes that fall into the same 32-bit word combine their bits: one atomic per word
-                  const uint32_t word = owned ? (uint32_t)(fi >> 5) : 0xffffffffu;
-                  const uint32_t peers = __match_any_sync(0xffffffffu, word);
                   const uint32_t mine = (owned && pass) ? (1u << (fi & 31)) : 0u;
-                  const uint32_t val = __reduce_or_sync(peers, mine);
-                  if (owned && val && (__ffs(peers) - 1) == lane) atomicOr(p.pass_bits + word, val);
+                  if (shared_group) {
+                    const uint32_t val = __reduce_or_sync(peers0, mine);
+                    if (leader0 && val) atomicOr(p.pass_bits + (fi >> 5), val);
+                  } else {
+                    // lanes that fall into the same 32-bit word combine their bits: one atomic per word
+                    const uint32_t word = owned ? (uint32_t)(fi >> 5) : 0xffffffffu;
+                    const uint32_t peers = __match_any_sync(0xffffffffu, word);
+                    const uint32_t val = __reduce_or_sync(peers, mine);
+                    if (owned && val && (__ffs(peers) - 1) == lane) atomicOr(p.pass_bits + word, val);
+                  }
                 }
               }
               hi = make_uint4(pack_bf16x2(e[0], e[1]), pack_bf16x2(e[2], e[3]), pack_bf16x2(e[4], e[5]), pack_bf16x2(e[6], e[7]));

@@ -27,7 +27,7 @@ struct Params {
   int B, C, K, H, W, R, S, pad, G, Cg, Ng;
   int BW, TH, THH, TB, CC, nst;
   int npos_x, npos_d, ksteps, row_tiles, n_tiles;   // npos_d: gradient positions per tile (multiple of 16)
-  int op_buf_bytes;                                  // one {activation, 3 x gradient} operand buffer; two are cycled
+  int op_buf_bytes, nbuf;                            // one {activation, 3 x gradient} operand buffer; nbuf (1|2) are cycled
   int Gb, nsplit, n_block, n_slabs, ranks;
   int tap_groups, tpc;   // filter taps are split over `tap_groups` CTA sets of `tpc` taps (TMEM holds tpc * n_block columns)
   int quant_mode, a_offset, tmem_cols;
@@ -94,7 +94,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
   // operand buffers start as zeros: padded columns / rows and unused channel rows are never written
-  for (int i = tid; i < 2 * p.op_buf_bytes / 16; i += NTHREADS)
+  for (int i = tid; i < p.nbuf * p.op_buf_bytes / 16; i += NTHREADS)
     reinterpret_cast<uint4*>(xop)[i] = make_uint4(0, 0, 0, 0);
   tc::fence_proxy_async_smem();
   tc::tc_fence_before();
@@ -136,7 +136,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
       const uint32_t a_term = (uint32_t)p.dop_term_bytes >> 4;
       uint32_t t = 0;
       for (int tile = rank; tile < p.n_tiles; tile += p.ranks, ++t) {
-        const uint32_t ob = t & 1u, oph = (t >> 1) & 1u;
+        const uint32_t ob = p.nbuf == 2 ? (t & 1u) : 0u, oph = p.nbuf == 2 ? ((t >> 1) & 1u) : (t & 1u);
         tc::mbar_wait_soft(&sh.op_full[ob], oph, p.err, 402, &sh.abort);
         tc::tc_fence_after();
         uint32_t d_col = 0;
@@ -204,7 +204,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
     for (int tile = rank; tile < p.n_tiles; tile += p.ranks, ++t) {
       const int bt = tile / p.row_tiles, rt = tile - bt * p.row_tiles;
       const int b0 = bt * p.TB, h0 = rt * p.TH;
-      const uint32_t ob = t & 1u, oph = (t >> 1) & 1u;
+      const uint32_t ob = p.nbuf == 2 ? (t & 1u) : 0u, oph = p.nbuf == 2 ? ((t >> 1) & 1u) : (t & 1u);
       if (!tc::mbar_wait(&sh.op_empty[ob], oph ^ 1, p.err, 404)) goto done;  // MMAs of the tile two back retired
       uint8_t* xop_b = xop + (size_t)ob * p.op_buf_bytes;
       uint8_t* dop_b = dop + (size_t)ob * p.op_buf_bytes;
@@ -382,8 +382,8 @@ static int plan(const mnb_conv_shape* s, int quant_mode, Params& p, int& smem_by
   // rows per tile: the largest that lets TWO operand buffers (converter and MMA overlap) plus a staging
   // ring of >= 3 slots fit in shared memory
   bool ok = false;
-  auto try_tile = [&](int TH, int TB) -> bool {
-    p.TH = TH; p.TB = TB;
+  auto try_tile = [&](int TH, int TB, int nbuf) -> bool {
+    p.TH = TH; p.TB = TB; p.nbuf = nbuf;
     p.THH = p.TH + 2 * p.pad;
     p.npos_d = ((p.pad > 0 ? p.TH * p.BW : p.TB * p.TH * p.W) + 15) / 16 * 16;
     if (p.npos_d > 128) return false;
@@ -401,24 +401,32 @@ static int plan(const mnb_conv_shape* s, int quant_mode, Params& p, int& smem_by
     p.op_buf_bytes = (p.xop_bytes + 3 * p.dop_term_bytes + 1023) / 1024 * 1024;
     p.off_xop = 0;
     p.off_dop = p.xop_bytes;
-    p.off_stage = 2 * p.op_buf_bytes;
+    p.off_stage = p.nbuf * p.op_buf_bytes;
     p.nst = MAXST;
     while (p.nst > 3 && p.off_stage + p.nst * p.slot_bytes > kMaxDynSmem) --p.nst;
     smem_bytes = p.off_stage + p.nst * p.slot_bytes;
     return smem_bytes <= kMaxDynSmem;
   };
-  // candidates: whole small images per tile first, then the row count with the fewest (and fullest) tiles
-  int best_th = 0, best_tb = 0, best_tiles = 1 << 30;
-  for (int TH = th_max; TH >= 1; --TH) {
-    const int tb_max = (p.pad == 0 && TH == p.H) ? std::max(1, std::min(p.B, 128 / (p.H * p.W))) : 1;
-    for (int TB = tb_max; TB >= 1; TB >>= 1) {
-      if (!try_tile(TH, TB)) continue;
-      const int tiles = ((p.B + TB - 1) / TB) * ((p.H + TH - 1) / TH);
-      if (tiles <= best_tiles) { best_tiles = tiles; best_th = TH; best_tb = TB; }  // ties: smaller tile
-      break;
-    }
+  // 1x1 filters (no halo re-reads, few MMAs per tile): one 128-position operand set, converter and MMA
+  // alternate.  Filters with taps: two smaller operand sets so that the (tap-heavy) MMAs overlap the converter.
+  if (p.pad == 0) {
+    const int TH = th_max;
+    const int tb = (TH == p.H) ? std::max(1, std::min(p.B, 128 / (p.H * p.W))) : 1;
+    ok = try_tile(TH, tb, 1);
   }
-  ok = best_th > 0 && try_tile(best_th, best_tb);
+  if (!ok) {
+    int best_th = 0, best_tb = 0, best_tiles = 1 << 30;
+    for (int TH = th_max; TH >= 1; --TH) {
+      const int tb_max = (p.pad == 0 && TH == p.H) ? std::max(1, std::min(p.B, 128 / (p.H * p.W))) : 1;
+      for (int TB = tb_max; TB >= 1; TB >>= 1) {
+        if (!try_tile(TH, TB, 2)) continue;
+        const int tiles = ((p.B + TB - 1) / TB) * ((p.H + TH - 1) / TH);
+        if (tiles <= best_tiles) { best_tiles = tiles; best_th = TH; best_tb = TB; }  // ties: smaller tile
+        break;
+      }
+    }
+    ok = best_th > 0 && try_tile(best_th, best_tb, 2);
+  }
   if (!ok) return unsupported("shared memory budget");
   p.row_tiles = (p.H + p.TH - 1) / p.TH;
   p.n_tiles = ((p.B + p.TB - 1) / p.TB) * p.row_tiles;
