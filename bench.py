@@ -50,7 +50,11 @@ class ClockSampler:
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, gpu_index=0):
-        self.rows, self.proc, self.gpu = [], None, gpu_index
+        self.rows, self.proc, self.gpu, self.first = [], None, gpu_index, 0
+
+    def mark(self):
+        """samples before this point (warm-up) are not reported"""
+        self.first = len(self.rows)
 
     def start(self):
         try:
@@ -74,7 +78,8 @@ class ClockSampler:
         except subprocess.TimeoutExpired:
             self.proc.kill()
         sm, mx, reasons = [], [], set()
-        for r in self.rows:
+        rows = self.rows[self.first:] or self.rows[-1:]
+        for r in rows:
             if len(r) < 9:
                 continue
             try:
@@ -224,11 +229,12 @@ def main():
         loss = stepper.step(x, t)
         loss_host.copy_(loss.detach(), non_blocking=False)  # D2H read of the step's result
 
-    for i in range(args.warmup):
-        step_resident(i)
     sampler = ClockSampler(local)
     if rank == 0:
-        sampler.start()
+        sampler.start()  # started before the warm-up so that nvidia-smi is already streaming in the timed region
+    for i in range(args.warmup):
+        step_resident(i)
+    sampler.mark()
     launches0 = L.launch_count()
     F_.TIMER = F_.KernelTimer()
     ms_total = timed(step_resident, args.steps)
