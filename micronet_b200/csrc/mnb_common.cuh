@@ -73,12 +73,13 @@ struct MnbSum { template <typename T> __device__ T operator()(T a, T b) const { 
 struct MnbActQ {
   int mode, qmin, qmax;
   float s, zp, lo, hi;
+  float rinv;  // fl(1 / s): reciprocal used by the certified fast path below
 };
 
 __device__ __forceinline__ MnbActQ mnb_load_actq(const mnb_act_qparams& p) {
   MnbActQ q;
   q.mode = p.mode; q.qmin = p.qmin; q.qmax = p.qmax;
-  q.s = 1.f; q.zp = 0.f; q.lo = 0.f; q.hi = 0.f;
+  q.s = 1.f; q.zp = 0.f; q.lo = 0.f; q.hi = 0.f; q.rinv = 1.f;
   if (p.mode == MNB_ACT_DOREFA) {
     q.s = (float)(1.0 / (double)((1 << p.bits) - 1));  // Python: 1 / float(2**a - 1), cast to fp32 by ATen
   } else if (p.mode == MNB_ACT_IAO) {
@@ -89,6 +90,7 @@ __device__ __forceinline__ MnbActQ mnb_load_actq(const mnb_act_qparams& p) {
     if (p.q_type == 0) { q.hi = fmaxf(fabsf(a), fabsf(b)); q.lo = -q.hi; }
     else { q.lo = a; q.hi = b; }
   }
+  q.rinv = __fdiv_rn(1.f, q.s);
   return q;
 }
 
@@ -112,6 +114,44 @@ __device__ __forceinline__ int mnb_act_quantize_one(const MnbActQ& q, float x, b
     bool pos = !(x < 0.f);
     pass = !(x >= 1.0f) && !(x <= -1.0f);
     xq = pos ? 1.f : -1.f;
+    return pos ? 2 : 0;
+  }
+}
+
+// Same level code and STE mask as mnb_act_quantize_one, without the IEEE division in the common case.
+// v' = x * fl(1/s) differs from the reference's fl(x / s) by at most ~3 ulp; the rounded level (and the
+// range comparisons) can only differ when v' lies within `delta` of a decision boundary, and exactly those
+// elements (about 1e-4 of them) take the exact path.  The result is therefore bit-identical.
+__device__ __forceinline__ int mnb_act_code_certified(const MnbActQ& q, float x, bool& pass) {
+  if (q.mode == MNB_ACT_DOREFA) {
+    const float t = __fmul_rn(x, 0.1f);
+    pass = (t >= 0.f) && (t <= 1.f);
+    const float c = fminf(fmaxf(t, 0.f), 1.f);
+    const float pa = c * q.rinv;
+    const float f = pa + 0.5f;
+    float r = floorf(f);
+    const float d = f - r, delta = 4e-7f * (pa + 1.f);
+    if (d < delta || d > 1.f - delta) r = floorf(__fadd_rn(__fdiv_rn(c, q.s), 0.5f));
+    return (int)r;
+  } else if (q.mode == MNB_ACT_IAO) {
+    const float xa = x * q.rinv;
+    float v = xa - q.zp;
+    const float av = fabsf(v);
+    const float f = av + 0.5f;
+    float ra = floorf(f);
+    const float d = f - ra, delta = 4e-7f * (fabsf(xa) + fabsf(q.zp) + 1.f);
+    const bool near_edge = fabsf(v - q.hi) < delta || fabsf(v - q.lo) < delta;
+    if (d < delta || d > 1.f - delta || near_edge || av < delta) {
+      v = __fsub_rn(__fdiv_rn(x, q.s), q.zp);
+      ra = floorf(__fadd_rn(fabsf(v), 0.5f));
+    }
+    const float r = v > 0.f ? ra : (v < 0.f ? -ra : 0.f);
+    const float cl = fminf(fmaxf(r, (float)q.qmin), (float)q.qmax);
+    pass = !(v > q.hi) && !(v < q.lo) && (r >= (float)q.qmin) && (r <= (float)q.qmax);
+    return (int)cl - q.qmin;
+  } else {
+    const bool pos = !(x < 0.f);
+    pass = !(x >= 1.0f) && !(x <= -1.0f);
     return pos ? 2 : 0;
   }
 }

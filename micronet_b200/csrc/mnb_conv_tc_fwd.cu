@@ -444,8 +444,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const Params p) {
               const bool leader0 = owned && (__ffs(peers0) - 1) == lane;
 #pragma unroll
               for (int j = 0; j < 8; ++j) {
-                bool pass; float xq;
-                const int code = mnb_act_quantize_one(q, __uint_as_float(u[j]), pass, xq);
+                bool pass;
+                const int code = mnb_act_code_certified(q, __uint_as_float(u[j]), pass);
                 e[j] = inside ? (float)(code + a_off) : 0.f;
                 const int64_t fi = fi0 + (int64_t)j * plane;
                 if (p.codes && owned) p.codes[fi] = (uint8_t)code;

@@ -239,8 +239,8 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
               float e[8];
 #pragma unroll
               for (int j = 0; j < 8; ++j) {
-                bool pass; float xq;
-                const int code = mnb_act_quantize_one(q, __uint_as_float(u[j]), pass, xq);
+                bool pass;
+                const int code = mnb_act_code_certified(q, __uint_as_float(u[j]), pass);
                 e[j] = inside ? (float)(code + a_off) : 0.f;
               }
               v = make_uint4(pack_bf16x2(e[0], e[1]), pack_bf16x2(e[2], e[3]), pack_bf16x2(e[4], e[5]), pack_bf16x2(e[6], e[7]));

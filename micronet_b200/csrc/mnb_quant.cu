@@ -48,8 +48,12 @@ __global__ void __launch_bounds__(256) act_quant_fwd_kernel(const float* __restr
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       int64_t i = base + lane + 32 * j;
-      bool pass; float o;
-      int c = mnb_act_quantize_one(q, v[j], pass, o);
+      bool pass;
+      const int c = mnb_act_code_certified(q, v[j], pass);  // bit-identical to mnb_act_quantize_one
+      float o;
+      if (q.mode == MNB_ACT_DOREFA) o = __fmul_rn((float)c, q.s);
+      else if (q.mode == MNB_ACT_IAO) o = __fmul_rn(__fadd_rn((float)(c + q.qmin), q.zp), q.s);
+      else o = c ? 1.f : -1.f;
       bool live = i < n;
       uint32_t word = __ballot_sync(0xffffffffu, live && pass);
       if (live) {

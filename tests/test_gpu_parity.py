@@ -377,3 +377,49 @@ def test_flat_adam_matches_torch_adam():
                 o.step()
             for p, q in zip(net.parameters(), ref.parameters()):
                 assert rel_err(p.detach(), q.detach()) <= 2e-6, (wd, step)
+
+
+@pytest.mark.parametrize("mode", ["dorefa2", "dorefa4", "dorefa8", "iao_sym", "iao_asym", "iao_sym4"])
+def test_certified_fast_quantizer_is_bit_exact_on_adversarial_inputs(mode):
+    """the division-free fast path of the activation quantizer must agree with the reference bit for bit,
+    in particular on values sitting exactly on / one ulp around every rounding boundary k + 0.5."""
+    from micronet_b200 import _lib as L, functional as F_
+    from oracle import reference_port as O
+    g = torch.Generator().manual_seed(123)
+    if mode.startswith("dorefa"):
+        bits = int(mode[6:])
+        n = 2 ** bits - 1
+        s = torch.tensor(1 / float(n), dtype=torch.float32)
+        k = torch.arange(0, n + 1, dtype=torch.float32)
+        edge = (k + 0.5) * s * 10.0                               # x with clamp(0.1 x)/s == k + 0.5 (about)
+        spec = F_.ActSpec(L.ACT_DOREFA, bits=bits)
+        ref = lambda t: O.dorefa_activation_levels(t, bits)
+        off = 0
+    else:
+        sym = mode != "iao_asym"
+        b = 4 if mode.endswith("4") else 8
+        qmin, qmax = ((-(1 << (b - 1)), (1 << (b - 1)) - 1) if sym else (0, (1 << b) - 1))
+        mn, mx = torch.tensor([-3.7]), torch.tensor([5.3])
+        if sym:
+            sc = torch.max(mn.abs(), mx.abs()) / ((qmax - qmin) / 2); zp = torch.zeros(1)
+        else:
+            sc = (mx - mn) / float(qmax - qmin); zp = torch.sign(mn) * torch.floor((mn / sc).abs() + 0.5)
+        k = torch.arange(qmin - 3, qmax + 4, dtype=torch.float32)
+        edge = (k + 0.5 + zp) * sc
+        bufs = {kk: v.to(DEV) for kk, v in dict(scale=sc, zero_point=zp, obs_min=mn, obs_max=mx).items()}
+        spec = F_.ActSpec(L.ACT_IAO, qmin=qmin, qmax=qmax, q_type=0 if sym else 1, **bufs)
+        ref = lambda t: torch.clamp(O.round_half_away(t / sc - zp), qmin, qmax)
+        off = qmin
+    # every boundary, +-8 ulps around it, plus dense random data
+    steps = torch.arange(-8, 9, dtype=torch.int32)
+    pts = []
+    for e in edge.tolist():
+        base = torch.tensor([e], dtype=torch.float32)
+        bits_i = base.view(torch.int32) + steps
+        pts.append(bits_i.view(torch.float32))
+    x = torch.cat(pts + [torch.randn(1 << 20, generator=g) * 6, torch.zeros(3)])
+    x = x[torch.isfinite(x)]
+    codes, _, _ = F_.act_quant_raw(x.to(DEV), spec, True, False, False)
+    got = codes.cpu().float() + off
+    want = ref(x)
+    assert torch.equal(got, want), f"{(got != want).sum().item()} level mismatches"
