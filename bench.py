@@ -191,7 +191,8 @@ def main():
     from micronet_b200 import _lib as L, functional as F_
 
     w = H.WORKLOADS[WORKLOAD]
-    model = H.prepare_engine(H.build_float_model(w["model"]), w["scheme"], **w["prepare"]).to(dev)
+    model = H.prepare_engine(H.build_float_model(w["model"]), w["scheme"], **w["prepare"],
+                             **w.get("engine_extra", {})).to(dev)
     stepper = H.QatStepper(model, lr=0.01, wd=w["wd"], flat=True)
     # distinct batches, pre-staged on the device for `value`, pinned on the host for `e2e`
     nbuf = 4

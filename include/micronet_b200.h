@@ -201,6 +201,18 @@ int mnb_conv2d_wgrad_tc(const mnb_conv_shape* s, const float* dy, const float* x
 int mnb_conv2d_wgrad_cond(const mnb_conv_shape* s, const float* dy, const mnb_conv_operands* op, float* dwq,
                           void* scratch, const int32_t* run_if_nonzero, mnb_stream_t stream);
 
+/* Fused BatchNorm2d + binarize (first producer fusion).  Replaces the block
+ * nn.BatchNorm2d -> ActivationQuantizer(A=2) of a wbwtab-prepared model (nin_gc.py:53-59 + WB:79-94):
+ *   fwd : y = sign(gamma (x - mean) invstd + beta), 0 -> +1; pass bit = |bn| < 1 (saturate STE)
+ *   bwd : training-mode batch-norm backward of the masked gradient (dgamma, dbeta, dx); `training` = 0
+ *         uses fixed statistics (dx = gamma invstd g pass).
+ * mean / invstd come from mnb_channel_stats(as_mean_var = 2: mean, biased var, unbiased var).      */
+int mnb_bn_sign_fwd(const float* x, int32_t batch, int32_t channels, int32_t hw, const float* mean, const float* invstd,
+                    const float* gamma, const float* beta, float* y, uint32_t* pass_bits, mnb_stream_t stream);
+int mnb_bn_sign_bwd(const float* g, const uint32_t* pass_bits, const float* x, int32_t batch, int32_t channels, int32_t hw,
+                    const float* mean, const float* invstd, const float* gamma, int32_t training, float* dx,
+                    float* dgamma, float* dbeta, void* scratch, mnb_stream_t stream);
+
 /* Optimizer step of the QAT loop (torch.optim.Adam semantics, L2 weight decay, no amsgrad;
  * wbwtab/main.py:84,331-339) over one flat fp32 parameter / gradient bucket: a single launch. */
 int mnb_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n, float lr,

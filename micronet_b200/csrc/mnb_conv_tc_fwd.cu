@@ -438,8 +438,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const Params p) {
               // the 8 channels of an entry sit at the same pixel: when H*W is a multiple of 32 they share
               // the bit position and the lane grouping, so one match_any serves all eight
               const bool shared_group = (plane & 31) == 0;
+              // un-padded tiles whose per-image part is a multiple of 32 pixels: the warp's 32 positions are
+              // exactly one aligned mask word -> plain ballot + store, no atomics
+              const bool whole_word = shared_group && p.pad == 0 && ((p.TH * p.W) & 31) == 0 &&
+                                      __all_sync(0xffffffffu, owned);  // (warp-uniform)
               uint32_t peers0 = 0;
-              if (p.pass_bits && shared_group)
+              if (p.pass_bits && shared_group && !whole_word)
                 peers0 = __match_any_sync(0xffffffffu, owned ? (uint32_t)(fi0 >> 5) : 0xffffffffu);
               const bool leader0 = owned && (__ffs(peers0) - 1) == lane;
 #pragma unroll
@@ -451,7 +455,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const Params p) {
                 if (p.codes && owned) p.codes[fi] = (uint8_t)code;
                 if (p.pass_bits) {
                   const uint32_t mine = (owned && pass) ? (1u << (fi & 31)) : 0u;
-                  if (shared_group) {
+                  if (whole_word) {
+                    const uint32_t wordv = __ballot_sync(0xffffffffu, mine != 0u);
+                    if (lane == 0) p.pass_bits[fi >> 5] = wordv;
+                  } else if (shared_group) {
                     const uint32_t val = __reduce_or_sync(peers0, mine);
                     if (leader0 && val) atomicOr(p.pass_bits + (fi >> 5), val);
                   } else {
