@@ -201,17 +201,36 @@ int mnb_conv2d_wgrad_tc(const mnb_conv_shape* s, const float* dy, const float* x
 int mnb_conv2d_wgrad_cond(const mnb_conv_shape* s, const float* dy, const mnb_conv_operands* op, float* dwq,
                           void* scratch, const int32_t* run_if_nonzero, mnb_stream_t stream);
 
-/* Fused BatchNorm2d + binarize (first producer fusion).  Replaces the block
- * nn.BatchNorm2d -> ActivationQuantizer(A=2) of a wbwtab-prepared model (nin_gc.py:53-59 + WB:79-94):
+/* Producer-side fusions of a wbwtab block:
+ *   conv -> nn.BatchNorm2d -> ActivationQuantizer(A=2) [-> nn.MaxPool2d] -> channel_shuffle -> next conv
+ * (nin_gc.py:9-21 shuffle, :53-59 block, WB:79-94 binarizer).
+ *
+ * mnb_bn_sign_fwd / _bwd replace BatchNorm2d + binarizer:
  *   fwd : y = sign(gamma (x - mean) invstd + beta), 0 -> +1; pass bit = |bn| < 1 (saturate STE)
  *   bwd : training-mode batch-norm backward of the masked gradient (dgamma, dbeta, dx); `training` = 0
- *         uses fixed statistics (dx = gamma invstd g pass).
- * mean / invstd come from mnb_channel_stats(as_mean_var = 2: mean, biased var, unbiased var).      */
+ *         uses fixed statistics (dx = gamma invstd g pass).  dx_channel_sum (may be NULL) receives
+ *         sum_{b,h,w} dx per channel: the bias gradient of the convolution that produced x.
+ * mean / invstd come from mnb_channel_stats(as_mean_var = 2: mean, biased var, unbiased var).
+ *
+ * out_shuffle_groups = sg > 1 folds the NEXT block's channel shuffle into the producer: the output is
+ * written as out[:, a*sg + b] = result[:, b*(C/sg) + a] and the incoming gradient is read through the same
+ * permutation; pass bits / argmax stay in the producer's own channel order.  sg = 1: no permutation.   */
 int mnb_bn_sign_fwd(const float* x, int32_t batch, int32_t channels, int32_t hw, const float* mean, const float* invstd,
-                    const float* gamma, const float* beta, float* y, uint32_t* pass_bits, mnb_stream_t stream);
+                    const float* gamma, const float* beta, int32_t out_shuffle_groups, float* y, uint32_t* pass_bits,
+                    mnb_stream_t stream);
 int mnb_bn_sign_bwd(const float* g, const uint32_t* pass_bits, const float* x, int32_t batch, int32_t channels, int32_t hw,
-                    const float* mean, const float* invstd, const float* gamma, int32_t training, float* dx,
-                    float* dgamma, float* dbeta, void* scratch, mnb_stream_t stream);
+                    const float* mean, const float* invstd, const float* gamma, int32_t training,
+                    int32_t out_shuffle_groups, float* dx, float* dgamma, float* dbeta, float* dx_channel_sum,
+                    void* scratch, mnb_stream_t stream);
+
+/* nn.MaxPool2d (square kernel <= 15, dilation 1, floor mode; nin_gc.py:85,89 / nin.py pools) with a one-byte
+ * window index per output instead of int64 indices.  Same first-maximum tie rule and gradient accumulation
+ * order as ATen, so results are bit-identical.  argmax: batch*channels*OH*OW bytes.                   */
+int mnb_maxpool2d_fwd(const float* x, int32_t batch, int32_t channels, int32_t H, int32_t W, int32_t kernel, int32_t stride,
+                      int32_t pad, int32_t out_shuffle_groups, float* y, uint8_t* argmax, mnb_stream_t stream);
+int mnb_maxpool2d_bwd(const float* g, const uint8_t* argmax, int32_t batch, int32_t channels, int32_t H, int32_t W,
+                      int32_t kernel, int32_t stride, int32_t pad, int32_t out_shuffle_groups, float* dx,
+                      mnb_stream_t stream);
 
 /* Optimizer step of the QAT loop (torch.optim.Adam semantics, L2 weight decay, no amsgrad;
  * wbwtab/main.py:84,331-339) over one flat fp32 parameter / gradient bucket: a single launch. */

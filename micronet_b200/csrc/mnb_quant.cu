@@ -618,7 +618,7 @@ extern "C" int mnb_iao_weight_bwd(const float* g_wq, const uint8_t* pass, const 
 // grid (channels, splits): fp64 partial sums, last split-block of a channel finalises.
 constexpr int STATS_SPLITS = 32;
 
-__global__ void __launch_bounds__(128) channel_stats_kernel(const float* __restrict__ x, int batch, int channels,
+__global__ void __launch_bounds__(256) channel_stats_kernel(const float* __restrict__ x, int batch, int channels,
                                                             int hw, int as_mean_var, float* __restrict__ stats,
                                                             uint32_t* counters, double* partial) {
   __shared__ double red[32];
@@ -626,28 +626,39 @@ __global__ void __launch_bounds__(128) channel_stats_kernel(const float* __restr
   const int c = blockIdx.x, sp = blockIdx.y, nsp = gridDim.y;
   const int64_t per = (int64_t)batch * hw;
   double s1 = 0.0, s2 = 0.0;
-  // images [b_lo, b_hi) of this split; within an image the channel plane is contiguous: no per-element
-  // index division, float4 loads when the plane allows it, fp32 partials per image row folded into fp64
+  // images [b_lo, b_hi) of this split.  The (image, offset) pairs of the split are walked as one flat index
+  // space so that small planes (8x8) still keep every thread loading; fp32 partials per thread, fp64 across.
   const int b_lo = (int)((int64_t)batch * sp / nsp), b_hi = (int)((int64_t)batch * (sp + 1) / nsp);
   const bool vec = (hw & 3) == 0 && ((reinterpret_cast<uintptr_t>(x) & 15) == 0);
-  for (int b = b_lo; b < b_hi; ++b) {
-    const float* plane = x + ((int64_t)b * channels + c) * hw;
-    float f1 = 0.f, f2 = 0.f;
-    if (vec) {
-      const float4* p4 = reinterpret_cast<const float4*>(plane);
-      for (int i = threadIdx.x; i < (hw >> 2); i += blockDim.x) {
-        const float4 v = __ldg(p4 + i);
-        f1 += (v.x + v.y) + (v.z + v.w);
-        f2 += (v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w);
+  if (vec) {
+    const uint32_t hw4 = (uint32_t)hw >> 2, total = (uint32_t)(b_hi - b_lo) * hw4;
+    const float4* base = reinterpret_cast<const float4*>(x);
+    float f1[4] = {0.f, 0.f, 0.f, 0.f}, f2[4] = {0.f, 0.f, 0.f, 0.f};
+    for (uint32_t t0 = threadIdx.x; t0 < total; t0 += 4 * blockDim.x) {
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const uint32_t t = t0 + u * blockDim.x;
+        if (t < total) {
+          const uint32_t b = t / hw4, i = t - b * hw4;
+          const float4 v = __ldg(base + ((int64_t)(b_lo + b) * channels + c) * hw4 + i);
+          f1[u] += (v.x + v.y) + (v.z + v.w);
+          f2[u] += (v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w);
+        }
       }
-    } else {
+    }
+    s1 = ((double)f1[0] + (double)f1[1]) + ((double)f1[2] + (double)f1[3]);
+    s2 = ((double)f2[0] + (double)f2[1]) + ((double)f2[2] + (double)f2[3]);
+  } else {
+    for (int b = b_lo; b < b_hi; ++b) {
+      const float* plane = x + ((int64_t)b * channels + c) * hw;
+      float f1 = 0.f, f2 = 0.f;
       for (int i = threadIdx.x; i < hw; i += blockDim.x) {
         const float v = __ldg(plane + i);
         f1 += v; f2 += v * v;
       }
+      s1 += (double)f1;
+      s2 += (double)f2;
     }
-    s1 += (double)f1;
-    s2 += (double)f2;
   }
   s1 = mnb_block_reduce(s1, MnbSum(), 0.0, red);
   s2 = mnb_block_reduce(s2, MnbSum(), 0.0, red);
@@ -706,7 +717,7 @@ extern "C" int mnb_channel_stats(const float* x, int32_t batch, int32_t channels
   int splits = (int)std::max<int64_t>(1, std::min<int64_t>(std::min<int64_t>(STATS_SPLITS, batch), per / 2048));
   uint32_t* counters = reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(scratch) + 16384);
   double* partial = reinterpret_cast<double*>(reinterpret_cast<char*>(scratch) + 49152);
-  channel_stats_kernel<<<dim3(channels, splits), 128, 0, S(stream)>>>(x, batch, channels, hw, as_mean_var, stats,
+  channel_stats_kernel<<<dim3(channels, splits), 256, 0, S(stream)>>>(x, batch, channels, hw, as_mean_var, stats,
                                                                        counters, partial);
   MNB_LAUNCHED(1);
   return 0;
@@ -755,241 +766,5 @@ extern "C" int mnb_adam_step(float* p, const float* g, float* m, float* v, int64
   int blocks = (int)std::min<int64_t>(mnb_ceil_div(n, 256), MNB_NUM_SMS * 8);
   adam_step_kernel<<<blocks, 256, 0, S(stream)>>>(p, g, m, v, n, lr, beta1, beta2, eps, weight_decay, bc1, sqrt_bc2);
   MNB_LAUNCHED(1);
-  return 0;
-}
-
-// ------------------------------------------------------------------ fused BatchNorm(train) + binarize  
-// y = sign(gamma * (x - mean) * invstd + beta) with 0 -> +1, saturate-STE mask |bn| < 1 (WB:11-36 applied to
-// the output of nn.BatchNorm2d): the block "bn -> ActivationQuantizer(A=2)" of a wbwtab-prepared model in one pass.
-__global__ void __launch_bounds__(256) bn_sign_fwd_kernel(const float* __restrict__ x, int64_t n, int channels, int hw,
-                                                          const float* __restrict__ mean, const float* __restrict__ invstd,
-                                                          const float* __restrict__ gamma, const float* __restrict__ beta,
-                                                          float* __restrict__ y, uint32_t* __restrict__ bits) {
-  const int lane = threadIdx.x & 31;
-  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-  for (int64_t base = warp * 128; base < n; base += nwarps * 128) {
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int64_t i = base + lane + 32 * j;
-      const bool live = i < n;
-      float o = 1.f; bool pass = false;
-      if (live) {
-        const int c = (int)((i / hw) % channels);
-        const float sc = __ldg(gamma + c) * __ldg(invstd + c);
-        const float bn = fmaf(__ldg(x + i) - __ldg(mean + c), sc, __ldg(beta + c));
-        o = bn < 0.f ? -1.f : 1.f;
-        pass = !(bn >= 1.0f) && !(bn <= -1.0f);
-        y[i] = o;
-      }
-      const uint32_t word = __ballot_sync(0xffffffffu, live && pass);
-      if (bits && lane == 0 && (base + 32 * j) < n) bits[(base >> 5) + j] = word;
-    }
-  }
-}
-
-// per-channel sums of the masked gradient: dbeta = sum g*pass, dgamma = sum g*pass*xhat
-__global__ void __launch_bounds__(128) bn_sign_bwd_reduce_kernel(const float* __restrict__ g, const uint32_t* __restrict__ bits,
-                                                                 const float* __restrict__ x, int batch, int channels, int hw,
-                                                                 const float* __restrict__ mean, const float* __restrict__ invstd,
-                                                                 float* __restrict__ dgamma, float* __restrict__ dbeta,
-                                                                 uint32_t* counters, double* partial) {
-  __shared__ double red[32];
-  __shared__ bool last;
-  const int c = blockIdx.x, sp = blockIdx.y, nsp = gridDim.y;
-  const float mu = __ldg(mean + c), is = __ldg(invstd + c);
-  double s1 = 0.0, s2 = 0.0;
-  const int b_lo = (int)((int64_t)batch * sp / nsp), b_hi = (int)((int64_t)batch * (sp + 1) / nsp);
-  for (int b = b_lo; b < b_hi; ++b) {
-    const int64_t off = ((int64_t)b * channels + c) * hw;
-    float f1 = 0.f, f2 = 0.f;
-    for (int i = threadIdx.x; i < hw; i += blockDim.x) {
-      const int64_t fi = off + i;
-      const bool pass = (__ldg(bits + (fi >> 5)) >> (fi & 31)) & 1u;
-      const float gv = pass ? __ldg(g + fi) : 0.f;
-      f1 += gv;
-      f2 += gv * ((__ldg(x + fi) - mu) * is);
-    }
-    s1 += (double)f1; s2 += (double)f2;
-  }
-  s1 = mnb_block_reduce(s1, MnbSum(), 0.0, red);
-  s2 = mnb_block_reduce(s2, MnbSum(), 0.0, red);
-  if (threadIdx.x == 0) {
-    partial[((int64_t)c * nsp + sp) * 2 + 0] = s1;
-    partial[((int64_t)c * nsp + sp) * 2 + 1] = s2;
-    __threadfence();
-    last = (atomicAdd(counters + c, 1u) == (uint32_t)nsp - 1);
-  }
-  __syncthreads();
-  if (!last || threadIdx.x != 0) return;
-  __threadfence();
-  s1 = 0.0; s2 = 0.0;
-  for (int j = 0; j < nsp; ++j) { s1 += partial[((int64_t)c * nsp + j) * 2]; s2 += partial[((int64_t)c * nsp + j) * 2 + 1]; }
-  dbeta[c] = (float)s1;
-  dgamma[c] = (float)s2;
-  counters[c] = 0;
-}
-
-// dx = gamma * invstd * (g*pass - dbeta/N - xhat * dgamma/N)   (training-mode batch-norm backward)
-__global__ void __launch_bounds__(256) bn_sign_bwd_apply_kernel(const float* __restrict__ g, const uint32_t* __restrict__ bits,
-                                                                const float* __restrict__ x, int64_t n, int channels, int hw,
-                                                                float inv_count, const float* __restrict__ mean,
-                                                                const float* __restrict__ invstd, const float* __restrict__ gamma,
-                                                                const float* __restrict__ dgamma, const float* __restrict__ dbeta,
-                                                                int training, float* __restrict__ dx) {
-  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  for (; i < n; i += stride) {
-    const int c = (int)((i / hw) % channels);
-    const bool pass = (__ldg(bits + (i >> 5)) >> (i & 31)) & 1u;
-    const float gv = pass ? __ldg(g + i) : 0.f;
-    const float is = __ldg(invstd + c), ga = __ldg(gamma + c);
-    float v = gv;
-    if (training) {
-      const float xh = (__ldg(x + i) - __ldg(mean + c)) * is;
-      v = gv - __ldg(dbeta + c) * inv_count - xh * (__ldg(dgamma + c) * inv_count);
-    }
-    dx[i] = ga * is * v;
-  }
-}
-
-
-// ---- float4 variants (hw % 4 == 0 and n < 2^31: every NIN / ResNet plane); the scalar kernels above are the fallback
-__global__ void __launch_bounds__(256) bn_sign_fwd_v4_kernel(const float4* __restrict__ x, uint32_t n4, uint32_t channels,
-                                                             uint32_t hw4, const float* __restrict__ mean,
-                                                             const float* __restrict__ invstd, const float* __restrict__ gamma,
-                                                             const float* __restrict__ beta, float4* __restrict__ y,
-                                                             uint32_t* __restrict__ bits) {
-  const uint32_t lane = threadIdx.x & 31;
-  const uint32_t stride = gridDim.x * blockDim.x;
-  const uint32_t n4_up = (n4 + 31u) & ~31u;  // warp-uniform trip count (shuffles below)
-  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n4_up; i += stride) {
-    uint32_t nib = 0;
-    if (i < n4) {
-      const uint32_t c = (i / hw4) % channels;
-      const float mu = __ldg(mean + c), sc = __ldg(gamma + c) * __ldg(invstd + c), be = __ldg(beta + c);
-      const float4 v = __ldg(x + i);
-      const float b0 = fmaf(v.x - mu, sc, be), b1 = fmaf(v.y - mu, sc, be), b2 = fmaf(v.z - mu, sc, be),
-                  b3 = fmaf(v.w - mu, sc, be);
-      y[i] = make_float4(b0 < 0.f ? -1.f : 1.f, b1 < 0.f ? -1.f : 1.f, b2 < 0.f ? -1.f : 1.f, b3 < 0.f ? -1.f : 1.f);
-      nib = (uint32_t)(fabsf(b0) < 1.f) | ((uint32_t)(fabsf(b1) < 1.f) << 1) | ((uint32_t)(fabsf(b2) < 1.f) << 2) |
-            ((uint32_t)(fabsf(b3) < 1.f) << 3);
-    }
-    uint32_t w = nib << (4 * (lane & 7));
-    w |= __shfl_xor_sync(0xffffffffu, w, 1);
-    w |= __shfl_xor_sync(0xffffffffu, w, 2);
-    w |= __shfl_xor_sync(0xffffffffu, w, 4);
-    if (bits && (lane & 7) == 0 && i < n4) bits[i >> 3] = w;
-  }
-}
-
-__global__ void __launch_bounds__(256) bn_sign_bwd_reduce_v4_kernel(const float4* __restrict__ g, const uint32_t* __restrict__ bits,
-                                                                    const float4* __restrict__ x, int batch, int channels,
-                                                                    uint32_t hw4, const float* __restrict__ mean,
-                                                                    const float* __restrict__ invstd, float* __restrict__ dgamma,
-                                                                    float* __restrict__ dbeta, uint32_t* counters,
-                                                                    double* partial) {
-  __shared__ double red[32];
-  __shared__ bool last;
-  const int c = blockIdx.x, sp = blockIdx.y, nsp = gridDim.y;
-  const float mu = __ldg(mean + c), is = __ldg(invstd + c);
-  const int b_lo = (int)((int64_t)batch * sp / nsp), b_hi = (int)((int64_t)batch * (sp + 1) / nsp);
-  const uint32_t total = (uint32_t)(b_hi - b_lo) * hw4;
-  float f1 = 0.f, f2 = 0.f;
-  for (uint32_t t = threadIdx.x; t < total; t += blockDim.x) {
-    const uint32_t b = t / hw4, i = t - b * hw4;
-    const uint32_t fi4 = ((uint32_t)(b_lo + b) * channels + c) * hw4 + i;
-    const uint32_t nib = (__ldg(bits + (fi4 >> 3)) >> (4 * (fi4 & 7))) & 15u;
-    const float4 gv = __ldg(g + fi4), xv = __ldg(x + fi4);
-    const float g0 = (nib & 1u) ? gv.x : 0.f, g1 = (nib & 2u) ? gv.y : 0.f, g2 = (nib & 4u) ? gv.z : 0.f,
-                g3 = (nib & 8u) ? gv.w : 0.f;
-    f1 += (g0 + g1) + (g2 + g3);
-    f2 += (g0 * ((xv.x - mu) * is) + g1 * ((xv.y - mu) * is)) + (g2 * ((xv.z - mu) * is) + g3 * ((xv.w - mu) * is));
-  }
-  double s1 = mnb_block_reduce((double)f1, MnbSum(), 0.0, red);
-  double s2 = mnb_block_reduce((double)f2, MnbSum(), 0.0, red);
-  if (threadIdx.x == 0) {
-    partial[((int64_t)c * nsp + sp) * 2 + 0] = s1;
-    partial[((int64_t)c * nsp + sp) * 2 + 1] = s2;
-    __threadfence();
-    last = (atomicAdd(counters + c, 1u) == (uint32_t)nsp - 1);
-  }
-  __syncthreads();
-  if (!last || threadIdx.x != 0) return;
-  __threadfence();
-  s1 = 0.0; s2 = 0.0;
-  for (int j = 0; j < nsp; ++j) { s1 += partial[((int64_t)c * nsp + j) * 2]; s2 += partial[((int64_t)c * nsp + j) * 2 + 1]; }
-  dbeta[c] = (float)s1;
-  dgamma[c] = (float)s2;
-  counters[c] = 0;
-}
-
-__global__ void __launch_bounds__(256) bn_sign_bwd_apply_v4_kernel(const float4* __restrict__ g, const uint32_t* __restrict__ bits,
-                                                                   const float4* __restrict__ x, uint32_t n4, uint32_t channels,
-                                                                   uint32_t hw4, float inv_count, const float* __restrict__ mean,
-                                                                   const float* __restrict__ invstd, const float* __restrict__ gamma,
-                                                                   const float* __restrict__ dgamma, const float* __restrict__ dbeta,
-                                                                   int training, float4* __restrict__ dx) {
-  const uint32_t stride = gridDim.x * blockDim.x;
-  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
-    const uint32_t c = (i / hw4) % channels;
-    const uint32_t nib = (__ldg(bits + (i >> 3)) >> (4 * (i & 7))) & 15u;
-    const float4 gv = __ldg(g + i);
-    float v0 = (nib & 1u) ? gv.x : 0.f, v1 = (nib & 2u) ? gv.y : 0.f, v2 = (nib & 4u) ? gv.z : 0.f,
-          v3 = (nib & 8u) ? gv.w : 0.f;
-    const float is = __ldg(invstd + c), k = __ldg(gamma + c) * is;
-    if (training) {
-      const float4 xv = __ldg(x + i);
-      const float mu = __ldg(mean + c), db = __ldg(dbeta + c) * inv_count, dg = __ldg(dgamma + c) * inv_count;
-      v0 = v0 - db - ((xv.x - mu) * is) * dg;
-      v1 = v1 - db - ((xv.y - mu) * is) * dg;
-      v2 = v2 - db - ((xv.z - mu) * is) * dg;
-      v3 = v3 - db - ((xv.w - mu) * is) * dg;
-    }
-    dx[i] = make_float4(k * v0, k * v1, k * v2, k * v3);
-  }
-}
-
-extern "C" int mnb_bn_sign_fwd(const float* x, int32_t batch, int32_t channels, int32_t hw, const float* mean,
-                               const float* invstd, const float* gamma, const float* beta, float* y,
-                               uint32_t* pass_bits, mnb_stream_t stream) {
-  MNB_REQUIRE(x && mean && invstd && gamma && beta && y && batch > 0 && channels > 0 && hw > 0, "bad bn_sign_fwd arguments");
-  const int64_t n = (int64_t)batch * channels * hw;
-  int blocks = (int)std::min<int64_t>(mnb_ceil_div(n, 256 * 4), MNB_NUM_SMS * 8);
-  if ((hw & 3) == 0 && n < (1ll << 31) && (((uintptr_t)x | (uintptr_t)y) & 15) == 0)
-    bn_sign_fwd_v4_kernel<<<blocks, 256, 0, S(stream)>>>(reinterpret_cast<const float4*>(x), (uint32_t)(n / 4),
-                                                         (uint32_t)channels, (uint32_t)(hw / 4), mean, invstd, gamma, beta,
-                                                         reinterpret_cast<float4*>(y), pass_bits);
-  else
-    bn_sign_fwd_kernel<<<blocks, 256, 0, S(stream)>>>(x, n, channels, hw, mean, invstd, gamma, beta, y, pass_bits);
-  MNB_LAUNCHED(1);
-  return 0;
-}
-
-extern "C" int mnb_bn_sign_bwd(const float* g, const uint32_t* pass_bits, const float* x, int32_t batch, int32_t channels,
-                               int32_t hw, const float* mean, const float* invstd, const float* gamma, int32_t training,
-                               float* dx, float* dgamma, float* dbeta, void* scratch, mnb_stream_t stream) {
-  MNB_REQUIRE(g && pass_bits && x && mean && invstd && gamma && dx && dgamma && dbeta && scratch, "NULL bn_sign_bwd pointer");
-  MNB_REQUIRE(batch > 0 && channels > 0 && channels <= 8192 && hw > 0, "bad bn_sign_bwd shape");
-  const int64_t n = (int64_t)batch * channels * hw;
-  const int64_t per = (int64_t)batch * hw;
-  int splits = (int)std::max<int64_t>(1, std::min<int64_t>(std::min<int64_t>(STATS_SPLITS, batch), per / 2048));
-  uint32_t* counters = reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(scratch) + 16384);
-  double* partial = reinterpret_cast<double*>(reinterpret_cast<char*>(scratch) + 49152);
-  int blocks = (int)std::min<int64_t>(mnb_ceil_div(n, 256 * 4), MNB_NUM_SMS * 8);
-  if ((hw & 3) == 0 && n < (1ll << 31) && (((uintptr_t)x | (uintptr_t)g | (uintptr_t)dx) & 15) == 0) {
-    bn_sign_bwd_reduce_v4_kernel<<<dim3(channels, splits), 256, 0, S(stream)>>>(
-        reinterpret_cast<const float4*>(g), pass_bits, reinterpret_cast<const float4*>(x), batch, channels, (uint32_t)(hw / 4),
-        mean, invstd, dgamma, dbeta, counters, partial);
-    bn_sign_bwd_apply_v4_kernel<<<blocks, 256, 0, S(stream)>>>(
-        reinterpret_cast<const float4*>(g), pass_bits, reinterpret_cast<const float4*>(x), (uint32_t)(n / 4), (uint32_t)channels,
-        (uint32_t)(hw / 4), 1.f / (float)per, mean, invstd, gamma, dgamma, dbeta, training, reinterpret_cast<float4*>(dx));
-  } else {
-    bn_sign_bwd_reduce_kernel<<<dim3(channels, splits), 128, 0, S(stream)>>>(g, pass_bits, x, batch, channels, hw, mean, invstd,
-                                                                              dgamma, dbeta, counters, partial);
-    bn_sign_bwd_apply_kernel<<<blocks, 256, 0, S(stream)>>>(g, pass_bits, x, n, channels, hw, 1.f / (float)per, mean, invstd,
-                                                            gamma, dgamma, dbeta, training, dx);
-  }
-  MNB_LAUNCHED(2);
   return 0;
 }

@@ -303,11 +303,13 @@ class QuantConv2dFn(Function):
     @staticmethod
     def backward(ctx, dy):
         lib = L.load()
+        # a fused BatchNorm+binarize consumer already reduced its dx (= this dy) over (B, H, W): fused.BNSignFn
+        presummed = getattr(dy, "_mnb_channel_sum", None)
         dy = dy.contiguous()
         sh, spec = ctx.sh, ctx.spec
         dx = dwq = db = None
         if ctx.has_bias and ctx.needs_input_grad[2]:
-            db = channel_sums(dy)
+            db = presummed if presummed is not None and presummed.numel() == dy.shape[1] else channel_sums(dy)
         if ctx.needs_input_grad[0]:
             dx = torch.empty((sh.batch, sh.in_c, sh.in_h, sh.in_w), dtype=torch.float32, device=dy.device)
             qp = spec.struct() if spec is not None else None

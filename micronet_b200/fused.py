@@ -1,13 +1,19 @@
-"""Producer-side fusion (first step): BatchNorm2d + binarizing ActivationQuantizer.
+"""Producer-side fusion for wbwtab-prepared models.
 
-A wbwtab-prepared block is ``conv -> bn -> ActivationQuantizer(A=2)`` (nin_gc.py:53-59 with the ReLU
-swapped by WB:319-322).  ``fuse_bn_binarize`` rewrites every such sibling pair into one
-``BatchNormBinarize2d`` (a ``nn.BatchNorm2d`` subclass: same parameters / buffers / state_dict keys) followed
-by ``nn.Identity``; semantics are unchanged: training-mode batch statistics, running-stat updates with the
-module's momentum, sign() with 0 -> +1 and the saturate STE |bn| < 1 in the backward pass."""
+A wbwtab block is ``[channel_shuffle ->] conv -> bn -> ActivationQuantizer(A=2)`` (nin_gc.py:36-59 with the
+ReLU swapped by WB:319-322), optionally followed by ``nn.MaxPool2d``.  ``fuse_wbwtab_blocks`` rewrites, in place:
+
+* every sibling pair (BatchNorm2d, ActivationQuantizer(A=2)) -> (``BatchNormBinarize2d``, Identity): batch
+  statistics, normalise + sign + STE mask in two kernels forward and two backward; the backward also hands the
+  producing convolution its bias gradient (channel sums of dx), saving that pass;
+* every plain ``nn.MaxPool2d`` -> ``EngineMaxPool2d`` (byte window index, bit-identical to ATen);
+* every block whose input shuffle (``channel_shuffle_flag`` / ``shuffle_groups`` attributes of the
+  reference's block class) directly follows one of those producers: the permutation moves into the producer's
+  output addressing and the shuffle copy disappears (max-pooling commutes with a channel permutation).
+
+Parameters, buffers, state_dict keys and the numbers are unchanged; only intermediate tensors between a
+producer and a shuffled block are stored in the shuffled channel order."""
 from __future__ import annotations
-
-import ctypes as C
 
 import torch
 import torch.nn as nn
@@ -28,7 +34,7 @@ def _channel_stats3(x):
 
 class BNSignFn(Function):
     @staticmethod
-    def forward(ctx, x, gamma, beta, mean, invstd, training):
+    def forward(ctx, x, gamma, beta, mean, invstd, training, shuffle_groups):
         lib = L.load()
         x = x.contiguous()
         b, c = x.shape[0], x.shape[1]
@@ -36,9 +42,10 @@ class BNSignFn(Function):
         y = torch.empty_like(x)
         bits = torch.empty((x.numel() + 31) // 32, dtype=torch.int32, device=x.device)
         L.check(lib.mnb_bn_sign_fwd(x.data_ptr(), b, c, hw, mean.data_ptr(), invstd.data_ptr(), gamma.data_ptr(),
-                                    beta.data_ptr(), y.data_ptr(), bits.data_ptr(), L.stream()), "bn_sign_fwd")
+                                    beta.data_ptr(), shuffle_groups, y.data_ptr(), bits.data_ptr(), L.stream()),
+                "bn_sign_fwd")
         ctx.save_for_backward(x, gamma, mean, invstd)
-        ctx.bits, ctx.training = bits, training
+        ctx.bits, ctx.training, ctx.shuffle_groups = bits, training, shuffle_groups
         return y
 
     @staticmethod
@@ -49,25 +56,28 @@ class BNSignFn(Function):
         b, c = x.shape[0], x.shape[1]
         hw = x.numel() // (b * c)
         dx = torch.empty_like(x)
-        dgamma = torch.empty_like(gamma)
-        dbeta = torch.empty_like(gamma)
+        out = torch.empty(3 * c, dtype=torch.float32, device=x.device)
+        dgamma, dbeta, dx_sum = out[:c], out[c:2 * c], out[2 * c:]
         L.check(lib.mnb_bn_sign_bwd(g.data_ptr(), ctx.bits.data_ptr(), x.data_ptr(), b, c, hw, mean.data_ptr(),
-                                    invstd.data_ptr(), gamma.data_ptr(), 1 if ctx.training else 0, dx.data_ptr(),
-                                    dgamma.data_ptr(), dbeta.data_ptr(), L.scratch(x.device, c).data_ptr(),
-                                    L.stream()), "bn_sign_bwd")
-        return dx, dgamma, dbeta, None, None, None
+                                    invstd.data_ptr(), gamma.data_ptr(), 1 if ctx.training else 0, ctx.shuffle_groups,
+                                    dx.data_ptr(), dgamma.data_ptr(), dbeta.data_ptr(), dx_sum.data_ptr(),
+                                    L.scratch(x.device, c).data_ptr(), L.stream()), "bn_sign_bwd")
+        # picked up by QuantConv2dFn.backward when this dx is its grad_output (saves its own channel-sum pass)
+        dx._mnb_channel_sum = dx_sum
+        return dx, dgamma, dbeta, None, None, None, None
 
 
 class BatchNormBinarize2d(nn.BatchNorm2d):
-    """nn.BatchNorm2d followed by wbwtab's binarizing ActivationQuantizer, as two kernels forward
-    (statistics, normalise+sign) and two backward (reductions, apply)."""
+    """nn.BatchNorm2d followed by wbwtab's binarizing ActivationQuantizer.  ``out_shuffle_groups`` > 1 writes
+    the result in the channel order ``shuffle_channels(., groups)`` would produce."""
+
+    out_shuffle_groups = 1
 
     def forward(self, input):
         L.require_cuda(input, self.weight)
         assert self.affine and self.track_running_stats and self.momentum is not None, \
             "BatchNormBinarize2d supports affine BN with running statistics and a float momentum"
-        use_batch = self.training
-        if use_batch:
+        if self.training:
             mean, var_b, var_u = _channel_stats3(input.detach().contiguous())
             with torch.no_grad():
                 m = self.momentum
@@ -78,11 +88,63 @@ class BatchNormBinarize2d(nn.BatchNorm2d):
         else:
             mean = self.running_mean
             invstd = torch.rsqrt(self.running_var + self.eps)
-        return BNSignFn.apply(input, self.weight, self.bias, mean.contiguous(), invstd.contiguous(), use_batch)
+        return BNSignFn.apply(input, self.weight, self.bias, mean.contiguous(), invstd.contiguous(), self.training,
+                              int(self.out_shuffle_groups))
+
+    def extra_repr(self):
+        return super().extra_repr() + f", out_shuffle_groups={self.out_shuffle_groups}"
 
 
-def fuse_bn_binarize(module: nn.Module) -> nn.Module:
-    """in place: every (BatchNorm2d, wbwtab.ActivationQuantizer(A=2)) sibling pair -> (BatchNormBinarize2d, Identity)"""
+class MaxPoolFn(Function):
+    @staticmethod
+    def forward(ctx, x, k, s, p, shuffle_groups):
+        lib = L.load()
+        x = x.contiguous()
+        b, c, h, w = x.shape
+        oh, ow = (h + 2 * p - k) // s + 1, (w + 2 * p - k) // s + 1
+        y = torch.empty((b, c, oh, ow), dtype=x.dtype, device=x.device)
+        arg = torch.empty(y.numel(), dtype=torch.uint8, device=x.device)
+        L.check(lib.mnb_maxpool2d_fwd(x.data_ptr(), b, c, h, w, k, s, p, shuffle_groups, y.data_ptr(), arg.data_ptr(),
+                                      L.stream()), "maxpool2d_fwd")
+        ctx.arg, ctx.cfg = arg, (b, c, h, w, k, s, p, shuffle_groups)
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        lib = L.load()
+        b, c, h, w, k, s, p, sg = ctx.cfg
+        g = g.contiguous()
+        dx = torch.empty((b, c, h, w), dtype=g.dtype, device=g.device)
+        L.check(lib.mnb_maxpool2d_bwd(g.data_ptr(), ctx.arg.data_ptr(), b, c, h, w, k, s, p, sg, dx.data_ptr(),
+                                      L.stream()), "maxpool2d_bwd")
+        return dx, None, None, None, None
+
+
+def _pool_cfg(m: nn.MaxPool2d):
+    """(k, s, p) if the engine kernel covers this pool (square, dilation 1, floor mode), else None"""
+    def one(v):
+        if isinstance(v, (tuple, list)):
+            return int(v[0]) if len(set(v)) == 1 else None
+        return int(v)
+    k, s, p, d = one(m.kernel_size), one(m.stride if m.stride is not None else m.kernel_size), one(m.padding), one(m.dilation)
+    if None in (k, s, p, d) or d != 1 or m.ceil_mode or m.return_indices or k > 15 or 2 * p > k:
+        return None
+    return k, s, p
+
+
+class EngineMaxPool2d(nn.MaxPool2d):
+    out_shuffle_groups = 1
+
+    def forward(self, input):
+        L.require_cuda(input)
+        k, s, p = _pool_cfg(self)
+        return MaxPoolFn.apply(input, k, s, p, int(self.out_shuffle_groups))
+
+    def extra_repr(self):
+        return super().extra_repr() + f", out_shuffle_groups={self.out_shuffle_groups}"
+
+
+def _fuse_pairs(module: nn.Module):
     from .wbwtab import ActivationQuantizer
     prev_name, prev = None, None
     for name, child in list(module.named_children()):
@@ -95,7 +157,48 @@ def fuse_bn_binarize(module: nn.Module) -> nn.Module:
             fused.train(prev.training)
             module._modules[prev_name] = fused
             module._modules[name] = nn.Identity()
+        elif type(child) is nn.MaxPool2d and _pool_cfg(child) is not None:
+            pool = EngineMaxPool2d(child.kernel_size, child.stride, child.padding, child.dilation,
+                                   child.return_indices, child.ceil_mode)
+            module._modules[name] = pool
         else:
-            fuse_bn_binarize(child)
+            _fuse_pairs(child)
         prev_name, prev = name, module._modules[name]
-    return module
+
+
+def _tail_producer(m: nn.Module):
+    """the module whose output IS ``m``'s output, if it is one of the shuffling producers"""
+    if isinstance(m, (BatchNormBinarize2d, EngineMaxPool2d)):
+        return m
+    if hasattr(m, "channel_shuffle_flag"):  # the reference's conv-bn-act block: children run in order
+        kids = [k for k in m.children() if not isinstance(k, nn.Identity)]
+        if kids and isinstance(kids[-1], BatchNormBinarize2d):
+            return kids[-1]
+    return None
+
+
+def _fold_shuffles(module: nn.Module):
+    for child in module.children():
+        _fold_shuffles(child)
+    if not isinstance(module, nn.Sequential):
+        return
+    kids = [k for k in module.children() if not isinstance(k, nn.Identity)]
+    for prev, blk in zip(kids, kids[1:]):
+        groups = int(getattr(blk, "shuffle_groups", 1))
+        if not getattr(blk, "channel_shuffle_flag", 0) or groups <= 1:
+            continue
+        prod = _tail_producer(prev)
+        if prod is None or prod.out_shuffle_groups != 1:
+            continue
+        prod.out_shuffle_groups = groups
+        blk.channel_shuffle_flag = 0
+
+
+def fuse_wbwtab_blocks(model: nn.Module, fold_shuffle: bool = True) -> nn.Module:
+    _fuse_pairs(model)
+    if fold_shuffle:
+        _fold_shuffles(model)
+    return model
+
+
+fuse_bn_binarize = fuse_wbwtab_blocks  # first name of this pass

@@ -94,13 +94,14 @@ def add_quant_op(module, layer_counter, layer_num, A=2, W=2, quant_inference=Fal
 
 
 def prepare(model, inplace=False, A=2, W=2, quant_inference=False, fuse_bn=False):
-    """``fuse_bn`` (extension, off by default): additionally merge every BatchNorm2d + binarizer pair
-    into one fused module (micronet_b200.fused); parameters, buffers and results are unchanged."""
+    """``fuse_bn`` (extension, off by default): additionally fuse BatchNorm2d + binarizer pairs, max-pools and
+    channel shuffles around the quantized convolutions (micronet_b200.fused); parameters, buffers, state_dict
+    keys and results are unchanged."""
     if not inplace:
         model = copy.deepcopy(model)
     layer_num = sum(isinstance(m, (nn.Conv2d, nn.ConvTranspose2d)) for m in model.modules())
     add_quant_op(model, [0], layer_num, A=A, W=W, quant_inference=quant_inference)
     if fuse_bn and A == 2:
-        from .fused import fuse_bn_binarize
-        fuse_bn_binarize(model)
+        from .fused import fuse_wbwtab_blocks
+        fuse_wbwtab_blocks(model)
     return model
