@@ -232,6 +232,20 @@ int mnb_maxpool2d_bwd(const float* g, const uint8_t* argmax, int32_t batch, int3
                       int32_t kernel, int32_t stride, int32_t pad, int32_t out_shuffle_groups, float* dx,
                       mnb_stream_t stream);
 
+/* fp32 convolution with few input channels on the tensor-core path: the un-quantized first layer of the QAT
+ * models (plain nn.Conv2d in the reference: nin_gc.py:82, nin.py:60, resnet.py first conv; WB:300-317 leaves it
+ * unquantized).  im2col operand built in shared memory, exact 3-piece bf16 split of both fp32 operands, the six
+ * leading piece products accumulated in fp32 (error <= 2^-23 relative, i.e. that of an fp32 convolution).
+ * Cover: groups 1, stride 1, dilation 1, 'same' odd square filter, C*R*S <= 128, Cout <= 256, 128 % W == 0,
+ * (H*W) % 128 == 0; anything else returns MNB_E_UNSUPPORTED (-2).
+ *   fwd   : y = conv2d(x, w) + bias (bias may be NULL)
+ *   wgrad : dw = corr(x, dy);  scratch >= mnb_fconv2d_wgrad_tc_scratch_bytes(s) (-1: unsupported)        */
+int mnb_fconv2d_fwd_tc(const mnb_conv_shape* s, const float* x, const float* w, const float* bias, float* y,
+                       int32_t* err_flag, mnb_stream_t stream);
+int64_t mnb_fconv2d_wgrad_tc_scratch_bytes(const mnb_conv_shape* s);
+int mnb_fconv2d_wgrad_tc(const mnb_conv_shape* s, const float* dy, const float* x, float* dw, void* scratch,
+                         int32_t* err_flag, mnb_stream_t stream);
+
 /* Optimizer step of the QAT loop (torch.optim.Adam semantics, L2 weight decay, no amsgrad;
  * wbwtab/main.py:84,331-339) over one flat fp32 parameter / gradient bucket: a single launch. */
 int mnb_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n, float lr,

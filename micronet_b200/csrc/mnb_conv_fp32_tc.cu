@@ -1,0 +1,509 @@
+// fp32 convolution with few input channels (the un-quantized FIRST layer of every QAT model: 3 -> 192/256,
+// 5x5 or 3x3; nin_gc.py:82, nin.py, resnet.py) on tcgen05 tensor cores: forward and weight gradient.
+//
+// C*R*S (75 for 3x5x5) is far too small a reduction for the per-tap implicit GEMM of mnb_conv_tc_fwd.cu
+// (one MMA K-step would carry 3 real channels out of 16), so this layer uses a real im2col operand, built in
+// shared memory from a zero-padded input patch:
+//
+//   forward : y[b, n, pos]  = bias[n] + sum_kk  Xcol[pos, kk] * w[n, kk]      M = 128 positions, N = Cout, K = kk
+//   wgrad   : dw[n, kk]     = sum_{b, pos}      dy[b, n, pos] * Xcol[pos, kk] M = 128 channels,  N = kk,   K = positions
+//
+// fp32 accuracy on bf16 tensor cores: every fp32 value is split exactly into three bf16 pieces (hi + mid + lo) and
+// the six products down to 2^-16 relative weight (hh, hm, mh, hl, lh, mm) are accumulated in fp32; the dropped
+// pieces are <= 2^-24 relative: the error is that of an fp32 convolution with a different summation order.
+//
+// Both kernels are persistent (one CTA per SM), HBM-bound by the one large tensor they stream (y written once,
+// dy read once): forward 128 positions x Cout x 4 B per tile, weight gradient 32 positions x Cout x 4 B per step.
+#include <cuda.h>
+#include <cuda_bf16.h>
+
+#include <algorithm>
+
+#include "mnb_common.cuh"
+#include "mnb_tc.cuh"
+
+namespace tcfp32 {
+
+constexpr int NTHREADS = 512;
+constexpr int kMaxDynSmem = 227 * 1024 - 1024;
+constexpr int SUB = 32;  // positions per weight-gradient step
+
+struct Params {
+  int B, C, K, H, W, R, pad;
+  int KR, KP;         // C*R*R and its multiple-of-16 padding
+  int NP;             // forward: Cout padded to 16 (MMA N); wgrad: Cout padded to 128 (MMA M halves)
+  int TH, PH, PW;     // tile = TH full rows (TH * W = 128); patch = C x PH x PW floats (zero padded)
+  int tiles_per_img, n_tiles;
+  int nbuf_a, acc_cols, tmem_cols;
+  int off_b, off_a, off_patch, off_tab, a_term_bytes, a_buf_bytes, b_term_bytes, patch_bytes;
+  const float* x; const float* w; const float* bias; float* y;
+  const float* dy; float* partial;
+  int* err;
+};
+
+struct alignas(16) Shared {
+  uint64_t a_full[2], a_empty[2], acc_full[2], acc_empty[2], done;
+  uint32_t tmem_slot;
+  uint32_t abort;
+};
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+__device__ __forceinline__ void split3_pair(float a, float b, uint32_t& hp, uint32_t& mp, uint32_t& lp) {
+  hp = pack_bf16x2(a, b);
+  const float ra = a - __uint_as_float(hp << 16), rb = b - __uint_as_float(hp & 0xffff0000u);
+  mp = pack_bf16x2(ra, rb);
+  const float la = ra - __uint_as_float(mp << 16), lb = rb - __uint_as_float(mp & 0xffff0000u);
+  lp = pack_bf16x2(la, lb);
+}
+// eight fp32 values -> one 16-byte row of each of the three operand planes
+__device__ __forceinline__ void store_split8(const float (&v)[8], uint8_t* dst, int term_bytes) {
+  uint32_t hp[4], mp[4], lp[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) split3_pair(v[2 * j], v[2 * j + 1], hp[j], mp[j], lp[j]);
+  *reinterpret_cast<uint4*>(dst) = make_uint4(hp[0], hp[1], hp[2], hp[3]);
+  *reinterpret_cast<uint4*>(dst + term_bytes) = make_uint4(mp[0], mp[1], mp[2], mp[3]);
+  *reinterpret_cast<uint4*>(dst + 2 * term_bytes) = make_uint4(lp[0], lp[1], lp[2], lp[3]);
+}
+__device__ __forceinline__ void conv_bar_sync(int nthreads) {  // named barrier 1: converter warps only
+  asm volatile("bar.sync 1, %0;" ::"r"(nthreads) : "memory");
+}
+
+// the six (A piece, B piece) products kept, smallest last
+__device__ __constant__ int kProdA[6] = {0, 0, 1, 0, 2, 1};
+__device__ __constant__ int kProdB[6] = {0, 1, 0, 2, 0, 1};
+
+// zero-padded input patch of one tile: patch[c][pr][pc] = x[b, c, h0 - pad + pr, pc - pad]
+__device__ __forceinline__ void load_patch(const Params& p, float* patch, int b, int h0, int ct, int nconv) {
+  const int n = p.C * p.PH * p.PW;
+  for (int i = ct; i < n; i += nconv) {
+    const int pc = i % p.PW, t = i / p.PW;
+    const int pr = t % p.PH, c = t / p.PH;
+    const int h = h0 - p.pad + pr, w = pc - p.pad;
+    float v = 0.f;
+    if (h >= 0 && h < p.H && w >= 0 && w < p.W) v = __ldg(p.x + (((int64_t)b * p.C + c) * p.H + h) * p.W + w);
+    patch[i] = v;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ forward
+// warps: 0 = MMA issue, 4..7 = epilogue (TMEM lane quarters), the other 11 = im2col converters
+constexpr int FWD_NCONV = NTHREADS - 32 - 128;
+
+__global__ void __launch_bounds__(NTHREADS, 1) fwd_kernel(const Params p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ Shared sh;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  uint8_t* bop = smem + p.off_b;
+  uint8_t* aop = smem + p.off_a;
+  int* tab = reinterpret_cast<int*>(smem + p.off_tab);
+  const int kchunks = p.KP / 8;
+
+  if (tid == 0) {
+    for (int i = 0; i < 2; ++i) {
+      tc::mbar_init(&sh.a_full[i], FWD_NCONV / 32); tc::mbar_init(&sh.a_empty[i], 1);
+      tc::mbar_init(&sh.acc_full[i], 1); tc::mbar_init(&sh.acc_empty[i], 4);
+    }
+    sh.abort = 0;
+    tc::fence_barrier_init();
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tc::smem_u32(&sh.tmem_slot)),
+                 "r"((uint32_t)p.tmem_cols));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  // resident B operand: w[n][kk] as K-major core matrices [piece][kk / 8][n][8], zero beyond Cout / KR
+  for (int i = tid; i < kchunks * p.NP; i += NTHREADS) {
+    const int j = i / p.NP, n = i - j * p.NP;
+    float v[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int kk = j * 8 + e;
+      v[e] = (n < p.K && kk < p.KR) ? __ldg(p.w + (int64_t)n * p.KR + kk) : 0.f;
+    }
+    store_split8(v, bop + (size_t)i * 16, p.b_term_bytes);
+  }
+  for (int kk = tid; kk < p.KP; kk += NTHREADS) {
+    int off = -1;
+    if (kk < p.KR) {
+      const int s = kk % p.R, t = kk / p.R;
+      const int r = t % p.R, c = t / p.R;
+      off = (c * p.PH + r) * p.PW + s;
+    }
+    tab[kk] = off;
+  }
+  tc::fence_proxy_async_smem();
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tmem = sh.tmem_slot;
+
+  if (warp == 0) {
+    // ================================================================= MMA issuer (warp-converged, lane 0 issues)
+    const uint32_t lead = lane == 0;
+    const uint32_t idesc = tc::make_idesc(1, 1, 1, 128, (uint32_t)p.NP);
+    const uint64_t a_desc0 = tc::smem_desc_kmajor_noswz(tc::smem_u32(aop), 128u * 16u, 128u);
+    const uint64_t b_desc0 = tc::smem_desc_kmajor_noswz(tc::smem_u32(bop), (uint32_t)p.NP * 16u, 128u);
+    const uint32_t a_term16 = (uint32_t)p.a_term_bytes >> 4, b_term16 = (uint32_t)p.b_term_bytes >> 4;
+    const uint32_t a_buf16 = (uint32_t)p.a_buf_bytes >> 4;
+    const uint32_t a_step16 = 2u * 128u, b_step16 = 2u * (uint32_t)p.NP;   // one K16 step = two 8-wide chunks
+    uint32_t t = 0;
+    for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++t) {
+      const uint32_t ab = p.nbuf_a == 2 ? (t & 1u) : 0u, aph = p.nbuf_a == 2 ? ((t >> 1) & 1u) : (t & 1u);
+      const uint32_t acc = t & 1u, cph = (t >> 1) & 1u;
+      tc::mbar_wait_soft(&sh.acc_empty[acc], cph ^ 1u, p.err, 501, &sh.abort);
+      tc::mbar_wait_soft(&sh.a_full[ab], aph, p.err, 502, &sh.abort);
+      tc::tc_fence_after();
+      const uint32_t d_tmem = tmem + acc * (uint32_t)p.acc_cols;
+      for (int ks = 0; ks < p.KP / 16; ++ks) {
+#pragma unroll
+        for (int q = 0; q < 6; ++q) {
+          const uint64_t ad = a_desc0 + (uint64_t)(ab * a_buf16 + (uint32_t)kProdA[q] * a_term16 + (uint32_t)ks * a_step16);
+          const uint64_t bd = b_desc0 + (uint64_t)((uint32_t)kProdB[q] * b_term16 + (uint32_t)ks * b_step16);
+          tc::mma_f16_guarded(d_tmem, ad, bd, idesc, (uint32_t)(ks | q) != 0u, lead);
+        }
+      }
+      if (lead) { tc::mma_commit(&sh.a_empty[ab]); tc::mma_commit(&sh.acc_full[acc]); }
+      __syncwarp();
+    }
+  } else if (warp >= 4 && warp < 8) {
+    // ================================================================= epilogue: TMEM -> + bias -> y (NCHW)
+    const int q = warp - 4, m = q * 32 + lane;
+    const int64_t plane = (int64_t)p.H * p.W;
+    uint32_t t = 0;
+    for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++t) {
+      const int b = tile / p.tiles_per_img, h0 = (tile - b * p.tiles_per_img) * p.TH;
+      const uint32_t acc = t & 1u, cph = (t >> 1) & 1u;
+      if (!tc::mbar_wait(&sh.acc_full[acc], cph, p.err, 503)) break;
+      tc::tc_fence_after();
+      float* dst = p.y + (int64_t)b * p.K * plane + (int64_t)h0 * p.W + m;
+      for (int n0 = 0; n0 < p.NP; n0 += 32) {
+        uint32_t r[32];
+        tc::tmem_ld_32x32(tmem + ((uint32_t)(q * 32) << 16) + acc * (uint32_t)p.acc_cols + (uint32_t)n0, r);
+        tc::tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const int n = n0 + j;
+          if (n < p.K) dst[(int64_t)n * plane] = __uint_as_float(r[j]) + (p.bias ? __ldg(p.bias + n) : 0.f);
+        }
+      }
+      tc::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(&sh.acc_empty[acc]);
+    }
+  } else {
+    // ================================================================= converters: patch -> im2col A operand
+    const int ct = warp < 4 ? tid - 32 : tid - 32 - 128;   // 0 .. FWD_NCONV-1
+    float* patch0 = reinterpret_cast<float*>(smem + p.off_patch);
+    const int items = 128 * kchunks;
+    uint32_t t = 0;
+    for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++t) {
+      const int b = tile / p.tiles_per_img, h0 = (tile - b * p.tiles_per_img) * p.TH;
+      float* patch = patch0 + (size_t)(t & 1u) * (p.patch_bytes / 4);
+      load_patch(p, patch, b, h0, ct, FWD_NCONV);
+      conv_bar_sync(FWD_NCONV);
+      const uint32_t ab = p.nbuf_a == 2 ? (t & 1u) : 0u, aph = p.nbuf_a == 2 ? ((t >> 1) & 1u) : (t & 1u);
+      if (!tc::mbar_wait(&sh.a_empty[ab], aph ^ 1u, p.err, 504)) break;
+      uint8_t* abuf = aop + (size_t)ab * p.a_buf_bytes;
+      for (int i = ct; i < items; i += FWD_NCONV) {
+        const int j = i >> 7, m = i & 127;
+        const int base = (m / p.W) * p.PW + (m % p.W);
+        float v[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const int off = tab[j * 8 + e];
+          v[e] = off >= 0 ? patch[off + base] : 0.f;
+        }
+        store_split8(v, abuf + (size_t)i * 16, p.a_term_bytes);
+      }
+      tc::fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(&sh.a_full[ab]);
+    }
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc::tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"((uint32_t)p.tmem_cols));
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ weight gradient
+// warps: 0 = MMA issue, 1..15 = converters (dy split + im2col of x); warps 4..7 also run the final epilogue
+constexpr int WG_NCONV = NTHREADS - 32;
+
+__global__ void __launch_bounds__(NTHREADS, 1) wgrad_kernel(const Params p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ Shared sh;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  uint8_t* bop = smem + p.off_b;   // Xcol^T : [buf][piece][pos / 8][kk][8 pos]
+  uint8_t* aop = smem + p.off_a;   // dy     : [buf][piece][pos / 8][channel][8 pos]
+  int* tab = reinterpret_cast<int*>(smem + p.off_tab);
+  const int halves = p.NP / 128;
+  const int nsub = 128 / SUB;
+  const int my_tiles = (p.n_tiles > (int)blockIdx.x) ? (p.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+
+  if (tid == 0) {
+    for (int i = 0; i < 2; ++i) { tc::mbar_init(&sh.a_full[i], WG_NCONV / 32); tc::mbar_init(&sh.a_empty[i], 1); }
+    tc::mbar_init(&sh.done, 1);
+    sh.abort = 0;
+    tc::fence_barrier_init();
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tc::smem_u32(&sh.tmem_slot)),
+                 "r"((uint32_t)p.tmem_cols));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  // operand buffers start as zeros: channel rows >= Cout and im2col rows >= KR are never written
+  for (int i = tid; i < (2 * (p.a_buf_bytes + 3 * p.b_term_bytes)) / 16; i += NTHREADS)
+    reinterpret_cast<uint4*>(smem + p.off_b)[i] = make_uint4(0, 0, 0, 0);
+  for (int kk = tid; kk < p.KP; kk += NTHREADS) {
+    int off = -1;
+    if (kk < p.KR) {
+      const int s = kk % p.R, t = kk / p.R;
+      const int r = t % p.R, c = t / p.R;
+      off = (c * p.PH + r) * p.PW + s;
+    }
+    tab[kk] = off;
+  }
+  tc::fence_proxy_async_smem();
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tmem = sh.tmem_slot;
+  const int b_buf_bytes = 3 * p.b_term_bytes;
+
+  if (warp == 0) {
+    // ================================================================= MMA issuer
+    const uint32_t lead = lane == 0;
+    const uint32_t idesc = tc::make_idesc(1, 1, 1, 128, (uint32_t)p.KP);
+    const uint64_t a_desc0 = tc::smem_desc_kmajor_noswz(tc::smem_u32(aop), (uint32_t)p.NP * 16u, 128u);
+    const uint64_t b_desc0 = tc::smem_desc_kmajor_noswz(tc::smem_u32(bop), (uint32_t)p.KP * 16u, 128u);
+    const uint32_t a_term16 = (uint32_t)p.a_term_bytes >> 4, b_term16 = (uint32_t)p.b_term_bytes >> 4;
+    const uint32_t a_buf16 = (uint32_t)p.a_buf_bytes >> 4, b_buf16 = (uint32_t)b_buf_bytes >> 4;
+    const uint32_t a_step16 = 2u * (uint32_t)p.NP, b_step16 = 2u * (uint32_t)p.KP;
+    uint32_t it = 0;
+    for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+      for (int sub = 0; sub < nsub; ++sub, ++it) {
+        const uint32_t ob = it & 1u, oph = (it >> 1) & 1u;
+        tc::mbar_wait_soft(&sh.a_full[ob], oph, p.err, 511, &sh.abort);
+        tc::tc_fence_after();
+        for (int ks = 0; ks < SUB / 16; ++ks) {
+          for (int hf = 0; hf < halves; ++hf) {
+#pragma unroll
+            for (int q = 0; q < 6; ++q) {
+              const uint64_t ad = a_desc0 + (uint64_t)(ob * a_buf16 + (uint32_t)kProdA[q] * a_term16 +
+                                                       (uint32_t)ks * a_step16 + (uint32_t)hf * 128u);
+              const uint64_t bd = b_desc0 + (uint64_t)(ob * b_buf16 + (uint32_t)kProdB[q] * b_term16 + (uint32_t)ks * b_step16);
+              tc::mma_f16_guarded(tmem + (uint32_t)hf * 128u, ad, bd, idesc, (it | (uint32_t)ks | (uint32_t)q) != 0u, lead);
+            }
+          }
+        }
+        if (lead) tc::mma_commit(&sh.a_empty[ob]);
+        __syncwarp();
+      }
+    }
+    if (lead) tc::mma_commit(&sh.done);
+    __syncwarp();
+  } else {
+    // ================================================================= converters
+    const int ct = tid - 32;
+    float* patch0 = reinterpret_cast<float*>(smem + p.off_patch);
+    const int64_t plane = (int64_t)p.H * p.W;
+    const int d_items = p.K * (SUB / 8), x_items = p.KR * (SUB / 8);
+    uint32_t it = 0, t = 0;
+    for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++t) {
+      const int b = tile / p.tiles_per_img, h0 = (tile - b * p.tiles_per_img) * p.TH;
+      float* patch = patch0 + (size_t)(t & 1u) * (p.patch_bytes / 4);
+      load_patch(p, patch, b, h0, ct, WG_NCONV);
+      conv_bar_sync(WG_NCONV);
+      const float* dy_tile = p.dy + (int64_t)b * p.K * plane + (int64_t)h0 * p.W;
+      for (int sub = 0; sub < nsub; ++sub, ++it) {
+        const uint32_t ob = it & 1u, oph = (it >> 1) & 1u;
+        if (!tc::mbar_wait(&sh.a_empty[ob], oph ^ 1u, p.err, 512)) goto done;
+        uint8_t* abuf = aop + (size_t)ob * p.a_buf_bytes;
+        uint8_t* bbuf = bop + (size_t)ob * b_buf_bytes;
+        // dy: item = (channel n, 8-position chunk j): 32 contiguous bytes of global memory
+        for (int i = ct; i < d_items; i += WG_NCONV) {
+          const int n = i / (SUB / 8), j = i - n * (SUB / 8);
+          const float4* src = reinterpret_cast<const float4*>(dy_tile + (int64_t)n * plane + sub * SUB + j * 8);
+          const float4 lo = __ldg(src), hi = __ldg(src + 1);
+          const float v[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
+          store_split8(v, abuf + ((size_t)j * p.NP + n) * 16, p.a_term_bytes);
+        }
+        // Xcol^T: item = (kk, 8-position chunk j): 8 consecutive patch columns
+        for (int i = ct; i < x_items; i += WG_NCONV) {
+          const int kk = i / (SUB / 8), j = i - kk * (SUB / 8);
+          const int m = sub * SUB + j * 8;
+          const float* src = patch + tab[kk] + (m / p.W) * p.PW + (m % p.W);
+          float v[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) v[e] = src[e];
+          store_split8(v, bbuf + ((size_t)j * p.KP + kk) * 16, p.b_term_bytes);
+        }
+        tc::fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) tc::mbar_arrive(&sh.a_full[ob]);
+      }
+    }
+  }
+  if (warp >= 4 && warp < 8) {
+    // ================================================================= final epilogue: TMEM -> partial dw of this CTA
+    const int q = warp - 4, m = q * 32 + lane;
+    float* mine = p.partial + (int64_t)blockIdx.x * p.K * p.KR;
+    const bool have = my_tiles > 0;
+    if (have) {
+      if (!tc::mbar_wait(&sh.done, 0, p.err, 513)) goto done;
+      tc::tc_fence_after();
+    }
+    for (int hf = 0; hf < halves; ++hf) {
+      const int n = hf * 128 + m;
+      for (int k0 = 0; k0 < p.KP; k0 += 32) {
+        uint32_t r[32];
+        if (have) {
+          tc::tmem_ld_32x32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(hf * 128 + k0), r);
+          tc::tmem_ld_wait();
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) r[j] = 0u;
+        }
+        if (n < p.K) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (k0 + j < p.KR) mine[(int64_t)n * p.KR + k0 + j] = __uint_as_float(r[j]);
+        }
+      }
+    }
+    tc::tc_fence_before();
+  }
+done:
+  tc::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc::tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"((uint32_t)p.tmem_cols));
+  }
+}
+
+__global__ void __launch_bounds__(256) reduce_partials_kernel(const float* __restrict__ partial, int n, int ranks,
+                                                              float* __restrict__ dw) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    float s = 0.f;
+    for (int j = 0; j < ranks; ++j) s += partial[(int64_t)j * n + i];
+    dw[i] = s;
+  }
+}
+
+static int plan(const mnb_conv_shape* s, bool wgrad, Params& p, int& smem_bytes) {
+  MNB_REQUIRE(s != nullptr, "conv shape is NULL");
+  auto unsupported = [](const char* why) { return mnb_fail(MNB_E_UNSUPPORTED, "fp32 tc conv: %s", why); };
+  p.B = s->batch; p.C = s->in_c; p.K = s->out_c; p.H = s->in_h; p.W = s->in_w; p.R = s->ker_h;
+  MNB_REQUIRE(p.B > 0 && p.C > 0 && p.K > 0 && p.H > 0 && p.W > 0 && s->groups > 0, "bad conv shape");
+  if (s->groups != 1 || s->stride_h != 1 || s->stride_w != 1 || s->dil_h != 1 || s->dil_w != 1)
+    return unsupported("groups / stride / dilation != 1");
+  if (s->ker_h != s->ker_w || (p.R & 1) == 0 || s->pad_h != p.R / 2 || s->pad_w != p.R / 2)
+    return unsupported("not a 'same' odd square filter");
+  p.pad = p.R / 2;
+  p.KR = p.C * p.R * p.R;
+  p.KP = (p.KR + 15) / 16 * 16;
+  if (p.KP > 128) return unsupported("C*R*S > 128 (use the per-tap implicit GEMM)");
+  if (p.K > 256) return unsupported("more than 256 output channels");
+  if (p.W < 8 || p.W > 128 || 128 % p.W || (p.H * p.W) % 128) return unsupported("image rows do not tile into 128 positions");
+  if ((int64_t)p.B * p.K * p.H * p.W >= (1ll << 31)) return unsupported("tensor too large");
+  p.TH = 128 / p.W;
+  p.PH = p.TH + 2 * p.pad; p.PW = p.W + 2 * p.pad;
+  p.tiles_per_img = p.H / p.TH;
+  p.n_tiles = p.B * p.tiles_per_img;
+  p.patch_bytes = (p.C * p.PH * p.PW * 4 + 8 * 4 + 15) / 16 * 16;   // + slack: the wgrad gather of a padded kk row may overrun
+  const int kchunks = p.KP / 8;
+  if (!wgrad) {
+    p.NP = (p.K + 15) / 16 * 16;
+    p.b_term_bytes = kchunks * p.NP * 16;
+    p.a_term_bytes = kchunks * 128 * 16;
+    p.a_buf_bytes = 3 * p.a_term_bytes;
+    p.off_b = 0;
+    p.off_a = 3 * p.b_term_bytes;
+    p.acc_cols = p.NP <= 32 ? 32 : p.NP <= 64 ? 64 : p.NP <= 128 ? 128 : 256;
+    p.tmem_cols = 2 * p.acc_cols;
+    for (p.nbuf_a = 2; p.nbuf_a >= 1; --p.nbuf_a) {
+      p.off_patch = p.off_a + p.nbuf_a * p.a_buf_bytes;
+      p.off_tab = p.off_patch + 2 * p.patch_bytes;
+      smem_bytes = p.off_tab + p.KP * 4;
+      if (smem_bytes <= kMaxDynSmem) break;
+    }
+    if (p.nbuf_a < 1) return unsupported("shared memory budget");
+  } else {
+    p.NP = (p.K + 127) / 128 * 128;
+    p.a_term_bytes = (SUB / 8) * p.NP * 16;
+    p.a_buf_bytes = 3 * p.a_term_bytes;
+    p.b_term_bytes = (SUB / 8) * p.KP * 16;
+    // [B buf0][B buf1][A buf0][A buf1] contiguous (zeroed in one sweep by the kernel)
+    p.off_b = 0;
+    p.off_a = 2 * 3 * p.b_term_bytes;
+    p.off_patch = p.off_a + 2 * p.a_buf_bytes;
+    p.off_tab = p.off_patch + 2 * p.patch_bytes;
+    smem_bytes = p.off_tab + p.KP * 4;
+    p.nbuf_a = 2;
+    p.acc_cols = 128;
+    p.tmem_cols = p.NP <= 128 ? 128 : 256;
+    if (smem_bytes > kMaxDynSmem) return unsupported("shared memory budget");
+  }
+  return 0;
+}
+
+static int grid_size(const Params& p) { return std::max(1, std::min(p.n_tiles, MNB_NUM_SMS)); }
+
+}  // namespace tcfp32
+
+extern "C" int mnb_fconv2d_fwd_tc(const mnb_conv_shape* s, const float* x, const float* w, const float* bias, float* y,
+                                  int32_t* err_flag, mnb_stream_t stream) {
+  using namespace tcfp32;
+  MNB_REQUIRE(s && x && w && y && err_flag, "NULL pointer");
+  Params p{};
+  int smem_bytes = 0;
+  if (int e = plan(s, false, p, smem_bytes)) return e;
+  p.x = x; p.w = w; p.bias = bias; p.y = y; p.err = err_flag;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t ce = cudaFuncSetAttribute(fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem);
+    if (ce != cudaSuccess) return mnb_fail((int)ce, "cudaFuncSetAttribute: %s", cudaGetErrorString(ce));
+    attr_set = true;
+  }
+  fwd_kernel<<<grid_size(p), NTHREADS, smem_bytes, (cudaStream_t)stream>>>(p);
+  MNB_LAUNCHED(1);
+  return 0;
+}
+
+extern "C" int64_t mnb_fconv2d_wgrad_tc_scratch_bytes(const mnb_conv_shape* s) {
+  tcfp32::Params p{};
+  int smem = 0;
+  if (tcfp32::plan(s, true, p, smem)) return -1;
+  return (int64_t)tcfp32::grid_size(p) * p.K * p.KR * 4;
+}
+
+extern "C" int mnb_fconv2d_wgrad_tc(const mnb_conv_shape* s, const float* dy, const float* x, float* dw, void* scratch,
+                                    int32_t* err_flag, mnb_stream_t stream) {
+  using namespace tcfp32;
+  MNB_REQUIRE(s && dy && x && dw && scratch && err_flag, "NULL pointer");
+  MNB_REQUIRE((reinterpret_cast<uintptr_t>(dy) & 15) == 0, "dy must be 16-byte aligned");
+  Params p{};
+  int smem_bytes = 0;
+  if (int e = plan(s, true, p, smem_bytes)) return e;
+  p.x = x; p.dy = dy; p.partial = reinterpret_cast<float*>(scratch); p.err = err_flag;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t ce = cudaFuncSetAttribute(wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem);
+    if (ce != cudaSuccess) return mnb_fail((int)ce, "cudaFuncSetAttribute: %s", cudaGetErrorString(ce));
+    attr_set = true;
+  }
+  const int grid = grid_size(p);
+  cudaStream_t st = (cudaStream_t)stream;
+  wgrad_kernel<<<grid, NTHREADS, smem_bytes, st>>>(p);
+  const int n = p.K * p.KR;
+  reduce_partials_kernel<<<std::min(mnb_ceil_div(n, 256), MNB_NUM_SMS * 4), 256, 0, st>>>(p.partial, n, grid, dw);
+  MNB_LAUNCHED(2);
+  return 0;
+}

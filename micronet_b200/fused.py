@@ -7,6 +7,8 @@ ReLU swapped by WB:319-322), optionally followed by ``nn.MaxPool2d``.  ``fuse_wb
   statistics, normalise + sign + STE mask in two kernels forward and two backward; the backward also hands the
   producing convolution its bias gradient (channel sums of dx), saving that pass;
 * every plain ``nn.MaxPool2d`` -> ``EngineMaxPool2d`` (byte window index, bit-identical to ATen);
+* the un-quantized first ``nn.Conv2d`` (few input channels) -> ``EngineFloatConv2d``: fp32-accurate im2col
+  convolution on the tensor cores (forward + weight gradient);
 * every block whose input shuffle (``channel_shuffle_flag`` / ``shuffle_groups`` attributes of the
   reference's block class) directly follows one of those producers: the permutation moves into the producer's
   output addressing and the shuffle copy disappears (max-pooling commutes with a channel permutation).
@@ -18,6 +20,10 @@ from __future__ import annotations
 import torch
 import torch.nn as nn
 from torch.autograd import Function
+
+import ctypes as C
+
+import torch.nn.functional as TF
 
 from . import _lib as L
 
@@ -144,6 +150,72 @@ class EngineMaxPool2d(nn.MaxPool2d):
         return super().extra_repr() + f", out_shuffle_groups={self.out_shuffle_groups}"
 
 
+class FloatConvFn(Function):
+    """fp32 conv2d with few input channels on the tensor-core im2col path (mnb_fconv2d_*_tc);
+    shapes outside its cover run ATen's convolution (what the reference runs for this layer)."""
+
+    @staticmethod
+    def forward(ctx, x, w, bias, padding):
+        lib = L.load()
+        x, w = x.contiguous(), w.contiguous()
+        b, c, h, wd = x.shape
+        k, _, r, s_ = w.shape
+        sh = L.ConvShape(b, c, h, wd, k, r, s_, 1, 1, padding, padding, 1, 1, 1)
+        y = torch.empty((b, k, h, wd), dtype=torch.float32, device=x.device)
+        rc = lib.mnb_fconv2d_fwd_tc(C.byref(sh), x.data_ptr(), w.data_ptr(), L.ptr(bias), y.data_ptr(),
+                                    L.tc_err_flag(x.device).data_ptr(), L.stream())
+        ctx.engine = rc == 0
+        if rc == L.E_UNSUPPORTED:
+            y = TF.conv2d(x, w, bias, 1, padding)
+        elif rc != 0:
+            L.check(rc, "fconv2d_fwd_tc")
+        ctx.save_for_backward(x, w)
+        ctx.sh, ctx.padding, ctx.has_bias = sh, padding, bias is not None
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        lib = L.load()
+        x, w = ctx.saved_tensors
+        presummed = getattr(dy, "_mnb_channel_sum", None)
+        dy = dy.contiguous()
+        dx = dw = db = None
+        if ctx.needs_input_grad[0]:
+            dx = torch.nn.grad.conv2d_input(x.shape, w, dy, 1, ctx.padding)
+        if ctx.needs_input_grad[1]:
+            need = int(lib.mnb_fconv2d_wgrad_tc_scratch_bytes(C.byref(ctx.sh))) if ctx.engine else -1
+            if need >= 0:
+                dw = torch.empty_like(w)
+                scratch = torch.empty(need, dtype=torch.uint8, device=dy.device)
+                L.check(lib.mnb_fconv2d_wgrad_tc(C.byref(ctx.sh), dy.data_ptr(), x.data_ptr(), dw.data_ptr(),
+                                                 scratch.data_ptr(), L.tc_err_flag(dy.device).data_ptr(), L.stream()),
+                        "fconv2d_wgrad_tc")
+            else:
+                dw = torch.nn.grad.conv2d_weight(x, w.shape, dy, 1, ctx.padding)
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            if presummed is not None and presummed.numel() == dy.shape[1]:
+                db = presummed
+            else:
+                from .functional import channel_sums
+                db = channel_sums(dy)
+        return dx, dw, db, None
+
+
+def _float_conv_cover(m: nn.Conv2d) -> bool:
+    k, p = m.kernel_size, m.padding
+    return (type(m) is nn.Conv2d and m.groups == 1 and tuple(m.stride) == (1, 1) and tuple(m.dilation) == (1, 1)
+            and k[0] == k[1] and k[0] % 2 == 1 and not isinstance(p, str) and tuple(p) == (k[0] // 2, k[0] // 2)
+            and m.padding_mode == "zeros" and m.in_channels * k[0] * k[1] <= 128 and m.out_channels <= 256)
+
+
+class EngineFloatConv2d(nn.Conv2d):
+    """drop-in for the un-quantized first nn.Conv2d of a QAT model (same parameters / state_dict keys)"""
+
+    def forward(self, input):
+        L.require_cuda(input, self.weight)
+        return FloatConvFn.apply(input, self.weight, self.bias, int(self.padding[0]))
+
+
 def _fuse_pairs(module: nn.Module):
     from .wbwtab import ActivationQuantizer
     prev_name, prev = None, None
@@ -157,6 +229,11 @@ def _fuse_pairs(module: nn.Module):
             fused.train(prev.training)
             module._modules[prev_name] = fused
             module._modules[name] = nn.Identity()
+        elif type(child) is nn.Conv2d and _float_conv_cover(child):
+            conv = EngineFloatConv2d(child.in_channels, child.out_channels, child.kernel_size, child.stride, child.padding,
+                                     child.dilation, child.groups, child.bias is not None)
+            conv.weight, conv.bias = child.weight, child.bias
+            module._modules[name] = conv
         elif type(child) is nn.MaxPool2d and _pool_cfg(child) is not None:
             pool = EngineMaxPool2d(child.kernel_size, child.stride, child.padding, child.dilation,
                                    child.return_indices, child.ceil_mode)

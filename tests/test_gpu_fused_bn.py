@@ -105,9 +105,14 @@ def test_bn_sign_backward_hands_over_channel_sums_of_dx():
         mean, var = x.detach().mean((0, 2, 3)), x.detach().var((0, 2, 3), unbiased=False)
         y = BNSignFn.apply(x, gamma, beta, mean, torch.rsqrt(var + 1e-5), training, 1)
         captured = {}
-        x.register_hook(lambda g: captured.setdefault("sum", getattr(g, "_mnb_channel_sum", None)))
+
+        def grab(g, captured=captured):
+            captured["sum"] = getattr(g, "_mnb_channel_sum", None)
+
+        handle = x.register_hook(grab)
         x.grad = None
         y.backward(torch.randn_like(y))
+        handle.remove()
         assert captured["sum"] is not None
         want = x.grad.double().sum((0, 2, 3))
         scale = x.grad.double().abs().sum((0, 2, 3))
