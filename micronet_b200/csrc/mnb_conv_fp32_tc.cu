@@ -18,6 +18,7 @@
 #include <cuda_bf16.h>
 
 #include <algorithm>
+#include <cstdlib>
 
 #include "mnb_common.cuh"
 #include "mnb_tc.cuh"
@@ -25,7 +26,7 @@
 namespace tcfp32 {
 
 constexpr int NTHREADS = 512;
-constexpr int kMaxDynSmem = 227 * 1024 - 1024;
+constexpr int kMaxDynSmem = 227 * 1024 - 2560;
 constexpr int SUB = 32;  // positions per weight-gradient step
 
 struct Params {
@@ -39,6 +40,7 @@ struct Params {
   const float* x; const float* w; const float* bias; float* y;
   const float* dy; float* partial;
   int* err;
+  int dbg;   // MNB_FCONV_DEBUG bit mask (timing experiments only): 1 skip im2col/dy conversion, 2 skip MMAs, 4 skip stores/drain adds, 8 skip x conversion
 };
 
 struct alignas(16) Shared {
@@ -77,17 +79,35 @@ __device__ __forceinline__ void conv_bar_sync(int nthreads) {  // named barrier 
 __device__ __constant__ int kProdA[6] = {1, 2, 0, 1, 0, 0};
 __device__ __constant__ int kProdB[6] = {1, 0, 2, 0, 1, 0};
 
-// zero-padded input patch of one tile: patch[c][pr][pc] = x[b, c, h0 - pad + pr, pc - pad]
-__device__ __forceinline__ void load_patch(const Params& p, float* patch, int b, int h0, int ct, int nconv) {
+// zero-padded input patch of one tile: patch[c][pr][pc] = x[b, c, h0 - pad + pr, pc - pad].  It is fetched one tile
+// ahead: the first PF elements of every converter thread wait in registers while the current tile is converted
+// (patch_fetch), and are written to the other patch buffer afterwards (patch_commit, which also moves the rare
+// remainder of a patch larger than PF * nconv directly).
+constexpr int PF = 4;
+__device__ __forceinline__ float patch_element(const Params& p, int i, int b, int h0) {
+  const int pc = i % p.PW, t = i / p.PW;
+  const int pr = t % p.PH, c = t / p.PH;
+  const int h = h0 - p.pad + pr, w = pc - p.pad;
+  return (h >= 0 && h < p.H && w >= 0 && w < p.W) ? __ldg(p.x + (((int64_t)b * p.C + c) * p.H + h) * p.W + w) : 0.f;
+}
+__device__ __forceinline__ void patch_fetch(const Params& p, int tile, int ct, int nconv, float (&v)[PF]) {
+  const int b = tile / p.tiles_per_img, h0 = (tile - b * p.tiles_per_img) * p.TH;
   const int n = p.C * p.PH * p.PW;
-  for (int i = ct; i < n; i += nconv) {
-    const int pc = i % p.PW, t = i / p.PW;
-    const int pr = t % p.PH, c = t / p.PH;
-    const int h = h0 - p.pad + pr, w = pc - p.pad;
-    float v = 0.f;
-    if (h >= 0 && h < p.H && w >= 0 && w < p.W) v = __ldg(p.x + (((int64_t)b * p.C + c) * p.H + h) * p.W + w);
-    patch[i] = v;
+#pragma unroll
+  for (int k = 0; k < PF; ++k) {
+    const int i = ct + k * nconv;
+    v[k] = i < n ? patch_element(p, i, b, h0) : 0.f;
   }
+}
+__device__ __forceinline__ void patch_commit(const Params& p, float* patch, int tile, int ct, int nconv, const float (&v)[PF]) {
+  const int b = tile / p.tiles_per_img, h0 = (tile - b * p.tiles_per_img) * p.TH;
+  const int n = p.C * p.PH * p.PW;
+#pragma unroll
+  for (int k = 0; k < PF; ++k) {
+    const int i = ct + k * nconv;
+    if (i < n) patch[i] = v[k];
+  }
+  for (int i = ct + PF * nconv; i < n; i += nconv) patch[i] = patch_element(p, i, b, h0);
 }
 
 // ------------------------------------------------------------------------------------------------ forward
@@ -97,6 +117,7 @@ constexpr int FWD_NCONV = NTHREADS - 32 - 128;
 __global__ void __launch_bounds__(NTHREADS, 1) fwd_kernel(const Params p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ Shared sh;
+  __shared__ __align__(16) float epi_bias[256];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   uint8_t* bop = smem + p.off_b;
   uint8_t* aop = smem + p.off_a;
@@ -116,6 +137,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) fwd_kernel(const Params p) {
                  "r"((uint32_t)p.tmem_cols));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
+  for (int n = tid; n < 256; n += NTHREADS) epi_bias[n] = (p.bias && n < p.K) ? __ldg(p.bias + n) : 0.f;
   // resident B operand: w[n][kk] as K-major core matrices [piece][kk / 8][n][8], zero beyond Cout / KR
   for (int i = tid; i < kchunks * p.NP; i += NTHREADS) {
     const int j = i / p.NP, n = i - j * p.NP;
@@ -159,7 +181,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) fwd_kernel(const Params p) {
       tc::mbar_wait_soft(&sh.a_full[ab], aph, p.err, 502, &sh.abort);
       tc::tc_fence_after();
       const uint32_t d_tmem = tmem + acc * (uint32_t)p.acc_cols;
-      for (int q = 0; q < 6; ++q) {
+      for (int q = (p.dbg & 2) ? 6 : 0; q < 6; ++q) {
         const uint64_t aq = a_desc0 + (uint64_t)(ab * a_buf16 + (uint32_t)kProdA[q] * a_term16);
         const uint64_t bq = b_desc0 + (uint64_t)((uint32_t)kProdB[q] * b_term16);
         for (int ks = 0; ks < p.KP / 16; ++ks)
@@ -180,14 +202,30 @@ __global__ void __launch_bounds__(NTHREADS, 1) fwd_kernel(const Params p) {
       if (!tc::mbar_wait(&sh.acc_full[acc], cph, p.err, 503)) break;
       tc::tc_fence_after();
       float* dst = p.y + (int64_t)b * p.K * plane + (int64_t)h0 * p.W + m;
-      for (int n0 = 0; n0 < p.NP; n0 += 32) {
-        uint32_t r[32];
-        tc::tmem_ld_32x32(tmem + ((uint32_t)(q * 32) << 16) + acc * (uint32_t)p.acc_cols + (uint32_t)n0, r);
+      const uint32_t t_row = tmem + ((uint32_t)(q * 32) << 16) + acc * (uint32_t)p.acc_cols;
+      for (int n0 = 0; n0 < p.NP; n0 += 64) {
+        // two 32-column chunks per TMEM round trip; bias as vector loads from shared memory up front so that the
+        // store loop is a pure FADD + STG stream (a per-element bias load serialises against the stores)
+        uint32_t r0[32], r1[32];
+        const bool two = n0 + 32 < p.NP;
+        tc::tmem_ld_32x32(t_row + (uint32_t)n0, r0);
+        if (two) tc::tmem_ld_32x32(t_row + (uint32_t)n0 + 32u, r1);
         tc::tmem_ld_wait();
+        if (p.dbg & 4) continue;
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const int n = n0 + j;
-          if (n < p.K) dst[(int64_t)n * plane] = __uint_as_float(r[j]) + (p.bias ? __ldg(p.bias + n) : 0.f);
+        for (int hc = 0; hc < 2; ++hc) {
+          if (hc == 1 && !two) break;
+          const int nb = n0 + 32 * hc;
+          float bs[32];
+#pragma unroll
+          for (int v = 0; v < 8; ++v) {
+            const float4 c4 = *reinterpret_cast<const float4*>(&epi_bias[nb + 4 * v]);
+            bs[4 * v] = c4.x; bs[4 * v + 1] = c4.y; bs[4 * v + 2] = c4.z; bs[4 * v + 3] = c4.w;
+          }
+          float* op = dst + (int64_t)nb * plane;
+#pragma unroll
+          for (int j = 0; j < 32; ++j, op += plane)
+            if (nb + j < p.K) *op = __uint_as_float(hc ? r1[j] : r0[j]) + bs[j];
         }
       }
       tc::tc_fence_before();
@@ -199,29 +237,36 @@ __global__ void __launch_bounds__(NTHREADS, 1) fwd_kernel(const Params p) {
     const int ct = warp < 4 ? tid - 32 : tid - 32 - 128;   // 0 .. FWD_NCONV-1
     float* patch0 = reinterpret_cast<float*>(smem + p.off_patch);
     const int items = 128 * kchunks;
+    const int patch_floats = p.patch_bytes / 4;
+    float pre[PF];
+    if ((int)blockIdx.x < p.n_tiles) {
+      patch_fetch(p, blockIdx.x, ct, FWD_NCONV, pre);
+      patch_commit(p, patch0, blockIdx.x, ct, FWD_NCONV, pre);
+    }
     uint32_t t = 0;
     for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++t) {
-      const int b = tile / p.tiles_per_img, h0 = (tile - b * p.tiles_per_img) * p.TH;
-      float* patch = patch0 + (size_t)(t & 1u) * (p.patch_bytes / 4);
-      load_patch(p, patch, b, h0, ct, FWD_NCONV);
-      conv_bar_sync(FWD_NCONV);
+      const float* patch = patch0 + (size_t)(t & 1u) * patch_floats;
+      conv_bar_sync(FWD_NCONV);   // every converter committed its part of this tile's patch
+      const int next = tile + (int)gridDim.x;
+      if (next < p.n_tiles) patch_fetch(p, next, ct, FWD_NCONV, pre);
       const uint32_t ab = p.nbuf_a == 2 ? (t & 1u) : 0u, aph = p.nbuf_a == 2 ? ((t >> 1) & 1u) : (t & 1u);
       if (!tc::mbar_wait(&sh.a_empty[ab], aph ^ 1u, p.err, 504)) break;
       uint8_t* abuf = aop + (size_t)ab * p.a_buf_bytes;
-      for (int i = ct; i < items; i += FWD_NCONV) {
+      for (int i = (p.dbg & 1) ? items : ct; i < items; i += FWD_NCONV) {
         const int j = i >> 7, m = i & 127;
         const int base = (m / p.W) * p.PW + (m % p.W);
+        int off[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) off[e] = tab[j * 8 + e];
         float v[8];
 #pragma unroll
-        for (int e = 0; e < 8; ++e) {
-          const int off = tab[j * 8 + e];
-          v[e] = off >= 0 ? patch[off + base] : 0.f;
-        }
+        for (int e = 0; e < 8; ++e) v[e] = off[e] >= 0 ? patch[off[e] + base] : 0.f;
         store_split8(v, abuf + (size_t)i * 16, p.a_term_bytes);
       }
       tc::fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) tc::mbar_arrive(&sh.a_full[ab]);
+      if (next < p.n_tiles) patch_commit(p, patch0 + (size_t)((t + 1) & 1u) * patch_floats, next, ct, FWD_NCONV, pre);
     }
   }
   tc::tc_fence_before();
@@ -304,7 +349,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) wgrad_kernel(const Params p) {
         const uint32_t ob = it & 1u, oph = (it >> 1) & 1u;
         tc::mbar_wait_soft(&sh.a_full[ob], oph, p.err, 511, &sh.abort);
         tc::tc_fence_after();
-        for (int hf = 0; hf < halves; ++hf) {
+        for (int hf = (p.dbg & 2) ? halves : 0; hf < halves; ++hf) {
           for (int q = 0; q < 6; ++q) {
             const uint64_t aq = a_desc0 + (uint64_t)(ob * a_buf16 + (uint32_t)kProdA[q] * a_term16 + (uint32_t)hf * 128u);
             const uint64_t bq = b_desc0 + (uint64_t)(ob * b_buf16 + (uint32_t)kProdB[q] * b_term16);
@@ -329,28 +374,61 @@ __global__ void __launch_bounds__(NTHREADS, 1) wgrad_kernel(const Params p) {
     float* patch0 = reinterpret_cast<float*>(smem + p.off_patch);
     const int64_t plane = (int64_t)p.H * p.W;
     const int d_items = p.K * (SUB / 8), x_items = p.KR * (SUB / 8);
+    const int patch_floats = p.patch_bytes / 4;
+    // dy is fetched one step (32 positions) ahead into registers: up to DMAX x 32 bytes per thread in flight while the
+    // previous step is split and stored
+    constexpr int DMAX = 3;
+    float4 dpre[DMAX][2];
+    auto fetch_dy = [&](int tile, int sub) {
+      const int b = tile / p.tiles_per_img, h0 = (tile - b * p.tiles_per_img) * p.TH;
+      const float* dy_tile = p.dy + (int64_t)b * p.K * plane + (int64_t)h0 * p.W + sub * SUB;
+#pragma unroll
+      for (int k = 0; k < DMAX; ++k) {
+        const int i = ct + k * WG_NCONV;
+        if (i < d_items) {
+          const int n = i / (SUB / 8), j = i - n * (SUB / 8);
+          const float4* src = reinterpret_cast<const float4*>(dy_tile + (int64_t)n * plane + j * 8);
+          dpre[k][0] = __ldg(src); dpre[k][1] = __ldg(src + 1);
+        }
+      }
+    };
+    float pre[PF];
+    if ((int)blockIdx.x < p.n_tiles) {
+      patch_fetch(p, blockIdx.x, ct, WG_NCONV, pre);
+      patch_commit(p, patch0, blockIdx.x, ct, WG_NCONV, pre);
+      fetch_dy(blockIdx.x, 0);
+    }
     uint32_t it = 0, t = 0;
     for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++t) {
-      const int b = tile / p.tiles_per_img, h0 = (tile - b * p.tiles_per_img) * p.TH;
-      float* patch = patch0 + (size_t)(t & 1u) * (p.patch_bytes / 4);
-      load_patch(p, patch, b, h0, ct, WG_NCONV);
+      const float* patch = patch0 + (size_t)(t & 1u) * patch_floats;
       conv_bar_sync(WG_NCONV);
-      const float* dy_tile = p.dy + (int64_t)b * p.K * plane + (int64_t)h0 * p.W;
+      const int next = tile + (int)gridDim.x;
+      if (next < p.n_tiles) patch_fetch(p, next, ct, WG_NCONV, pre);
       for (int sub = 0; sub < nsub; ++sub, ++it) {
         const uint32_t ob = it & 1u, oph = (it >> 1) & 1u;
+        float4 dcur[DMAX][2];
+#pragma unroll
+        for (int k = 0; k < DMAX; ++k) { dcur[k][0] = dpre[k][0]; dcur[k][1] = dpre[k][1]; }
+        if (sub + 1 < nsub) fetch_dy(tile, sub + 1);
+        else if (next < p.n_tiles) fetch_dy(next, 0);
         if (!tc::mbar_wait(&sh.a_empty[ob], oph ^ 1u, p.err, 512)) goto done;
         uint8_t* abuf = aop + (size_t)ob * p.a_buf_bytes;
         uint8_t* bbuf = bop + (size_t)ob * b_buf_bytes;
         // dy: item = (channel n, 8-position chunk j): 32 contiguous bytes of global memory
-        for (int i = ct; i < d_items; i += WG_NCONV) {
-          const int n = i / (SUB / 8), j = i - n * (SUB / 8);
-          const float4* src = reinterpret_cast<const float4*>(dy_tile + (int64_t)n * plane + sub * SUB + j * 8);
-          const float4 lo = __ldg(src), hi = __ldg(src + 1);
-          const float v[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
-          store_split8(v, abuf + ((size_t)j * p.NP + n) * 16, p.a_term_bytes);
+        if (!(p.dbg & 1)) {
+#pragma unroll
+          for (int k = 0; k < DMAX; ++k) {
+            const int i = ct + k * WG_NCONV;
+            if (i < d_items) {
+              const int n = i / (SUB / 8), j = i - n * (SUB / 8);
+              const float v[8] = {dcur[k][0].x, dcur[k][0].y, dcur[k][0].z, dcur[k][0].w,
+                                  dcur[k][1].x, dcur[k][1].y, dcur[k][1].z, dcur[k][1].w};
+              store_split8(v, abuf + ((size_t)j * p.NP + n) * 16, p.a_term_bytes);
+            }
+          }
         }
         // Xcol^T: item = (kk, 8-position chunk j): 8 consecutive patch columns
-        for (int i = ct; i < x_items; i += WG_NCONV) {
+        for (int i = (p.dbg & 8) ? x_items : ct; i < x_items; i += WG_NCONV) {
           const int kk = i / (SUB / 8), j = i - kk * (SUB / 8);
           const int m = sub * SUB + j * 8;
           const float* src = patch + tab[kk] + (m / p.W) * p.PW + (m % p.W);
@@ -363,6 +441,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) wgrad_kernel(const Params p) {
         __syncwarp();
         if (lane == 0) tc::mbar_arrive(&sh.a_full[ob]);
       }
+      if (next < p.n_tiles) patch_commit(p, patch0 + (size_t)((t + 1) & 1u) * patch_floats, next, ct, WG_NCONV, pre);
     }
   } else {
     // ================================================================= drain: TMEM accumulators -> fp32 running sum -> partial dw
@@ -380,7 +459,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) wgrad_kernel(const Params p) {
           tc::tmem_ld_wait();
 #pragma unroll
           for (int j = 0; j < 32; ++j)
-            if (k0 + j < p.KP) sum[((hf * p.KP) + k0 + j) * 128 + m] += __uint_as_float(r[j]);
+            if (k0 + j < p.KP && !(p.dbg & 4)) sum[((hf * p.KP) + k0 + j) * 128 + m] += __uint_as_float(r[j]);
         }
       }
       tc::tc_fence_before();
@@ -425,7 +504,7 @@ static int plan(const mnb_conv_shape* s, bool wgrad, Params& p, int& smem_bytes)
   p.KR = p.C * p.R * p.R;
   p.KP = (p.KR + 15) / 16 * 16;
   if (p.KP > 128) return unsupported("C*R*S > 128 (use the per-tap implicit GEMM)");
-  if (p.K > 256) return unsupported("more than 256 output channels");
+  if (p.K > 256) return unsupported("more than 256 output channels");   // also: K * 4 dy items <= DMAX * WG_NCONV
   if (p.W < 8 || p.W > 128 || 128 % p.W || (p.H * p.W) % 128) return unsupported("image rows do not tile into 128 positions");
   if ((int64_t)p.B * p.K * p.H * p.W >= (1ll << 31)) return unsupported("tensor too large");
   p.TH = 128 / p.W;
@@ -472,6 +551,10 @@ static int plan(const mnb_conv_shape* s, bool wgrad, Params& p, int& smem_bytes)
 }
 
 static int grid_size(const Params& p) { return std::max(1, std::min(p.n_tiles, MNB_NUM_SMS)); }
+static int debug_mask() {
+  static const int m = [] { const char* e = getenv("MNB_FCONV_DEBUG"); return e ? atoi(e) : 0; }();
+  return m;
+}
 
 }  // namespace tcfp32
 
@@ -482,7 +565,7 @@ extern "C" int mnb_fconv2d_fwd_tc(const mnb_conv_shape* s, const float* x, const
   Params p{};
   int smem_bytes = 0;
   if (int e = plan(s, false, p, smem_bytes)) return e;
-  p.x = x; p.w = w; p.bias = bias; p.y = y; p.err = err_flag;
+  p.x = x; p.w = w; p.bias = bias; p.y = y; p.err = err_flag; p.dbg = debug_mask();
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t ce = cudaFuncSetAttribute(fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem);
@@ -509,7 +592,7 @@ extern "C" int mnb_fconv2d_wgrad_tc(const mnb_conv_shape* s, const float* dy, co
   Params p{};
   int smem_bytes = 0;
   if (int e = plan(s, true, p, smem_bytes)) return e;
-  p.x = x; p.dy = dy; p.partial = reinterpret_cast<float*>(scratch); p.err = err_flag;
+  p.x = x; p.dy = dy; p.partial = reinterpret_cast<float*>(scratch); p.err = err_flag; p.dbg = debug_mask();
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t ce = cudaFuncSetAttribute(wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem);
