@@ -15,11 +15,13 @@ WORKLOADS = {
     # configs[1]: the configuration the headline metric is quoted on
     "nin_gc_wbwtab_w3a2": dict(model="nin_gc", scheme="wbwtab", prepare=dict(W=3, A=2), wd=0.0, hw=32,
                                engine_extra=dict(fuse_bn=True)),
-    "nin_dorefa_w8a8": dict(model="nin", scheme="dorefa", prepare=dict(a_bits=8, w_bits=8), wd=1e-5, hw=32),
+    "nin_dorefa_w8a8": dict(model="nin", scheme="dorefa", prepare=dict(a_bits=8, w_bits=8), wd=1e-5, hw=32,
+                            engine_extra=dict(fuse=True)),
     "resnet18_iao_w8a8_bnfuse": dict(model="resnet18", scheme="iao",
                                      prepare=dict(a_bits=8, w_bits=8, q_type=0, q_level=0, weight_observer=0,
                                                   bn_fuse=True), wd=1e-5, hw=32),
-    "nin_gc_dorefa_w4a4": dict(model="nin_gc", scheme="dorefa", prepare=dict(a_bits=4, w_bits=4), wd=1e-5, hw=32),
+    "nin_gc_dorefa_w4a4": dict(model="nin_gc", scheme="dorefa", prepare=dict(a_bits=4, w_bits=4), wd=1e-5, hw=32,
+                               engine_extra=dict(fuse=True)),
 }
 
 

@@ -215,6 +215,12 @@ int mnb_conv2d_wgrad_cond(const mnb_conv_shape* s, const float* dy, const mnb_co
  * out_shuffle_groups = sg > 1 folds the NEXT block's channel shuffle into the producer: the output is
  * written as out[:, a*sg + b] = result[:, b*(C/sg) + a] and the incoming gradient is read through the same
  * permutation; pass bits / argmax stay in the producer's own channel order.  sg = 1: no permutation.   */
+/* nn.BatchNorm2d's training-mode statistics in one launch: mean_invstd[0..C) = batch mean,
+ * mean_invstd[C..2C) = 1/sqrt(biased var + eps); running_mean / running_var are updated in place with `momentum`
+ * (unbiased variance, torch semantics) and *num_batches_tracked (may be NULL) is incremented.              */
+int mnb_bn_batch_stats(const float* x, int32_t batch, int32_t channels, int32_t hw, double eps, double momentum,
+                       float* running_mean, float* running_var, int64_t* num_batches_tracked, float* mean_invstd,
+                       void* scratch, mnb_stream_t stream);
 int mnb_bn_sign_fwd(const float* x, int32_t batch, int32_t channels, int32_t hw, const float* mean, const float* invstd,
                     const float* gamma, const float* beta, int32_t out_shuffle_groups, float* y, uint32_t* pass_bits,
                     mnb_stream_t stream);

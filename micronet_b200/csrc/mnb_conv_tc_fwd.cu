@@ -59,6 +59,10 @@ struct Params {
   uint8_t* codes; uint32_t* pass_bits;  // fwd side outputs of the fused quantizer
   int* err;
   long long* prof;  // optional debug counters (cycles): see mnb_set_tc_profile_buffer
+  // per (tap, k-step): start-address offsets (16-byte units) of the A and B operands.  Kept in the kernel parameters
+  // (constant bank), NOT in shared memory: the MMA warp's descriptor arithmetic then stays in uniform registers; a
+  // table read with LDS forces an ELECT + five R2UR.BROADCAST in front of every tcgen05.mma.
+  uint2 mma_off[64];
 };
 
 struct alignas(16) Shared {
@@ -66,7 +70,6 @@ struct alignas(16) Shared {
   uint32_t tmem_slot;
   uint32_t abort;
   uint32_t op_flags[NOP][NCW];
-  uint2 mma_off[64];   // per (tap, k-step): start-address offsets (16-byte units) of the A and B operands
   alignas(16) float epi_scale[288];   // per output channel of the slab (fixed for the whole kernel)
   alignas(16) float epi_bias[288];
 };
@@ -131,12 +134,6 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const Params p) {
   }
   if (tid < NOP * NCW) sh.op_flags[tid / NCW][tid % NCW] = 0;
   if (tid == 0) sh.abort = 0;
-  if (tid < RS * (p.CC / 16)) {
-    const int ks = p.CC / 16, tap = tid / ks, j = tid - tap * ks;
-    const int r = tap / p.S, s2 = tap - r * p.S;
-    sh.mma_off[tid] = make_uint2((uint32_t)(r * p.BW + s2) + (uint32_t)j * (uint32_t)(2 * p.npos_in),
-                                 (uint32_t)tap * (uint32_t)(c8_per_group * p.cout_g) + (uint32_t)j * (uint32_t)(2 * p.cout_g));
-  }
   if (warp == 2) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tc::smem_u32(&sh.tmem_slot)),
                  "r"((uint32_t)p.tmem_cols));
@@ -226,7 +223,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const Params p) {
               uint32_t any = 0;
 #pragma unroll
               for (int w8 = 0; w8 < NCW; ++w8) any |= sh.op_flags[ob][w8];
-              need_low = any != 0;
+              need_low = __any_sync(0xffffffffu, any != 0);   // a vote result is provably warp-uniform (uniform datapath below)
             }
             const uint64_t a_chunk = a_desc0 + (uint64_t)((uint32_t)ob * a_buf);
             const uint64_t b_chunk_d = b_desc0 + (uint64_t)((uint32_t)gi * b_group + (uint32_t)ch * b_chunk);
@@ -236,7 +233,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const Params p) {
             const int n_off = RS * ksteps;
             if (max_terms == 3 && need_low) {
               for (int e = 0; e < n_off; ++e) {
-                const uint2 off = sh.mma_off[e];
+                const uint2 off = p.mma_off[e];
                 const uint64_t ad = a_chunk + (uint64_t)off.x, bd = b_chunk_d + (uint64_t)off.y;
                 tc::mma_f16_guarded(d_tmem, ad, bd, idesc, accumulate, lead);
                 tc::mma_f16_guarded(d_tmem, ad + a_term, bd, idesc, 1, lead);
@@ -245,7 +242,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const Params p) {
               }
             } else {
               for (int e = 0; e < n_off; ++e) {
-                const uint2 off = sh.mma_off[e];
+                const uint2 off = p.mma_off[e];
                 tc::mma_f16_guarded(d_tmem, a_chunk + (uint64_t)off.x, b_chunk_d + (uint64_t)off.y, idesc, accumulate, lead);
                 accumulate = 1;
               }
@@ -617,6 +614,15 @@ static int launch(const Params& p, const void* in, int smem_bytes, cudaStream_t 
   grid = std::max(grid, p.n_slabs);
   Params pp = p;
   pp.prof = g_prof_buffer;
+  {
+    const int ks = p.CC / 16, c8_per_group = p.cin_g / 8;
+    for (int e = 0; e < p.R * p.S * ks && e < 64; ++e) {
+      const int tap = e / ks, j = e - tap * ks;
+      const int r = tap / p.S, s2 = tap - r * p.S;
+      pp.mma_off[e] = make_uint2((uint32_t)(r * p.BW + s2) + (uint32_t)j * (uint32_t)(2 * p.npos_in),
+                                 (uint32_t)tap * (uint32_t)(c8_per_group * p.cout_g) + (uint32_t)j * (uint32_t)(2 * p.cout_g));
+    }
+  }
   conv_tc_kernel<<<grid, NTHREADS, smem_bytes, st>>>(tmap, pp);
   MNB_LAUNCHED(2);
   return 0;

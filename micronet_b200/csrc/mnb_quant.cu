@@ -618,9 +618,14 @@ extern "C" int mnb_iao_weight_bwd(const float* g_wq, const uint8_t* pass, const 
 // grid (channels, splits): fp64 partial sums, last split-block of a channel finalises.
 constexpr int STATS_SPLITS = 32;
 
+struct MnbBnUpdate {
+  double eps; float momentum;
+  float* running_mean; float* running_var; long long* num_batches_tracked;
+};
+
 __global__ void __launch_bounds__(256) channel_stats_kernel(const float* __restrict__ x, int batch, int channels,
                                                             int hw, int as_mean_var, float* __restrict__ stats,
-                                                            uint32_t* counters, double* partial) {
+                                                            uint32_t* counters, double* partial, MnbBnUpdate bn) {
   __shared__ double red[32];
   __shared__ bool last;
   const int c = blockIdx.x, sp = blockIdx.y, nsp = gridDim.y;
@@ -682,6 +687,14 @@ __global__ void __launch_bounds__(256) channel_stats_kernel(const float* __restr
     if (as_mean_var == 2) {  // batch-norm flavour: biased variance for normalisation, unbiased for the running estimate
       stats[channels + c] = (float)(ss / (double)per);
       stats[2 * channels + c] = (float)var;
+    } else if (as_mean_var == 3) {
+      // nn.BatchNorm2d training step in the finaliser: invstd for the normalisation, running statistics updated
+      // with the module's momentum (running = (1 - m) * running + m * batch; unbiased variance), step counter
+      stats[channels + c] = (float)(1.0 / sqrt(ss / (double)per + bn.eps));
+      const float m = bn.momentum;
+      bn.running_mean[c] = __fadd_rn(__fmul_rn(1.f - m, bn.running_mean[c]), __fmul_rn(m, (float)mean));
+      bn.running_var[c] = __fadd_rn(__fmul_rn(1.f - m, bn.running_var[c]), __fmul_rn(m, (float)var));
+      if (c == 0 && bn.num_batches_tracked) *bn.num_batches_tracked += 1;
     } else {
       stats[channels + c] = (float)var;
     }
@@ -717,8 +730,27 @@ extern "C" int mnb_channel_stats(const float* x, int32_t batch, int32_t channels
   int splits = (int)std::max<int64_t>(1, std::min<int64_t>(std::min<int64_t>(STATS_SPLITS, batch), per / 2048));
   uint32_t* counters = reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(scratch) + 16384);
   double* partial = reinterpret_cast<double*>(reinterpret_cast<char*>(scratch) + 49152);
+  MNB_REQUIRE(as_mean_var >= 0 && as_mean_var <= 2, "as_mean_var must be 0, 1 or 2");
   channel_stats_kernel<<<dim3(channels, splits), 256, 0, S(stream)>>>(x, batch, channels, hw, as_mean_var, stats,
-                                                                       counters, partial);
+                                                                       counters, partial, MnbBnUpdate{});
+  MNB_LAUNCHED(1);
+  return 0;
+}
+
+extern "C" int mnb_bn_batch_stats(const float* x, int32_t batch, int32_t channels, int32_t hw, double eps, double momentum,
+                                  float* running_mean, float* running_var, int64_t* num_batches_tracked,
+                                  float* mean_invstd, void* scratch, mnb_stream_t stream) {
+  MNB_REQUIRE(x && running_mean && running_var && mean_invstd && scratch && batch > 0 && channels > 0 && hw > 0,
+              "bad bn_batch_stats arguments");
+  MNB_REQUIRE(channels <= 8192, "bn_batch_stats supports at most 8192 channels, got %d", channels);
+  MNB_REQUIRE((int64_t)batch * hw > 1, "batch statistics need more than one value per channel");
+  int64_t per = (int64_t)batch * hw;
+  int splits = (int)std::max<int64_t>(1, std::min<int64_t>(std::min<int64_t>(STATS_SPLITS, batch), per / 2048));
+  uint32_t* counters = reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(scratch) + 16384);
+  double* partial = reinterpret_cast<double*>(reinterpret_cast<char*>(scratch) + 49152);
+  MnbBnUpdate bn{eps, (float)momentum, running_mean, running_var, reinterpret_cast<long long*>(num_batches_tracked)};
+  channel_stats_kernel<<<dim3(channels, splits), 256, 0, S(stream)>>>(x, batch, channels, hw, 3, mean_invstd, counters,
+                                                                       partial, bn);
   MNB_LAUNCHED(1);
   return 0;
 }

@@ -122,8 +122,13 @@ def add_quant_op(module, layer_counter, a_bits=8, w_bits=8, quant_inference=Fals
             add_quant_op(child, layer_counter, a_bits=a_bits, w_bits=w_bits, quant_inference=quant_inference)
 
 
-def prepare(model, inplace=False, a_bits=8, w_bits=8, quant_inference=False):
+def prepare(model, inplace=False, a_bits=8, w_bits=8, quant_inference=False, fuse=False):
+    """``fuse`` (extension, off by default): engine max-pool kernels and channel-shuffle folding around the
+    quantized convolutions (micronet_b200.fused); parameters, state_dict keys and results are unchanged."""
     if not inplace:
         model = copy.deepcopy(model)
     add_quant_op(model, [0], a_bits=a_bits, w_bits=w_bits, quant_inference=quant_inference)
+    if fuse:
+        from .fused import fuse_blocks
+        fuse_blocks(model)
     return model

@@ -275,6 +275,16 @@ class QuantConv2dFn(Function):
                 codes = bits = None
             else:
                 L.check(rc, "fq_conv2d_fwd_tc")
+        ctx.fconv = False
+        if not done and L.USE_TC and spec is None and x.dtype == torch.float32:
+            # un-quantized input with few channels (first layer): fp32-accurate im2col conv on the tensor cores
+            rc = _timed("fconv_fwd_tc", sh, lambda: lib.mnb_fconv2d_fwd_tc(
+                C.byref(sh), x.data_ptr(), wq.data_ptr(), L.ptr(bias), y.data_ptr(),
+                L.tc_err_flag(x.device).data_ptr(), L.stream()))
+            if rc == 0:
+                done = ctx.fconv = True
+            elif rc != L.E_UNSUPPORTED:
+                L.check(rc, "fconv2d_fwd_tc")
         if not done:
             ops = L.ConvOperands()
             if spec is not None:
@@ -338,7 +348,15 @@ class QuantConv2dFn(Function):
                 ops.a_f32 = ctx.x.data_ptr()
             nbytes = int(lib.mnb_wgrad_scratch_bytes(C.byref(sh)))
             done = False
-            if L.USE_TC and ctx.w_int is not None and ctx.x is not None:
+            if ctx.fconv:
+                fbytes = int(lib.mnb_fconv2d_wgrad_tc_scratch_bytes(C.byref(sh)))
+                if fbytes >= 0:
+                    ws = torch.empty(max(fbytes, 4), dtype=torch.uint8, device=dy.device)
+                    L.check(_timed("fconv_wgrad_tc", sh, lambda: lib.mnb_fconv2d_wgrad_tc(
+                        C.byref(sh), dy.data_ptr(), ctx.x.data_ptr(), dwq.data_ptr(), ws.data_ptr(),
+                        L.tc_err_flag(dy.device).data_ptr(), L.stream())), "fconv2d_wgrad_tc")
+                    done = True
+            if not done and L.USE_TC and ctx.w_int is not None and ctx.x is not None:
                 tbytes = int(lib.mnb_wgrad_tc_scratch_bytes(C.byref(sh)))
                 if tbytes > 0:
                     qp = spec.struct() if spec is not None else None

@@ -28,16 +28,6 @@ import torch.nn.functional as TF
 from . import _lib as L
 
 
-def _channel_stats3(x):
-    lib = L.load()
-    b, c = x.shape[0], x.shape[1]
-    hw = x.numel() // (b * c)
-    out = torch.empty(3 * c, dtype=torch.float32, device=x.device)
-    L.check(lib.mnb_channel_stats(x.data_ptr(), b, c, hw, 2, out.data_ptr(), L.scratch(x.device, c).data_ptr(),
-                                  L.stream()), "channel_stats")
-    return out[:c], out[c:2 * c], out[2 * c:]
-
-
 class BNSignFn(Function):
     @staticmethod
     def forward(ctx, x, gamma, beta, mean, invstd, training, shuffle_groups):
@@ -84,17 +74,19 @@ class BatchNormBinarize2d(nn.BatchNorm2d):
         assert self.affine and self.track_running_stats and self.momentum is not None, \
             "BatchNormBinarize2d supports affine BN with running statistics and a float momentum"
         if self.training:
-            mean, var_b, var_u = _channel_stats3(input.detach().contiguous())
-            with torch.no_grad():
-                m = self.momentum
-                self.running_mean.mul_(1 - m).add_(mean, alpha=m)
-                self.running_var.mul_(1 - m).add_(var_u, alpha=m)
-                self.num_batches_tracked.add_(1)
-            invstd = torch.rsqrt(var_b + self.eps)
+            lib = L.load()
+            x = input.detach().contiguous()
+            b, c = x.shape[0], x.shape[1]
+            stats = torch.empty(2 * c, dtype=torch.float32, device=x.device)
+            L.check(lib.mnb_bn_batch_stats(x.data_ptr(), b, c, x.numel() // (b * c), float(self.eps), float(self.momentum),
+                                           self.running_mean.data_ptr(), self.running_var.data_ptr(),
+                                           self.num_batches_tracked.data_ptr(), stats.data_ptr(),
+                                           L.scratch(x.device, c).data_ptr(), L.stream()), "bn_batch_stats")
+            mean, invstd = stats[:c], stats[c:]
         else:
             mean = self.running_mean
             invstd = torch.rsqrt(self.running_var + self.eps)
-        return BNSignFn.apply(input, self.weight, self.bias, mean.contiguous(), invstd.contiguous(), self.training,
+        return BNSignFn.apply(input, self.weight, self.bias, mean, invstd, self.training,
                               int(self.out_shuffle_groups))
 
     def extra_repr(self):
@@ -278,4 +270,5 @@ def fuse_wbwtab_blocks(model: nn.Module, fold_shuffle: bool = True) -> nn.Module
     return model
 
 
+fuse_blocks = fuse_wbwtab_blocks      # the pool / first-conv / shuffle rewrites apply to every scheme
 fuse_bn_binarize = fuse_wbwtab_blocks  # first name of this pass

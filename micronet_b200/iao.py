@@ -515,11 +515,16 @@ def add_quant_op(module, a_bits=8, w_bits=8, q_type=0, q_level=0, weight_observe
 
 def prepare(model, inplace=False, a_bits=8, w_bits=8, q_type=0, q_level=0, weight_observer=0, bn_fuse=False,
             bn_fuse_calib=False, quant_inference=False, pretrained_model=False, qaft=False, ptq=False,
-            percentile=0.9999):
+            percentile=0.9999, fuse=False):
+    """``fuse`` (extension, off by default): engine max-pool kernels and channel-shuffle folding
+    (micronet_b200.fused); parameters, state_dict keys and results are unchanged."""
     if not inplace:
         model = copy.deepcopy(model)
     add_quant_op(model, a_bits=a_bits, w_bits=w_bits, q_type=q_type, q_level=q_level,
                  weight_observer=weight_observer, bn_fuse=bn_fuse, bn_fuse_calib=bn_fuse_calib,
                  quant_inference=quant_inference, pretrained_model=pretrained_model, qaft=qaft, ptq=ptq,
                  percentile=percentile)
+    if fuse:
+        from .fused import fuse_blocks
+        fuse_blocks(model)
     return model

@@ -200,3 +200,24 @@ def test_fused_model_step_matches_unfused_engine_model():
     flat = {k: torch.cat([g.flatten() for g in out[k][1].values()]).double() for k in out}
     cos = torch.dot(flat["plain"], flat["fused"]) / (flat["plain"].norm() * flat["fused"].norm())
     assert cos > 0.98, float(cos)
+
+
+def test_dorefa_fuse_option_changes_no_number():
+    """pool kernels are bit-identical to ATen and a folded shuffle is only an addressing change: the fused DoReFa
+    model must reproduce the unfused engine model exactly"""
+    import micronet_b200 as E
+    from harness import models as zoo
+    torch.manual_seed(2)
+    base = zoo.NINGC()
+    zoo.init_like_reference(base)
+    x = torch.randn(8, 3, 32, 32).to(DEV)
+    t = torch.randint(0, 10, (8,)).to(DEV)
+    out = {}
+    for name, kw in (("plain", {}), ("fused", {"fuse": True})):
+        m = E.dorefa.prepare(base, a_bits=4, w_bits=4, **kw).to(DEV).train()
+        loss = nn.functional.cross_entropy(m(x), t)
+        loss.backward()
+        out[name] = (loss.detach().clone(), {n: p.grad.clone() for n, p in m.named_parameters()})
+    assert torch.equal(out["plain"][0], out["fused"][0])
+    for n, g in out["plain"][1].items():
+        assert torch.equal(g, out["fused"][1][n]), n
