@@ -229,6 +229,18 @@ int mnb_bn_sign_bwd(const float* g, const uint32_t* pass_bits, const float* x, i
                     int32_t out_shuffle_groups, float* dx, float* dgamma, float* dbeta, float* dx_channel_sum,
                     void* scratch, mnb_stream_t stream);
 
+/* BatchNorm2d + binarizer + nn.MaxPool2d(2, 2) in one pass (the block before a 2x2 pool: nin_gc.py:84-85, :88-89): the
+ * full-resolution +-1 tensor and the un-pooled gradient are never materialised.  y / g: [B, C, H/2, W/2] (through the
+ * output permutation), pass_bits: B*C*H*W bits, argmax: B*C*(H/2)*(W/2) bytes (window index, ATen's first-maximum
+ * rule).  Needs even H and W % 8 == 0, else MNB_E_UNSUPPORTED (run mnb_bn_sign_* and mnb_maxpool2d_* instead).   */
+int mnb_bn_sign_pool_fwd(const float* x, int32_t batch, int32_t channels, int32_t H, int32_t W, const float* mean,
+                         const float* invstd, const float* gamma, const float* beta, int32_t out_shuffle_groups, float* y,
+                         uint32_t* pass_bits, uint8_t* argmax, mnb_stream_t stream);
+int mnb_bn_sign_pool_bwd(const float* g, const uint32_t* pass_bits, const uint8_t* argmax, const float* x, int32_t batch,
+                         int32_t channels, int32_t H, int32_t W, const float* mean, const float* invstd, const float* gamma,
+                         int32_t training, int32_t out_shuffle_groups, float* dx, float* dgamma, float* dbeta,
+                         float* dx_channel_sum, void* scratch, mnb_stream_t stream);
+
 /* nn.MaxPool2d (square kernel <= 15, dilation 1, floor mode; nin_gc.py:85,89 / nin.py pools) with a one-byte
  * window index per output instead of int64 indices.  Same first-maximum tie rule and gradient accumulation
  * order as ATen, so results are bit-identical.  argmax: batch*channels*OH*OW bytes.                   */

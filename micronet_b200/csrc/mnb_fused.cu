@@ -299,6 +299,228 @@ extern "C" int mnb_bn_sign_bwd(const float* g, const uint32_t* pass_bits, const 
   return 0;
 }
 
+// ------------------------------------------------------------------ BatchNorm + sign + MaxPool2d(2, 2) in one pass
+// The full-resolution +-1 tensor is never written: forward reads x once and writes the pooled signs (plus the STE
+// pass bits of all inputs and the window argmax); backward routes the pooled gradient to the window winner, applies
+// the STE mask and the batch-norm backward without materialising the un-pooled gradient.
+// One thread owns two horizontally adjacent windows = two float4 of x (rows 2oh and 2oh + 1).  W % 8 == 0, H even.
+struct PoolGeom { uint32_t channels, H, W4, OH, OW2, sg; };
+
+__device__ __forceinline__ uint32_t first_max_of_signs(bool p0, bool p1, bool p2, bool p3) {
+  // ATen's max_pool scan order (r0c0, r0c1, r1c0, r1c1), replace on strictly greater: the first +1, else element 0
+  return p0 ? 0u : (p1 ? 1u : (p2 ? 2u : (p3 ? 3u : 0u)));
+}
+
+__global__ void __launch_bounds__(256) bn_sign_pool_fwd_kernel(const float4* __restrict__ x, uint32_t n_pairs, PoolGeom gm,
+                                                               const float* __restrict__ mean, const float* __restrict__ invstd,
+                                                               const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                               float2* __restrict__ y, uchar2* __restrict__ arg,
+                                                               uint8_t* __restrict__ bits8) {
+  const uint32_t stride = gridDim.x * blockDim.x;
+  const uint32_t n_up = (n_pairs + 31u) & ~31u;
+  const uint32_t cpg = gm.channels / gm.sg;
+  for (uint32_t o = blockIdx.x * blockDim.x + threadIdx.x; o < n_up; o += stride) {
+    uint32_t nib = 0, i0 = 0;
+    const bool live = o < n_pairs;
+    if (live) {
+      const uint32_t j = o % gm.OW2, t = o / gm.OW2;
+      const uint32_t oh = t % gm.OH, plane = t / gm.OH;
+      const uint32_t b = plane / gm.channels, c = plane - b * gm.channels;
+      i0 = (plane * gm.H + 2 * oh) * gm.W4 + j;
+      const float mu = __ldg(mean + c), sc = __ldg(gamma + c) * __ldg(invstd + c), be = __ldg(beta + c);
+      const float4 r0 = __ldg(x + i0), r1 = __ldg(x + i0 + gm.W4);
+      const float v[8] = {fmaf(r0.x - mu, sc, be), fmaf(r0.y - mu, sc, be), fmaf(r0.z - mu, sc, be), fmaf(r0.w - mu, sc, be),
+                          fmaf(r1.x - mu, sc, be), fmaf(r1.y - mu, sc, be), fmaf(r1.z - mu, sc, be), fmaf(r1.w - mu, sc, be)};
+      bool pos[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) { pos[e] = !(v[e] < 0.f); nib |= (uint32_t)(fabsf(v[e]) < 1.f) << e; }
+      const uint32_t a0 = first_max_of_signs(pos[0], pos[1], pos[4], pos[5]);
+      const uint32_t a1 = first_max_of_signs(pos[2], pos[3], pos[6], pos[7]);
+      const float m0 = (pos[0] | pos[1] | pos[4] | pos[5]) ? 1.f : -1.f, m1 = (pos[2] | pos[3] | pos[6] | pos[7]) ? 1.f : -1.f;
+      const uint32_t oplane = b * gm.channels + shuffled_channel(c, gm.sg, cpg);
+      y[(oplane * gm.OH + oh) * gm.OW2 + j] = make_float2(m0, m1);
+      arg[o] = make_uchar2((unsigned char)a0, (unsigned char)a1);
+    }
+    // pass nibbles: bits 0-3 = row 2oh (float4 index i0), bits 4-7 = row 2oh+1 (i0 + W4); two lanes share a byte
+    const uint32_t other = __shfl_xor_sync(0xffffffffu, nib, 1);
+    if (live && (threadIdx.x & 1) == 0) {
+      bits8[i0 >> 1] = (uint8_t)((nib & 15u) | ((other & 15u) << 4));
+      bits8[(i0 + gm.W4) >> 1] = (uint8_t)((nib >> 4) | (other & 0xf0u));
+    }
+  }
+}
+
+// pass 1 of the backward: dbeta = sum gm, dgamma = sum gm * xhat with gm = pooled gradient at the window winner x pass bit
+__global__ void __launch_bounds__(256) bn_sign_pool_bwd_reduce_kernel(const float2* __restrict__ g, const uchar2* __restrict__ arg,
+                                                                      const uint8_t* __restrict__ bits8, const float* __restrict__ x,
+                                                                      int batch, PoolGeom gm, const float* __restrict__ mean,
+                                                                      const float* __restrict__ invstd, float* __restrict__ dgamma,
+                                                                      float* __restrict__ dbeta, uint32_t* counters, double* partial) {
+  __shared__ double red[32];
+  __shared__ bool last;
+  const uint32_t c = blockIdx.x, sp = blockIdx.y, nsp = gridDim.y;
+  const uint32_t oc = shuffled_channel(c, gm.sg, gm.channels / gm.sg);
+  const float mu = __ldg(mean + c), is = __ldg(invstd + c);
+  const uint32_t b_lo = (uint32_t)((int64_t)batch * sp / nsp), b_hi = (uint32_t)((int64_t)batch * (sp + 1) / nsp);
+  const uint32_t per_img = gm.OH * gm.OW2, total = (b_hi - b_lo) * per_img;
+  float f1[2] = {0.f, 0.f}, f2[2] = {0.f, 0.f};
+  for (uint32_t t0 = threadIdx.x; t0 < total; t0 += 2 * blockDim.x) {
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const uint32_t t = t0 + u * blockDim.x;
+      if (t < total) {
+        const uint32_t b = b_lo + t / per_img, rem = t % per_img;
+        const uint32_t oh = rem / gm.OW2, j = rem - oh * gm.OW2;
+        const uint32_t plane = b * gm.channels + c;
+        const float2 gv = __ldg(g + ((b * gm.channels + oc) * gm.OH + oh) * gm.OW2 + j);
+        const uchar2 a = arg[(plane * gm.OH + oh) * gm.OW2 + j];
+        const uint32_t i0 = (plane * gm.H + 2 * oh) * gm.W4 + j;
+#pragma unroll
+        for (int w = 0; w < 2; ++w) {
+          const uint32_t aw = w ? a.y : a.x;
+          const uint32_t i4 = i0 + (aw >> 1) * gm.W4, col = 2u * w + (aw & 1u);
+          const bool pass = (bits8[i4 >> 1] >> (4u * (i4 & 1u) + col)) & 1u;
+          const float gmv = pass ? (w ? gv.y : gv.x) : 0.f;
+          f1[u] += gmv;
+          f2[u] += gmv * ((__ldg(x + 4u * i4 + col) - mu) * is);
+        }
+      }
+    }
+  }
+  double s1 = mnb_block_reduce((double)f1[0] + (double)f1[1], MnbSum(), 0.0, red);
+  double s2 = mnb_block_reduce((double)f2[0] + (double)f2[1], MnbSum(), 0.0, red);
+  if (threadIdx.x == 0) {
+    partial[((int64_t)c * nsp + sp) * 2 + 0] = s1;
+    partial[((int64_t)c * nsp + sp) * 2 + 1] = s2;
+    __threadfence();
+    last = (atomicAdd(counters + c, 1u) == nsp - 1);
+  }
+  __syncthreads();
+  if (!last || threadIdx.x != 0) return;
+  __threadfence();
+  s1 = 0.0; s2 = 0.0;
+  for (uint32_t j = 0; j < nsp; ++j) { s1 += partial[((int64_t)c * nsp + j) * 2]; s2 += partial[((int64_t)c * nsp + j) * 2 + 1]; }
+  dbeta[c] = (float)s1;
+  dgamma[c] = (float)s2;
+  counters[c] = 0;
+}
+
+// pass 2: dx over the full-resolution plane (+ its channel sums)
+__global__ void __launch_bounds__(256) bn_sign_pool_bwd_apply_kernel(const float2* __restrict__ g, const uchar2* __restrict__ arg,
+                                                                     const uint8_t* __restrict__ bits8, const float4* __restrict__ x,
+                                                                     int batch, PoolGeom gm, float inv_count,
+                                                                     const float* __restrict__ mean, const float* __restrict__ invstd,
+                                                                     const float* __restrict__ gamma, const float* __restrict__ dgamma,
+                                                                     const float* __restrict__ dbeta, int training,
+                                                                     float4* __restrict__ dx, float* __restrict__ dx_sum,
+                                                                     uint32_t* counters, double* partial) {
+  __shared__ double red[32];
+  __shared__ bool last;
+  const uint32_t c = blockIdx.x, sp = blockIdx.y, nsp = gridDim.y;
+  const uint32_t oc = shuffled_channel(c, gm.sg, gm.channels / gm.sg);
+  const float mu = __ldg(mean + c), is = __ldg(invstd + c), k = __ldg(gamma + c) * is;
+  const float db = training ? __ldg(dbeta + c) * inv_count : 0.f, dg = training ? __ldg(dgamma + c) * inv_count : 0.f;
+  const uint32_t b_lo = (uint32_t)((int64_t)batch * sp / nsp), b_hi = (uint32_t)((int64_t)batch * (sp + 1) / nsp);
+  const uint32_t per_img = gm.OH * gm.OW2, total = (b_hi - b_lo) * per_img;
+  float f = 0.f;
+  for (uint32_t t = threadIdx.x; t < total; t += blockDim.x) {
+    const uint32_t b = b_lo + t / per_img, rem = t % per_img;
+    const uint32_t oh = rem / gm.OW2, j = rem - oh * gm.OW2;
+    const uint32_t plane = b * gm.channels + c;
+    const float2 gv = __ldg(g + ((b * gm.channels + oc) * gm.OH + oh) * gm.OW2 + j);
+    const uchar2 a = arg[(plane * gm.OH + oh) * gm.OW2 + j];
+    const uint32_t i0 = (plane * gm.H + 2 * oh) * gm.W4 + j, i1 = i0 + gm.W4;
+    const uint32_t n0 = (bits8[i0 >> 1] >> (4u * (i0 & 1u))) & 15u, n1 = (bits8[i1 >> 1] >> (4u * (i1 & 1u))) & 15u;
+    // masked gradient of the eight inputs: the pooled gradient at each window's winner, if its pass bit is set
+    float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    {
+      const uint32_t e0 = (a.x >> 1) * 4u + (a.x & 1u), e1 = (a.y >> 1) * 4u + 2u + (a.y & 1u);
+      const uint32_t nib = n0 | (n1 << 4);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        if ((uint32_t)e == e0 && ((nib >> e) & 1u)) v[e] = gv.x;
+        if ((uint32_t)e == e1 && ((nib >> e) & 1u)) v[e] = gv.y;
+      }
+    }
+    if (training) {
+      const float4 r0 = __ldg(x + i0), r1 = __ldg(x + i1);
+      const float xs[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+#pragma unroll
+      for (int e = 0; e < 8; ++e) v[e] = v[e] - db - ((xs[e] - mu) * is) * dg;
+    }
+    const float4 o0 = make_float4(k * v[0], k * v[1], k * v[2], k * v[3]), o1 = make_float4(k * v[4], k * v[5], k * v[6], k * v[7]);
+    dx[i0] = o0;
+    dx[i1] = o1;
+    f += ((o0.x + o0.y) + (o0.z + o0.w)) + ((o1.x + o1.y) + (o1.z + o1.w));
+  }
+  if (!dx_sum) return;
+  double s = mnb_block_reduce((double)f, MnbSum(), 0.0, red);
+  if (threadIdx.x == 0) {
+    partial[((int64_t)c * nsp + sp) * 2] = s;
+    __threadfence();
+    last = (atomicAdd(counters + c, 1u) == nsp - 1);
+  }
+  __syncthreads();
+  if (!last || threadIdx.x != 0) return;
+  __threadfence();
+  s = 0.0;
+  for (uint32_t j = 0; j < nsp; ++j) s += partial[((int64_t)c * nsp + j) * 2];
+  dx_sum[c] = (float)s;
+  counters[c] = 0;
+}
+
+static int pool_geom(int batch, int channels, int H, int W, int sg, const void* a, const void* b, const void* c, PoolGeom& gm) {
+  MNB_REQUIRE(batch > 0 && channels > 0 && channels <= 8192 && H > 0 && W > 0, "bad bn_sign_pool shape");
+  MNB_REQUIRE(sg >= 1 && channels % sg == 0, "shuffle groups %d do not divide %d channels", sg, channels);
+  if ((H & 1) || (W & 7) || (int64_t)batch * channels * H * W >= (1ll << 31) ||
+      (((uintptr_t)a | (uintptr_t)b | (uintptr_t)c) & 15))
+    return mnb_fail(MNB_E_UNSUPPORTED, "bn_sign_pool needs even H, W %% 8 == 0, < 2^31 elements, 16-byte aligned tensors");
+  gm = PoolGeom{(uint32_t)channels, (uint32_t)H, (uint32_t)(W / 4), (uint32_t)(H / 2), (uint32_t)(W / 4), (uint32_t)sg};
+  return 0;
+}
+
+extern "C" int mnb_bn_sign_pool_fwd(const float* x, int32_t batch, int32_t channels, int32_t H, int32_t W, const float* mean,
+                                    const float* invstd, const float* gamma, const float* beta, int32_t out_shuffle_groups,
+                                    float* y, uint32_t* pass_bits, uint8_t* argmax, mnb_stream_t stream) {
+  MNB_REQUIRE(x && mean && invstd && gamma && beta && y && pass_bits && argmax, "NULL bn_sign_pool_fwd pointer");
+  PoolGeom gm;
+  if (int e = pool_geom(batch, channels, H, W, out_shuffle_groups, x, y, nullptr, gm)) return e;
+  const uint32_t n_pairs = (uint32_t)((int64_t)batch * channels * gm.OH * gm.OW2);
+  int blocks = (int)std::min<int64_t>(mnb_ceil_div(n_pairs, 256), MNB_NUM_SMS * 16);
+  bn_sign_pool_fwd_kernel<<<blocks, 256, 0, S(stream)>>>(reinterpret_cast<const float4*>(x), n_pairs, gm, mean, invstd, gamma, beta,
+                                                         reinterpret_cast<float2*>(y), reinterpret_cast<uchar2*>(argmax),
+                                                         reinterpret_cast<uint8_t*>(pass_bits));
+  MNB_LAUNCHED(1);
+  return 0;
+}
+
+extern "C" int mnb_bn_sign_pool_bwd(const float* g, const uint32_t* pass_bits, const uint8_t* argmax, const float* x, int32_t batch,
+                                    int32_t channels, int32_t H, int32_t W, const float* mean, const float* invstd,
+                                    const float* gamma, int32_t training, int32_t out_shuffle_groups, float* dx, float* dgamma,
+                                    float* dbeta, float* dx_channel_sum, void* scratch, mnb_stream_t stream) {
+  MNB_REQUIRE(g && pass_bits && argmax && x && mean && invstd && gamma && dx && dgamma && dbeta && scratch,
+              "NULL bn_sign_pool_bwd pointer");
+  PoolGeom gm;
+  if (int e = pool_geom(batch, channels, H, W, out_shuffle_groups, x, dx, nullptr, gm)) return e;
+  MNB_REQUIRE((reinterpret_cast<uintptr_t>(g) & 7) == 0, "pooled gradient must be 8-byte aligned");
+  const int64_t per = (int64_t)batch * H * W;
+  const int splits = plane_splits(batch, per);
+  uint32_t* counters = reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(scratch) + 16384);
+  double* partial = reinterpret_cast<double*>(reinterpret_cast<char*>(scratch) + 49152);
+  const dim3 grid(channels, splits);
+  const uint8_t* bits8 = reinterpret_cast<const uint8_t*>(pass_bits);
+  bn_sign_pool_bwd_reduce_kernel<<<grid, 256, 0, S(stream)>>>(reinterpret_cast<const float2*>(g),
+                                                              reinterpret_cast<const uchar2*>(argmax), bits8, x, batch, gm, mean,
+                                                              invstd, dgamma, dbeta, counters, partial);
+  bn_sign_pool_bwd_apply_kernel<<<grid, 256, 0, S(stream)>>>(reinterpret_cast<const float2*>(g),
+                                                             reinterpret_cast<const uchar2*>(argmax), bits8,
+                                                             reinterpret_cast<const float4*>(x), batch, gm, 1.f / (float)per, mean,
+                                                             invstd, gamma, dgamma, dbeta, training,
+                                                             reinterpret_cast<float4*>(dx), dx_channel_sum, counters, partial);
+  MNB_LAUNCHED(2);
+  return 0;
+}
+
 // ------------------------------------------------------------------ MaxPool2d with a one-byte window index
 // Tie rule of ATen's max_pool_forward_nchw: scan the window row-major, replace on (v > best) || isnan(v): the first
 // maximum wins.  The stored byte is r * k + s of the winner (window coordinates, counted from the unclipped corner).

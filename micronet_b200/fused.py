@@ -6,7 +6,8 @@ ReLU swapped by WB:319-322), optionally followed by ``nn.MaxPool2d``.  ``fuse_wb
 * every sibling pair (BatchNorm2d, ActivationQuantizer(A=2)) -> (``BatchNormBinarize2d``, Identity): batch
   statistics, normalise + sign + STE mask in two kernels forward and two backward; the backward also hands the
   producing convolution its bias gradient (channel sums of dx), saving that pass;
-* every plain ``nn.MaxPool2d`` -> ``EngineMaxPool2d`` (byte window index, bit-identical to ATen);
+* every plain ``nn.MaxPool2d`` -> ``EngineMaxPool2d`` (byte window index, bit-identical to ATen); a 2x2 pool
+  that directly follows a fused BN+binarizer is absorbed by it (the un-pooled +-1 tensor is never written);
 * the un-quantized first ``nn.Conv2d`` (few input channels) -> ``EngineFloatConv2d``: fp32-accurate im2col
   convolution on the tensor cores (forward + weight gradient);
 * every block whose input shuffle (``channel_shuffle_flag`` / ``shuffle_groups`` attributes of the
@@ -29,19 +30,30 @@ from . import _lib as L
 
 
 class BNSignFn(Function):
+    """sign(batch_norm(x)) [-> max_pool2d(2, 2)] [-> channel_shuffle] with the saturate STE"""
+
     @staticmethod
-    def forward(ctx, x, gamma, beta, mean, invstd, training, shuffle_groups):
+    def forward(ctx, x, gamma, beta, mean, invstd, training, shuffle_groups, pool):
         lib = L.load()
         x = x.contiguous()
         b, c = x.shape[0], x.shape[1]
         hw = x.numel() // (b * c)
-        y = torch.empty_like(x)
         bits = torch.empty((x.numel() + 31) // 32, dtype=torch.int32, device=x.device)
-        L.check(lib.mnb_bn_sign_fwd(x.data_ptr(), b, c, hw, mean.data_ptr(), invstd.data_ptr(), gamma.data_ptr(),
-                                    beta.data_ptr(), shuffle_groups, y.data_ptr(), bits.data_ptr(), L.stream()),
-                "bn_sign_fwd")
+        arg = None
+        if pool:
+            h, w = x.shape[2], x.shape[3]
+            y = torch.empty((b, c, h // 2, w // 2), dtype=x.dtype, device=x.device)
+            arg = torch.empty(y.numel(), dtype=torch.uint8, device=x.device)
+            L.check(lib.mnb_bn_sign_pool_fwd(x.data_ptr(), b, c, h, w, mean.data_ptr(), invstd.data_ptr(), gamma.data_ptr(),
+                                             beta.data_ptr(), shuffle_groups, y.data_ptr(), bits.data_ptr(), arg.data_ptr(),
+                                             L.stream()), "bn_sign_pool_fwd")
+        else:
+            y = torch.empty_like(x)
+            L.check(lib.mnb_bn_sign_fwd(x.data_ptr(), b, c, hw, mean.data_ptr(), invstd.data_ptr(), gamma.data_ptr(),
+                                        beta.data_ptr(), shuffle_groups, y.data_ptr(), bits.data_ptr(), L.stream()),
+                    "bn_sign_fwd")
         ctx.save_for_backward(x, gamma, mean, invstd)
-        ctx.bits, ctx.training, ctx.shuffle_groups = bits, training, shuffle_groups
+        ctx.bits, ctx.arg, ctx.training, ctx.shuffle_groups = bits, arg, training, shuffle_groups
         return y
 
     @staticmethod
@@ -54,20 +66,30 @@ class BNSignFn(Function):
         dx = torch.empty_like(x)
         out = torch.empty(3 * c, dtype=torch.float32, device=x.device)
         dgamma, dbeta, dx_sum = out[:c], out[c:2 * c], out[2 * c:]
-        L.check(lib.mnb_bn_sign_bwd(g.data_ptr(), ctx.bits.data_ptr(), x.data_ptr(), b, c, hw, mean.data_ptr(),
-                                    invstd.data_ptr(), gamma.data_ptr(), 1 if ctx.training else 0, ctx.shuffle_groups,
-                                    dx.data_ptr(), dgamma.data_ptr(), dbeta.data_ptr(), dx_sum.data_ptr(),
-                                    L.scratch(x.device, c).data_ptr(), L.stream()), "bn_sign_bwd")
+        scratch = L.scratch(x.device, c)
+        if ctx.arg is not None:
+            L.check(lib.mnb_bn_sign_pool_bwd(g.data_ptr(), ctx.bits.data_ptr(), ctx.arg.data_ptr(), x.data_ptr(), b, c,
+                                             x.shape[2], x.shape[3], mean.data_ptr(), invstd.data_ptr(), gamma.data_ptr(),
+                                             1 if ctx.training else 0, ctx.shuffle_groups, dx.data_ptr(), dgamma.data_ptr(),
+                                             dbeta.data_ptr(), dx_sum.data_ptr(), scratch.data_ptr(), L.stream()),
+                    "bn_sign_pool_bwd")
+        else:
+            L.check(lib.mnb_bn_sign_bwd(g.data_ptr(), ctx.bits.data_ptr(), x.data_ptr(), b, c, hw, mean.data_ptr(),
+                                        invstd.data_ptr(), gamma.data_ptr(), 1 if ctx.training else 0, ctx.shuffle_groups,
+                                        dx.data_ptr(), dgamma.data_ptr(), dbeta.data_ptr(), dx_sum.data_ptr(),
+                                        scratch.data_ptr(), L.stream()), "bn_sign_bwd")
         # picked up by QuantConv2dFn.backward when this dx is its grad_output (saves its own channel-sum pass)
         dx._mnb_channel_sum = dx_sum
-        return dx, dgamma, dbeta, None, None, None, None
+        return dx, dgamma, dbeta, None, None, None, None, None
 
 
 class BatchNormBinarize2d(nn.BatchNorm2d):
-    """nn.BatchNorm2d followed by wbwtab's binarizing ActivationQuantizer.  ``out_shuffle_groups`` > 1 writes
-    the result in the channel order ``shuffle_channels(., groups)`` would produce."""
+    """nn.BatchNorm2d followed by wbwtab's binarizing ActivationQuantizer.  ``pool2`` additionally applies the
+    nn.MaxPool2d(2, 2) that follows the block; ``out_shuffle_groups`` > 1 writes the result in the channel
+    order ``shuffle_channels(., groups)`` would produce."""
 
     out_shuffle_groups = 1
+    pool2 = False
 
     def forward(self, input):
         L.require_cuda(input, self.weight)
@@ -86,11 +108,15 @@ class BatchNormBinarize2d(nn.BatchNorm2d):
         else:
             mean = self.running_mean
             invstd = torch.rsqrt(self.running_var + self.eps)
-        return BNSignFn.apply(input, self.weight, self.bias, mean, invstd, self.training,
-                              int(self.out_shuffle_groups))
+        sg = int(self.out_shuffle_groups)
+        if self.pool2 and (input.dim() != 4 or input.shape[2] % 2 or input.shape[3] % 8):
+            # plane shape outside the fused pool kernel's cover: the same result in two steps
+            y = BNSignFn.apply(input, self.weight, self.bias, mean, invstd, self.training, 1, False)
+            return MaxPoolFn.apply(y, 2, 2, 0, sg)
+        return BNSignFn.apply(input, self.weight, self.bias, mean, invstd, self.training, sg, bool(self.pool2))
 
     def extra_repr(self):
-        return super().extra_repr() + f", out_shuffle_groups={self.out_shuffle_groups}"
+        return super().extra_repr() + f", pool2={self.pool2}, out_shuffle_groups={self.out_shuffle_groups}"
 
 
 class MaxPoolFn(Function):
@@ -246,6 +272,23 @@ def _tail_producer(m: nn.Module):
     return None
 
 
+def _fold_pools(module: nn.Module):
+    """BatchNormBinarize2d directly followed by a 2x2 / stride 2 max-pool sibling -> one fused producer"""
+    for child in module.children():
+        _fold_pools(child)
+    if not isinstance(module, nn.Sequential):
+        return
+    names = [n for n, k in module.named_children() if not isinstance(k, nn.Identity)]
+    for pn, cn in zip(names, names[1:]):
+        prev, cur = module._modules[pn], module._modules[cn]
+        if not isinstance(cur, EngineMaxPool2d) or _pool_cfg(cur) != (2, 2, 0) or cur.out_shuffle_groups != 1:
+            continue
+        prod = _tail_producer(prev)
+        if isinstance(prod, BatchNormBinarize2d) and not prod.pool2 and prod.out_shuffle_groups == 1:
+            prod.pool2 = True
+            module._modules[cn] = nn.Identity()
+
+
 def _fold_shuffles(module: nn.Module):
     for child in module.children():
         _fold_shuffles(child)
@@ -265,6 +308,7 @@ def _fold_shuffles(module: nn.Module):
 
 def fuse_wbwtab_blocks(model: nn.Module, fold_shuffle: bool = True) -> nn.Module:
     _fuse_pairs(model)
+    _fold_pools(model)
     if fold_shuffle:
         _fold_shuffles(model)
     return model

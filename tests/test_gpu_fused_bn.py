@@ -28,12 +28,14 @@ def _pair(c, seed):
     return bn
 
 
-def _reference(bn, x, go, groups=1):
-    """fp64 BatchNorm + the oracle's binarizer [+ channel shuffle]; returns y, bn output, dx, dgamma, dbeta"""
+def _reference(bn, x, go, groups=1, pool=False):
+    """fp64 BatchNorm + the oracle's binarizer [+ 2x2 max-pool] [+ channel shuffle]; returns y, bn output, dx, dgamma, dbeta"""
     ref = copy.deepcopy(bn).double()
     xr = x.double().requires_grad_(True)
     pre = ref(xr)
     y = O.wb_binarize_activation(pre)
+    if pool:
+        y = nn.functional.max_pool2d(y, 2, 2)
     if groups > 1:
         y = _shuffle(y, groups)
     y.backward(go.double())
@@ -93,6 +95,45 @@ def test_fused_bn_binarize_matches_bn_then_oracle_binarizer(shape, training, shu
         assert torch.equal(fused.running_mean.cpu(), bn.running_mean)
 
 
+POOLED = [(8, 256, 32, 32), (8, 64, 16, 16), (4, 32, 8, 8), (3, 12, 4, 24), (2, 33, 6, 6), (2, 6, 10, 12)]  # last two: two-step path
+
+
+@pytest.mark.parametrize("shape", POOLED, ids=[str(s) for s in POOLED])
+@pytest.mark.parametrize("training", [True, False], ids=["train", "eval"])
+@pytest.mark.parametrize("shuffled", [False, True], ids=["plain", "shuffled"])
+def test_fused_bn_binarize_pool_matches_reference_chain(shape, training, shuffled):
+    """BatchNorm -> binarizer -> MaxPool2d(2, 2) [-> shuffle] in one module: +-1 windows are all ties, so the
+    first-maximum rule decides which input receives the pooled gradient"""
+    from micronet_b200.fused import BatchNormBinarize2d
+    B, C, H, W = shape
+    groups = _groups_for(C) if shuffled else 1
+    bn = _pair(C, sum(shape) + 1)
+    bn.train(training)
+    x = torch.randn(B, C, H, W) * 1.5 + 0.2
+    go = torch.randn(B, C, H // 2, W // 2)
+    for _ in range(6):
+        with torch.no_grad():
+            pre = copy.deepcopy(bn).double()(x.double())
+        edge = (pre.abs() < 1e-4) | ((pre.abs() - 1).abs() < 1e-4)
+        if not edge.any():
+            break
+        x = torch.where(edge, x + 0.01, x)
+    assert not edge.any()
+    y_r, pre, dx_r, dg_r, db_r, ref = _reference(bn, x, go, groups, pool=True)
+    fused = BatchNormBinarize2d(C)
+    fused.load_state_dict(bn.state_dict())
+    fused = fused.to(DEV).train(training)
+    fused.out_shuffle_groups, fused.pool2 = groups, True
+    xg = x.to(DEV).requires_grad_(True)
+    y = fused(xg)
+    y.backward(go.to(DEV))
+    assert torch.equal(y.detach().cpu().double(), y_r)
+    assert rel_err(xg.grad, dx_r) < 2e-5
+    assert rel_err(fused.weight.grad, dg_r) < 2e-5 and rel_err(fused.bias.grad, db_r) < 2e-5
+    if training:
+        assert rel_err(fused.running_mean, ref.running_mean) < 1e-6 and rel_err(fused.running_var, ref.running_var) < 1e-6
+
+
 def test_bn_sign_backward_hands_over_channel_sums_of_dx():
     """conv(bias) -> fused BN: the bias gradient comes from the BN backward's by-product; it must equal the
     channel sums of the dx the kernel wrote (pure rounding noise for a training-mode BN: compare to |dx| scale)"""
@@ -103,7 +144,7 @@ def test_bn_sign_backward_hands_over_channel_sums_of_dx():
     gamma, beta = (torch.rand(C) + 0.5).to(DEV).requires_grad_(True), torch.randn(C).to(DEV).requires_grad_(True)
     for training in (True, False):
         mean, var = x.detach().mean((0, 2, 3)), x.detach().var((0, 2, 3), unbiased=False)
-        y = BNSignFn.apply(x, gamma, beta, mean, torch.rsqrt(var + 1e-5), training, 1)
+        y = BNSignFn.apply(x, gamma, beta, mean, torch.rsqrt(var + 1e-5), training, 1, False)
         captured = {}
 
         def grab(g, captured=captured):
@@ -163,7 +204,10 @@ def test_prepare_fuse_bn_rewrites_pairs_and_keeps_state_dict_layout():
     assert sum(isinstance(m, BatchNormBinarize2d) for m in fused.modules()) == n_aq
     assert not any(isinstance(m, E.wbwtab.ActivationQuantizer) for m in fused.modules())
     from micronet_b200.fused import EngineMaxPool2d
-    assert sum(isinstance(m, EngineMaxPool2d) for m in fused.modules()) == 2
+    # both 2x2 pools follow a fused BN+binarizer and are absorbed by it
+    assert sum(isinstance(m, EngineMaxPool2d) for m in fused.modules()) == 0
+    assert sum(bool(getattr(m, "pool2", False)) for m in fused.modules()) == 2
+    assert not any(isinstance(m, nn.MaxPool2d) for m in fused.modules())
     # every channel shuffle moved into its producer: flags cleared on the copy, groups recorded upstream
     assert not any(getattr(m, "channel_shuffle_flag", 0) for m in fused.modules())
     moved = sorted(m.out_shuffle_groups for m in fused.modules() if getattr(m, "out_shuffle_groups", 1) > 1)
