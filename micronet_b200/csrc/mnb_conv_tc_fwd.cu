@@ -23,6 +23,7 @@
 //   4 epilogue  : tcgen05.ld accumulator rows -> scale + bias (fwd) or STE mask (dgrad) -> coalesced
 //     warps       fp32 NCHW stores
 #include <cuda.h>
+#include <cstdlib>
 #include <cuda_bf16.h>
 
 #include "mnb_common.cuh"
@@ -34,17 +35,18 @@ constexpr int NTHREADS = 512;
 constexpr int NCONV = 320;  // converter threads (warps 2, 3 and 8..15)
 constexpr int NCW = NCONV / 32;
 constexpr int NEPI = 128;   // epilogue threads (warps 4..7)
-constexpr int MAXST = 4, NOP = 2, NACC = 2;
+constexpr int MAXST = 8, BASEST = 4, MAXOP = 4, NACC = 2;  // staging ring / operand ring: as deep as shared memory allows (plan())
 constexpr int KMAX = 6;     // operand entries per converter thread and chunk
 constexpr int kMaxDynSmem = 227 * 1024 - 6144;  // 227 KB per CTA minus the static block below (5 KB)
 
 struct Params {
   // tensors: input [B, Cin, H, W], output [B, Cout, H, W]
   int B, Cin, Cout, H, W, R, S, pad, G, cin_g, cout_g;
-  int BW, TH, THH, TB, CC, nchunk, nst;
+  int BW, TH, THH, TB, CC, nchunk, nst, nop;
   int npos_in, row_tiles, n_tiles, slab_groups, n_slabs;
   int quant_mode;   // 0: raw fp32 input (exact 3-term split); else MNB_ACT_DOREFA / MNB_ACT_IAO
   int dgrad;        // 1: weights transposed + flipped, per-input-channel pre-scale, STE epilogue
+  int dbg;          // MNB_TC_DEBUG (timing experiments only): 1 no converter fence, 2 no converter work, 4 no epilogue stores, 8 no MMAs
   int a_offset, tmem_cols;
   int stage_bytes, op_term_bytes, op_buf_bytes, b_group_bytes, off_stage, off_op, off_b;
   float a_scale_const;
@@ -66,10 +68,10 @@ struct Params {
 };
 
 struct alignas(16) Shared {
-  uint64_t stage_full[MAXST], stage_empty[MAXST], op_full[NOP], op_empty[NOP], acc_full[NACC], acc_empty[NACC], b_full;
+  uint64_t stage_full[MAXST], stage_empty[MAXST], op_full[MAXOP], op_empty[MAXOP], acc_full[NACC], acc_empty[NACC], b_full;
   uint32_t tmem_slot;
   uint32_t abort;
-  uint32_t op_flags[NOP][NCW];
+  uint32_t op_flags[MAXOP][NCW];
   alignas(16) float epi_scale[288];   // per output channel of the slab (fixed for the whole kernel)
   alignas(16) float epi_bias[288];
 };
@@ -126,13 +128,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const Params p) {
   // ---- one-time setup
   if (tid == 0) {
     for (int i = 0; i < p.nst; ++i) { tc::mbar_init(&sh.stage_full[i], 1); tc::mbar_init(&sh.stage_empty[i], NCONV / 32); }
-    for (int i = 0; i < NOP; ++i) { tc::mbar_init(&sh.op_full[i], NCONV / 32); tc::mbar_init(&sh.op_empty[i], 1); }
+    for (int i = 0; i < MAXOP; ++i) { tc::mbar_init(&sh.op_full[i], NCONV / 32); tc::mbar_init(&sh.op_empty[i], 1); }
     for (int i = 0; i < NACC; ++i) { tc::mbar_init(&sh.acc_full[i], 1); tc::mbar_init(&sh.acc_empty[i], NEPI); }
     tc::mbar_init(&sh.b_full, 1);
     tc::fence_barrier_init();
     tc::prefetch_tmap(&tmap_in);
   }
-  if (tid < NOP * NCW) sh.op_flags[tid / NCW][tid % NCW] = 0;
+  if (tid < MAXOP * NCW) sh.op_flags[tid / NCW][tid % NCW] = 0;
   if (tid == 0) sh.abort = 0;
   if (warp == 2) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tc::smem_u32(&sh.tmem_slot)),
@@ -140,7 +142,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const Params p) {
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
   // zero the operand buffers once: the mid / lo planes are only rewritten when a chunk needs them
-  for (int i = tid; i < NOP * p.op_buf_bytes / 16; i += NTHREADS)
+  for (int i = tid; i < p.nop * p.op_buf_bytes / 16; i += NTHREADS)
     reinterpret_cast<uint4*>(op_base)[i] = make_uint4(0, 0, 0, 0);
   // per-channel constants of this slab, loaded once: forward = epilogue scale / bias per output channel,
   // dgrad = weight scale per INPUT channel (folded into dy while it is converted)
@@ -170,18 +172,25 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const Params p) {
         tc::mbar_arrive_expect_tx(&sh.b_full, bytes);
         tc::bulk_load_1d(b_base, p.w_pack + (size_t)g_first * p.b_group_bytes, bytes, &sh.b_full);
       }
-      uint32_t it = 0;
+      // ring positions are advanced incrementally: a runtime `it % nst` costs a ~100-cycle integer division, and these
+      // per-chunk loops are pure latency chains (nothing else to issue while the quotient is computed)
+      int st = -1;
+      uint32_t ph = 1;
       for (int tile = rank_in_slab; tile < p.n_tiles; tile += ctas_in_slab) {
         const int bt = tile / p.row_tiles, rt = tile - bt * p.row_tiles;
         const int b0 = bt * p.TB, h0 = rt * p.TH;
         for (int gi = 0; gi < g_count; ++gi) {
-          for (int ch = 0; ch < p.nchunk; ++ch, ++it) {
-            const int st = it % p.nst;
-            const uint32_t ph = (it / p.nst) & 1;
+          for (int ch = 0; ch < p.nchunk; ++ch) {
+            if (++st == p.nst) st = 0;
+            ph ^= (st == 0);
             PROF_WAIT(0, tc::mbar_wait(&sh.stage_empty[st], ph ^ 1, p.err, 301));
             tc::mbar_arrive_expect_tx(&sh.stage_full[st], (uint32_t)p.stage_bytes);
-            tc::tma_load_4d(stage_base + (size_t)st * p.stage_bytes, &tmap_in, &sh.stage_full[st], 0, h0 - p.pad,
-                            (g_first + gi) * p.cin_g + ch * p.CC, b0);
+            if (p.pad == 0)   // un-padded tile rows are contiguous: one long row per channel (see launch())
+              tc::tma_load_3d(stage_base + (size_t)st * p.stage_bytes, &tmap_in, &sh.stage_full[st], h0 * p.W,
+                              (g_first + gi) * p.cin_g + ch * p.CC, b0);
+            else
+              tc::tma_load_4d(stage_base + (size_t)st * p.stage_bytes, &tmap_in, &sh.stage_full[st], 0, h0 - p.pad,
+                              (g_first + gi) * p.cin_g + ch * p.CC, b0);
           }
         }
       }
@@ -204,7 +213,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const Params p) {
       const int ksteps = p.CC / 16, slab_cols = g_count * p.cout_g;
       const int max_terms = p.quant_mode == 0 ? 3 : 1;
       PROF_SOFT(0, tc::mbar_wait_soft(&sh.b_full, 0, p.err, 307, &sh.abort));
-      uint32_t it = 0, item = 0;
+      uint32_t item = 0;
+      int ob = -1;
+      uint32_t oph = 1;
       for (int tile = rank_in_slab; tile < p.n_tiles; tile += ctas_in_slab, ++item) {
         const int acc = item % NACC;
         const uint32_t aph = (item / NACC) & 1;
@@ -213,9 +224,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const Params p) {
         for (int gi = 0; gi < g_count; ++gi) {
           const uint32_t d_tmem = tmem + (uint32_t)(acc * slab_cols + gi * p.cout_g);
           uint32_t accumulate = 0;
-          for (int ch = 0; ch < p.nchunk; ++ch, ++it) {
-            const int ob = it % NOP;
-            const uint32_t oph = (it / NOP) & 1;
+          for (int ch = 0; ch < p.nchunk; ++ch) {
+            if (++ob == p.nop) ob = 0;
+            oph ^= (ob == 0);
             PROF_SOFT(1, tc::mbar_wait_soft(&sh.op_full[ob], oph, p.err, 303, &sh.abort));
             tc::tc_fence_after();
             bool need_low = false;  // mid / lo planes needed for this chunk?
@@ -230,7 +241,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const Params p) {
             const long long tmma0 = p.prof ? clock64() : 0;
             // one flat loop over (tap, k-step): the offsets come from a small shared-memory table so the
             // single issuing thread spends a handful of instructions per MMA
-            const int n_off = RS * ksteps;
+            const int n_off = (p.dbg & 8) ? 0 : RS * ksteps;
             if (max_terms == 3 && need_low) {
               for (int e = 0; e < n_off; ++e) {
                 const uint2 off = p.mma_off[e];
@@ -282,7 +293,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const Params p) {
         uint32_t r[32];
         tc::tmem_ld_32x32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * slab_cols + n0), r);
         tc::tmem_ld_wait();
-        if (valid) {
+        if (valid && !(p.dbg & 4)) {
           if (!p.dgrad) {
             // scale / bias of the 32 columns as 16 vector loads up front (the per-element LDS latency
             // chain was the kernel's bottleneck), then a pure FFMA + STG stream
@@ -360,20 +371,23 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const Params p) {
         }
       }
     }
-    uint32_t dirty_mask[NOP] = {0, 0};
-    uint32_t it = 0;
+    uint32_t dirty_all = 0;   // 8 bits per operand buffer (KMAX <= 8 entries per thread), kept in one register
+    int st = -1, ob = -1;
+    uint32_t ph = 1, oph = 1;
     for (int tile = rank_in_slab; tile < p.n_tiles; tile += ctas_in_slab) {
       const int bt = tile / p.row_tiles, rt = tile - bt * p.row_tiles;
       const int b0 = bt * p.TB, h0 = rt * p.TH;
       for (int gi = 0; gi < g_count; ++gi) {
-        for (int ch = 0; ch < p.nchunk; ++ch, ++it) {
-          const int st = it % p.nst, ob = it % NOP;
-          const uint32_t ph = (it / p.nst) & 1, oph = (it / NOP) & 1;
+        for (int ch = 0; ch < p.nchunk; ++ch) {
+          if (++st == p.nst) st = 0;
+          ph ^= (st == 0);
+          if (++ob == p.nop) ob = 0;
+          oph ^= (ob == 0);
           PROF_WAIT(0, tc::mbar_wait(&sh.op_empty[ob], oph ^ 1, p.err, 306));
           PROF_WAIT(1, tc::mbar_wait(&sh.stage_full[st], ph, p.err, 305));
           // did THIS thread leave non-zero mid / lo pieces in its entries of this buffer last time?
           // (entries are owned by fixed threads, so dirtiness is thread-private state)
-          const uint32_t dirty = dirty_mask[ob];
+          const uint32_t dirty = (dirty_all >> (8 * ob)) & 0xffu;
           uint32_t now_dirty = 0;
           const float* stg = reinterpret_cast<const float*>(stage_base + (size_t)st * p.stage_bytes);
           uint8_t* opb = op_base + (size_t)ob * p.op_buf_bytes;
@@ -381,7 +395,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const Params p) {
           uint32_t any_low = 0;
 #pragma unroll
           for (int k = 0; k < KMAX; ++k) {
-            if ((ct & ~31) + k * NCONV >= total) break;  // warp-uniform
+            if ((ct & ~31) + k * NCONV >= total || (p.dbg & 2)) break;  // warp-uniform
             const int idx = ct + k * NCONV;
             const bool live = idx < total;
             const int so = soff[k];
@@ -471,12 +485,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const Params p) {
             }
             if (live) *reinterpret_cast<uint4*>(opb + (size_t)idx * 16) = hi;
           }
-          dirty_mask[ob] = now_dirty;
+          dirty_all = (dirty_all & ~(0xffu << (8 * ob))) | (now_dirty << (8 * ob));
           if (p.quant_mode == 0) {
             any_low = __reduce_or_sync(0xffffffffu, any_low);
             if (lane == 0) sh.op_flags[ob][cw] = any_low;
           }
-          tc::fence_proxy_async_smem();   // every writer publishes its smem stores to the async proxy
+          if (!(p.dbg & 1)) tc::fence_proxy_async_smem();   // every writer publishes its smem stores to the async proxy
           __syncwarp();
           if (lane == 0) {                // one arrival per warp: 16 instead of 512 smem atomics per chunk
             tc::mbar_arrive(&sh.op_full[ob]);
@@ -565,10 +579,11 @@ static int plan(const mnb_conv_shape* s, bool dgrad, int quant_mode, Params& p, 
   p.op_term_bytes = p.npos_in * (p.CC / 8) * 16;
   p.op_buf_bytes = p.op_term_bytes * (quant_mode == 0 ? 3 : 1);
   p.b_group_bytes = p.R * p.S * p.cin_g * p.cout_g * 2;
-  p.nst = MAXST;
+  p.nst = BASEST;
+  p.nop = 2;
   int fixed = 0, budget = 0;
   for (;; --p.nst) {
-    fixed = (p.nst * p.stage_bytes + 1023) / 1024 * 1024 + (NOP * p.op_buf_bytes + 1023) / 1024 * 1024;
+    fixed = (p.nst * p.stage_bytes + 1023) / 1024 * 1024 + (p.nop * p.op_buf_bytes + 1023) / 1024 * 1024;
     budget = kMaxDynSmem - fixed;
     if (budget >= p.b_group_bytes || p.nst == 2) break;
   }
@@ -582,9 +597,20 @@ static int plan(const mnb_conv_shape* s, bool dgrad, int quant_mode, Params& p, 
   while (p.G % max_groups) --max_groups;  // equal slabs: every CTA does the same work per tile
   p.slab_groups = max_groups;
   p.n_slabs = p.G / p.slab_groups;
+  // The pipeline floor is TMA latency x bytes in flight (measured: 4 slots of 16 KB sustain ~22 B/ns per SM, half of
+  // what the HBM share of an SM needs), so every kilobyte the weights and operands leave free becomes staging slots.
+  auto fits = [&](int nst, int nop) {
+    return (nst * p.stage_bytes + 1023) / 1024 * 1024 + (nop * p.op_buf_bytes + 1023) / 1024 * 1024 +
+               p.slab_groups * p.b_group_bytes <= kMaxDynSmem;
+  };
+  // Spare shared memory goes to the OPERAND ring first: the converter -> MMA -> commit -> converter round trip costs
+  // ~1300 cycles even with no work in it (measured with the kernel's parts switched off), so with two operand buffers
+  // a chunk cannot take less than ~650 cycles; extra staging slots were measured to change nothing.
+  while (p.nop < MAXOP && fits(p.nst, p.nop + 1)) ++p.nop;
+  while (p.nst < MAXST && fits(p.nst + 1, p.nop)) ++p.nst;
   p.off_stage = 0;
   p.off_op = (p.nst * p.stage_bytes + 1023) / 1024 * 1024;
-  p.off_b = p.off_op + (NOP * p.op_buf_bytes + 1023) / 1024 * 1024;
+  p.off_b = p.off_op + (p.nop * p.op_buf_bytes + 1023) / 1024 * 1024;
   smem_bytes = p.off_b + p.slab_groups * p.b_group_bytes;
   if (smem_bytes > kMaxDynSmem) return unsupported("shared memory budget");
   int cols = 32;
@@ -600,9 +626,18 @@ static int launch(const Params& p, const void* in, int smem_bytes, cudaStream_t 
         p.w_int, reinterpret_cast<__nv_bfloat16*>(const_cast<uint8_t*>(p.w_pack)), p.G, p.cin_g, p.cout_g, p.R * p.S, p.dgrad);
   }
   CUtensorMap tmap;
-  uint64_t dims[4] = {(uint64_t)p.W, (uint64_t)p.H, (uint64_t)p.Cin, (uint64_t)p.B};
-  uint32_t box[4] = {(uint32_t)p.W, (uint32_t)p.THH, (uint32_t)p.CC, (uint32_t)p.TB};
-  if (int e = mnb_make_tmap(&tmap, in, 4, 4, dims, box)) return e;
+  if (p.pad == 0) {
+    // The TMA unit's cost is per box row (measured ~12 cycles per row per SM, whatever its length): a 1x1 filter
+    // needs no halo, so H and W collapse into one dimension and a tile is TH*W contiguous floats per channel
+    // (4 x fewer rows than W-wide ones at 32x32).  Same shared-memory image as the 4-D box.
+    uint64_t dims[3] = {(uint64_t)p.H * p.W, (uint64_t)p.Cin, (uint64_t)p.B};
+    uint32_t box[3] = {(uint32_t)(p.TH * p.W), (uint32_t)p.CC, (uint32_t)p.TB};
+    if (int e = mnb_make_tmap(&tmap, in, 4, 3, dims, box)) return e;
+  } else {
+    uint64_t dims[4] = {(uint64_t)p.W, (uint64_t)p.H, (uint64_t)p.Cin, (uint64_t)p.B};
+    uint32_t box[4] = {(uint32_t)p.W, (uint32_t)p.THH, (uint32_t)p.CC, (uint32_t)p.TB};
+    if (int e = mnb_make_tmap(&tmap, in, 4, 4, dims, box)) return e;
+  }
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t ce = cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem);
@@ -614,6 +649,10 @@ static int launch(const Params& p, const void* in, int smem_bytes, cudaStream_t 
   grid = std::max(grid, p.n_slabs);
   Params pp = p;
   pp.prof = g_prof_buffer;
+  {
+    static const int dbg = [] { const char* e = getenv("MNB_TC_DEBUG"); return e ? atoi(e) : 0; }();
+    pp.dbg = dbg;
+  }
   {
     const int ks = p.CC / 16, c8_per_group = p.cin_g / 8;
     for (int e = 0; e < p.R * p.S * ks && e < 64; ++e) {

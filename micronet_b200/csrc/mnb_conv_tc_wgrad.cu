@@ -19,7 +19,7 @@
 
 namespace tcwgrad {
 
-constexpr int NTHREADS = 512, NCONV = 448, NEPI = 128, MAXST = 4;  // converters: warps 2..15 (4..7 also run the final epilogue)
+constexpr int NTHREADS = 512, NCONV = 448, NEPI = 128, MAXST = 8, BASEST = 4;  // converters: warps 2..15 (4..7 also run the final epilogue)
 constexpr int KX = 4, KD = 3;  // operand entries per converter thread: activation / gradient chunks
 constexpr int kMaxDynSmem = 227 * 1024 - 2048;
 
@@ -116,10 +116,11 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
           uint8_t* dst = stage_base + (size_t)st * p.slot_bytes;
           if (ch < x_chunks) {
             tc::mbar_arrive_expect_tx(&sh.stage_full[st], (uint32_t)p.stage_x_bytes);
-            tc::tma_load_4d(dst, &tmap_x, &sh.stage_full[st], 0, h0 - p.pad, x_ch0 + ch * p.CC, b0);
+            if (p.pad == 0) tc::tma_load_3d(dst, &tmap_x, &sh.stage_full[st], h0 * p.W, x_ch0 + ch * p.CC, b0);
+            else tc::tma_load_4d(dst, &tmap_x, &sh.stage_full[st], 0, h0 - p.pad, x_ch0 + ch * p.CC, b0);
           } else {
             tc::mbar_arrive_expect_tx(&sh.stage_full[st], (uint32_t)p.stage_d_bytes);
-            tc::tma_load_4d(dst, &tmap_dy, &sh.stage_full[st], 0, h0, dy_ch0 + (ch - x_chunks) * p.CC, b0);
+            tc::tma_load_3d(dst, &tmap_dy, &sh.stage_full[st], h0 * p.W, dy_ch0 + (ch - x_chunks) * p.CC, b0);
           }
         }
       }
@@ -402,10 +403,12 @@ static int plan(const mnb_conv_shape* s, int quant_mode, Params& p, int& smem_by
     p.off_xop = 0;
     p.off_dop = p.xop_bytes;
     p.off_stage = p.nbuf * p.op_buf_bytes;
-    p.nst = MAXST;
+    p.nst = BASEST;
     while (p.nst > 3 && p.off_stage + p.nst * p.slot_bytes > kMaxDynSmem) --p.nst;
+    if (p.off_stage + p.nst * p.slot_bytes > kMaxDynSmem) return false;
+    while (p.nst < MAXST && p.off_stage + (p.nst + 1) * p.slot_bytes <= kMaxDynSmem) ++p.nst;  // more bytes in flight
     smem_bytes = p.off_stage + p.nst * p.slot_bytes;
-    return smem_bytes <= kMaxDynSmem;
+    return true;
   };
   // 1x1 filters (no halo re-reads, few MMAs per tile): one 128-position operand set, converter and MMA
   // alternate.  Filters with taps: two smaller operand sets so that the (tap-heavy) MMAs overlap the converter.
@@ -463,12 +466,20 @@ extern "C" int mnb_conv2d_wgrad_tc(const mnb_conv_shape* s, const float* dy, con
   }
   p.partial = reinterpret_cast<float*>(scratch); p.err = err_flag; p.inexact = inexact_flag;
   CUtensorMap tx, td;
-  uint64_t dx[4] = {(uint64_t)p.W, (uint64_t)p.H, (uint64_t)p.C, (uint64_t)p.B};
-  uint32_t bx[4] = {(uint32_t)p.W, (uint32_t)p.THH, (uint32_t)p.CC, (uint32_t)p.TB};
-  uint64_t dd[4] = {(uint64_t)p.W, (uint64_t)p.H, (uint64_t)p.K, (uint64_t)p.B};
-  uint32_t bd[4] = {(uint32_t)p.W, (uint32_t)p.TH, (uint32_t)p.CC, (uint32_t)p.TB};
-  if (int e = mnb_make_tmap(&tx, x, 4, 4, dx, bx)) return e;
-  if (int e = mnb_make_tmap(&td, dy, 4, 4, dd, bd)) return e;
+  // TMA cost is per box row: tiles without a halo (dy always, x of a 1x1 filter) are read as ONE contiguous row of
+  // TH*W floats per channel over a collapsed (H*W, C, B) view; rows past the image end are zero-filled as before.
+  uint64_t dd[3] = {(uint64_t)p.H * p.W, (uint64_t)p.K, (uint64_t)p.B};
+  uint32_t bd[3] = {(uint32_t)(p.TH * p.W), (uint32_t)p.CC, (uint32_t)p.TB};
+  if (int e = mnb_make_tmap(&td, dy, 4, 3, dd, bd)) return e;
+  if (p.pad == 0) {
+    uint64_t dx[3] = {(uint64_t)p.H * p.W, (uint64_t)p.C, (uint64_t)p.B};
+    uint32_t bx[3] = {(uint32_t)(p.TH * p.W), (uint32_t)p.CC, (uint32_t)p.TB};
+    if (int e = mnb_make_tmap(&tx, x, 4, 3, dx, bx)) return e;
+  } else {
+    uint64_t dx[4] = {(uint64_t)p.W, (uint64_t)p.H, (uint64_t)p.C, (uint64_t)p.B};
+    uint32_t bx[4] = {(uint32_t)p.W, (uint32_t)p.THH, (uint32_t)p.CC, (uint32_t)p.TB};
+    if (int e = mnb_make_tmap(&tx, x, 4, 4, dx, bx)) return e;
+  }
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t ce = cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem);
