@@ -105,13 +105,14 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
   if (warp == 0) {
     // ================================================================= TMA producer
     if (lane == 0) {
-      uint32_t it = 0;
+      int st = -1;          // ring position advanced incrementally (no per-chunk integer division)
+      uint32_t ph = 1;
       for (int tile = rank; tile < p.n_tiles; tile += p.ranks) {
         const int bt = tile / p.row_tiles, rt = tile - bt * p.row_tiles;
         const int b0 = bt * p.TB, h0 = rt * p.TH;
-        for (int ch = 0; ch < x_chunks + d_chunks; ++ch, ++it) {
-          const int st = it % p.nst;
-          const uint32_t ph = (it / p.nst) & 1;
+        for (int ch = 0; ch < x_chunks + d_chunks; ++ch) {
+          if (++st == p.nst) st = 0;
+          ph ^= (st == 0);
           if (!tc::mbar_wait(&sh.stage_empty[st], ph ^ 1, p.err, 401)) goto done;
           uint8_t* dst = stage_base + (size_t)st * p.slot_bytes;
           if (ch < x_chunks) {
@@ -201,7 +202,9 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
       }
     }
     const int x_chstride = p.THH * p.W, d_chstride = p.TH * p.W;
-    uint32_t it = 0, t = 0;
+    uint32_t t = 0;
+    int st = -1;
+    uint32_t ph = 1;
     for (int tile = rank; tile < p.n_tiles; tile += p.ranks, ++t) {
       const int bt = tile / p.row_tiles, rt = tile - bt * p.row_tiles;
       const int b0 = bt * p.TB, h0 = rt * p.TH;
@@ -209,9 +212,9 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
       if (!tc::mbar_wait(&sh.op_empty[ob], oph ^ 1, p.err, 404)) goto done;  // MMAs of the tile two back retired
       uint8_t* xop_b = xop + (size_t)ob * p.op_buf_bytes;
       uint8_t* dop_b = dop + (size_t)ob * p.op_buf_bytes;
-      for (int ch = 0; ch < x_chunks + d_chunks; ++ch, ++it) {
-        const int st = it % p.nst;
-        const uint32_t ph = (it / p.nst) & 1;
+      for (int ch = 0; ch < x_chunks + d_chunks; ++ch) {
+        if (++st == p.nst) st = 0;
+        ph ^= (st == 0);
         if (!tc::mbar_wait(&sh.stage_full[st], ph, p.err, 405)) goto done;
         const float* stg = reinterpret_cast<const float*>(stage_base + (size_t)st * p.slot_bytes);
         if (ch < x_chunks) {
