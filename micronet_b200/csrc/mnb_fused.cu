@@ -243,8 +243,11 @@ static bool planes_vectorizable(int64_t n, int hw, const void* a, const void* b,
   return (hw & 3) == 0 && n < (1ll << 31) &&
          (((uintptr_t)a | (uintptr_t)b | (uintptr_t)c) & 15) == 0;
 }
-static int plane_splits(int batch, int64_t per) {
-  return (int)std::max<int64_t>(1, std::min<int64_t>(std::min<int64_t>(FUSED_SPLITS, batch), per / 2048));
+// (channels x splits) blocks: about two waves of 8 resident 256-thread blocks per SM, so that every block streams
+// >= ~100 KB (blocks of 32 KB spend as long being scheduled as loading: 2.4 TB/s instead of 4.5+)
+static int plane_splits(int batch, int64_t per, int channels) {
+  const int64_t want = (2 * 8 * MNB_NUM_SMS + channels - 1) / channels;
+  return (int)std::max<int64_t>(1, std::min<int64_t>(std::min<int64_t>(std::min<int64_t>(FUSED_SPLITS, batch), per / 2048), want));
 }
 
 extern "C" int mnb_bn_sign_fwd(const float* x, int32_t batch, int32_t channels, int32_t hw, const float* mean,
@@ -277,7 +280,7 @@ extern "C" int mnb_bn_sign_bwd(const float* g, const uint32_t* pass_bits, const 
               out_shuffle_groups, channels);
   const int64_t n = (int64_t)batch * channels * hw;
   const int64_t per = (int64_t)batch * hw;
-  const int splits = plane_splits(batch, per);
+  const int splits = plane_splits(batch, per, channels);
   uint32_t* counters = reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(scratch) + 16384);
   double* partial = reinterpret_cast<double*>(reinterpret_cast<char*>(scratch) + 49152);
   const dim3 grid(channels, splits);
@@ -504,7 +507,7 @@ extern "C" int mnb_bn_sign_pool_bwd(const float* g, const uint32_t* pass_bits, c
   if (int e = pool_geom(batch, channels, H, W, out_shuffle_groups, x, dx, nullptr, gm)) return e;
   MNB_REQUIRE((reinterpret_cast<uintptr_t>(g) & 7) == 0, "pooled gradient must be 8-byte aligned");
   const int64_t per = (int64_t)batch * H * W;
-  const int splits = plane_splits(batch, per);
+  const int splits = plane_splits(batch, per, channels);
   uint32_t* counters = reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(scratch) + 16384);
   double* partial = reinterpret_cast<double*>(reinterpret_cast<char*>(scratch) + 49152);
   const dim3 grid(channels, splits);

@@ -728,6 +728,7 @@ extern "C" int mnb_channel_stats(const float* x, int32_t batch, int32_t channels
   MNB_REQUIRE(channels <= 8192, "channel_stats supports at most 8192 channels, got %d", channels);
   int64_t per = (int64_t)batch * hw;
   int splits = (int)std::max<int64_t>(1, std::min<int64_t>(std::min<int64_t>(STATS_SPLITS, batch), per / 2048));
+  splits = std::max(1, std::min(splits, (2 * 8 * MNB_NUM_SMS + channels - 1) / channels));  // ~2 waves of fat blocks
   uint32_t* counters = reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(scratch) + 16384);
   double* partial = reinterpret_cast<double*>(reinterpret_cast<char*>(scratch) + 49152);
   MNB_REQUIRE(as_mean_var >= 0 && as_mean_var <= 2, "as_mean_var must be 0, 1 or 2");
@@ -746,6 +747,7 @@ extern "C" int mnb_bn_batch_stats(const float* x, int32_t batch, int32_t channel
   MNB_REQUIRE((int64_t)batch * hw > 1, "batch statistics need more than one value per channel");
   int64_t per = (int64_t)batch * hw;
   int splits = (int)std::max<int64_t>(1, std::min<int64_t>(std::min<int64_t>(STATS_SPLITS, batch), per / 2048));
+  splits = std::max(1, std::min(splits, (2 * 8 * MNB_NUM_SMS + channels - 1) / channels));  // ~2 waves of fat blocks
   uint32_t* counters = reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(scratch) + 16384);
   double* partial = reinterpret_cast<double*>(reinterpret_cast<char*>(scratch) + 49152);
   MnbBnUpdate bn{eps, (float)momentum, running_mean, running_var, reinterpret_cast<long long*>(num_batches_tracked)};
