@@ -58,13 +58,3 @@ def test_float_conv_falls_back_outside_cover():
     assert rel_err(y.detach(), TF.conv2d(x, conv.weight, conv.bias, 1, 1).detach()) < 1e-6
     y.sum().backward()
     assert conv.weight.grad is not None and torch.isfinite(conv.weight.grad).all()
-
-
-def test_prepare_swaps_only_covered_plain_convs():
-    import micronet_b200 as E
-    from harness import models as zoo
-    from micronet_b200.fused import EngineFloatConv2d
-    m = E.wbwtab.prepare(zoo.NINGC(), A=2, W=3, fuse_bn=True)
-    swapped = [n for n, c in m.named_modules() if isinstance(c, EngineFloatConv2d)]
-    assert swapped == ["model.0.conv"]
-    assert type(dict(m.named_modules())["model.10.conv"]) is nn.Conv2d   # 1024-channel classifier conv stays

@@ -191,33 +191,6 @@ def test_engine_maxpool_is_bit_identical_to_aten(cfg, binary):
     assert torch.equal(xe.grad, xr.grad)
 
 
-def test_prepare_fuse_bn_rewrites_pairs_and_keeps_state_dict_layout():
-    import micronet_b200 as E
-    from harness import models as zoo
-    from micronet_b200.fused import BatchNormBinarize2d
-    torch.manual_seed(0)
-    base = zoo.NINGC()
-    plain = E.wbwtab.prepare(base, A=2, W=3)
-    fused = E.wbwtab.prepare(base, A=2, W=3, fuse_bn=True)
-    assert list(plain.state_dict().keys()) == list(fused.state_dict().keys())
-    n_aq = sum(isinstance(m, E.wbwtab.ActivationQuantizer) for m in plain.modules())
-    assert sum(isinstance(m, BatchNormBinarize2d) for m in fused.modules()) == n_aq
-    assert not any(isinstance(m, E.wbwtab.ActivationQuantizer) for m in fused.modules())
-    from micronet_b200.fused import EngineMaxPool2d
-    # both 2x2 pools follow a fused BN+binarizer and are absorbed by it
-    assert sum(isinstance(m, EngineMaxPool2d) for m in fused.modules()) == 0
-    assert sum(bool(getattr(m, "pool2", False)) for m in fused.modules()) == 2
-    assert not any(isinstance(m, nn.MaxPool2d) for m in fused.modules())
-    # every channel shuffle moved into its producer: flags cleared on the copy, groups recorded upstream
-    assert not any(getattr(m, "channel_shuffle_flag", 0) for m in fused.modules())
-    moved = sorted(m.out_shuffle_groups for m in fused.modules() if getattr(m, "out_shuffle_groups", 1) > 1)
-    assert moved == sorted(m.shuffle_groups for m in plain.modules() if getattr(m, "channel_shuffle_flag", 0))
-    assert any(getattr(m, "channel_shuffle_flag", 0) for m in base.modules()), "the user's model is left untouched"
-    # A != 2 keeps the ReLU path untouched
-    relu = E.wbwtab.prepare(base, A=32, W=2, fuse_bn=True)
-    assert not any(isinstance(m, BatchNormBinarize2d) for m in relu.modules())
-
-
 def test_fused_model_step_matches_unfused_engine_model():
     """whole NIN-GC step, fused vs unfused engine models: same loss and (up to sign flips at |bn| ~ 0)
     the same gradients"""

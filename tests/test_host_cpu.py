@@ -50,6 +50,72 @@ def test_cpu_tensors_fail_loudly():
         E.dorefa.QuantConv2d(4, 4, 3, a_bits=1).activation_quantizer.spec()
 
 
+def test_fused_entry_points_validate_before_launching():
+    """argument checks and geometry cover of the producer / first-layer entry points run on the host"""
+    import ctypes as C
+    from micronet_b200 import _lib as L
+    lib = L.load()
+    fake = 4096  # never dereferenced: every call below must be refused before a launch
+    assert lib.mnb_bn_sign_fwd(fake, 2, 4, 16, fake, fake, fake, fake, 3, fake, fake, None) == -1
+    assert b"shuffle groups" in lib.mnb_last_error()
+    assert lib.mnb_bn_sign_bwd(fake, fake, fake, 2, 4, 16, fake, fake, fake, 1, 1, fake, fake, fake, None, None, None) == -1
+    assert lib.mnb_maxpool2d_fwd(fake, 1, 4, 8, 8, 16, 2, 0, 1, fake, fake, None) == -1      # kernel > 15
+    assert lib.mnb_maxpool2d_bwd(fake, fake, 1, 4, 8, 8, 3, 2, 2, 1, fake, None) == -1       # pad > kernel / 2
+    assert lib.mnb_bn_sign_pool_fwd(fake, 1, 4, 7, 8, fake, fake, fake, fake, 1, fake, fake, fake, None) == L.E_UNSUPPORTED
+    assert lib.mnb_bn_sign_pool_fwd(fake, 1, 4, 8, 12, fake, fake, fake, fake, 1, fake, fake, fake, None) == L.E_UNSUPPORTED
+    assert lib.mnb_bn_batch_stats(fake, 1, 4, 1, 1e-5, 0.1, fake, fake, None, fake, fake, None) == -1   # one value per channel
+    first = L.ConvShape(8, 3, 32, 32, 256, 5, 5, 1, 1, 2, 2, 1, 1, 1)
+    need = lib.mnb_fconv2d_wgrad_tc_scratch_bytes(C.byref(first))
+    assert need == min(8 * 8, 148) * 256 * 75 * 4          # one partial dw per CTA, one CTA per 128-position tile
+    for bad in (L.ConvShape(8, 3, 32, 32, 256, 5, 5, 1, 1, 2, 2, 1, 1, 3),      # groups
+                L.ConvShape(8, 3, 32, 32, 256, 5, 5, 2, 2, 2, 2, 1, 1, 1),      # stride
+                L.ConvShape(8, 8, 32, 32, 256, 5, 5, 1, 1, 2, 2, 1, 1, 1),      # C*R*S = 200 > 128
+                L.ConvShape(8, 3, 48, 48, 64, 3, 3, 1, 1, 1, 1, 1, 1, 1),       # rows do not tile into 128 positions
+                L.ConvShape(8, 3, 32, 32, 512, 3, 3, 1, 1, 1, 1, 1, 1, 1)):     # more than 256 output channels
+        assert lib.mnb_fconv2d_wgrad_tc_scratch_bytes(C.byref(bad)) == -1
+        assert lib.mnb_fconv2d_fwd_tc(C.byref(bad), fake, fake, None, fake, fake, None) == L.E_UNSUPPORTED
+
+
+def test_fuse_pass_rewrites_the_prepared_graph_only():
+    """wbwtab.prepare(fuse_bn=True): BN+binarizer pairs, pools, shuffles and the first float conv are rewritten on
+    the engine's copy; state_dict layout and the user's model stay as they were"""
+    import torch.nn as nn
+    import micronet_b200 as E
+    from harness import models as zoo
+    from micronet_b200.fused import BatchNormBinarize2d, EngineFloatConv2d, EngineMaxPool2d
+    torch.manual_seed(0)
+    base = zoo.NINGC()
+    plain = E.wbwtab.prepare(base, A=2, W=3)
+    fused = E.wbwtab.prepare(base, A=2, W=3, fuse_bn=True)
+    assert list(plain.state_dict().keys()) == list(fused.state_dict().keys())
+    for (k, a), b in zip(plain.state_dict().items(), fused.state_dict().values()):
+        assert torch.equal(a, b), k
+    n_aq = sum(isinstance(m, E.wbwtab.ActivationQuantizer) for m in plain.modules())
+    assert sum(isinstance(m, BatchNormBinarize2d) for m in fused.modules()) == n_aq
+    assert not any(isinstance(m, E.wbwtab.ActivationQuantizer) for m in fused.modules())
+    # both 2x2 pools follow a fused BN+binarizer and are absorbed by it
+    assert not any(isinstance(m, nn.MaxPool2d) for m in fused.modules())
+    assert sum(bool(getattr(m, "pool2", False)) for m in fused.modules()) == 2
+    # every channel shuffle moved into its producer: flags cleared on the copy, groups recorded upstream
+    assert not any(getattr(m, "channel_shuffle_flag", 0) for m in fused.modules())
+    moved = sorted(m.out_shuffle_groups for m in fused.modules() if getattr(m, "out_shuffle_groups", 1) > 1)
+    assert moved == sorted(m.shuffle_groups for m in plain.modules() if getattr(m, "channel_shuffle_flag", 0))
+    assert any(getattr(m, "channel_shuffle_flag", 0) for m in base.modules()), "the user's model is left untouched"
+    # only the covered plain conv (3 -> 256, 5x5) is swapped; the 1024-channel classifier conv stays
+    assert [n for n, c in fused.named_modules() if isinstance(c, EngineFloatConv2d)] == ["model.0.conv"]
+    assert type(dict(fused.named_modules())["model.10.conv"]) is nn.Conv2d
+    # A != 2 keeps the ReLU path: nothing to fuse
+    relu = E.wbwtab.prepare(base, A=32, W=2, fuse_bn=True)
+    assert not any(isinstance(m, BatchNormBinarize2d) for m in relu.modules())
+    # dorefa: pools (3x3 / stride 2 here: not absorbed) and the shuffles behind them
+    nin = E.dorefa.prepare(zoo.NIN(), a_bits=8, w_bits=8, fuse=True)
+    assert sum(isinstance(m, EngineMaxPool2d) for m in nin.modules()) == 2
+    gc = E.dorefa.prepare(zoo.NINGC(), a_bits=4, w_bits=4, fuse=True)
+    assert sorted(m.out_shuffle_groups for m in gc.modules() if isinstance(m, EngineMaxPool2d)) == [2, 4]
+    with pytest.raises(RuntimeError, match="CUDA"):
+        fused(torch.randn(2, 3, 32, 32))
+
+
 def _types(model):
     return [(n, type(m).__name__) for n, m in model.named_modules()]
 
