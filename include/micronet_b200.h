@@ -250,6 +250,17 @@ int mnb_maxpool2d_bwd(const float* g, const uint8_t* argmax, int32_t batch, int3
                       int32_t kernel, int32_t stride, int32_t pad, int32_t out_shuffle_groups, float* dx,
                       mnb_stream_t stream);
 
+/* EXPERIMENTAL, not enabled by default (MNB_PACKED_OPERANDS=1) and not yet validated on hardware: packed bf16
+ * activations between the BatchNorm + binarizer producer and the tensor-core forward convolution (DESIGN.md 6,
+ * "Plan for the next round").  x_packed: bf16 [B][C/8][H][W][8] in the OUTPUT channel order (B*C*H*W*2 bytes,
+ * 16-byte aligned); needs C % 8 == 0 and H*W % 32 == 0.  The convolution takes the same geometry cover as
+ * mnb_fq_conv2d_fwd_tc with qp == NULL and reads only x_packed.                                              */
+int mnb_bn_sign_fwd_packed(const float* x, int32_t batch, int32_t channels, int32_t hw, const float* mean,
+                           const float* invstd, const float* gamma, const float* beta, int32_t out_shuffle_groups, float* y,
+                           uint32_t* pass_bits, void* x_packed, mnb_stream_t stream);
+int mnb_fq_conv2d_fwd_packed_tc(const mnb_conv_shape* s, const void* x_packed, const int16_t* w_int, const float* w_scale,
+                                const float* bias, float* y, void* wpack_scratch, int32_t* err_flag, mnb_stream_t stream);
+
 /* fp32 convolution with few input channels on the tensor-core path: the un-quantized first layer of the QAT
  * models (plain nn.Conv2d in the reference: nin_gc.py:82, nin.py:60, resnet.py first conv; WB:300-317 leaves it
  * unquantized).  im2col operand built in shared memory, exact 3-piece bf16 split of both fp32 operands, the six

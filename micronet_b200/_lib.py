@@ -68,6 +68,8 @@ PROTOTYPES = {
     "mnb_bn_sign_bwd": (C.c_int, [_P, _P, _P, _I, _I, _I, _P, _P, _P, _I, _I, _P, _P, _P, _P, _P, _P]),
     "mnb_bn_sign_pool_fwd": (C.c_int, [_P, _I, _I, _I, _I, _P, _P, _P, _P, _I, _P, _P, _P, _P]),
     "mnb_bn_sign_pool_bwd": (C.c_int, [_P, _P, _P, _P, _I, _I, _I, _I, _P, _P, _P, _I, _I, _P, _P, _P, _P, _P, _P]),
+    "mnb_bn_sign_fwd_packed": (C.c_int, [_P, _I, _I, _I, _P, _P, _P, _P, _I, _P, _P, _P, _P]),
+    "mnb_fq_conv2d_fwd_packed_tc": (C.c_int, [_SHAPE, _P, _P, _P, _P, _P, _P, _P, _P]),
     "mnb_fconv2d_fwd_tc": (C.c_int, [_SHAPE, _P, _P, _P, _P, _P, _P]),
     "mnb_fconv2d_wgrad_tc_scratch_bytes": (_L, [_SHAPE]),
     "mnb_fconv2d_wgrad_tc": (C.c_int, [_SHAPE, _P, _P, _P, _P, _P, _P]),
@@ -148,6 +150,8 @@ def tc_check(device=None):
 
 E_UNSUPPORTED = -2
 USE_TC = os.environ.get("MNB_DISABLE_TC", "0") != "1"
+# experimental packed bf16 operands between BN+binarizer and the next conv (round-2 groundwork, off by default)
+USE_PACKED = os.environ.get("MNB_PACKED_OPERANDS", "0") == "1"
 
 _scratch = {}
 

@@ -60,6 +60,28 @@ int mnb_make_tmap(CUtensorMap* out, const void* base, int elem_bytes, int rank, 
   return 0;
 }
 
+int mnb_make_tmap_strided(CUtensorMap* out, const void* base, int elem_bytes, int rank, const uint64_t* dims,
+                          const uint64_t* strides_bytes, const uint32_t* box) {
+  EncodeTiledFn enc = get_encode_tiled();
+  if (!enc) return mnb_fail(MNB_E_UNSUPPORTED, "cuTensorMapEncodeTiled is not available from this driver");
+  cudaFree(nullptr);
+  cuuint64_t gdim[5], gstr[5];
+  cuuint32_t bdim[5], estr[5];
+  for (int i = 0; i < rank; ++i) {
+    gdim[i] = dims[i];
+    bdim[i] = box[i];
+    estr[i] = 1;
+    if (i < rank - 1) gstr[i] = strides_bytes[i];
+  }
+  CUtensorMapDataType dt = elem_bytes == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32
+                           : elem_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_UINT8;
+  CUresult r = enc(out, dt, (cuuint32_t)rank, const_cast<void*>(base), gdim, gstr, bdim, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return mnb_fail(MNB_E_ARG, "cuTensorMapEncodeTiled (strided) failed with CUresult %d", (int)r);
+  return 0;
+}
+
 // ------------------------------------------------------------------ self-test 1: UMMA descriptors
 // D[128 x N] = A[128 x K] * B[N x K]^T, operands converted by threads into the K-major no-swizzle
 // canonical layout  buf[k_chunk][row][16 bytes]  (SBO = 128 B, LBO = rows * 16 B).

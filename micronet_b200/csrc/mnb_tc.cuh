@@ -95,6 +95,15 @@ __device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* m
       : "memory");
 }
 
+__device__ __forceinline__ void tma_load_5d(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1,
+                                            int c2, int c3, int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cta.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2),
+      "r"(c3), "r"(c4)
+      : "memory");
+}
+
 // plain 1-D bulk copy global -> shared (size multiple of 16 bytes), completion on an mbarrier
 __device__ __forceinline__ void bulk_load_1d(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
@@ -207,3 +216,7 @@ __device__ __forceinline__ uint64_t smem_desc_mnmajor_noswz(uint32_t saddr, uint
 // host: rank-`rank` tiled tensor map over a dense tensor (dims / box innermost-first)
 int mnb_make_tmap(CUtensorMap* out, const void* base, int elem_bytes, int rank, const uint64_t* dims,
                   const uint32_t* box);
+// same with explicit byte strides of dimensions 1 .. rank-1 (any order, multiples of 16): lets the box traversal
+// order differ from the memory order (e.g. a channel-octet dimension declared last)
+int mnb_make_tmap_strided(CUtensorMap* out, const void* base, int elem_bytes, int rank, const uint64_t* dims,
+                          const uint64_t* strides_bytes, const uint32_t* box);

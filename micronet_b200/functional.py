@@ -246,6 +246,7 @@ class QuantConv2dFn(Function):
     def forward(ctx, x, wq, bias, w_int, w_scale, spec, stride, padding, dilation, groups):
         L.require_cuda(x, wq)
         lib = L.load()
+        packed = getattr(x, "_mnb_packed", None) if L.USE_PACKED else None   # experimental, see fused.BNSignFn
         x = x.contiguous()
         wq = wq.contiguous()
         sh = _shape_struct(x.shape, wq.shape, stride, padding, dilation, groups)
@@ -256,7 +257,16 @@ class QuantConv2dFn(Function):
         if spec is not None and spec.mode != L.ACT_SIGN:
             a_scale = spec.scale if spec.mode == L.ACT_IAO else _dorefa_scale_tensor(spec.bits, x.device)
         done = False
-        if L.USE_TC and w_int is not None and x.dtype == torch.float32:
+        if packed is not None and spec is None and w_int is not None and packed.numel() == x.numel():
+            wpack = torch.empty(w_int.numel(), dtype=torch.int16, device=x.device)
+            rc = _timed("fwd_packed_tc", sh, lambda: lib.mnb_fq_conv2d_fwd_packed_tc(
+                C.byref(sh), packed.data_ptr(), w_int.data_ptr(), w_scale.data_ptr(), L.ptr(bias), y.data_ptr(),
+                wpack.data_ptr(), L.tc_err_flag(x.device).data_ptr(), L.stream()))
+            if rc == 0:
+                done = True
+            elif rc != L.E_UNSUPPORTED:
+                L.check(rc, "fq_conv2d_fwd_packed_tc")
+        if not done and L.USE_TC and w_int is not None and x.dtype == torch.float32:
             # fused tcgen05 path: quantize inside the operand staging of the tensor-core conv
             qp = None
             if spec is not None:

@@ -49,9 +49,23 @@ class BNSignFn(Function):
                                              L.stream()), "bn_sign_pool_fwd")
         else:
             y = torch.empty_like(x)
-            L.check(lib.mnb_bn_sign_fwd(x.data_ptr(), b, c, hw, mean.data_ptr(), invstd.data_ptr(), gamma.data_ptr(),
-                                        beta.data_ptr(), shuffle_groups, y.data_ptr(), bits.data_ptr(), L.stream()),
-                    "bn_sign_fwd")
+            packed = None
+            if L.USE_PACKED and c % 8 == 0 and hw % 32 == 0:
+                # experimental (MNB_PACKED_OPERANDS=1): also emit the bf16 position-major operand of the next conv
+                packed = torch.empty(x.numel(), dtype=torch.bfloat16, device=x.device)
+                rc = lib.mnb_bn_sign_fwd_packed(x.data_ptr(), b, c, hw, mean.data_ptr(), invstd.data_ptr(), gamma.data_ptr(),
+                                                beta.data_ptr(), shuffle_groups, y.data_ptr(), bits.data_ptr(),
+                                                packed.data_ptr(), L.stream())
+                if rc == L.E_UNSUPPORTED:
+                    packed = None
+                else:
+                    L.check(rc, "bn_sign_fwd_packed")
+            if packed is None:
+                L.check(lib.mnb_bn_sign_fwd(x.data_ptr(), b, c, hw, mean.data_ptr(), invstd.data_ptr(), gamma.data_ptr(),
+                                            beta.data_ptr(), shuffle_groups, y.data_ptr(), bits.data_ptr(), L.stream()),
+                        "bn_sign_fwd")
+            else:
+                y._mnb_packed = packed   # picked up by QuantConv2dFn.forward when y is its input
         ctx.save_for_backward(x, gamma, mean, invstd)
         ctx.bits, ctx.arg, ctx.training, ctx.shuffle_groups = bits, arg, training, shuffle_groups
         return y

@@ -1,0 +1,54 @@
+"""EXPERIMENTAL packed-operand path (micronet_b200/csrc/mnb_conv_packed.cu): skipped unless MNB_PACKED_OPERANDS=1.
+The path is round-2 groundwork and has not run on hardware yet; these tests are its acceptance gate:
+
+    MNB_PACKED_OPERANDS=1 python -m pytest tests/test_gpu_packed_experimental.py -m gpu -x -q"""
+import os
+
+import pytest
+import torch
+import torch.nn.functional as TF
+
+from tests.oracle_util import rel_err
+
+pytestmark = [pytest.mark.gpu,
+              pytest.mark.skipif(os.environ.get("MNB_PACKED_OPERANDS", "0") != "1",
+                                 reason="experimental path, enable with MNB_PACKED_OPERANDS=1")]
+DEV = "cuda"
+
+# B, C, H, W, K, R, groups, shuffle groups of the producer
+CASES = [(4, 256, 32, 32, 256, 1, 2, 1), (4, 256, 32, 32, 256, 1, 2, 2), (4, 512, 16, 16, 512, 1, 4, 16),
+         (5, 1024, 8, 8, 1024, 1, 8, 32), (4, 256, 16, 16, 512, 3, 16, 2), (4, 512, 8, 8, 1024, 3, 32, 4),
+         (3, 64, 16, 16, 32, 3, 1, 1)]
+
+
+def _shuffle(x, groups):
+    b, c, h, w = x.shape
+    return x.view(b, groups, c // groups, h, w).transpose(1, 2).contiguous().view(b, c, h, w)
+
+
+@pytest.mark.parametrize("case", CASES, ids=[str(c) for c in CASES])
+def test_packed_producer_and_conv_match_the_unpacked_path(case):
+    from micronet_b200 import _lib as L, functional as F_
+    from micronet_b200.fused import BatchNormBinarize2d
+    B, C, H, W, K, R, G, sg = case
+    torch.manual_seed(sum(case))
+    bn = BatchNormBinarize2d(C).to(DEV).train()
+    bn.out_shuffle_groups = sg
+    with torch.no_grad():
+        bn.weight.copy_(torch.rand(C) + 0.5)
+        bn.bias.copy_(torch.randn(C) * 0.3)
+    x = (torch.randn(B, C, H, W) * 1.5).to(DEV)
+    y = bn(x)
+    packed = getattr(y, "_mnb_packed", None)
+    assert packed is not None, "producer did not emit the packed operand"
+    # packed tensor = the +-1 plane in [B][C/8][H][W][8] order
+    want = y.detach().view(B, C // 8, 8, H, W).permute(0, 1, 3, 4, 2).contiguous().to(torch.bfloat16).flatten()
+    assert torch.equal(packed, want)
+    w_int = torch.randint(-1, 2, (K, C // G, R, R), dtype=torch.int16).to(DEV)
+    w_scale = (torch.rand(K) * 0.02 + 0.001).to(DEV)
+    bias = torch.randn(K).to(DEV)
+    wq = w_int.float() * w_scale.view(-1, 1, 1, 1)
+    out = F_.quant_conv2d(y, wq, bias, w_int, w_scale, None, (1, 1), (R // 2, R // 2), (1, 1), G)
+    L.tc_check()
+    ref = TF.conv2d(y.detach().double().cpu(), wq.double().cpu(), bias.double().cpu(), 1, R // 2, 1, G)
+    assert rel_err(out.detach(), ref) < 2e-6
