@@ -28,8 +28,21 @@ constexpr int kMaxDynSmem = 227 * 1024 - 4096;
 struct Params {
   int B, Cin, Cout, H, W, R, pad, G, cin_g, cout_g;
   int BW, TH, THH, TB, npos;          // npos = TB * THH * BW positions per box and channel octet
-  int row_tiles, n_tiles, slab_groups, n_slabs, nbuf;
+  int row_tiles, n_tiles, slab_groups, n_slabs, nbuf, nbuf_log2;
   int op_bytes, op_box_bytes, b_group_bytes, off_b, tmem_cols;
+  // Private copy of everything the MMA-issue warp needs, precomputed on the host.  Goal: descriptor arithmetic in
+  // UNIFORM registers (no ELECT + 4-5 R2UR.BROADCAST in front of every tcgen05.mma).  What SASS inspection of this
+  // kernel's variants established (cuobjdump, no GPU needed): the MMA warp alone compiles to the uniform form only if
+  // (1) no integer division / modulo feeds addresses or loop bounds (2-D grid instead of blockIdx.x / n_slabs, nested
+  // r / s loops instead of tap / R), (2) ring indices are counter & mask, not a loop-carried conditional reset,
+  // (3) no barrier wait sits in front of the tile loop, (4) its inputs are not common sub-expressions of per-thread code
+  // elsewhere (hence this block).  Still open: as soon as ANOTHER warp role contains a loop with the same induction
+  // (tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) ptxas falls back to the broadcast form here - although
+  // mnb_conv_fp32_tc.cu's forward kernel has exactly that and stays uniform.
+  struct Mma {
+    uint32_t idesc, a_lbo, b_lbo, a_buf16, a_group16, a_kstep16, b_kstep16, b_tap16, b_group16;
+    uint32_t ksteps, R, BW, slab_groups, slab_cols, cout_g, buf_mask, buf_log2, off_b, n_tiles;
+  } m;
   const uint8_t* w_pack;    // bf16 [g][tap][k/8][n][8]
   const float* w_scale; const float* bias;
   float* out;
@@ -65,8 +78,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) fwd_packed_kernel(const __grid_co
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   uint8_t* b_base = smem + p.off_b;
   const int RS = p.R * p.R, c8_per_group = p.cin_g / 8;
-  const int slab = blockIdx.x % p.n_slabs, rank_in_slab = blockIdx.x / p.n_slabs;
-  const int ctas_in_slab = (gridDim.x - slab + p.n_slabs - 1) / p.n_slabs;
+  // grid = (CTAs per slab, slabs): the tile loops then run on blockIdx / gridDim only.  An integer division in the
+  // work assignment (blockIdx.x / n_slabs) makes ptxas treat the tile loop's trip count as possibly divergent, and
+  // everything inside it - the MMA issue included - leaves the uniform datapath.
+  const int slab = blockIdx.y, rank_in_slab = blockIdx.x, ctas_in_slab = gridDim.x;
   const int g_first = slab * p.slab_groups;
   const int slab_cols = p.slab_groups * p.cout_g;
 
@@ -101,12 +116,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) fwd_packed_kernel(const __grid_co
       const uint32_t bytes = (uint32_t)(p.slab_groups * p.b_group_bytes);
       tc::mbar_arrive_expect_tx(&sh.b_full, bytes);
       tc::bulk_load_1d(b_base, p.w_pack + (size_t)g_first * p.b_group_bytes, bytes, &sh.b_full);
-      int buf = -1;
-      uint32_t ph = 1;
-      for (int tile = rank_in_slab; tile < p.n_tiles; tile += ctas_in_slab) {
+      uint32_t item = 0;
+      for (int tile = rank_in_slab; tile < p.n_tiles; tile += ctas_in_slab, ++item) {
         const int bt = tile / p.row_tiles, rt = tile - bt * p.row_tiles;
-        if (++buf == p.nbuf) buf = 0;
-        ph ^= (buf == 0);
+        const uint32_t buf = item & (uint32_t)(p.nbuf - 1), ph = (item >> p.nbuf_log2) & 1u;
         if (!tc::mbar_wait(&sh.op_empty[buf], ph ^ 1, p.err, 601)) break;
         tc::mbar_arrive_expect_tx(&sh.op_full[buf], (uint32_t)p.op_box_bytes);
         tc::tma_load_5d(smem + (size_t)buf * p.op_bytes, &tmap, &sh.op_full[buf], 0, -p.pad, rt * p.TH - p.pad, bt * p.TB,
@@ -115,36 +128,29 @@ __global__ void __launch_bounds__(NTHREADS, 1) fwd_packed_kernel(const __grid_co
     }
   } else if (warp == 1) {
     // ================================================================= MMA issuer (warp-converged, lane 0 issues)
+    // uses p.m.* (private parameters), blockIdx / gridDim and its own counters only - see Params::Mma
     const uint32_t lead = lane == 0;
-    const uint32_t idesc = tc::make_idesc(1, 1, 1, 128, (uint32_t)p.cout_g);
-    const uint32_t a_lbo = (uint32_t)p.npos * 16u, b_lbo = (uint32_t)p.cout_g * 16u;
-    const uint64_t a_desc0 = tc::smem_desc_kmajor_noswz(tc::smem_u32(smem), a_lbo, 128);
-    const uint64_t b_desc0 = tc::smem_desc_kmajor_noswz(tc::smem_u32(b_base), b_lbo, 128);
-    const uint32_t a_buf16 = (uint32_t)p.op_bytes >> 4, a_group16 = (uint32_t)(c8_per_group * p.npos);
-    const uint32_t a_kstep16 = 2u * (uint32_t)p.npos, b_kstep16 = 2u * (uint32_t)p.cout_g;
-    const uint32_t b_tap16 = (uint32_t)(c8_per_group * p.cout_g), b_group16 = (uint32_t)p.b_group_bytes >> 4;
-    const int ksteps = p.cin_g / 16;
-    tc::mbar_wait_soft(&sh.b_full, 0, p.err, 602, &sh.abort);
-    int buf = -1;
-    uint32_t ph = 1, item = 0;
-    for (int tile = rank_in_slab; tile < p.n_tiles; tile += ctas_in_slab, ++item) {
+    const uint32_t tmem_m = tmem;
+    const uint64_t a_desc0 = tc::smem_desc_kmajor_noswz(tc::smem_u32(smem), p.m.a_lbo, 128);
+    const uint64_t b_desc0 = tc::smem_desc_kmajor_noswz(tc::smem_u32(smem) + p.m.off_b, p.m.b_lbo, 128);
+    uint32_t item = 0;
+    for (uint32_t tile = blockIdx.x; tile < p.m.n_tiles; tile += gridDim.x, ++item) {
       const uint32_t acc = item & 1u, aph = (item >> 1) & 1u;
-      if (++buf == p.nbuf) buf = 0;
-      ph ^= (buf == 0);
+      const uint32_t buf = item & p.m.buf_mask, ph = (item >> p.m.buf_log2) & 1u;   // ring of 2 or 4 operand buffers
+      tc::mbar_wait_soft(&sh.b_full, 0, p.err, 602, &sh.abort);   // weights resident (a wait in FRONT of the loop costs the uniform datapath)
       tc::mbar_wait_soft(&sh.acc_empty[acc], aph ^ 1u, p.err, 603, &sh.abort);
       tc::mbar_wait_soft(&sh.op_full[buf], ph, p.err, 604, &sh.abort);
       tc::tc_fence_after();
-      for (int gi = 0; gi < p.slab_groups; ++gi) {
-        const uint32_t d_tmem = tmem + acc * (uint32_t)slab_cols + (uint32_t)(gi * p.cout_g);
-        const uint64_t a_g = a_desc0 + (uint64_t)((uint32_t)buf * a_buf16 + (uint32_t)gi * a_group16);
-        const uint64_t b_g = b_desc0 + (uint64_t)((uint32_t)gi * b_group16);
-        for (int tap = 0; tap < RS; ++tap) {
-          const uint32_t tap_off = (uint32_t)((tap / p.R) * p.BW + (tap % p.R));
-          for (int j = 0; j < ksteps; ++j)
-            tc::mma_f16_guarded(d_tmem, a_g + (uint64_t)(tap_off + (uint32_t)j * a_kstep16),
-                                b_g + (uint64_t)((uint32_t)tap * b_tap16 + (uint32_t)j * b_kstep16), idesc,
-                                (uint32_t)(tap | j) != 0u, lead);
-        }
+      for (uint32_t gi = 0; gi < p.m.slab_groups; ++gi) {
+        const uint32_t d_tmem = tmem_m + acc * p.m.slab_cols + gi * p.m.cout_g;
+        const uint64_t a_g = a_desc0 + (uint64_t)(buf * p.m.a_buf16 + gi * p.m.a_group16);
+        const uint64_t b_g = b_desc0 + (uint64_t)(gi * p.m.b_group16);
+        for (uint32_t r = 0; r < p.m.R; ++r)          // no tap / R: integer division has no uniform-datapath form
+          for (uint32_t s2 = 0; s2 < p.m.R; ++s2)
+            for (uint32_t j = 0; j < p.m.ksteps; ++j)
+              tc::mma_f16_guarded(d_tmem, a_g + (uint64_t)(r * p.m.BW + s2 + j * p.m.a_kstep16),
+                                  b_g + (uint64_t)((r * p.m.R + s2) * p.m.b_tap16 + j * p.m.b_kstep16), p.m.idesc,
+                                  (r | s2 | j) != 0u, lead);
       }
       if (lead) { tc::mma_commit(&sh.op_empty[buf]); tc::mma_commit(&sh.acc_full[acc]); }
       __syncwarp();
@@ -233,8 +239,8 @@ static int plan(const mnb_conv_shape* s, Params& p, int& smem_bytes) {
   p.n_slabs = p.G / best;
   p.op_box_bytes = (best * p.cin_g / 8) * p.npos * 16;
   p.op_bytes = (p.op_box_bytes + (halo + 128) * 16 + 1023) / 1024 * 1024;
-  p.nbuf = 2;
-  while (p.nbuf < MAXBUF && best * p.b_group_bytes + (p.nbuf + 1) * p.op_bytes <= kMaxDynSmem) ++p.nbuf;
+  p.nbuf = (best * p.b_group_bytes + 4 * p.op_bytes <= kMaxDynSmem) ? 4 : 2;   // power of two: ring index = counter & mask
+  p.nbuf_log2 = p.nbuf == 4 ? 2 : 1;
   p.off_b = p.nbuf * p.op_bytes;
   smem_bytes = p.off_b + best * p.b_group_bytes;
   p.row_tiles = (p.H + p.TH - 1) / p.TH;
@@ -310,6 +316,14 @@ extern "C" int mnb_fq_conv2d_fwd_packed_tc(const mnb_conv_shape* s, const void* 
   if (int e = plan(s, p, smem_bytes)) return e;
   p.w_pack = reinterpret_cast<const uint8_t*>(wpack_scratch);
   p.w_scale = w_scale; p.bias = bias; p.out = y; p.err = err_flag;
+  {
+    const uint32_t c8g = (uint32_t)p.cin_g / 8;
+    p.m = Params::Mma{tc::make_idesc(1, 1, 1, 128, (uint32_t)p.cout_g), (uint32_t)p.npos * 16u, (uint32_t)p.cout_g * 16u,
+                      (uint32_t)p.op_bytes >> 4, c8g * (uint32_t)p.npos, 2u * (uint32_t)p.npos, 2u * (uint32_t)p.cout_g,
+                      c8g * (uint32_t)p.cout_g, (uint32_t)p.b_group_bytes >> 4, (uint32_t)p.cin_g / 16, (uint32_t)p.R,
+                      (uint32_t)p.BW, (uint32_t)p.slab_groups, (uint32_t)(p.slab_groups * p.cout_g), (uint32_t)p.cout_g,
+                      (uint32_t)p.nbuf - 1, (uint32_t)p.nbuf_log2, (uint32_t)p.off_b, (uint32_t)p.n_tiles};
+  }
   cudaStream_t st = (cudaStream_t)stream;
   const int total = p.G * p.b_group_bytes / 2;
   pack_weights_kernel<<<std::min(mnb_ceil_div(total, 256), MNB_NUM_SMS * 4), 256, 0, st>>>(
@@ -327,9 +341,8 @@ extern "C" int mnb_fq_conv2d_fwd_packed_tc(const mnb_conv_shape* s, const void* 
     if (ce != cudaSuccess) return mnb_fail((int)ce, "cudaFuncSetAttribute: %s", cudaGetErrorString(ce));
     attr_set = true;
   }
-  const int64_t items = (int64_t)p.n_tiles * p.n_slabs;
-  int grid = (int)std::max<int64_t>(p.n_slabs, std::min<int64_t>(items, MNB_NUM_SMS));
-  fwd_packed_kernel<<<grid, NTHREADS, smem_bytes, st>>>(tmap, p);
+  const int per_slab = std::max(1, std::min(p.n_tiles, MNB_NUM_SMS / p.n_slabs));
+  fwd_packed_kernel<<<dim3(per_slab, p.n_slabs), NTHREADS, smem_bytes, st>>>(tmap, p);
   MNB_LAUNCHED(2);
   return 0;
 }
