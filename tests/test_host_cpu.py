@@ -218,3 +218,11 @@ def test_flat_bucket_allreduce_gloo_world2(tmp_path):
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=240)
     assert out.returncode == 0, out.stdout + out.stderr
     assert out.stdout.count("ok") == 2
+
+
+def test_packed_conv_index_arithmetic_model():
+    """numpy replay of the staged packed-operand forward conv (TMA box layout, UMMA descriptor offsets per group / tap /
+    k-step, epilogue row mapping) against a plain grouped correlation: the arithmetic of mnb_conv_packed.cu"""
+    from harness import packed_conv_model as M
+    M.run(3, 32, 32, 8, 8, 1, 2)
+    M.run(2, 32, 32, 8, 8, 3, 2)
