@@ -125,6 +125,13 @@ def require_cuda(*tensors):
                 "got a CPU tensor - there is deliberately no CPU fallback")
 
 
+def require_f32(*tensors):
+    """the C-ABI takes raw fp32 pointers: any other dtype would be misread silently"""
+    for t in tensors:
+        if t is not None and t.dtype != torch.float32:
+            raise TypeError(f"micronet_b200: fp32 tensors only (the reference's QAT modules are fp32), got {t.dtype}")
+
+
 def launch_count() -> int:
     return int(load().mnb_launch_count())
 

@@ -107,6 +107,7 @@ class BatchNormBinarize2d(nn.BatchNorm2d):
 
     def forward(self, input):
         L.require_cuda(input, self.weight)
+        L.require_f32(input, self.weight)
         assert self.affine and self.track_running_stats and self.momentum is not None, \
             "BatchNormBinarize2d supports affine BN with running statistics and a float momentum"
         if self.training:
@@ -175,6 +176,7 @@ class EngineMaxPool2d(nn.MaxPool2d):
 
     def forward(self, input):
         L.require_cuda(input)
+        L.require_f32(input)
         k, s, p = _pool_cfg(self)
         return MaxPoolFn.apply(input, k, s, p, int(self.out_shuffle_groups))
 
@@ -245,6 +247,7 @@ class EngineFloatConv2d(nn.Conv2d):
 
     def forward(self, input):
         L.require_cuda(input, self.weight)
+        L.require_f32(input, self.weight)
         return FloatConvFn.apply(input, self.weight, self.bias, int(self.padding[0]))
 
 
