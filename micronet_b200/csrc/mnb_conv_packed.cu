@@ -31,14 +31,17 @@ struct Params {
   int row_tiles, n_tiles, slab_groups, n_slabs, nbuf, nbuf_log2;
   int op_bytes, op_box_bytes, b_group_bytes, off_b, tmem_cols;
   // Private copy of everything the MMA-issue warp needs, precomputed on the host.  Goal: descriptor arithmetic in
-  // UNIFORM registers (no ELECT + 4-5 R2UR.BROADCAST in front of every tcgen05.mma).  What SASS inspection of this
-  // kernel's variants established (cuobjdump, no GPU needed): the MMA warp alone compiles to the uniform form only if
-  // (1) no integer division / modulo feeds addresses or loop bounds (2-D grid instead of blockIdx.x / n_slabs, nested
-  // r / s loops instead of tap / R), (2) ring indices are counter & mask, not a loop-carried conditional reset,
-  // (3) no barrier wait sits in front of the tile loop, (4) its inputs are not common sub-expressions of per-thread code
-  // elsewhere (hence this block).  Still open: as soon as ANOTHER warp role contains a loop with the same induction
-  // (tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) ptxas falls back to the broadcast form here - although
-  // mnb_conv_fp32_tc.cu's forward kernel has exactly that and stays uniform.
+  // UNIFORM registers - no ELECT + 4-5 R2UR.BROADCAST in front of every tcgen05.mma (this kernel: 0 of them, ~18
+  // uniform-datapath instructions per MMA).  Rules established by SASS inspection of this kernel's variants
+  // (cuobjdump -sass, count R2UR.BROADCAST per UTCHMMA; no GPU needed):
+  //   (1) no integer division / modulo in the address or loop-bound chain (2-D grid instead of blockIdx.x / n_slabs,
+  //       nested r / s loops instead of tap / R);
+  //   (2) ring index = counter & mask, never a loop-carried conditional reset (if (++i == n) i = 0);
+  //   (3) no barrier wait in front of the tile loop (wait for the weights inside it);
+  //   (4) no input shared with per-thread code of other roles - common sub-expressions are computed once, in vector
+  //       registers (hence this block) - and that includes blockIdx.x / gridDim.x: a copy made at kernel scope
+  //       (const int rank = blockIdx.x;) and used by other roles' tile loops was the last thing that kept this kernel on
+  //       the broadcast form.  Every role reads the special registers itself.
   struct Mma {
     uint32_t idesc, a_lbo, b_lbo, a_buf16, a_group16, a_kstep16, b_kstep16, b_tap16, b_group16;
     uint32_t ksteps, R, BW, slab_groups, slab_cols, cout_g, buf_mask, buf_log2, off_b, n_tiles;
@@ -81,7 +84,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) fwd_packed_kernel(const __grid_co
   // grid = (CTAs per slab, slabs): the tile loops then run on blockIdx / gridDim only.  An integer division in the
   // work assignment (blockIdx.x / n_slabs) makes ptxas treat the tile loop's trip count as possibly divergent, and
   // everything inside it - the MMA issue included - leaves the uniform datapath.
-  const int slab = blockIdx.y, rank_in_slab = blockIdx.x, ctas_in_slab = gridDim.x;
+  // NOTE: every role reads blockIdx.x / gridDim.x ITSELF inside its own branch.  Copies made here, at kernel scope,
+  // are materialised in vector registers and shared by all roles, and the MMA warp's tile loop then leaves the uniform
+  // datapath (41 instead of 0 R2UR.BROADCAST in this kernel's SASS).
+  const int slab = blockIdx.y;
   const int g_first = slab * p.slab_groups;
   const int slab_cols = p.slab_groups * p.cout_g;
 
@@ -117,7 +123,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) fwd_packed_kernel(const __grid_co
       tc::mbar_arrive_expect_tx(&sh.b_full, bytes);
       tc::bulk_load_1d(b_base, p.w_pack + (size_t)g_first * p.b_group_bytes, bytes, &sh.b_full);
       uint32_t item = 0;
-      for (int tile = rank_in_slab; tile < p.n_tiles; tile += ctas_in_slab, ++item) {
+      for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++item) {
         const int bt = tile / p.row_tiles, rt = tile - bt * p.row_tiles;
         const uint32_t buf = item & (uint32_t)(p.nbuf - 1), ph = (item >> p.nbuf_log2) & 1u;
         if (!tc::mbar_wait(&sh.op_empty[buf], ph ^ 1, p.err, 601)) break;
@@ -165,7 +171,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) fwd_packed_kernel(const __grid_co
     const int64_t plane = (int64_t)p.H * p.W;
     const int ch_first = g_first * p.cout_g;
     uint32_t item = 0;
-    for (int tile = rank_in_slab; tile < p.n_tiles; tile += ctas_in_slab, ++item) {
+    for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++item) {
       const int bt = tile / p.row_tiles, rt = tile - bt * p.row_tiles;
       const int b = bt * p.TB + tb, h = rt * p.TH + th;
       const bool valid = tb < p.TB && th < p.TH && wc < p.W && b < p.B && h < p.H;
