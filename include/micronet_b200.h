@@ -258,6 +258,7 @@ int mnb_maxpool2d_bwd(const float* g, const uint8_t* argmax, int32_t batch, int3
 int mnb_bn_sign_fwd_packed(const float* x, int32_t batch, int32_t channels, int32_t hw, const float* mean,
                            const float* invstd, const float* gamma, const float* beta, int32_t out_shuffle_groups, float* y,
                            uint32_t* pass_bits, void* x_packed, mnb_stream_t stream);
+int mnb_fq_conv2d_fwd_packed_plan(const mnb_conv_shape* s, int32_t* out8); /* host only: {slab_groups, n_slabs, nbuf, smem_bytes, tmem_cols, TH, TB, n_tiles} */
 int mnb_fq_conv2d_fwd_packed_tc(const mnb_conv_shape* s, const void* x_packed, const int16_t* w_int, const float* w_scale,
                                 const float* bias, float* y, void* wpack_scratch, int32_t* err_flag, mnb_stream_t stream);
 

@@ -312,6 +312,18 @@ extern "C" int mnb_bn_sign_fwd_packed(const float* x, int32_t batch, int32_t cha
   return 0;
 }
 
+// host-only: the tile / slab / pipeline plan of a shape (for tests and sizing), out[8] = {slab_groups, n_slabs, nbuf,
+// smem_bytes, tmem_cols, TH, TB, n_tiles}; returns 0 or MNB_E_UNSUPPORTED
+extern "C" int mnb_fq_conv2d_fwd_packed_plan(const mnb_conv_shape* s, int32_t* out) {
+  MNB_REQUIRE(out != nullptr, "NULL plan output");
+  tcpacked::Params p{};
+  int smem_bytes = 0;
+  if (int e = tcpacked::plan(s, p, smem_bytes)) return e;
+  const int v[8] = {p.slab_groups, p.n_slabs, p.nbuf, smem_bytes, p.tmem_cols, p.TH, p.TB, p.n_tiles};
+  for (int i = 0; i < 8; ++i) out[i] = v[i];
+  return 0;
+}
+
 extern "C" int mnb_fq_conv2d_fwd_packed_tc(const mnb_conv_shape* s, const void* x_packed, const int16_t* w_int,
                                            const float* w_scale, const float* bias, float* y, void* wpack_scratch,
                                            int32_t* err_flag, mnb_stream_t stream) {
