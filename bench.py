@@ -3,16 +3,19 @@
 
     python bench.py --gpus 1 --steps 20 --warmup 5            # this repo's CUDA engine
     python bench.py --impl reference --gpus 1 --steps 3 --warmup 2   # CPU reference path (oracle port)
+    python bench.py --workload resnet18_iao_w8a8_bnfuse       # another BASELINE.json config as the measured workload
 
 Workload (BASELINE.json configs[1]): NIN-GC, wbwtab W-ternary / A-binary, batch 256 per GPU,
 3x32x32 inputs, CrossEntropy + Adam(lr 0.01) - the reference's training step
 (wbwtab/main.py:70-98).  N > 1: one process per GPU under torchrun, batch sharded (256 per
-rank, weak scaling), one NCCL all-reduce of the flat gradient bucket per step.
+rank, weak scaling), one NCCL all-reduce of the flat gradient bucket per step (PTQ inference,
+configs[4]: independent replicas, no collective).
 
 One JSON line on stdout (rank 0).  `value` is timed with inputs resident in HBM; `e2e` is the
-same step fed from pinned HOST buffers (H2D of the batch + D2H of the loss inside the timed
+same step fed from pinned HOST buffers (H2D of the batch + D2H of the loss / logits inside the timed
 region); `roofline` is for the dominant engine kernel, timed live with CUDA events on the
-launching stream; `cpu_baseline` is the oracle port of the reference timed on the host cores."""
+launching stream; `cpu_baseline` is the oracle port of the reference timed on the host cores;
+`extra_workloads` (N = 1 only) are short runs of the other BASELINE.json configs in the same process."""
 import argparse
 import json
 import os
@@ -29,10 +32,26 @@ sys.path.insert(0, ROOT)
 
 from harness import train as H  # noqa: E402
 
-WORKLOAD = "nin_gc_wbwtab_w3a2"   # BASELINE.json configs[1]; --workload picks another config for side measurements
+WORKLOAD = "nin_gc_wbwtab_w3a2"   # BASELINE.json configs[1]; --workload picks another config
 BATCH_PER_GPU = 256
 CPU_SAMPLE_BATCH = 32
-METRIC = "qat_step_images_per_sec"
+NAMES = {"nin_gc_wbwtab_w3a2": "NIN-GC wbwtab W-ternary/A-binary QAT step (BASELINE.json configs[1])",
+         "nin_dorefa_w8a8": "NIN DoReFa W8A8 QAT step (configs[0] model)",
+         "resnet18_iao_w8a8_bnfuse": "ResNet-18 IAO W8A8 per-channel + BN-fuse QAT step (configs[2])",
+         "nin_gc_dorefa_w4a4": "NIN-GC DoReFa W4A4 QAT step (configs[3] model)",
+         "resnet18_iao_ptq_224": "ResNet-18 IAO int8 PTQ inference forward (configs[4])"}
+
+
+def metric_name(workload):
+    return "ptq_inference_images_per_sec" if H.WORKLOADS[workload].get("inference") else "qat_step_images_per_sec"
+
+
+def batch_per_gpu(workload):
+    return H.WORKLOADS[workload].get("batch", BATCH_PER_GPU)
+
+
+def cpu_sample_batch(workload):
+    return 2 if H.WORKLOADS[workload].get("inference") else CPU_SAMPLE_BATCH
 
 
 def _peaks():
@@ -104,14 +123,40 @@ def conv_algorithmic(shape, kind):
     return flops, nbytes
 
 
-def run_cpu_baseline(steps=3, warmup=2):
-    """the reference's own CPU path (oracle port), all host threads, bounded sample (B=32)."""
+def config_dict(workload, n_gpus, cpu_arm=False):
+    w = H.WORKLOADS[workload]
+    hw = w["hw"]
+    if cpu_arm:
+        # the CPU arm runs ONE host process on a bounded sample, whatever --gpus says: state exactly that
+        b = cpu_sample_batch(workload)
+        return {"workload": f"{NAMES[workload]}, synthetic 3x{hw}x{hw}, CPU sample batch {b} (same model, same step)",
+                "global_batch": b, "per_gpu_batch": None, "parallelism": "1 host process",
+                "note": "bounded CPU sample of the engine arm's workload; it does not scale with --gpus"}
+    b = batch_per_gpu(workload)
+    return {"workload": f"{NAMES[workload]}, synthetic 3x{hw}x{hw}, batch {b}/GPU",
+            "global_batch": b * n_gpus, "per_gpu_batch": b,
+            "optimizer": "none (inference)" if w.get("inference") else "Adam lr=0.01",
+            "parallelism": f"{n_gpus} independent replicas" if w.get("inference") else f"dp{n_gpus}",
+            "l2": "per-step activation working set >> 126 MB L2, 4 rotating input batches (no flush needed)"}
+
+
+# ----------------------------------------------------------------------------------------------------------
+# CPU arm: the reference's own path (oracle port) on the host cores, bounded sample
+# ----------------------------------------------------------------------------------------------------------
+def run_cpu_baseline(workload, steps=3, warmup=2):
     ncpu = os.cpu_count() or 1
-    w = H.WORKLOADS[WORKLOAD]
+    w = H.WORKLOADS[workload]
+    b = cpu_sample_batch(workload)
     model = H.prepare_oracle(H.build_float_model(w["model"]), w["scheme"], **w["prepare"])
-    stepper = H.QatStepper(model, lr=0.01, wd=w["wd"])
-    x, t = H.synthetic_batch(CPU_SAMPLE_BATCH, w["hw"], seed=1)
-    # use as many host threads as actually help: at batch 32 ATen's intra-op pool stops scaling
+    if w.get("inference"):
+        stepper = H.InferStepper(model)
+        stepper.calibrate([H.synthetic_batch(b, w["hw"], seed=50 + i)[0] for i in range(1)])
+        what = "eval forward passes"
+    else:
+        stepper = H.QatStepper(model, lr=0.01, wd=w["wd"])
+        what = "QAT steps"
+    x, t = H.synthetic_batch(b, w["hw"], seed=1)
+    # use as many host threads as actually help: at these batch sizes ATen's intra-op pool stops scaling
     # (and then collapses) well before 100+ threads, so probe a few pool sizes with one step each
     best, cores = None, 1
     for n in sorted({c for c in (8, 16, 32, 64, ncpu) if c <= ncpu}):
@@ -131,32 +176,121 @@ def run_cpu_baseline(steps=3, warmup=2):
     for _ in range(steps):
         stepper.step(x, t)
     dt = (time.perf_counter() - t0) / steps
-    return {"value": CPU_SAMPLE_BATCH / dt, "unit": "img/s", "cores": cores, "kind": "port",
-            "sample": f"{steps} QAT steps of the same model at batch {CPU_SAMPLE_BATCH} (oracle/reference_port.py, "
+    return {"value": b / dt, "unit": "img/s", "cores": cores, "kind": "port",
+            "sample": f"{steps} {what} of the same model at batch {b} (oracle/reference_port.py, "
                       f"torch CPU, best of the probed thread counts = {cores} of {ncpu} host cores), {dt * 1e3:.0f} ms/step"}, dt
-
-
-def config_dict(n_gpus):
-    names = {"nin_gc_wbwtab_w3a2": "NIN-GC wbwtab W-ternary/A-binary QAT step (BASELINE.json configs[1])",
-             "nin_dorefa_w8a8": "NIN DoReFa W8A8 QAT step (configs[0] model)",
-             "resnet18_iao_w8a8_bnfuse": "ResNet-18 IAO W8A8 per-channel + BN-fuse QAT step (configs[2])",
-             "nin_gc_dorefa_w4a4": "NIN-GC DoReFa W4A4 QAT step (configs[3] model)"}
-    return {"workload": f"{names[WORKLOAD]}, synthetic 3x32x32, batch {BATCH_PER_GPU}/GPU",
-            "global_batch": BATCH_PER_GPU * n_gpus, "per_gpu_batch": BATCH_PER_GPU, "optimizer": "Adam lr=0.01",
-            "parallelism": f"dp{n_gpus}", "l2": "per-step working set ~2.4 GB of activations >> 126 MB L2 (no flush needed)"}
 
 
 def main_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    base, dt = run_cpu_baseline(steps=max(1, args.steps), warmup=max(0, args.warmup))
-    line = {"impl": "reference", "metric": METRIC, "value": base["value"], "unit": "img/s", "n_gpus": args.gpus,
+    wl = args.workload
+    base, dt = run_cpu_baseline(wl, steps=max(1, args.steps), warmup=max(0, args.warmup))
+    line = {"impl": "reference", "metric": metric_name(wl), "value": base["value"], "unit": "img/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
-            "config": config_dict(args.gpus), "cpu_baseline": base,
+            "config": config_dict(wl, args.gpus, cpu_arm=True), "cpu_baseline": base,
             "e2e": {"value": base["value"], "unit": "img/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
+
+
+# ----------------------------------------------------------------------------------------------------------
+# engine arm
+# ----------------------------------------------------------------------------------------------------------
+def run_engine(workload, steps, warmup, dev, rank, world, detail):
+    """time `steps` steps of one workload; returns the measurement dict (rank-local, max over ranks for times)"""
+    from micronet_b200 import _lib as L, functional as F_
+    w = H.WORKLOADS[workload]
+    inference = bool(w.get("inference"))
+    B = batch_per_gpu(workload)
+    model = H.prepare_engine(H.build_float_model(w["model"]), w["scheme"], **w["prepare"],
+                             **w.get("engine_extra", {})).to(dev)
+    nbuf = 4
+    host = [H.synthetic_batch(B, w["hw"], seed=100 + rank * 17 + i, pin=True) for i in range(nbuf)]
+    devb = [(x.to(dev), t.to(dev)) for x, t in host]
+    if inference:
+        stepper = H.InferStepper(model)
+        stepper.calibrate([devb[i][0][: max(2, B // 8)] for i in range(w.get("calib_batches", 2))])
+    else:
+        stepper = H.QatStepper(model, lr=0.01, wd=w["wd"], flat=True)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(step_fn, n):
+        barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for i in range(n):
+            step_fn(i)
+        b.record()
+        barrier()
+        ms = torch.tensor([a.elapsed_time(b)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return ms.item()
+
+    def step_resident(i):
+        x, t = devb[i % nbuf]
+        stepper.step(x, t)
+
+    out_host = torch.empty((B, 10) if inference else (), dtype=torch.float32).pin_memory()
+
+    def step_e2e(i):
+        hx, ht = host[i % nbuf]
+        x = hx.to(dev, non_blocking=True)
+        t = ht.to(dev, non_blocking=True)
+        res = stepper.step(x, t)
+        out_host.copy_(res.detach(), non_blocking=False)  # D2H read of the step's result (loss / logits)
+
+    sampler = ClockSampler(dev.index or 0) if detail and rank == 0 else None
+    if sampler:
+        sampler.start()  # started before the warm-up so that nvidia-smi is already streaming in the timed region
+    for i in range(warmup):
+        step_resident(i)
+    if sampler:
+        sampler.mark()
+    launches0 = L.launch_count()
+    if detail:
+        F_.TIMER = F_.KernelTimer()
+    ms_total = timed(step_resident, steps)
+    torch.cuda.synchronize()
+    timer, F_.TIMER = F_.TIMER, None
+    launches = L.launch_count() - launches0
+    L.tc_check()   # a bounded pipeline wait that gave up would have produced garbage: fail loudly instead
+    clocks = sampler.stop() if sampler else None
+    for i in range(2):
+        step_e2e(i)
+    ms_e2e = timed(step_e2e, steps)
+    L.tc_check()
+    imgs = B * world * steps
+    res = {"workload": workload, "metric": metric_name(workload), "value": imgs / (ms_total / 1e3), "unit": "img/s",
+           "ms_per_step": ms_total / steps, "steps": steps, "warmup": warmup, "per_gpu_batch": B,
+           "e2e": {"value": imgs / (ms_e2e / 1e3), "unit": "img/s", "ms_per_step": ms_e2e / steps,
+                   "h2d_bytes_per_step": (B * 3 * w["hw"] * w["hw"] * 4 + B * 8) * world,
+                   "d2h_bytes_per_step": (B * 10 * 4 if inference else 4) * world},
+           "gpu_launches": int(launches), "clocks": clocks, "timer": timer, "ms_total": ms_total}
+    del stepper, model
+    torch.cuda.empty_cache()
+    return res
+
+
+def kernel_table(timer, ms_total, steps, hbm, tfl):
+    agg = {}
+    for (kind, shape), times in timer.summary().items():
+        agg[(kind, shape)] = (sum(times), len(times))
+    rows = []
+    for (kind, shape), (tot, n) in sorted(agg.items(), key=lambda kv: -kv[1][0]):
+        fl, nb = conv_algorithmic(shape, kind)
+        t_roof = max(nb / (hbm * 1e9), fl / (tfl * 1e12))
+        rows.append({"kind": kind, "shape": list(shape), "launches": n, "avg_us": tot / n * 1e3,
+                     "algo_GBps": nb / (tot / n / 1e3) / 1e9, "algo_TFLOPs": fl / (tot / n / 1e3) / 1e12,
+                     "hbm_roof_us": nb / (hbm * 1e9) * 1e6, "roof_us": t_roof * 1e6,
+                     "frac_of_roof": t_roof / (tot / n / 1e3)})
+    return agg, rows
 
 
 def main():
@@ -166,11 +300,11 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="engine", choices=["engine", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip the short runs of the other BASELINE configs")
     ap.add_argument("--kernels-json", default=None, help="dump the per-kernel CUDA-event timings of the timed region")
     ap.add_argument("--workload", default=WORKLOAD, choices=sorted(H.WORKLOADS),
                     help="default: the headline configuration (BASELINE.json configs[1])")
     args = ap.parse_args()
-    globals()["WORKLOAD"] = args.workload
     if args.impl == "reference":
         return main_reference(args)
     args.warmup = max(args.warmup, 3)
@@ -188,115 +322,72 @@ def main():
     torch.backends.cudnn.allow_tf32 = False
     torch.backends.cuda.matmul.allow_tf32 = False
 
-    from micronet_b200 import _lib as L, functional as F_
-
-    w = H.WORKLOADS[WORKLOAD]
-    model = H.prepare_engine(H.build_float_model(w["model"]), w["scheme"], **w["prepare"],
-                             **w.get("engine_extra", {})).to(dev)
-    stepper = H.QatStepper(model, lr=0.01, wd=w["wd"], flat=True)
-    # distinct batches, pre-staged on the device for `value`, pinned on the host for `e2e`
-    nbuf = 4
-    host = [H.synthetic_batch(BATCH_PER_GPU, w["hw"], seed=100 + rank * 17 + i, pin=True) for i in range(nbuf)]
-    devb = [(x.to(dev), t.to(dev)) for x, t in host]
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def timed(step_fn, steps):
-        barrier()
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record()
-        for i in range(steps):
-            step_fn(i)
-        b.record()
-        barrier()
-        ms = torch.tensor([a.elapsed_time(b)], device=dev)
-        if world > 1:
-            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        return ms.item()
-
-    def step_resident(i):
-        x, t = devb[i % nbuf]
-        stepper.step(x, t)
-
-    loss_host = torch.empty((), dtype=torch.float32).pin_memory()
-
-    def step_e2e(i):
-        hx, ht = host[i % nbuf]
-        x = hx.to(dev, non_blocking=True)
-        t = ht.to(dev, non_blocking=True)
-        loss = stepper.step(x, t)
-        loss_host.copy_(loss.detach(), non_blocking=False)  # D2H read of the step's result
-
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()  # started before the warm-up so that nvidia-smi is already streaming in the timed region
-    for i in range(args.warmup):
-        step_resident(i)
-    sampler.mark()
-    launches0 = L.launch_count()
-    F_.TIMER = F_.KernelTimer()
-    ms_total = timed(step_resident, args.steps)
-    torch.cuda.synchronize()
-    timer, F_.TIMER = F_.TIMER, None
-    launches = L.launch_count() - launches0
-    clocks = sampler.stop() if rank == 0 else None
-    for i in range(2):
-        step_e2e(i)
-    ms_e2e = timed(step_e2e, args.steps)
-
+    wl = args.workload
+    main_res = run_engine(wl, args.steps, args.warmup, dev, rank, world, detail=True)
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
 
-    imgs = BATCH_PER_GPU * world * args.steps
-    value = imgs / (ms_total / 1e3)
-    e2e_value = imgs / (ms_e2e / 1e3)
     hbm, tfl, peak_src = _peaks()
-    # dominant engine kernel by total device time
-    agg = {}
-    for (kind, shape), times in timer.summary().items():
-        agg[(kind, shape)] = (sum(times), len(times))
+    timer, ms_total = main_res.pop("timer"), main_res.pop("ms_total")
+    agg, rows = kernel_table(timer, ms_total, args.steps, hbm, tfl)
     if args.kernels_json:
-        rows = []
-        for (kind, shape), (tot, n) in sorted(agg.items(), key=lambda kv: -kv[1][0]):
-            fl, nb = conv_algorithmic(shape, kind)
-            rows.append({"kind": kind, "shape": list(shape), "launches": n, "avg_us": tot / n * 1e3,
-                         "algo_GBps": nb / (tot / n / 1e3) / 1e9, "algo_TFLOPs": fl / (tot / n / 1e3) / 1e12,
-                         "hbm_roof_us": nb / (hbm * 1e9) * 1e6})
-        json.dump({"ms_per_step": ms_total / args.steps, "kernels": rows}, open(args.kernels_json, "w"), indent=1)
-    (dk, dshape), (dtot, dn) = max(agg.items(), key=lambda kv: kv[1][0])
-    flops, nbytes = conv_algorithmic(dshape, dk)
-    avg_s = dtot / dn / 1e3
-    t_hbm, t_tc = nbytes / (hbm * 1e9), flops / (tfl * 1e12)
-    if t_hbm >= t_tc:
-        roof = {"bound": "hbm", "achieved": nbytes / avg_s / 1e9, "peak": hbm, "unit": "GB/s"}
-    else:
-        roof = {"bound": "tensor", "achieved": flops / avg_s / 1e12, "peak": tfl, "unit": "TFLOP/s"}
-    roof["frac"] = roof["achieved"] / roof["peak"]
-    traffic = None
-    tpath = os.path.join(ROOT, "profiles", "kernel_traffic.json")
-    if os.path.exists(tpath):  # measured dram__bytes_{read,write}.sum per launch from the committed ncu capture
-        rec = json.load(open(tpath))["kernels"].get(f"{dk}:{list(dshape)}")
-        traffic = rec["dram_bytes"] if rec else None
-    roof.update({"traffic": traffic, "algorithmic_bytes": nbytes, "algorithmic_flops": flops, "peak_source": peak_src,
-                 "kernel": f"conv2d_{dk} shape(B,C,H,W,K,R,S,sh,sw,ph,pw,dh,dw,G)={list(dshape)}",
-                 "avg_launch_us": avg_s * 1e6, "launches_timed": dn,
-                 "share_of_step": dtot / ms_total,
-                 "engine_conv_share_of_step": sum(v[0] for v in agg.values()) / ms_total})
-    line = {"metric": METRIC, "value": value, "unit": "img/s", "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f32 (bf16 tensor-core products of exact integer levels, fp32 accumulate)", "data": "synthetic",
-            "config": config_dict(world), "clocks": clocks,
-            "e2e": {"value": e2e_value, "unit": "img/s", "ms_per_step": ms_e2e / args.steps,
-                    "h2d_bytes_per_step": (BATCH_PER_GPU * 3 * w["hw"] * w["hw"] * 4 + BATCH_PER_GPU * 8) * world,
-                    "d2h_bytes_per_step": 4 * world},
-            "gpu_launches": int(launches), "roofline": roof}
+        json.dump({"ms_per_step": main_res["ms_per_step"], "kernels": rows}, open(args.kernels_json, "w"), indent=1)
+    roof = None
+    if agg:
+        # dominant engine kernel by total device time
+        (dk, dshape), (dtot, dn) = max(agg.items(), key=lambda kv: kv[1][0])
+        flops, nbytes = conv_algorithmic(dshape, dk)
+        avg_s = dtot / dn / 1e3
+        t_hbm, t_tc = nbytes / (hbm * 1e9), flops / (tfl * 1e12)
+        if t_hbm >= t_tc:
+            roof = {"bound": "hbm", "achieved": nbytes / avg_s / 1e9, "peak": hbm, "unit": "GB/s"}
+        else:
+            roof = {"bound": "tensor", "achieved": flops / avg_s / 1e12, "peak": tfl, "unit": "TFLOP/s"}
+        roof["frac"] = roof["achieved"] / roof["peak"]
+        traffic = tsrc = None
+        tpath = os.path.join(ROOT, "profiles", "kernel_traffic.json")
+        if os.path.exists(tpath):  # measured dram__bytes_{read,write}.sum per launch from the committed ncu capture
+            tj = json.load(open(tpath))
+            rec = tj["kernels"].get(f"{dk}:{list(dshape)}")
+            traffic = rec["dram_bytes"] if rec else None
+            tsrc = tj.get("source")
+        t_roof_sum = sum(max(conv_algorithmic(sh, k)[1] / (hbm * 1e9), conv_algorithmic(sh, k)[0] / (tfl * 1e12)) * n
+                         for (k, sh), (_, n) in agg.items())
+        roof.update({"traffic": traffic, "traffic_source": tsrc, "algorithmic_bytes": nbytes, "algorithmic_flops": flops,
+                     "peak_source": peak_src,
+                     "kernel": f"conv2d_{dk} shape(B,C,H,W,K,R,S,sh,sw,ph,pw,dh,dw,G)={list(dshape)}",
+                     "avg_launch_us": avg_s * 1e6, "launches_timed": dn, "share_of_step": dtot / ms_total,
+                     "engine_conv_share_of_step": sum(v[0] for v in agg.values()) / ms_total,
+                     # all engine conv launches of the timed region: sum of their rooflines / sum of their measured times
+                     "all_conv_kernels_frac": t_roof_sum * 1e3 / max(1e-9, sum(v[0] for v in agg.values()))})
+    line = {"metric": main_res["metric"], "value": main_res["value"], "unit": "img/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": main_res["ms_per_step"], "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None,
+            "dtype": "f32 (bf16 tensor-core products of exact integer levels / exact bf16 pieces, fp32 accumulate)",
+            "data": "synthetic", "config": config_dict(wl, world), "clocks": main_res["clocks"], "e2e": main_res["e2e"],
+            "gpu_launches": main_res["gpu_launches"], "roofline": roof}
+    if world == 1 and not args.no_extra:
+        # the other BASELINE.json configs, a few steps each, so that the driver-run record covers them too
+        extras = []
+        for name in H.WORKLOADS:
+            if name == wl:
+                continue
+            try:
+                r = run_engine(name, 5, 3, dev, rank, world, detail=True)
+                t2, ms2 = r.pop("timer"), r.pop("ms_total")
+                agg2, _ = kernel_table(t2, ms2, 5, hbm, tfl)
+                r.pop("clocks")
+                r["config"] = config_dict(name, world)["workload"]
+                r["engine_conv_share_of_step"] = sum(v[0] for v in agg2.values()) / ms2 if agg2 else None
+                r["conv_kinds"] = sorted({k for k, _ in agg2})
+                extras.append(r)
+            except Exception as e:  # an extra must never take the headline line down with it
+                extras.append({"workload": name, "error": f"{type(e).__name__}: {e}"[:300]})
+        line["extra_workloads"] = extras
     if not args.no_cpu_baseline and world == 1:
-        line["cpu_baseline"], _ = run_cpu_baseline()
+        line["cpu_baseline"], _ = run_cpu_baseline(wl)
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -22,6 +22,12 @@ WORKLOADS = {
                                                   bn_fuse=True), wd=1e-5, hw=32),
     "nin_gc_dorefa_w4a4": dict(model="nin_gc", scheme="dorefa", prepare=dict(a_bits=4, w_bits=4), wd=1e-5, hw=32,
                                engine_extra=dict(fuse=True)),
+    # configs[4]: IAO int8 PTQ inference, ResNet-18 at 224x224 (iao/main.py:109-142 calibrate, :511-519 eval):
+    # prepare with ptq=True (HistogramObserver activations), 2 calibration batches in train mode / no_grad, then eval()
+    "resnet18_iao_ptq_224": dict(model="resnet18", scheme="iao",
+                                 prepare=dict(a_bits=8, w_bits=8, q_type=0, q_level=0, weight_observer=0, bn_fuse=True,
+                                              pretrained_model=True, ptq=True, percentile=0.999999),
+                                 wd=0.0, hw=224, inference=True, batch=64, calib_batches=2),
 }
 
 
@@ -88,3 +94,27 @@ class QatStepper:
             self.opt.all_reduce()
         self.opt.step()
         return loss
+
+
+class InferStepper:
+    """PTQ inference (BASELINE.json configs[4]): ``calibrate`` = the reference's ptq_calibration loop
+    (iao/main.py:109-142: train mode, no_grad, observers + scale update only), then ``eval()``; a step is one
+    forward pass of a batch."""
+
+    def __init__(self, model):
+        self.model = model
+
+    @torch.no_grad()
+    def calibrate(self, batches):
+        self.model.train()
+        for x in batches:
+            self.model(x)
+        self.model.eval()
+        freeze = getattr(self.model, "freeze_inference", None)
+        if freeze is not None:
+            freeze()
+        return self
+
+    @torch.no_grad()
+    def step(self, x, t=None):
+        return self.model(x)

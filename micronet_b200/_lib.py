@@ -77,6 +77,14 @@ PROTOTYPES = {
     "mnb_maxpool2d_fwd": (C.c_int, [_P, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P]),
     "mnb_maxpool2d_bwd": (C.c_int, [_P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P]),
     "mnb_adam_step": (C.c_int, [_P, _P, _P, _P, _L, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, _I, _P]),
+    "mnb_pk_act_bytes": (_L, [_I, _I, _I, _I, _I]),
+    "mnb_pk_pack_act": (C.c_int, [_P, _I, _I, _I, _I, _ACTQ, _I, _P, _I, _P, _P, _P]),
+    "mnb_pk_conv_plan": (C.c_int, [_SHAPE, _I, _I, _I, _P]),
+    "mnb_pk_wimage_bytes": (_L, [_SHAPE, _I, _I, _I]),
+    "mnb_pk_pack_weight": (C.c_int, [_SHAPE, _I, _I, _I, _P, _P, _P, _P, _P]),
+    "mnb_pk_conv": (C.c_int, [_SHAPE, _I, _P, _I, _P, _I, _P, _P, C.c_float, _P, _P, C.c_float, _P, _P, _P]),
+    "mnb_pk_wgrad_scratch_bytes": (_L, [_SHAPE, _I, _I]),
+    "mnb_pk_wgrad": (C.c_int, [_SHAPE, _P, _I, _P, _I, _P, _P, _P, _P, _P, _P]),
     "mnb_set_tc_profile_buffer": (None, [_P]),
     "mnb_selftest_mma_rate": (C.c_int, [_I, _I, _I, _I, _I, _P, _P, _P]),
     "mnb_selftest_umma": (C.c_int, [_P, _P, _P, _I, _I, _I, _P, _P]),
@@ -160,6 +168,11 @@ E_UNSUPPORTED = -2
 USE_TC = os.environ.get("MNB_DISABLE_TC", "0") != "1"
 # experimental packed bf16 operands between BN+binarizer and the next conv (round-2 groundwork, off by default)
 USE_PACKED = os.environ.get("MNB_PACKED_OPERANDS", "0") == "1"
+# packed-operand tensor-core family (mnb_pk.cu): "auto" = wherever the fused kernels have no cover and for every fused-quantizer
+# layer; "all" = every conv it supports; "off" = never
+PK_MODE = os.environ.get("MNB_PK", "auto")
+# exact bf16 pieces per fp32 operand on the pk path (3 = exact 24-bit split; 2 = 16 bits, ~4e-6 relative)
+PK_TERMS = int(os.environ.get("MNB_PK_TERMS", "3"))
 
 _scratch = {}
 

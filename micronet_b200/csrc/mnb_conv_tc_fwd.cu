@@ -572,6 +572,11 @@ static int plan(const mnb_conv_shape* s, bool dgrad, int quant_mode, Params& p, 
     p.CC = 16; p.nchunk = p.cin_g / 16;
     if (p.npos_in * 2 > KMAX * NCONV) return unsupported("tile too large for the converter");
   }
+  // the per-(tap, k-step) descriptor offsets live in a 64-entry kernel-parameter table (Params::mma_off)
+  if (p.R * p.S * (p.CC / 16) > 64) {
+    p.CC = 16; p.nchunk = p.cin_g / 16;
+    if (p.R * p.S > 64) return unsupported("more than 64 filter taps");
+  }
   p.row_tiles = (p.H + p.TH - 1) / p.TH;
   p.n_tiles = ((p.B + p.TB - 1) / p.TB) * p.row_tiles;
   p.quant_mode = quant_mode;

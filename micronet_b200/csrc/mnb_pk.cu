@@ -1,0 +1,1159 @@
+// Packed-operand ("pk") tensor-core convolution family: any conv geometry of the QAT models on tcgen05.
+//
+// Why a second family next to mnb_conv_tc_fwd.cu / mnb_conv_tc_wgrad.cu: those kernels keep the whole weight
+// slab of a group resident in shared memory and convert fp32 activations inside the kernel, which limits them
+// to small grouped layers (NIN-GC).  ResNet-18 (up to 512 -> 512 3x3 = 9.4 MB of weights, stride 2, 4x4 images),
+// NIN's 5x5 96 -> 192 and 224x224 inputs need the B operand STREAMED and N / W tiling.  Here every operand
+// reaches the kernel already in the layout the tensor core reads:
+//
+//   activations / gradients : bf16 "term planes"  pk[t][b][c/8][h][w][8]   (16 bytes = 8 channels of one pixel)
+//                             t = 0 .. T-1 exact pieces of an fp32 value (x = p0 + p1 + p2, 8 significand bits each)
+//                             or ONE plane of exact integer levels (fake-quantized activations);
+//   weights                 : bf16 image [n-tile][group][stage][term][tap][c/8][n][8] (K-major, rows = n), written
+//                             once per optimizer step by pk_pack_weight_kernel;
+//
+// so the convolution itself is the canonical Blackwell pipeline TMA -> tcgen05.mma -> TMEM -> epilogue with no
+// converter warps.  A 5-D tensor map (8, W, H, B, C/8) with the channel-octet dimension declared LAST makes one
+// box land in shared memory as op[c/8][position][8]: the UMMA K-major no-swizzle canonical layout with the
+// positions of the zero-padded tile as GEMM rows (halo rows AND columns zero-filled by the TMA unit), so filter tap
+// (r, s) is the same buffer with the descriptor start address moved by (r*BW + s)*16 bytes: implicit GEMM without
+// im2col.  The same buffers read as MN-major operands give the weight gradient (positions = reduction dimension).
+//
+// Stride-2 convolutions use the space-to-depth form: the pack kernel writes the four (h%2, w%2) phase planes as extra
+// channel octets, every filter tap then is a stride-1 tap of ONE phase plane with a shift in {-1, 0} (data gradient:
+// four output phases, each a stride-1 conv of dy with a subset of the taps).
+//
+// Exactness: integer levels (|e| <= 256) are exact in bf16, products exact, fp32 accumulation in TMEM.  fp32 operands
+// are split into T exact bf16 pieces; the products p_i * q_j with i + j < max(Ta, Tb) are accumulated, smallest first.
+#include <cuda.h>
+#include <cuda_bf16.h>
+
+#include <algorithm>
+#include <cstdlib>
+#include <cstring>
+
+#include "mnb_common.cuh"
+#include "mnb_tc.cuh"
+
+namespace pk {
+
+constexpr int NTHREADS = 256;      // warp 0 TMA, warp 1 MMA issue, warp 2 TMEM alloc, warps 4..7 epilogue
+constexpr int MAXST = 8;           // operand ring (power of two: ring index = counter & mask)
+constexpr int MAXTAP = 64, MAXTMPL = 16, MAXY = 4, MAXPAIR = 6;
+constexpr int kSmemBudget = 227 * 1024 - 3072;   // dynamic shared memory the kernels may ask for
+
+// ---------------------------------------------------------------------------------------------------------
+// plan: everything about a (shape, mode) pair that the weight packer and the convolution must agree on
+// ---------------------------------------------------------------------------------------------------------
+struct Tmpl { int kph, tap0, ntap, blk_off, blk_bytes; };   // one (k-phase, tap group): a pipeline stage template
+
+struct Plan {
+  int mode;                 // 0 forward, 1 data gradient
+  int B, G, R, S, stride;
+  int HA, WA, C8A, nkph;    // A planes as stored: spatial dims, octets per k-phase (all groups), k-phases
+  int kg, ng, NOUT;         // GEMM-K / GEMM-N channels per group, total output channels
+  int OHr, OWr, OH, OW, omul, ny;   // raster (per output phase) and real output dims
+  int hlo, hhi, wlo, whi;
+  int Wt, BW, TH, THH, TB, npos, col_tiles, row_tiles, img_tiles, n_mtiles;
+  int Nt, n_ntiles, MT, n_mgroups, n_items;
+  int CC, ksteps, chunks;   // K-chunk channels (multiple of 16), MMAs along K per chunk, chunks per k-phase
+  int TA, TBk, npairs, pair_a[MAXPAIR], pair_b[MAXPAIR];
+  int ntmpl[MAXY], ntap[MAXY];
+  Tmpl tmpl[MAXY][MAXTMPL];
+  int tap_aoff[MAXY][MAXTAP];            // A start-row offset of a tap inside the box (16-byte units)
+  short tap_r[MAXY][MAXTAP], tap_s[MAXY][MAXTAP];
+  int img_bytes[MAXY], y_off[MAXY];      // bytes of one (n-tile, group) weight image of output phase y; prefix offsets
+  int64_t wimg_bytes;
+  int a_box_bytes, a_bytes, b_off, stage_bytes, nstage, st_log2, smem_bytes, tmem_cols;
+  int segmented, seg_len;   // stages per accumulation segment (segmented mode)
+};
+
+static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+static inline int round_up(int a, int b) { return ceil_div(a, b) * b; }
+
+static void make_pairs(int TA, int TBk, Plan& p) {
+  // pieces have magnitudes 2^-8i: accumulate the products p_i q_j with i + j <= max(TA, TBk) - 1, smallest first
+  const int lim = std::max(TA, TBk) - 1;
+  p.npairs = 0;
+  for (int sum = lim; sum >= 0; --sum)
+    for (int a = 0; a < TA; ++a) {
+      const int b = sum - a;
+      if (b < 0 || b >= TBk) continue;
+      if (p.npairs < MAXPAIR) { p.pair_a[p.npairs] = a; p.pair_b[p.npairs] = b; ++p.npairs; }
+    }
+}
+
+static int unsupported(const char* why) { return mnb_fail(MNB_E_UNSUPPORTED, "pk conv: %s", why); }
+
+// mode 0: y = conv2d(x, w); mode 1: dx = conv_transpose(dy, w).  TA / TBk: term planes of the streamed / weight operand.
+static int make_plan(const mnb_conv_shape* s, int mode, int TA, int TBk, Plan& p) {
+  MNB_REQUIRE(s != nullptr, "conv shape is NULL");
+  memset(&p, 0, sizeof(p));
+  const int C = s->in_c, K = s->out_c, G = s->groups, H = s->in_h, W = s->in_w, R = s->ker_h, S = s->ker_w;
+  MNB_REQUIRE(s->batch > 0 && C > 0 && K > 0 && H > 0 && W > 0 && G > 0 && C % G == 0 && K % G == 0 && R > 0 && S > 0,
+              "bad conv shape");
+  MNB_REQUIRE(TA >= 1 && TA <= 3 && TBk >= 1 && TBk <= 3, "term counts must be 1..3");
+  if (s->dil_h != 1 || s->dil_w != 1) return unsupported("dilation != 1");
+  if (s->stride_h != s->stride_w || (s->stride_h != 1 && s->stride_h != 2)) return unsupported("stride must be 1 or 2");
+  const int st = s->stride_h, ph_ = s->pad_h, pw_ = s->pad_w;
+  if (ph_ > R - 1 || pw_ > S - 1) return unsupported("padding larger than the filter");
+  const int P = (H + 2 * ph_ - R) / st + 1, Q = (W + 2 * pw_ - S) / st + 1;
+  if (P < 1 || Q < 1) return unsupported("empty output");
+  if (st == 2 && ((H | W) & 1)) return unsupported("stride 2 needs even H and W");
+  const int cin_g = C / G, cout_g = K / G;
+  p.mode = mode; p.B = s->batch; p.G = G; p.R = R; p.S = S; p.stride = st;
+  p.TA = TA; p.TBk = TBk;
+  make_pairs(TA, TBk, p);
+  if (mode == 0) {
+    p.kg = cin_g; p.ng = cout_g; p.NOUT = K;
+    p.nkph = st == 2 ? 4 : 1;
+    p.HA = H / st; p.WA = W / st; p.C8A = ceil_div(C, 8);
+    p.OHr = P; p.OWr = Q; p.OH = P; p.OW = Q; p.omul = 1; p.ny = 1;
+  } else {
+    p.kg = cout_g; p.ng = cin_g; p.NOUT = C;
+    p.nkph = 1; p.HA = P; p.WA = Q; p.C8A = ceil_div(K, 8);
+    p.OHr = H / st; p.OWr = W / st; p.OH = H; p.OW = W; p.omul = st; p.ny = st == 2 ? 4 : 1;
+  }
+  if (G > 1 && (p.kg % 8)) return unsupported("grouped conv needs GEMM-K channels per group % 8 == 0");
+  // ---- taps: (k-phase, shift) of every filter tap, per output phase
+  struct Tap { int kph, sh, sw, r, s; };
+  Tap taps[MAXY][MAXTAP];
+  int hlo = 0, hhi = 0, wlo = 0, whi = 0;
+  for (int y = 0; y < p.ny; ++y) {
+    int n = 0;
+    const int ya = y >> 1, yb = y & 1;
+    for (int kph = 0; kph < p.nkph; ++kph)       // taps sorted by k-phase
+      for (int r = 0; r < R; ++r)
+        for (int q = 0; q < S; ++q) {
+          int kp = 0, sh, sw;
+          if (mode == 0) {
+            const int dr = r - ph_, ds = q - pw_;
+            if (st == 1) { sh = dr; sw = ds; }
+            else {
+              const int fh = dr & 1, fw = ds & 1;
+              kp = fh * 2 + fw; sh = (dr - fh) / 2; sw = (ds - fw) / 2;
+            }
+          } else {
+            if (st == 1) { sh = ph_ - r; sw = pw_ - q; }
+            else {
+              const int th = ya + ph_ - r, tw = yb + pw_ - q;
+              if ((th & 1) || (tw & 1)) continue;
+              sh = th / 2; sw = tw / 2;   // exact (even), also for negatives
+            }
+          }
+          if (kp != kph) continue;
+          if (n >= MAXTAP) return unsupported("more than 64 filter taps");
+          taps[y][n++] = Tap{kph, sh, sw, r, q};
+          hlo = std::max(hlo, -sh); hhi = std::max(hhi, sh); wlo = std::max(wlo, -sw); whi = std::max(whi, sw);
+        }
+    p.ntap[y] = n;
+  }
+  p.hlo = hlo; p.hhi = hhi; p.wlo = wlo; p.whi = whi;
+  // ---- M tile: 128 consecutive positions of the zero-padded tile raster (tb, row, col)
+  const int halo_w = wlo + whi;
+  if (halo_w >= 96) return unsupported("filter too wide");
+  p.col_tiles = ceil_div(p.OWr, 128 - halo_w);
+  p.Wt = ceil_div(p.OWr, p.col_tiles);
+  p.BW = p.Wt + halo_w;
+  p.TH = std::max(1, std::min(p.OHr, 128 / p.BW));
+  p.THH = p.TH + hlo + hhi;
+  p.TB = 1;
+  if (p.TH == p.OHr && p.col_tiles == 1) {
+    const int last = (p.TH - 1) * p.BW + p.Wt;             // rows used by the last image of a tile
+    p.TB = std::max(1, std::min(p.B, (128 - last) / (p.THH * p.BW) + 1));
+  }
+  if (p.BW > 256 || p.THH > 256 || p.TB > 256) return unsupported("box dimension");
+  p.npos = p.TB * p.THH * p.BW;
+  p.row_tiles = ceil_div(p.OHr, p.TH);
+  p.img_tiles = ceil_div(p.B, p.TB);
+  p.n_mtiles = p.img_tiles * p.row_tiles * p.col_tiles;
+  // ---- N tile
+  const int ng16 = round_up(p.ng, 16);
+  // Split fp32 operands (more than one piece product per K-step) run in SEGMENTED mode: tcgen05.mma truncates the running
+  // fp32 accumulator after every instruction (a bias of ~2e-8 of |D| per MMA, measured: 3e-5 after 1700 chained MMAs),
+  // so the K loop is cut into segments of <= ~64 MMAs, each into a fresh TMEM accumulator, and the epilogue warps add
+  // the segments in registers with round-to-nearest adds.  That needs the whole N tile in registers: Nt <= 128, MT = 1.
+  p.segmented = p.npairs > 1;
+  if (ng16 <= 128) p.Nt = ng16;
+  else if (ng16 % 128 == 0) p.Nt = 128;
+  else if (ng16 <= 256 && !p.segmented) p.Nt = ng16;
+  else if (ng16 <= 256) p.Nt = round_up(ceil_div(p.ng, 2), 16);
+  else p.Nt = 128;
+  p.n_ntiles = ceil_div(p.ng, p.Nt);
+  p.MT = 1;
+  if (!p.segmented && p.Nt <= 128 && p.n_mtiles >= 2 &&
+      (int64_t)ceil_div(p.n_mtiles, 2) * p.n_ntiles * G * p.ny >= 120) p.MT = 2;
+  if (const char* e = getenv("MNB_PK_MT")) { const int v = atoi(e); if (v == 1 || (v == 2 && p.Nt <= 128 && !p.segmented)) p.MT = v; }
+  p.n_mgroups = ceil_div(p.n_mtiles, p.MT);
+  p.n_items = p.n_mgroups * p.n_ntiles * G;
+  // ---- K chunking and tap groups: one stage = MT * TA boxes of CC channels + the weights of (chunk, tap group)
+  const int nk16 = ceil_div(p.kg, 16);
+  int maxtap_kph = 1;
+  for (int y = 0; y < p.ny; ++y)
+    for (int i = 0, run = 0; i < p.ntap[y]; ++i) {
+      run = (i > 0 && taps[y][i].kph == taps[y][i - 1].kph) ? run + 1 : 1;
+      maxtap_kph = std::max(maxtap_kph, run);
+    }
+  const int a16 = p.MT * TA * round_up(2 * p.npos * 16, 128);     // A bytes per 16 channels (2 octets)
+  auto b16 = [&](int tg) { return TBk * tg * 2 * p.Nt * 16; };   // B bytes per 16 channels
+  const int stage_target = 56 * 1024;
+  int TG = std::min(maxtap_kph, 25);
+  while (TG > 1 && a16 + b16(TG) > stage_target) --TG;
+  if (a16 + b16(TG) > (kSmemBudget - 8192) / 2) return unsupported("one 16-channel stage does not fit in shared memory");
+  int cc16 = std::max(1, std::min(nk16, stage_target / (a16 + b16(TG))));
+  cc16 = std::min(cc16, 16);
+  p.chunks = ceil_div(nk16, cc16);
+  cc16 = ceil_div(nk16, p.chunks);            // balance the chunks
+  p.CC = cc16 * 16; p.ksteps = cc16;
+  p.a_box_bytes = (p.CC / 8) * p.npos * 16;
+  p.a_bytes = round_up(p.a_box_bytes, 128);
+  p.b_off = p.MT * TA * p.a_bytes;
+  // ---- stage templates and the weight-image layout
+  int64_t total = 0;
+  int max_blk = 0;
+  for (int y = 0; y < p.ny; ++y) {
+    int nt = 0, off = 0;
+    for (int i = 0; i < p.ntap[y];) {
+      int j = i;
+      while (j < p.ntap[y] && taps[y][j].kph == taps[y][i].kph && j - i < TG) ++j;
+      if (nt >= MAXTMPL) return unsupported("too many tap groups");
+      Tmpl& t = p.tmpl[y][nt++];
+      t.kph = taps[y][i].kph; t.tap0 = i; t.ntap = j - i;
+      t.blk_bytes = TBk * t.ntap * (p.CC / 8) * p.Nt * 16;
+      t.blk_off = off;
+      off += p.chunks * t.blk_bytes;
+      max_blk = std::max(max_blk, t.blk_bytes);
+      i = j;
+    }
+    p.ntmpl[y] = nt;
+    p.img_bytes[y] = off;
+    p.y_off[y] = (int)total;
+    total += (int64_t)off * p.n_ntiles * G;
+    if (total > (int64_t)1 << 30) return unsupported("weight image larger than 1 GiB");
+    for (int i = 0; i < p.ntap[y]; ++i) {
+      p.tap_aoff[y][i] = (taps[y][i].sh + hlo) * p.BW + (taps[y][i].sw + wlo);
+      p.tap_r[y][i] = (short)taps[y][i].r; p.tap_s[y][i] = (short)taps[y][i].s;
+    }
+  }
+  p.wimg_bytes = std::max<int64_t>(total, 16);
+  p.seg_len = 1 << 30;
+  if (p.segmented) {
+    const int per_stage = TG * p.npairs * p.ksteps;     // MMAs per accumulator and stage (upper bound)
+    int target = 64;
+    if (const char* e = getenv("MNB_PK_SEG_MMAS")) target = std::max(1, atoi(e));
+    p.seg_len = std::max(1, target / per_stage);
+  }
+  p.stage_bytes = round_up(p.b_off + max_blk, 1024);
+  // slack behind the last stage: MMAs of invalid halo rows read up to 128 + max tap offset rows past a plane start
+  const int slack = round_up((128 + (hlo + hhi) * p.BW + halo_w + 8) * 16, 1024);
+  int nst = (kSmemBudget - slack) / p.stage_bytes;
+  if (nst < 2) return unsupported("fewer than two pipeline stages fit");
+  p.nstage = nst >= 8 ? 8 : (nst >= 4 ? 4 : 2);
+  if (const char* e = getenv("MNB_PK_STAGES")) { const int v = atoi(e); if ((v == 2 || v == 4 || v == 8) && v <= nst) p.nstage = v; }
+  p.st_log2 = p.nstage == 8 ? 3 : (p.nstage == 4 ? 2 : 1);
+  p.smem_bytes = p.nstage * p.stage_bytes + slack;
+  int cols = 32;
+  while (cols < 2 * p.MT * p.Nt) cols <<= 1;
+  if (cols > 512) return unsupported("accumulators exceed tensor memory");
+  p.tmem_cols = cols;
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// operand packers
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t pack2(float a, float b) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+
+// fp32 NCHW -> bf16 term planes [t][b][octet][h][w][8]; one thread = one pixel of one channel octet.
+//   QUANT = 0: planes are the exact pieces of x (* ch_scale[c] when given)
+//   QUANT = 1: plane 0.. hold the fake-quantized integer level e = code + a_off (+ zero point) (exact; two pieces when
+//              |e| can exceed 256), bits8[b][c/8][h][w] bit j = STE pass flag of channel 8*(c/8) + j
+// phase_split: octet index (h%2 * 2 + w%2) * C8 + c/8 of a [.., H/2, W/2] plane (stride-2 consumers)
+template <int QUANT>
+__global__ void __launch_bounds__(256) pack_act_kernel(const float* __restrict__ x, int B, int C, int H, int W, int C8,
+                                                       int terms, const float* __restrict__ ch_scale, mnb_act_qparams qp,
+                                                       int a_off, int phase_split, uint4* __restrict__ out,
+                                                       int64_t plane_vecs, uint8_t* __restrict__ bits8) {
+  const int64_t total = (int64_t)B * C8 * H * W;
+  MnbActQ q;
+  float zp = 0.f;
+  if (QUANT) {
+    q = mnb_load_actq(qp);
+    if (qp.mode == MNB_ACT_IAO && qp.zero_point) zp = __ldg(qp.zero_point);
+  }
+  const int64_t HW = (int64_t)H * W;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+    const int w = (int)(idx % W);
+    int64_t t = idx / W;
+    const int h = (int)(t % H);
+    t /= H;
+    const int c8 = (int)(t % C8), b = (int)(t / C8);
+    float v[8];
+    uint32_t passbits = 0;
+    const float* src = x + ((int64_t)b * C + c8 * 8) * HW + (int64_t)h * W + w;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int c = c8 * 8 + j;
+      float val = c < C ? __ldg(src + j * HW) : 0.f;
+      if (QUANT) {
+        bool pass;
+        const int code = mnb_act_code_certified(q, val, pass);
+        val = c < C ? (float)(code + a_off) + zp : 0.f;
+        passbits |= (pass && c < C) ? (1u << j) : 0u;
+      } else if (ch_scale) {
+        val = c < C ? __fmul_rn(val, __ldg(ch_scale + c)) : 0.f;
+      }
+      v[j] = val;
+    }
+    int64_t dst;
+    if (phase_split) {
+      const int oct = ((h & 1) * 2 + (w & 1)) * C8 + c8;
+      dst = (((int64_t)b * 4 * C8 + oct) * (H >> 1) + (h >> 1)) * (W >> 1) + (w >> 1);
+    } else {
+      dst = idx;
+    }
+    for (int tm = 0; tm < terms; ++tm) {
+      uint32_t pk4[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        pk4[j] = pack2(v[2 * j], v[2 * j + 1]);
+        v[2 * j] -= __uint_as_float(pk4[j] << 16);
+        v[2 * j + 1] -= __uint_as_float(pk4[j] & 0xffff0000u);
+      }
+      out[(int64_t)tm * plane_vecs + dst] = make_uint4(pk4[0], pk4[1], pk4[2], pk4[3]);
+    }
+    if (QUANT && bits8) bits8[idx] = (uint8_t)passbits;
+  }
+}
+
+struct PackWParams {
+  Plan pl;
+  const int16_t* w_int; const float* w_f32; const float* kzero;   // kzero[k] == 0 -> the weights of channel k read as 0 (dgrad)
+  int cin_g, cout_g;
+};
+
+// weights (int16 levels or fp32) -> bf16 image of the plan; one thread = one 16-byte vector (8 GEMM-K channels)
+__global__ void __launch_bounds__(256) pack_weight_kernel(const __grid_constant__ PackWParams pp, uint4* __restrict__ out) {
+  const Plan& p = pp.pl;
+  const int64_t total = p.wimg_bytes / 16;
+  const int RS = p.R * p.S;
+  for (int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < total; v += (int64_t)gridDim.x * blockDim.x) {
+    int64_t byte = v * 16;
+    int y = 0;
+    for (int yy = 1; yy < p.ny; ++yy) if (byte >= p.y_off[yy]) y = yy;
+    byte -= p.y_off[y];
+    if (p.img_bytes[y] == 0) continue;
+    const int ntg = (int)(byte / p.img_bytes[y]);
+    int rem = (int)(byte - (int64_t)ntg * p.img_bytes[y]);
+    if (ntg >= p.n_ntiles * p.G) continue;
+    const int nt = ntg / p.G, g = ntg - nt * p.G;
+    int t = 0;
+    for (int tt = 1; tt < p.ntmpl[y]; ++tt) if (rem >= p.tmpl[y][tt].blk_off) t = tt;
+    const Tmpl tp = p.tmpl[y][t];
+    rem -= tp.blk_off;
+    const int cc = rem / tp.blk_bytes;
+    rem -= cc * tp.blk_bytes;
+    const int per_tap = (p.CC / 8) * p.Nt * 16, per_term = tp.ntap * per_tap;
+    const int term = rem / per_term;
+    rem -= term * per_term;
+    const int tapi = rem / per_tap;
+    rem -= tapi * per_tap;
+    const int c8l = rem / (p.Nt * 16), n = (rem - c8l * (p.Nt * 16)) / 16;
+    const int r = p.tap_r[y][tp.tap0 + tapi], s = p.tap_s[y][tp.tap0 + tapi];
+    const int nn = nt * p.Nt + n;                 // GEMM-N channel within the group
+    float val[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int kk = cc * p.CC + c8l * 8 + e;     // GEMM-K channel within the group
+      float x = 0.f;
+      if (kk < p.kg && nn < p.ng) {
+        int64_t src;
+        int kout;
+        if (p.mode == 0) { kout = g * pp.cout_g + nn; src = ((int64_t)kout * pp.cin_g + kk) * RS + r * p.S + s; }
+        else { kout = g * pp.cout_g + kk; src = ((int64_t)kout * pp.cin_g + nn) * RS + r * p.S + s; }
+        x = pp.w_int ? (float)__ldg(pp.w_int + src) : __ldg(pp.w_f32 + src);
+        if (pp.kzero && __ldg(pp.kzero + kout) == 0.f) x = 0.f;
+      }
+      val[e] = x;
+    }
+    uint32_t pk4[4];
+    for (int tm = 0; tm <= term; ++tm) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        pk4[j] = pack2(val[2 * j], val[2 * j + 1]);
+        val[2 * j] -= __uint_as_float(pk4[j] << 16);
+        val[2 * j + 1] -= __uint_as_float(pk4[j] & 0xffff0000u);
+      }
+    }
+    out[v] = make_uint4(pk4[0], pk4[1], pk4[2], pk4[3]);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// the convolution kernel (forward and data gradient)
+// ---------------------------------------------------------------------------------------------------------
+struct ConvParams {
+  // private parameter block of the MMA-issue warp (uniform datapath: see mnb_conv_packed.cu for the rules)
+  struct Mma {
+    uint32_t n_items, chunks, ksteps, MT, Nt, npairs, st_mask, st_log2, stage16, a_mt16, a_term16, a_k16, b_off16,
+        b_tap16, b_k16, idesc, a_lbo, b_lbo, seg_len;
+    uint32_t pair_a[MAXPAIR], pair_b[MAXPAIR];
+    uint32_t ntmpl[MAXY];
+    uint32_t tmpl_tap0[MAXY][MAXTMPL], tmpl_ntap[MAXY][MAXTMPL];
+    uint32_t tap_aoff[MAXY][MAXTAP];
+  } m;
+  // TMA role
+  int n_items, n_ntiles, G, MT, TA, chunks, CC8, C8A, kg8, stage_bytes, a_bytes, a_box_bytes, b_off, st_mask, st_log2;
+  int Wt, TH, TB, wlo, hlo, col_tiles, row_tiles, n_mtiles;
+  int ntmpl[MAXY], tmpl_kph[MAXY][MAXTMPL], tmpl_blk_off[MAXY][MAXTMPL], tmpl_blk_bytes[MAXY][MAXTMPL];
+  int img_bytes[MAXY], y_off[MAXY];
+  const uint8_t* w_img;
+  // epilogue
+  int B, THH, BW, OHr, OWr, OH, OW, omul, ny, ng, Nt, NOUT, C8O, smem_bytes, tmem_cols, mode, zero_y[MAXY];
+  int nseg[MAXY];           // accumulation segments per work item (1 unless segmented)
+  const float* n_scale;     // [NOUT] per-output-channel scale or NULL
+  const float* a_scale;     // device scalar multiplied into n_scale, or NULL
+  float a_scale_const;
+  const float* bias;        // [NOUT] or NULL
+  const uint8_t* bits8;     // dgrad STE mask [B][C8O][OH][OW] or NULL
+  float gain;               // dgrad: factor on passed gradients (DoReFa 0.1)
+  float* out;
+  int* err;
+};
+
+struct alignas(16) ConvShared {
+  uint64_t full[MAXST], empty[MAXST], acc_full[2], acc_empty[2];
+  uint32_t tmem_slot, abort;
+  alignas(16) float epi_scale[256];
+  alignas(16) float epi_bias[256];
+};
+
+__device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+}
+
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+
+template <bool SEG>   // SEG: segmented accumulation (split fp32 operands), the epilogue keeps the N tile in registers
+__global__ void __launch_bounds__(NTHREADS, 1)
+pk_conv_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_constant__ CUtensorMap tmap1,
+               const __grid_constant__ CUtensorMap tmap2, const __grid_constant__ ConvParams p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ ConvShared sh;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+  if (tid == 0) {
+    for (int i = 0; i < MAXST; ++i) { tc::mbar_init(&sh.full[i], 1); tc::mbar_init(&sh.empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { tc::mbar_init(&sh.acc_full[i], 1); tc::mbar_init(&sh.acc_empty[i], 128); }
+    sh.abort = 0;
+    tc::fence_barrier_init();
+    tc::prefetch_tmap(&tmap0);
+    if (p.TA > 1) tc::prefetch_tmap(&tmap1);
+    if (p.TA > 2) tc::prefetch_tmap(&tmap2);
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tc::smem_u32(&sh.tmem_slot)),
+                 "r"((uint32_t)p.tmem_cols));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  // rows behind a box that only invalid accumulator rows read must at least be finite
+  for (int i = tid; i < p.smem_bytes / 16; i += NTHREADS) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
+  tc::fence_proxy_async_smem();
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tmem = sh.tmem_slot;
+
+  if (warp == 0) {
+    // ================================================================= TMA producer
+    if (lane == 0) {
+      const int y = blockIdx.y;
+      uint32_t sc = 0;
+      for (int it = blockIdx.x; it < p.n_items; it += gridDim.x) {
+        const int nt = it % p.n_ntiles;
+        const int r1 = it / p.n_ntiles;
+        const int g = r1 % p.G, mg = r1 / p.G;
+        const uint8_t* wsrc = p.w_img + (size_t)p.y_off[y] + (size_t)(nt * p.G + g) * (size_t)p.img_bytes[y];
+        for (int t = 0; t < p.ntmpl[y]; ++t) {
+          const int kph = p.tmpl_kph[y][t];
+          const uint32_t blk = (uint32_t)p.tmpl_blk_bytes[y][t];
+          const uint8_t* bsrc = wsrc + p.tmpl_blk_off[y][t];
+          for (int cc = 0; cc < p.chunks; ++cc, ++sc) {
+            const uint32_t slot = sc & (uint32_t)p.st_mask, ph = (sc >> p.st_log2) & 1u;
+            if (!tc::mbar_wait(&sh.empty[slot], ph ^ 1u, p.err, 701)) goto done;
+            tc::mbar_arrive_expect_tx(&sh.full[slot], (uint32_t)(p.MT * p.TA * p.a_box_bytes) + blk);
+            uint8_t* sbase = smem + (size_t)slot * p.stage_bytes;
+            const int c8 = kph * p.C8A + g * p.kg8 + cc * p.CC8;
+            for (int mt = 0; mt < p.MT; ++mt) {
+              const int tile = mg * p.MT + mt;
+              const int ct = tile % p.col_tiles;
+              const int r2 = tile / p.col_tiles;
+              const int rt = r2 % p.row_tiles, bt = r2 / p.row_tiles;
+              const int cw = ct * p.Wt - p.wlo, chh = rt * p.TH - p.hlo, cb = bt * p.TB;
+              tc::tma_load_5d(sbase + (size_t)(mt * p.TA) * p.a_bytes, &tmap0, &sh.full[slot], 0, cw, chh, cb, c8);
+              if (p.TA > 1) tc::tma_load_5d(sbase + (size_t)(mt * p.TA + 1) * p.a_bytes, &tmap1, &sh.full[slot], 0, cw, chh, cb, c8);
+              if (p.TA > 2) tc::tma_load_5d(sbase + (size_t)(mt * p.TA + 2) * p.a_bytes, &tmap2, &sh.full[slot], 0, cw, chh, cb, c8);
+            }
+            tc::bulk_load_1d(sbase + p.b_off, bsrc + (size_t)cc * blk, blk, &sh.full[slot]);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================================================================= MMA issuer (warp-converged, lane 0 issues)
+    const uint32_t lead = lane == 0;
+    const uint32_t y = blockIdx.y;
+    const uint64_t a_desc0 = tc::smem_desc_kmajor_noswz(tc::smem_u32(smem), p.m.a_lbo, 128);
+    const uint64_t b_desc0 = tc::smem_desc_kmajor_noswz(tc::smem_u32(smem), p.m.b_lbo, 128) + (uint64_t)p.m.b_off16;
+    uint32_t sc = 0, accq = 0;   // accq counts accumulator hand-offs (one per segment)
+    for (uint32_t it = blockIdx.x; it < p.m.n_items; it += gridDim.x) {
+      uint32_t started = 0, seg_pos = 0, open = 0;
+      for (uint32_t t = 0; t < p.m.ntmpl[y]; ++t) {
+        const uint32_t tap0 = p.m.tmpl_tap0[y][t], ntap = p.m.tmpl_ntap[y][t];
+        const uint32_t b_term16 = ntap * p.m.b_tap16;
+        for (uint32_t cc = 0; cc < p.m.chunks; ++cc, ++sc) {
+          const uint32_t acc = accq & 1u, aph = (accq >> 1) & 1u;
+          if (!open) {   // first stage of a segment: the accumulator must have been drained
+            tc::mbar_wait_soft(&sh.acc_empty[acc], aph ^ 1u, p.err, 702, &sh.abort);
+            open = 1; started = 0;
+          }
+          const uint32_t slot = sc & p.m.st_mask, ph = (sc >> p.m.st_log2) & 1u;
+          tc::mbar_wait_soft(&sh.full[slot], ph, p.err, 703, &sh.abort);
+          tc::tc_fence_after();
+          const uint32_t s16 = slot * p.m.stage16;
+          for (uint32_t mt = 0; mt < p.m.MT; ++mt) {
+            const uint32_t d = tmem + (acc * p.m.MT + mt) * p.m.Nt;
+            for (uint32_t i = 0; i < ntap; ++i) {
+              const uint32_t aoff = s16 + mt * p.m.a_mt16 + p.m.tap_aoff[y][tap0 + i];
+              const uint32_t boff = s16 + i * p.m.b_tap16;
+              for (uint32_t pr = 0; pr < p.m.npairs; ++pr) {
+                const uint32_t a2 = aoff + p.m.pair_a[pr] * p.m.a_term16, b2 = boff + p.m.pair_b[pr] * b_term16;
+                for (uint32_t j = 0; j < p.m.ksteps; ++j)
+                  tc::mma_f16_guarded(d, a_desc0 + (uint64_t)(a2 + j * p.m.a_k16), b_desc0 + (uint64_t)(b2 + j * p.m.b_k16),
+                                      p.m.idesc, (started | i | pr | j) != 0u, lead);
+              }
+            }
+          }
+          if (lead) tc::mma_commit(&sh.empty[slot]);
+          __syncwarp();
+          started = 1;
+          if (++seg_pos == p.m.seg_len) {   // segment complete: hand the accumulator to the epilogue
+            if (lead) tc::mma_commit(&sh.acc_full[acc]);
+            __syncwarp();
+            seg_pos = 0; open = 0; ++accq;
+          }
+        }
+      }
+      if (open || p.m.ntmpl[y] == 0) {      // last (partial) segment, or an output phase without any filter tap
+        const uint32_t acc = accq & 1u, aph = (accq >> 1) & 1u;
+        if (!open) tc::mbar_wait_soft(&sh.acc_empty[acc], aph ^ 1u, p.err, 702, &sh.abort);
+        if (lead) tc::mma_commit(&sh.acc_full[acc]);
+        __syncwarp();
+        ++accq;
+      }
+    }
+  } else if (warp >= 4) {
+    // ================================================================= epilogue: TMEM -> scale/bias or STE -> fp32 NCHW
+    const int q = warp - 4, et = tid - 128;
+    const int m = q * 32 + lane;                     // accumulator row = position of the zero-padded tile raster
+    const int tb = m / (p.THH * p.BW);
+    const int rem = m - tb * (p.THH * p.BW);
+    const int th = rem / p.BW, wc = rem - th * p.BW;
+    const bool row_ok = tb < p.TB && th < p.TH && wc < p.Wt;
+    const int y = blockIdx.y, ya = p.ny == 4 ? (y >> 1) : 0, yb = p.ny == 4 ? (y & 1) : 0;
+    const int64_t plane = (int64_t)p.OH * p.OW;
+    const float a_sc = p.a_scale ? __ldg(p.a_scale) : p.a_scale_const;
+    uint32_t accq = 0;
+    for (int it = blockIdx.x; it < p.n_items; it += gridDim.x) {
+      const int nt = it % p.n_ntiles;
+      const int r1 = it / p.n_ntiles;
+      const int g = r1 % p.G, mg = r1 / p.G;
+      const int n_base = g * p.ng + nt * p.Nt;                // first output channel of this N tile
+      const int n_cnt = min(p.Nt, p.ng - nt * p.Nt);
+      // per-channel constants of this N tile (the previous item's readers are done: barrier at the end of the loop body)
+      for (int n = et; n < p.Nt; n += 128) {
+        float sc = 1.f, bs = 0.f;
+        if (n < n_cnt) {
+          sc = p.n_scale ? __fmul_rn(a_sc, __ldg(p.n_scale + n_base + n)) : a_sc;
+          if (p.bias) bs = __ldg(p.bias + n_base + n);
+        }
+        sh.epi_scale[n] = sc; sh.epi_bias[n] = bs;
+      }
+      epi_bar_sync();
+      const int nseg = SEG ? p.nseg[y] : 1;
+      float rs[SEG ? 8 : 1][16];   // running sums of the N tile (segmented mode only: Nt <= 128, MT = 1)
+      for (int seg = 0; seg < nseg; ++seg, ++accq) {
+        const uint32_t acc = accq & 1u, aph = (accq >> 1) & 1u;
+        if (!tc::mbar_wait(&sh.acc_full[acc], aph, p.err, 704)) goto done;
+        tc::tc_fence_after();
+        const bool last = seg == nseg - 1;
+        for (int mt = 0; mt < p.MT; ++mt) {
+          const int tile = mg * p.MT + mt;
+          const int ct = tile % p.col_tiles;
+          const int r2 = tile / p.col_tiles;
+          const int rt = r2 % p.row_tiles, bt = r2 / p.row_tiles;
+          const int b = bt * p.TB + tb, i = rt * p.TH + th, j = ct * p.Wt + wc;
+          const bool valid = row_ok && tile < p.n_mtiles && b < p.B && i < p.OHr && j < p.OWr;
+          const int oh = i * p.omul + ya, ow = j * p.omul + yb;
+          float* orow = p.out + ((int64_t)b * p.NOUT + n_base) * plane + (int64_t)oh * p.OW + ow;
+          const uint8_t* brow = p.bits8 ? p.bits8 + (int64_t)b * p.C8O * plane + (int64_t)oh * p.OW + ow : nullptr;
+#pragma unroll
+          for (int c16 = 0; c16 < (SEG ? 8 : 16); ++c16) {
+            const int n0 = c16 * 16;
+            if (n0 >= p.Nt) break;
+            uint32_t r[16];
+            if (!p.zero_y[y]) {
+              tmem_ld_32x16(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)((acc * p.MT + mt) * p.Nt + n0), r);
+              tc::tmem_ld_wait();
+            } else {
+#pragma unroll
+              for (int k = 0; k < 16; ++k) r[k] = 0u;
+            }
+            if (SEG) {   // accumulate the segment (round-to-nearest fp32 adds), write only after the last one
+#pragma unroll
+              for (int k = 0; k < 16; ++k) {
+                const float v = seg == 0 ? __uint_as_float(r[k]) : __fadd_rn(rs[SEG ? c16 : 0][k], __uint_as_float(r[k]));
+                rs[SEG ? c16 : 0][k] = v;
+                r[k] = __float_as_uint(v);
+              }
+              if (!last) continue;
+            }
+            if (!valid || n0 >= n_cnt) continue;
+            float sc[16], bs[16];
+#pragma unroll
+            for (int v = 0; v < 4; ++v) {
+              const float4 a = *reinterpret_cast<const float4*>(&sh.epi_scale[n0 + 4 * v]);
+              const float4 c = *reinterpret_cast<const float4*>(&sh.epi_bias[n0 + 4 * v]);
+              sc[4 * v] = a.x; sc[4 * v + 1] = a.y; sc[4 * v + 2] = a.z; sc[4 * v + 3] = a.w;
+              bs[4 * v] = c.x; bs[4 * v + 1] = c.y; bs[4 * v + 2] = c.z; bs[4 * v + 3] = c.w;
+            }
+            float* op = orow + (int64_t)n0 * plane;
+            if (p.mode == 0 || !brow) {
+#pragma unroll
+              for (int k = 0; k < 16; ++k, op += plane)
+                if (n0 + k < n_cnt) *op = fmaf(__uint_as_float(r[k]), sc[k], bs[k]);
+            } else {
+              // STE of the activation quantizer that fed the forward conv: the reference computes ((g*s)*pass)/s (IAO) or
+              // (((g*s)/s)*pass)*0.1 (DoReFa); (g*s)/s is g to within one ulp, so g itself is passed
+              const int oc0 = (n_base + n0) >> 3;     // n_base + n0 is a multiple of 8 (checked on the host)
+              const uint32_t m0 = __ldg(brow + (int64_t)oc0 * plane);
+              const uint32_t m1 = (n0 + 8 < n_cnt) ? __ldg(brow + (int64_t)(oc0 + 1) * plane) : 0u;
+              const uint32_t mask = m0 | (m1 << 8);
+#pragma unroll
+              for (int k = 0; k < 16; ++k, op += plane)
+                if (n0 + k < n_cnt) *op = ((mask >> k) & 1u) ? __uint_as_float(r[k]) * p.gain : 0.f;
+            }
+          }
+        }
+        tc::tc_fence_before();
+        tc::mbar_arrive(&sh.acc_empty[acc]);
+      }
+      epi_bar_sync();   // everyone is done with epi_scale / epi_bias of this item
+    }
+  }
+done:
+  tc::tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc::tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"((uint32_t)p.tmem_cols));
+  }
+}
+
+// 5-D map over term plane `t` of a packed tensor: box traversal order (8, w, h, b, octet)
+static int make_pk_tmap(CUtensorMap* m, const void* base, int64_t plane_bytes, int t, int B, int C8tot, int H, int W,
+                        int bw, int bh, int bb, int bc8) {
+  const uint64_t HW = (uint64_t)H * W;
+  uint64_t dims[5] = {8, (uint64_t)W, (uint64_t)H, (uint64_t)B, (uint64_t)C8tot};
+  uint64_t strides[4] = {16, (uint64_t)W * 16, (uint64_t)C8tot * HW * 16, HW * 16};
+  uint32_t box[5] = {8, (uint32_t)bw, (uint32_t)bh, (uint32_t)bb, (uint32_t)bc8};
+  return mnb_make_tmap_strided(m, reinterpret_cast<const uint8_t*>(base) + (int64_t)t * plane_bytes, 2, 5, dims, strides, box);
+}
+
+template <typename K>
+static int set_max_smem(K kernel, int bytes) {
+  // per device (the attribute is a property of the function on the current device), cheap enough to repeat
+  cudaError_t ce = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (ce != cudaSuccess) return mnb_fail((int)ce, "cudaFuncSetAttribute: %s", cudaGetErrorString(ce));
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// weight gradient: dW[k][c][tap] = sum over positions of dy[pos][k] * x[pos + tap][c]   (MN-major operands)
+// ---------------------------------------------------------------------------------------------------------
+struct WgPlan {
+  int B, G, R, S, stride, ntap;
+  int P, Q, K8, HX, WX, C8X, nkph;      // dy dims / octets; x planes as stored
+  int cin_g, cout_g;
+  int hlo, hhi, wlo, whi, BW, TH, THH, rows_dy, rows_x, row_tiles;
+  int Nc, n_ctiles, n_ktiles, NI, nsub, nstg_total, splits, stg_per_split;
+  int TA, TX, npairs, pair_a[MAXPAIR], pair_b[MAXPAIR];
+  int tap_kph[MAXTAP], tap_off[MAXTAP];   // per tap: k-phase plane and start-row offset in the x block
+  int kph_used[4], nkph_used, kph_slot[4];
+  int dy_box_bytes, x_box_bytes, dy_bytes, x_bytes, sub_bytes, stage_bytes, nstage, st_log2, smem_bytes, tmem_cols;
+  int64_t partial_floats;
+};
+
+static int make_wg_plan(const mnb_conv_shape* s, int TA, int TX, WgPlan& p) {
+  MNB_REQUIRE(s != nullptr, "conv shape is NULL");
+  memset(&p, 0, sizeof(p));
+  const int C = s->in_c, K = s->out_c, G = s->groups, H = s->in_h, W = s->in_w, R = s->ker_h, S = s->ker_w;
+  MNB_REQUIRE(s->batch > 0 && C > 0 && K > 0 && H > 0 && W > 0 && G > 0 && C % G == 0 && K % G == 0, "bad conv shape");
+  if (s->dil_h != 1 || s->dil_w != 1) return mnb_fail(MNB_E_UNSUPPORTED, "pk wgrad: dilation != 1");
+  if (s->stride_h != s->stride_w || (s->stride_h != 1 && s->stride_h != 2)) return mnb_fail(MNB_E_UNSUPPORTED, "pk wgrad: stride");
+  const int st = s->stride_h, ph_ = s->pad_h, pw_ = s->pad_w;
+  if (ph_ > R - 1 || pw_ > S - 1) return mnb_fail(MNB_E_UNSUPPORTED, "pk wgrad: padding larger than the filter");
+  if (st == 2 && ((H | W) & 1)) return mnb_fail(MNB_E_UNSUPPORTED, "pk wgrad: stride 2 needs even H and W");
+  if (R * S > MAXTAP) return mnb_fail(MNB_E_UNSUPPORTED, "pk wgrad: more than 64 taps");
+  p.B = s->batch; p.G = G; p.R = R; p.S = S; p.stride = st; p.ntap = R * S;
+  p.P = (H + 2 * ph_ - R) / st + 1; p.Q = (W + 2 * pw_ - S) / st + 1;
+  if (p.P < 1 || p.Q < 1) return mnb_fail(MNB_E_UNSUPPORTED, "pk wgrad: empty output");
+  p.cin_g = C / G; p.cout_g = K / G;
+  if (G > 1 && ((p.cin_g % 8) || (p.cout_g % 8))) return mnb_fail(MNB_E_UNSUPPORTED, "pk wgrad: grouped conv needs channels per group % 8 == 0");
+  p.K8 = ceil_div(K, 8); p.C8X = ceil_div(C, 8);
+  p.nkph = st == 2 ? 4 : 1; p.HX = H / st; p.WX = W / st;
+  p.TA = TA; p.TX = TX;
+  { Plan tmp; memset(&tmp, 0, sizeof(tmp)); make_pairs(TA, TX, tmp); p.npairs = tmp.npairs;
+    for (int i = 0; i < tmp.npairs; ++i) { p.pair_a[i] = tmp.pair_a[i]; p.pair_b[i] = tmp.pair_b[i]; } }
+  int sh_[MAXTAP], sw_[MAXTAP];
+  int hlo = 0, hhi = 0, wlo = 0, whi = 0;
+  for (int i = 0; i < 4; ++i) p.kph_slot[i] = -1;
+  for (int r = 0; r < R; ++r)
+    for (int q = 0; q < S; ++q) {
+      const int t = r * S + q, dr = r - ph_, ds = q - pw_;
+      int kp = 0, sh = dr, sw = ds;
+      if (st == 2) { const int fh = dr & 1, fw = ds & 1; kp = fh * 2 + fw; sh = (dr - fh) / 2; sw = (ds - fw) / 2; }
+      p.tap_kph[t] = kp; sh_[t] = sh; sw_[t] = sw;
+      if (p.kph_slot[kp] < 0) { p.kph_slot[kp] = p.nkph_used; p.kph_used[p.nkph_used++] = kp; }
+      hlo = std::max(hlo, -sh); hhi = std::max(hhi, sh); wlo = std::max(wlo, -sw); whi = std::max(whi, sw);
+    }
+  p.hlo = hlo; p.hhi = hhi; p.wlo = wlo; p.whi = whi;
+  // raster: rows of BW >= Q + halo columns; TH * BW must be a multiple of 16 (MMA K-steps of 16 positions)
+  const int need = p.Q + wlo + whi;
+  if (need > 256) return mnb_fail(MNB_E_UNSUPPORTED, "pk wgrad: row wider than 256 positions");
+  // N tile over input channels: taps * Nc accumulator columns
+  int nc = (512 / p.ntap) / 16 * 16;
+  if (nc < 16) return mnb_fail(MNB_E_UNSUPPORTED, "pk wgrad: more than 32 taps");
+  nc = std::min(nc, 256);
+  nc = std::min(nc, round_up(p.cin_g, 16));
+  p.n_ctiles = ceil_div(p.cin_g, nc);
+  p.Nc = round_up(ceil_div(p.cin_g, p.n_ctiles), 16);      // balance the tiles
+  p.n_ctiles = ceil_div(p.cin_g, p.Nc);
+  p.n_ktiles = ceil_div(p.cout_g, 128);
+  int cols = 32;
+  while (cols < p.ntap * p.Nc) cols <<= 1;
+  if (cols > 512) return mnb_fail(MNB_E_UNSUPPORTED, "pk wgrad: accumulators exceed tensor memory");
+  p.tmem_cols = cols;
+  // stage = NI sub-blocks (one image row-tile each): dy [TA][16 octets][rows_dy], x [TX][k-phase][Nc/8][rows_x].
+  // Pick the raster (BW, TH) with the best useful fraction whose sub-block fits four times (else twice).
+  auto sub_bytes_of = [&](int bw, int th) {
+    const int dyb = round_up(16 * th * bw * 16, 128);
+    const int xb = round_up((p.Nc / 8) * (th + hlo + hhi) * bw * 16 + 16 * 16, 128);
+    return TA * dyb + TX * p.nkph_used * xb;
+  };
+  int best_bw = 0, best_th = 0;
+  double best_score = -1;
+  for (int pass = 0; pass < 2 && !best_bw; ++pass) {
+    const int limit = (kSmemBudget - 2048) / (pass == 0 ? 4 : 2);
+    for (int bw = need; bw <= std::min(256, need + 15); ++bw)
+      for (int th = 1; th <= p.P; ++th) {
+        if ((th * bw) % 16) continue;
+        if (th + hlo + hhi > 256 || sub_bytes_of(bw, th) > limit) continue;
+        const double eff = (double)p.Q / bw, fill = std::min(1.0, (double)th * bw / 64.0);
+        const double score = eff * (0.5 + 0.5 * fill);
+        if (score > best_score) { best_score = score; best_bw = bw; best_th = th; }
+      }
+  }
+  if (!best_bw) return mnb_fail(MNB_E_UNSUPPORTED, "pk wgrad: no raster fits shared memory");
+  p.BW = best_bw; p.TH = best_th; p.THH = p.TH + hlo + hhi;
+  p.rows_dy = p.TH * p.BW; p.rows_x = p.THH * p.BW;
+  p.row_tiles = ceil_div(p.P, p.TH);
+  for (int t = 0; t < p.ntap; ++t) p.tap_off[t] = (sh_[t] + hlo) * p.BW + (sw_[t] + wlo);
+  p.dy_box_bytes = 16 * p.rows_dy * 16;
+  p.x_box_bytes = (p.Nc / 8) * p.rows_x * 16;
+  p.dy_bytes = round_up(p.dy_box_bytes, 128);
+  p.x_bytes = round_up(p.x_box_bytes + 16 * 16, 128);       // + slack rows read past the last plane (must stay finite: zeroed)
+  p.sub_bytes = TA * p.dy_bytes + TX * p.nkph_used * p.x_bytes;
+  p.nsub = p.B * p.row_tiles;
+  const int stage_target = 52 * 1024;
+  p.NI = std::max(1, std::min(std::min(p.nsub, 8), stage_target / p.sub_bytes));
+  p.stage_bytes = round_up(p.NI * p.sub_bytes, 1024);
+  const int nst = (kSmemBudget - 1024) / p.stage_bytes;
+  if (nst < 2) return mnb_fail(MNB_E_UNSUPPORTED, "pk wgrad: fewer than two stages fit");
+  p.nstage = nst >= 4 ? 4 : 2;
+  p.st_log2 = p.nstage == 4 ? 2 : 1;
+  p.smem_bytes = p.nstage * p.stage_bytes + 1024;
+  p.nstg_total = ceil_div(p.nsub, p.NI);
+  const int n_kc = p.n_ktiles * p.n_ctiles * G;
+  p.splits = std::max(1, std::min(p.nstg_total, MNB_NUM_SMS / n_kc));
+  // keep accumulation chains short: tcgen05.mma truncates the running fp32 sum after every instruction (a bias of
+  // ~2e-8 of |D| per MMA), so one accumulator takes <= ~192 MMAs; the partial sums are added with RN adds
+  const int chain_per_stage = p.NI * (p.rows_dy / 16) * p.npairs;
+  int chain_max = 192;
+  if (const char* e = getenv("MNB_PK_WG_CHAIN")) chain_max = std::max(1, atoi(e));
+  while (p.splits < p.nstg_total && (int64_t)ceil_div(p.nstg_total, p.splits) * chain_per_stage > chain_max) ++p.splits;
+  p.stg_per_split = ceil_div(p.nstg_total, p.splits);
+  p.splits = ceil_div(p.nstg_total, p.stg_per_split);
+  p.partial_floats = (int64_t)p.splits * G * p.n_ktiles * p.n_ctiles * p.ntap * p.Nc * 128;
+  return 0;
+}
+
+struct WgParams {
+  struct Mma {
+    uint32_t stg_per_split, nstg_total, NI, ksteps, ntap, Nc, npairs, st_mask, st_log2, stage16, sub16, dy_term16, x_off16,
+        x_term16, x_kph16, idesc, dy_sbo, x_sbo, nsub;
+    uint32_t pair_a[MAXPAIR], pair_b[MAXPAIR];
+    uint32_t tap_off[MAXTAP];       // x block start offset per tap (k-phase slot * x_kph16 + row offset), 16-byte units
+  } m;
+  int G, n_ktiles, n_ctiles, splits, stg_per_split, nstg_total, NI, nsub, row_tiles, TA, TX, nkph_used, kph_used[4];
+  int K8, C8X, cout_g8, cin_g8, Nc8, TH, hlo, wlo, stage_bytes, sub_bytes, dy_bytes, x_bytes, dy_box_bytes, x_box_bytes,
+      st_mask, st_log2, smem_bytes, tmem_cols, ntap, Nc, cout_g, cin_g;
+  float* partial;
+  int* err;
+};
+
+struct alignas(16) WgShared {
+  uint64_t full[MAXST], empty[MAXST], acc_full;
+  uint32_t tmem_slot, abort;
+};
+
+__global__ void __launch_bounds__(NTHREADS, 1)
+pk_wgrad_kernel(const __grid_constant__ CUtensorMap dy0, const __grid_constant__ CUtensorMap dy1,
+                const __grid_constant__ CUtensorMap dy2, const __grid_constant__ CUtensorMap x0,
+                const __grid_constant__ CUtensorMap x1, const __grid_constant__ CUtensorMap x2,
+                const __grid_constant__ WgParams p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ WgShared sh;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (tid == 0) {
+    for (int i = 0; i < MAXST; ++i) { tc::mbar_init(&sh.full[i], 1); tc::mbar_init(&sh.empty[i], 1); }
+    tc::mbar_init(&sh.acc_full, 1);
+    sh.abort = 0;
+    tc::fence_barrier_init();
+    tc::prefetch_tmap(&dy0); tc::prefetch_tmap(&x0);
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tc::smem_u32(&sh.tmem_slot)),
+                 "r"((uint32_t)p.tmem_cols));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  // every row an MMA can read must be finite (positions are the reduction dimension here): zero everything once,
+  // the TMA boxes never touch the slack rows
+  for (int i = tid; i < p.smem_bytes / 16; i += NTHREADS) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
+  tc::fence_proxy_async_smem();
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tmem = sh.tmem_slot;
+  // work item of this CTA: blockIdx.x = ((g * n_ktiles + kt) * n_ctiles + ct), blockIdx.y = split
+  const int split = blockIdx.y;
+  const int ct = blockIdx.x % p.n_ctiles;
+  const int r1 = blockIdx.x / p.n_ctiles;
+  const int kt = r1 % p.n_ktiles, g = r1 / p.n_ktiles;
+  const int stg0 = split * p.stg_per_split, stg1 = min(p.nstg_total, stg0 + p.stg_per_split);
+
+  if (warp == 0) {
+    if (lane == 0) {
+      uint32_t sc = 0;
+      const int k8 = g * p.cout_g8 + kt * 16, c8 = g * p.cin_g8 + ct * p.Nc8;
+      for (int stg = stg0; stg < stg1; ++stg, ++sc) {
+        const uint32_t slot = sc & (uint32_t)p.st_mask, ph = (sc >> p.st_log2) & 1u;
+        if (!tc::mbar_wait(&sh.empty[slot], ph ^ 1u, p.err, 711)) goto done;
+        const int sub0 = stg * p.NI, nsubs = min(p.NI, p.nsub - sub0);
+        tc::mbar_arrive_expect_tx(&sh.full[slot], (uint32_t)(nsubs * (p.TA * p.dy_box_bytes + p.TX * p.nkph_used * p.x_box_bytes)));
+        for (int si = 0; si < nsubs; ++si) {
+          const int sub = sub0 + si;
+          const int b = sub / p.row_tiles, rt = sub - b * p.row_tiles;
+          uint8_t* sb = smem + (size_t)slot * p.stage_bytes + (size_t)si * p.sub_bytes;
+          const int h0 = rt * p.TH;
+          tc::tma_load_5d(sb, &dy0, &sh.full[slot], 0, 0, h0, b, k8);
+          if (p.TA > 1) tc::tma_load_5d(sb + p.dy_bytes, &dy1, &sh.full[slot], 0, 0, h0, b, k8);
+          if (p.TA > 2) tc::tma_load_5d(sb + 2 * p.dy_bytes, &dy2, &sh.full[slot], 0, 0, h0, b, k8);
+          uint8_t* xb = sb + (size_t)p.TA * p.dy_bytes;
+          for (int tx = 0; tx < p.TX; ++tx)
+            for (int ks = 0; ks < p.nkph_used; ++ks) {
+              const CUtensorMap* tm = tx == 0 ? &x0 : (tx == 1 ? &x1 : &x2);
+              tc::tma_load_5d(xb + (size_t)(tx * p.nkph_used + ks) * p.x_bytes, tm, &sh.full[slot], 0, -p.wlo, h0 - p.hlo, b,
+                              p.kph_used[ks] * p.C8X + c8);
+            }
+        }
+        // sub-blocks of a short last stage keep their previous (finite) contents; the MMA loop skips them
+      }
+    }
+  } else if (warp == 1) {
+    const uint32_t lead = lane == 0;
+    const uint64_t a_desc0 = tc::smem_desc_mnmajor_noswz(tc::smem_u32(smem), 128, p.m.dy_sbo);
+    const uint64_t b_desc0 = tc::smem_desc_mnmajor_noswz(tc::smem_u32(smem), 128, p.m.x_sbo) + (uint64_t)p.m.x_off16;
+    const uint32_t split_u = blockIdx.y;
+    const uint32_t s0 = split_u * p.m.stg_per_split;
+    const uint32_t s1 = min(p.m.nstg_total, s0 + p.m.stg_per_split);
+    uint32_t sc = 0, started = 0;
+    for (uint32_t stg = s0; stg < s1; ++stg, ++sc) {
+      const uint32_t slot = sc & p.m.st_mask, ph = (sc >> p.m.st_log2) & 1u;
+      tc::mbar_wait_soft(&sh.full[slot], ph, p.err, 712, &sh.abort);
+      tc::tc_fence_after();
+      const uint32_t nsubs = min(p.m.NI, p.m.nsub - stg * p.m.NI);
+      for (uint32_t si = 0; si < nsubs; ++si) {
+        const uint32_t s16 = slot * p.m.stage16 + si * p.m.sub16;
+        for (uint32_t j = 0; j < p.m.ksteps; ++j) {
+          const uint32_t arow = s16 + j * 16u, brow = s16 + j * 16u;
+          for (uint32_t pr = 0; pr < p.m.npairs; ++pr) {
+            const uint64_t ad = a_desc0 + (uint64_t)(arow + p.m.pair_a[pr] * p.m.dy_term16);
+            const uint32_t b2 = brow + p.m.pair_b[pr] * p.m.x_term16;
+            for (uint32_t t = 0; t < p.m.ntap; ++t)
+              tc::mma_f16_guarded(tmem + t * p.m.Nc, ad, b_desc0 + (uint64_t)(b2 + p.m.tap_off[t]), p.m.idesc,
+                                  (started | si | j | pr) != 0u, lead);
+          }
+        }
+      }
+      if (lead) tc::mma_commit(&sh.empty[slot]);
+      __syncwarp();
+      started = 1;
+    }
+    if (lead) tc::mma_commit(&sh.acc_full);
+    __syncwarp();
+  } else if (warp >= 4) {
+    // partial[split][g][kt][ct][tap][c][k]: lanes = k -> coalesced
+    const int q = warp - 4;
+    const int kl = q * 32 + lane;
+    if (!tc::mbar_wait(&sh.acc_full, 0, p.err, 713)) goto done;
+    tc::tc_fence_after();
+    float* dst = p.partial + ((((int64_t)split * p.G + g) * p.n_ktiles + kt) * p.n_ctiles + ct) * (int64_t)(p.ntap * p.Nc * 128) + kl;
+    const bool any = stg1 > stg0;
+    for (int col = 0; col < p.ntap * p.Nc; col += 16) {
+      uint32_t r[16];
+      tmem_ld_32x16(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)col, r);
+      tc::tmem_ld_wait();
+#pragma unroll
+      for (int k = 0; k < 16; ++k) dst[(int64_t)(col + k) * 128] = any ? __uint_as_float(r[k]) : 0.f;
+    }
+    tc::tc_fence_before();
+  }
+done:
+  tc::tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc::tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"((uint32_t)p.tmem_cols));
+  }
+}
+
+// dw[k][c][tap] = mul(k) * sum over splits (fixed order: deterministic); mul = a_scale / kdiv[k] (either may be NULL)
+__global__ void __launch_bounds__(256) wg_reduce_kernel(const float* __restrict__ partial, int splits, int G, int n_ktiles,
+                                                        int n_ctiles, int ntap, int Nc, int cout_g, int cin_g,
+                                                        const float* __restrict__ a_scale, const float* __restrict__ kdiv,
+                                                        float* __restrict__ dw) {
+  const int64_t total = (int64_t)G * cout_g * cin_g * ntap;
+  const float as = a_scale ? __ldg(a_scale) : 1.f;
+  const int64_t tile = (int64_t)ntap * Nc * 128;
+  const int64_t split_stride = (int64_t)G * n_ktiles * n_ctiles * tile;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+    const int tap = (int)(idx % ntap);
+    int64_t t = idx / ntap;
+    const int c = (int)(t % cin_g);
+    t /= cin_g;
+    const int kk = (int)(t % cout_g), g = (int)(t / cout_g);
+    const int kt = kk >> 7, kl = kk & 127, ct = c / Nc, cl = c - ct * Nc;
+    const float* src = partial + (((int64_t)g * n_ktiles + kt) * n_ctiles + ct) * tile + ((int64_t)tap * Nc + cl) * 128 + kl;
+    float acc = 0.f;
+    for (int s = 0; s < splits; ++s) acc = __fadd_rn(acc, src[(int64_t)s * split_stride]);
+    float mul = as;
+    if (kdiv) mul = __fdiv_rn(as, __ldg(kdiv + g * cout_g + kk));
+    dw[idx] = (a_scale || kdiv) ? __fmul_rn(acc, mul) : acc;
+  }
+}
+
+}  // namespace pk
+
+// =========================================================================================================
+// C-ABI
+// =========================================================================================================
+extern "C" int64_t mnb_pk_act_bytes(int32_t batch, int32_t channels, int32_t h, int32_t w, int32_t terms) {
+  return (int64_t)terms * batch * ((channels + 7) / 8) * h * w * 16;
+}
+
+extern "C" int mnb_pk_pack_act(const float* x, int32_t batch, int32_t channels, int32_t h, int32_t w,
+                               const mnb_act_qparams* qp, int32_t terms, const float* ch_scale, int32_t phase_split,
+                               void* out_pk, uint8_t* bits8, mnb_stream_t stream) {
+  MNB_REQUIRE(x && out_pk, "NULL pk_pack_act pointer");
+  MNB_REQUIRE(batch > 0 && channels > 0 && h > 0 && w > 0 && terms >= 1 && terms <= 3, "bad pk_pack_act arguments");
+  MNB_REQUIRE((reinterpret_cast<uintptr_t>(out_pk) & 15) == 0, "packed tensor must be 16-byte aligned");
+  if (phase_split) MNB_REQUIRE(((h | w) & 1) == 0, "phase split needs even H and W");
+  const int C8 = (channels + 7) / 8;
+  const int64_t plane_vecs = (int64_t)batch * C8 * h * w, total = plane_vecs;
+  const int blocks = (int)std::min<int64_t>((total + 255) / 256, (int64_t)MNB_NUM_SMS * 16);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (qp) {
+    MNB_REQUIRE(qp->mode == MNB_ACT_DOREFA || qp->mode == MNB_ACT_IAO || qp->mode == MNB_ACT_SIGN, "unknown activation quantizer");
+    if (qp->mode == MNB_ACT_DOREFA) MNB_REQUIRE(qp->bits >= 2 && qp->bits <= 8, "DoReFa a_bits must be in [2,8]");
+    const int a_off = qp->mode == MNB_ACT_IAO ? qp->qmin : (qp->mode == MNB_ACT_SIGN ? -1 : 0);
+    pk::pack_act_kernel<1><<<blocks, 256, 0, st>>>(x, batch, channels, h, w, C8, terms, nullptr, *qp, a_off, phase_split,
+                                                   reinterpret_cast<uint4*>(out_pk), plane_vecs, bits8);
+  } else {
+    mnb_act_qparams none{};
+    pk::pack_act_kernel<0><<<blocks, 256, 0, st>>>(x, batch, channels, h, w, C8, terms, ch_scale, none, 0, phase_split,
+                                                   reinterpret_cast<uint4*>(out_pk), plane_vecs, nullptr);
+  }
+  MNB_LAUNCHED(1);
+  return 0;
+}
+
+// host only: out[16] = {wimg_bytes(lo), wimg_bytes(hi), Nt, n_ntiles, MT, CC, chunks, nstage, smem_bytes, tmem_cols, TH, TB,
+//                       BW, n_mtiles, n_items, ny}
+extern "C" int mnb_pk_conv_plan(const mnb_conv_shape* s, int32_t mode, int32_t terms_a, int32_t terms_w, int32_t* out16) {
+  pk::Plan p;
+  if (int e = pk::make_plan(s, mode, terms_a, terms_w, p)) return e;
+  if (out16) {
+    const int v[16] = {(int)(p.wimg_bytes & 0x7fffffff), (int)(p.wimg_bytes >> 31), p.Nt, p.n_ntiles, p.MT, p.CC, p.chunks, p.nstage,
+                       p.smem_bytes, p.tmem_cols, p.TH, p.TB, p.BW, p.n_mtiles, p.n_items, p.ny};
+    for (int i = 0; i < 16; ++i) out16[i] = v[i];
+  }
+  return 0;
+}
+
+extern "C" int64_t mnb_pk_wimage_bytes(const mnb_conv_shape* s, int32_t mode, int32_t terms_a, int32_t terms_w) {
+  pk::Plan p;
+  if (pk::make_plan(s, mode, terms_a, terms_w, p)) return -1;
+  return p.wimg_bytes;
+}
+
+extern "C" int mnb_pk_pack_weight(const mnb_conv_shape* s, int32_t mode, int32_t terms_a, int32_t terms_w,
+                                  const int16_t* w_int, const float* w_f32, const float* kzero, void* w_img,
+                                  mnb_stream_t stream) {
+  MNB_REQUIRE((w_int != nullptr) != (w_f32 != nullptr), "exactly one of w_int / w_f32");
+  MNB_REQUIRE(w_img && (reinterpret_cast<uintptr_t>(w_img) & 15) == 0, "weight image must be 16-byte aligned");
+  pk::PackWParams pp;
+  if (int e = pk::make_plan(s, mode, terms_a, terms_w, pp.pl)) return e;
+  pp.w_int = w_int; pp.w_f32 = w_f32; pp.kzero = kzero;
+  pp.cin_g = s->in_c / s->groups; pp.cout_g = s->out_c / s->groups;
+  const int64_t vecs = pp.pl.wimg_bytes / 16;
+  const int blocks = (int)std::min<int64_t>((vecs + 255) / 256, (int64_t)MNB_NUM_SMS * 8);
+  pk::pack_weight_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(pp, reinterpret_cast<uint4*>(w_img));
+  MNB_LAUNCHED(1);
+  return 0;
+}
+
+extern "C" int mnb_pk_conv(const mnb_conv_shape* s, int32_t mode, const void* a_pk, int32_t terms_a, const void* w_img,
+                           int32_t terms_w, const float* n_scale, const float* a_scale, float a_scale_const,
+                           const float* bias, const uint8_t* bits8, float gain, float* out, int32_t* err_flag,
+                           mnb_stream_t stream) {
+  using namespace pk;
+  MNB_REQUIRE(s && a_pk && w_img && out && err_flag, "NULL pk_conv pointer");
+  Plan pl;
+  if (int e = make_plan(s, mode, terms_a, terms_w, pl)) return e;
+  if (bits8 && pl.G > 1 && (pl.ng % 8)) return unsupported("STE mask of a grouped conv needs channels per group % 8 == 0");
+  static ConvParams p;   // large POD: filled per call (single host thread per process)
+  memset(&p, 0, sizeof(p));
+  ConvParams::Mma& m = p.m;
+  m.n_items = pl.n_items; m.chunks = pl.chunks; m.ksteps = pl.ksteps; m.MT = pl.MT; m.Nt = pl.Nt; m.npairs = pl.npairs;
+  m.st_mask = pl.nstage - 1; m.st_log2 = pl.st_log2; m.stage16 = pl.stage_bytes >> 4;
+  m.a_term16 = pl.a_bytes >> 4; m.a_mt16 = (pl.TA * pl.a_bytes) >> 4; m.a_k16 = 2 * pl.npos;
+  m.b_off16 = pl.b_off >> 4; m.b_tap16 = (pl.CC / 8) * pl.Nt; m.b_k16 = 2 * pl.Nt;
+  m.idesc = tc::make_idesc(1, 1, 1, 128, (uint32_t)pl.Nt);
+  m.a_lbo = (uint32_t)pl.npos * 16u; m.b_lbo = (uint32_t)pl.Nt * 16u;
+  m.seg_len = (uint32_t)pl.seg_len;
+  for (int i = 0; i < pl.npairs; ++i) { m.pair_a[i] = pl.pair_a[i]; m.pair_b[i] = pl.pair_b[i]; }
+  for (int y = 0; y < pl.ny; ++y) {
+    m.ntmpl[y] = pl.ntmpl[y]; p.ntmpl[y] = pl.ntmpl[y];
+    for (int t = 0; t < pl.ntmpl[y]; ++t) {
+      m.tmpl_tap0[y][t] = pl.tmpl[y][t].tap0; m.tmpl_ntap[y][t] = pl.tmpl[y][t].ntap;
+      p.tmpl_kph[y][t] = pl.tmpl[y][t].kph; p.tmpl_blk_off[y][t] = pl.tmpl[y][t].blk_off; p.tmpl_blk_bytes[y][t] = pl.tmpl[y][t].blk_bytes;
+    }
+    for (int i = 0; i < pl.ntap[y]; ++i) m.tap_aoff[y][i] = pl.tap_aoff[y][i];
+    p.img_bytes[y] = pl.img_bytes[y]; p.y_off[y] = pl.y_off[y];
+    p.zero_y[y] = pl.ntap[y] == 0;
+    const int nstages = pl.ntmpl[y] * pl.chunks;
+    p.nseg[y] = nstages == 0 ? 1 : (int)(((int64_t)nstages + pl.seg_len - 1) / pl.seg_len);
+  }
+  p.n_items = pl.n_items; p.n_ntiles = pl.n_ntiles; p.G = pl.G; p.MT = pl.MT; p.TA = pl.TA; p.chunks = pl.chunks;
+  p.CC8 = pl.CC / 8; p.C8A = pl.C8A; p.kg8 = pl.kg / 8; p.stage_bytes = pl.stage_bytes; p.a_bytes = pl.a_bytes;
+  p.a_box_bytes = pl.a_box_bytes; p.b_off = pl.b_off; p.st_mask = pl.nstage - 1; p.st_log2 = pl.st_log2;
+  p.Wt = pl.Wt; p.TH = pl.TH; p.TB = pl.TB; p.wlo = pl.wlo; p.hlo = pl.hlo; p.col_tiles = pl.col_tiles; p.row_tiles = pl.row_tiles;
+  p.n_mtiles = pl.n_mtiles;
+  p.w_img = reinterpret_cast<const uint8_t*>(w_img);
+  p.B = pl.B; p.THH = pl.THH; p.BW = pl.BW; p.OHr = pl.OHr; p.OWr = pl.OWr; p.OH = pl.OH; p.OW = pl.OW; p.omul = pl.omul; p.ny = pl.ny;
+  p.ng = pl.ng; p.Nt = pl.Nt; p.NOUT = pl.NOUT; p.C8O = (pl.NOUT + 7) / 8; p.smem_bytes = pl.smem_bytes; p.tmem_cols = pl.tmem_cols;
+  p.mode = mode;
+  p.n_scale = n_scale; p.a_scale = a_scale; p.a_scale_const = a_scale_const; p.bias = bias; p.bits8 = bits8; p.gain = gain;
+  p.out = out; p.err = err_flag;
+  CUtensorMap tm[3];
+  const int C8tot = pl.nkph * pl.C8A;
+  const int64_t plane_bytes = (int64_t)pl.B * C8tot * pl.HA * pl.WA * 16;
+  for (int t = 0; t < 3; ++t) {
+    const int tt = t < pl.TA ? t : 0;
+    if (int e = make_pk_tmap(&tm[t], a_pk, plane_bytes, tt, pl.B, C8tot, pl.HA, pl.WA, pl.BW, pl.THH, pl.TB, pl.CC / 8)) return e;
+  }
+  const int gx = std::max(1, std::min(pl.n_items, MNB_NUM_SMS / pl.ny));
+  if (pl.segmented) {
+    if (pl.Nt > 128 || pl.MT != 1) return mnb_fail(MNB_E_ARG, "pk conv: segmented plan with Nt %d, MT %d", pl.Nt, pl.MT);
+    if (int e = set_max_smem(pk_conv_kernel<true>, kSmemBudget)) return e;
+    pk_conv_kernel<true><<<dim3(gx, pl.ny), NTHREADS, pl.smem_bytes, (cudaStream_t)stream>>>(tm[0], tm[1], tm[2], p);
+  } else {
+    if (int e = set_max_smem(pk_conv_kernel<false>, kSmemBudget)) return e;
+    pk_conv_kernel<false><<<dim3(gx, pl.ny), NTHREADS, pl.smem_bytes, (cudaStream_t)stream>>>(tm[0], tm[1], tm[2], p);
+  }
+  MNB_LAUNCHED(1);
+  return 0;
+}
+
+extern "C" int64_t mnb_pk_wgrad_scratch_bytes(const mnb_conv_shape* s, int32_t terms_dy, int32_t terms_x) {
+  pk::WgPlan p;
+  if (pk::make_wg_plan(s, terms_dy, terms_x, p)) return -1;
+  return p.partial_floats * 4;
+}
+
+// dw[k][c][r][s] = mul(k) * sum_{b,p,q} dy[b,k,p,q] * x[b,c,p*st+r-pad, q*st+s-pad];  mul(k) = a_scale[0] / kdiv[k]
+// (a_scale: activation scale when x_pk holds integer levels; kdiv: the per-channel factor dy_pk was pre-multiplied with)
+extern "C" int mnb_pk_wgrad(const mnb_conv_shape* s, const void* dy_pk, int32_t terms_dy, const void* x_pk, int32_t terms_x,
+                            const float* a_scale, const float* kdiv, float* dw, void* scratch, int32_t* err_flag,
+                            mnb_stream_t stream) {
+  using namespace pk;
+  MNB_REQUIRE(s && dy_pk && x_pk && dw && scratch && err_flag, "NULL pk_wgrad pointer");
+  WgPlan pl;
+  if (int e = make_wg_plan(s, terms_dy, terms_x, pl)) return e;
+  static WgParams p;
+  memset(&p, 0, sizeof(p));
+  WgParams::Mma& m = p.m;
+  m.stg_per_split = pl.stg_per_split; m.nstg_total = pl.nstg_total; m.NI = pl.NI; m.ksteps = pl.rows_dy / 16; m.ntap = pl.ntap;
+  m.Nc = pl.Nc; m.npairs = pl.npairs; m.st_mask = pl.nstage - 1; m.st_log2 = pl.st_log2; m.stage16 = pl.stage_bytes >> 4;
+  m.sub16 = pl.sub_bytes >> 4; m.dy_term16 = pl.dy_bytes >> 4; m.x_off16 = (pl.TA * pl.dy_bytes) >> 4;
+  m.x_term16 = (pl.nkph_used * pl.x_bytes) >> 4; m.x_kph16 = pl.x_bytes >> 4;
+  m.idesc = tc::make_idesc_major(1, 1, 1, 128, (uint32_t)pl.Nc, 1, 1);
+  m.dy_sbo = (uint32_t)pl.rows_dy * 16u; m.x_sbo = (uint32_t)pl.rows_x * 16u; m.nsub = pl.nsub;
+  for (int i = 0; i < pl.npairs; ++i) { m.pair_a[i] = pl.pair_a[i]; m.pair_b[i] = pl.pair_b[i]; }
+  for (int t = 0; t < pl.ntap; ++t) m.tap_off[t] = pl.kph_slot[pl.tap_kph[t]] * m.x_kph16 + pl.tap_off[t];
+  p.G = pl.G; p.n_ktiles = pl.n_ktiles; p.n_ctiles = pl.n_ctiles; p.splits = pl.splits; p.stg_per_split = pl.stg_per_split;
+  p.nstg_total = pl.nstg_total; p.NI = pl.NI; p.nsub = pl.nsub; p.row_tiles = pl.row_tiles; p.TA = pl.TA; p.TX = pl.TX;
+  p.nkph_used = pl.nkph_used;
+  for (int i = 0; i < 4; ++i) p.kph_used[i] = pl.kph_used[i];
+  p.K8 = pl.K8; p.C8X = pl.C8X; p.cout_g8 = pl.cout_g / 8; p.cin_g8 = pl.cin_g / 8; p.Nc8 = pl.Nc / 8; p.TH = pl.TH; p.hlo = pl.hlo;
+  p.wlo = pl.wlo; p.stage_bytes = pl.stage_bytes; p.sub_bytes = pl.sub_bytes; p.dy_bytes = pl.dy_bytes; p.x_bytes = pl.x_bytes;
+  p.dy_box_bytes = pl.dy_box_bytes; p.x_box_bytes = pl.x_box_bytes; p.st_mask = pl.nstage - 1; p.st_log2 = pl.st_log2;
+  p.smem_bytes = pl.smem_bytes; p.tmem_cols = pl.tmem_cols; p.ntap = pl.ntap; p.Nc = pl.Nc; p.cout_g = pl.cout_g; p.cin_g = pl.cin_g;
+  p.partial = reinterpret_cast<float*>(scratch); p.err = err_flag;
+  CUtensorMap tdy[3], tx[3];
+  const int64_t dy_plane = (int64_t)pl.B * pl.K8 * pl.P * pl.Q * 16;
+  const int C8tot = pl.nkph * pl.C8X;
+  const int64_t x_plane = (int64_t)pl.B * C8tot * pl.HX * pl.WX * 16;
+  for (int t = 0; t < 3; ++t) {
+    if (int e = make_pk_tmap(&tdy[t], dy_pk, dy_plane, t < pl.TA ? t : 0, pl.B, pl.K8, pl.P, pl.Q, pl.BW, pl.TH, 1, 16)) return e;
+    if (int e = make_pk_tmap(&tx[t], x_pk, x_plane, t < pl.TX ? t : 0, pl.B, C8tot, pl.HX, pl.WX, pl.BW, pl.THH, 1, pl.Nc / 8)) return e;
+  }
+  if (int e = set_max_smem(pk_wgrad_kernel, kSmemBudget)) return e;
+  cudaStream_t st = (cudaStream_t)stream;
+  pk_wgrad_kernel<<<dim3(pl.G * pl.n_ktiles * pl.n_ctiles, pl.splits), NTHREADS, pl.smem_bytes, st>>>(tdy[0], tdy[1], tdy[2], tx[0],
+                                                                                                      tx[1], tx[2], p);
+  const int64_t total = (int64_t)s->out_c * pl.cin_g * pl.ntap;
+  wg_reduce_kernel<<<(int)std::min<int64_t>((total + 255) / 256, MNB_NUM_SMS * 8), 256, 0, st>>>(
+      p.partial, pl.splits, pl.G, pl.n_ktiles, pl.n_ctiles, pl.ntap, pl.Nc, pl.cout_g, pl.cin_g, a_scale, kdiv, dw);
+  MNB_LAUNCHED(2);
+  return 0;
+}

@@ -238,6 +238,79 @@ def channel_sums(x4):
     return out[:c]
 
 
+
+def _pk_terms(spec, w_int):
+    """(terms of the activation operand, terms of the weight operand) on the packed-operand path"""
+    T = L.PK_TERMS
+    if spec is None:
+        ta = T
+    else:
+        ta = 2 if (spec.mode == L.ACT_IAO and spec.q_type == 1) else 1   # asymmetric: |level + zero_point| may exceed 256
+    return ta, (1 if w_int is not None else T)
+
+
+def _pk_forward(ctx, x, wq, bias, w_int, w_scale, spec, sh, y, need_dx):
+    """forward on the packed-operand tensor-core family; returns False when the shape is outside its cover"""
+    from . import pk as PK
+    ta, tw = _pk_terms(spec, w_int)
+    if not PK.supported(sh, 0, ta, tw):
+        return False
+    # the backward of a layer stays in the family its forward ran in (saved operands are packed): check its cover now
+    T = L.PK_TERMS
+    if need_dx and not PK.supported(sh, 1, T, 1 if w_int is not None else T):
+        return False
+    if ctx.needs_input_grad[1] and not PK.wgrad_supported(sh, T, ta):
+        return False
+    qp = spec.struct() if spec is not None else None
+    split = sh.stride_h == 2
+    x_pk, bits8 = PK.pack_act(x, qp, ta, phase_split=split, want_bits=need_dx)
+    w_img = PK.pack_weight(sh, 0, ta, tw, w_int=w_int, w_f32=None if w_int is not None else wq)
+    a_scale, a_const = None, 1.0
+    if spec is not None:
+        if spec.mode == L.ACT_IAO:
+            a_scale = spec.scale.clone()      # backward must see the forward-time scale (the reference clones it too)
+        elif spec.mode == L.ACT_DOREFA:
+            a_const = 1.0 / float(2 ** spec.bits - 1)
+    rc = _timed("fwd_pk", sh, lambda: PK.conv(sh, 0, x_pk, ta, w_img, tw, y, n_scale=w_scale if w_int is not None else None,
+                                              a_scale=a_scale, a_scale_const=a_const, bias=bias))
+    if rc == L.E_UNSUPPORTED:
+        return False
+    L.check(rc, "pk_conv fwd")
+    ctx.pk = True
+    ctx.pk_x, ctx.pk_ta, ctx.pk_bits8, ctx.pk_a_scale = x_pk, ta, bits8, a_scale
+    return True
+
+
+def _pk_backward(ctx, dy):
+    """data and weight gradients of a layer whose forward ran on the packed-operand path"""
+    from . import pk as PK
+    sh, spec = ctx.sh, ctx.spec
+    T = L.PK_TERMS
+    int_w = ctx.w_int is not None
+    need_dx, need_dw = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+    # dy is packed once for both gradients; the data gradient wants the per-channel weight scale folded in (it sits on
+    # the reduction dimension there), the weight gradient divides it out again (mnb_pk_wgrad's kdiv)
+    fold = int_w and need_dx
+    dy_pk, _ = PK.pack_act(dy, None, T, ch_scale=ctx.w_scale if fold else None)
+    dx = dwq = None
+    if need_dx:
+        tw = 1 if int_w else T
+        w_img = PK.pack_weight(sh, 1, T, tw, w_int=ctx.w_int, w_f32=None if int_w else ctx.wq,
+                               kzero=ctx.w_scale if int_w else None)
+        dx = torch.empty((sh.batch, sh.in_c, sh.in_h, sh.in_w), dtype=torch.float32, device=dy.device)
+        gain = 0.1 if (spec is not None and spec.mode == L.ACT_DOREFA) else 1.0
+        L.check(_timed("dgrad_pk", sh, lambda: PK.conv(sh, 1, dy_pk, T, w_img, tw, dx, bits8=ctx.pk_bits8, gain=gain)),
+                "pk_conv dgrad")
+    if need_dw:
+        dwq = torch.empty_like(ctx.wq)
+        a_scale = None
+        if spec is not None:
+            a_scale = ctx.pk_a_scale if spec.mode == L.ACT_IAO else _dorefa_scale_tensor(spec.bits, dy.device)
+        L.check(_timed("wgrad_pk", sh, lambda: PK.wgrad(sh, dy_pk, T, ctx.pk_x, ctx.pk_ta, dwq, a_scale=a_scale,
+                                                        kdiv=ctx.w_scale if fold else None)), "pk_wgrad")
+    return dx, dwq
+
+
 class QuantConv2dFn(Function):
     """y = conv2d(Q_a(x), wq, bias) with the activation quantizer fused on the input side
     and the clip-STE fused into dgrad.  ``spec`` None => x is used as fp32 (wbwtab, a_bits=32)."""
@@ -257,7 +330,10 @@ class QuantConv2dFn(Function):
         if spec is not None and spec.mode != L.ACT_SIGN:
             a_scale = spec.scale if spec.mode == L.ACT_IAO else _dorefa_scale_tensor(spec.bits, x.device)
         done = False
-        if packed is not None and spec is None and w_int is not None and packed.numel() == x.numel():
+        ctx.pk = False
+        if L.PK_MODE != "off" and x.dtype == torch.float32 and (L.PK_MODE == "all" or spec is not None):
+            done = _pk_forward(ctx, x, wq, bias, w_int, w_scale, spec, sh, y, ctx.needs_input_grad[0])
+        if not done and packed is not None and spec is None and w_int is not None and packed.numel() == x.numel():
             wpack = torch.empty(w_int.numel(), dtype=torch.int16, device=x.device)
             rc = _timed("fwd_packed_tc", sh, lambda: lib.mnb_fq_conv2d_fwd_packed_tc(
                 C.byref(sh), packed.data_ptr(), w_int.data_ptr(), w_scale.data_ptr(), L.ptr(bias), y.data_ptr(),
@@ -295,6 +371,8 @@ class QuantConv2dFn(Function):
                 done = ctx.fconv = True
             elif rc != L.E_UNSUPPORTED:
                 L.check(rc, "fconv2d_fwd_tc")
+        if not done and L.PK_MODE != "off" and x.dtype == torch.float32:
+            done = _pk_forward(ctx, x, wq, bias, w_int, w_scale, spec, sh, y, ctx.needs_input_grad[0])
         if not done:
             ops = L.ConvOperands()
             if spec is not None:
@@ -314,7 +392,7 @@ class QuantConv2dFn(Function):
                     "conv2d_fwd")
         ctx.sh, ctx.spec, ctx.a_scale = sh, spec, a_scale
         ctx.codes, ctx.bits = codes, bits
-        ctx.x = x if (codes is None or (L.USE_TC and w_int is not None)) else None
+        ctx.x = x if (not ctx.pk and (codes is None or (L.USE_TC and w_int is not None))) else None
         ctx.wq = wq
         ctx.w_int, ctx.w_scale = (w_int, w_scale) if w_int is not None else (None, None)
         ctx.has_bias = bias is not None
@@ -330,6 +408,9 @@ class QuantConv2dFn(Function):
         dx = dwq = db = None
         if ctx.has_bias and ctx.needs_input_grad[2]:
             db = presummed if presummed is not None and presummed.numel() == dy.shape[1] else channel_sums(dy)
+        if ctx.pk:
+            dx, dwq = _pk_backward(ctx, dy)
+            return dx, dwq, db, None, None, None, None, None, None, None
         if ctx.needs_input_grad[0]:
             dx = torch.empty((sh.batch, sh.in_c, sh.in_h, sh.in_w), dtype=torch.float32, device=dy.device)
             qp = spec.struct() if spec is not None else None

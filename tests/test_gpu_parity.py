@@ -258,19 +258,13 @@ QUANT_TYPES = ("QuantConv2d", "QuantBNFuseConv2d", "QuantLinear", "QuantAdd", "Q
                "QuantMaxPool2d", "QuantAvgPool2d", "ActivationQuantizer")
 
 
-@pytest.mark.parametrize("case", MODEL_CASES, ids=[c["name"] for c in MODEL_CASES])
-def test_model_layers_teacher_forced(case):
+def _teacher_forced(om, em, x, t, wtol=2e-5):
     """every engine module of the prepared model (quant conv / linear / bn-fuse conv, binarizer,
     quantized add / pool), fed the ORACLE's own inputs and output-gradient at that layer (captured
     with hooks during one oracle QAT step), must reproduce the oracle's output, input gradients and
-    parameter gradients to 1e-5 / 2e-5."""
-    from tests.test_oracle_golden import prepare_oracle
-    gold = load_golden("model", case["name"])
-    init = {k[5:]: torch.from_numpy(v) for k, v in gold.items() if k.startswith("init.")}
+    parameter gradients to 1e-5 (parameter gradients: ``wtol``)."""
     import copy
-    om = _zoo_model(case); om.load_state_dict(init); om = prepare_oracle(om, case); om.train()
     pristine = copy.deepcopy(om)  # per-layer replay needs first-call observer state
-    em = _zoo_model(case); em.load_state_dict(init); em = _prepare_engine(em, case).to(DEV); em.train()
     names = [n for n, mod in em.named_modules() if type(mod).__name__ in QUANT_TYPES
              and not n.endswith("activation_quantizer")]
     cap = {}
@@ -284,7 +278,6 @@ def test_model_layers_teacher_forced(case):
 
     omods = dict(om.named_modules())
     hooks = [omods[n].register_forward_hook(fwd_hook(n)) for n in names]
-    x, t = torch.from_numpy(gold["s0.x"]), torch.from_numpy(gold["s0.t"])
     torch.nn.functional.cross_entropy(om(x), t).backward()
     for h in hooks:
         h.remove()
@@ -304,6 +297,8 @@ def test_model_layers_teacher_forced(case):
         e.zero_grad()
         y.backward(c["go"].to(DEV))
         for i in range(len(xin)):
+            if xo[i].grad is None:
+                continue
             assert rel_err(xin[i].grad, xo[i].grad) <= TOL, f"{n}: dx[{i}] {rel_err(xin[i].grad, xo[i].grad)}"
         ograds = {k: p.grad for k, p in o.named_parameters()}
         wscale = max((g.abs().max().item() for k, g in ograds.items() if g is not None and k != "bias"), default=1.0)
@@ -316,7 +311,36 @@ def test_model_layers_teacher_forced(case):
                 tol = max(1e-6, 2e-5 * max(wscale, ograds[k].abs().max().item()))
                 assert (p.grad.cpu() - ograds[k]).abs().max().item() <= tol, f"{n}.bias"
                 continue
-            assert rel_err(p.grad, ograds[k]) <= 2e-5, f"{n}.{k}: {rel_err(p.grad, ograds[k])}"
+            assert rel_err(p.grad, ograds[k]) <= wtol, f"{n}.{k}: {rel_err(p.grad, ograds[k])}"
+    from micronet_b200 import _lib as L
+    L.tc_check()
+
+
+@pytest.mark.parametrize("case", MODEL_CASES, ids=[c["name"] for c in MODEL_CASES])
+def test_model_layers_teacher_forced(case):
+    from tests.test_oracle_golden import prepare_oracle
+    gold = load_golden("model", case["name"])
+    init = {k[5:]: torch.from_numpy(v) for k, v in gold.items() if k.startswith("init.")}
+    om = _zoo_model(case); om.load_state_dict(init); om = prepare_oracle(om, case); om.train()
+    em = _zoo_model(case); em.load_state_dict(init); em = _prepare_engine(em, case).to(DEV); em.train()
+    _teacher_forced(om, em, torch.from_numpy(gold["s0.x"]), torch.from_numpy(gold["s0.t"]))
+
+
+# the FULL-WIDTH models of BASELINE.json configs 1 / 3 / 4 (the golden model cases are reduced-width and mostly land
+# on other kernels than the full models do): NIN DoReFa W8A8, ResNet-18 IAO W8A8 + BN-fuse, NIN-GC DoReFa W4A4
+FULL_MODELS = ["nin_dorefa_w8a8", "resnet18_iao_w8a8_bnfuse", "nin_gc_dorefa_w4a4"]
+
+
+@pytest.mark.parametrize("workload", FULL_MODELS)
+def test_full_width_model_layers_teacher_forced(workload):
+    import copy
+    from harness import train as H
+    w = H.WORKLOADS[workload]
+    base = H.build_float_model(w["model"], seed=1)
+    om = H.prepare_oracle(copy.deepcopy(base), w["scheme"], **w["prepare"]); om.train()
+    em = H.prepare_engine(copy.deepcopy(base), w["scheme"], **w["prepare"]).to(DEV); em.train()
+    x, t = H.synthetic_batch(8, w["hw"], seed=21)
+    _teacher_forced(om, em, x, t)
 
 
 # ---------------------------------------------------------------- BASELINE-size layers vs the CPU oracle
