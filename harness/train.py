@@ -110,9 +110,9 @@ class InferStepper:
         for x in batches:
             self.model(x)
         self.model.eval()
-        freeze = getattr(self.model, "freeze_inference", None)
-        if freeze is not None:
-            freeze()
+        if any(type(m).__module__.startswith("micronet_b200") for m in self.model.modules()):
+            from micronet_b200 import iao
+            iao.freeze_inference(self.model)
         return self
 
     @torch.no_grad()

@@ -76,6 +76,13 @@ int mnb_act_quant_fwd(const float* x, int64_t n, const mnb_act_qparams* qp, uint
 int mnb_act_quant_bwd(const float* g, const uint32_t* pass_bits, int64_t n, const mnb_act_qparams* qp,
                       float* dx, mnb_stream_t stream);
 
+/* IAO QuantAdd (IAO:1441-1498) in one pass: out = Q(a) + Q(b) with the shared union-range quantizer (read both addends
+ * once, write the sum; pass masks for the backward pass, either may be NULL).  Backward: da = STE_a(g), db = STE_b(g). */
+int mnb_quant_add_fwd(const float* a, const float* b, int64_t n, const mnb_act_qparams* qp, float* out,
+                      uint32_t* pass_bits_a, uint32_t* pass_bits_b, mnb_stream_t stream);
+int mnb_quant_add_bwd(const float* g, const uint32_t* pass_bits_a, const uint32_t* pass_bits_b, int64_t n,
+                      const mnb_act_qparams* qp, float* da, float* db, mnb_stream_t stream);
+
 /* ------------------------------------------------------------------------
  * IAO observers + update_qparams (IAO:15-139, 292-321), all on device, no host sync.
  *   observer kinds: 0 = MinMaxObserver (running extremum), 1 = MovingAverageMinMaxObserver,

@@ -43,6 +43,8 @@ PROTOTYPES = {
     "mnb_launch_count": (_L, []),
     "mnb_act_quant_fwd": (C.c_int, [_P, _L, _ACTQ, _P, _P, _P, _P]),
     "mnb_act_quant_bwd": (C.c_int, [_P, _P, _L, _ACTQ, _P, _P]),
+    "mnb_quant_add_fwd": (C.c_int, [_P, _P, _L, _ACTQ, _P, _P, _P, _P]),
+    "mnb_quant_add_bwd": (C.c_int, [_P, _P, _P, _L, _ACTQ, _P, _P, _P]),
     "mnb_observe_scratch_bytes": (_L, [_L, _I]),
     "mnb_iao_observe": (C.c_int, [_P, _L, _I, _I, _I, _D, _D, _P, _P, _I, _I, _I, _I, _P, _P, _P, _P]),
     "mnb_iao_update_qparams": (C.c_int, [_P, _P, _I, _I, _I, _I, _P, _P, _P]),
@@ -165,6 +167,7 @@ def tc_check(device=None):
 
 
 E_UNSUPPORTED = -2
+KEEP_DEBUG = False   # tests only: modules keep the fake-quantized weight of their last call
 USE_TC = os.environ.get("MNB_DISABLE_TC", "0") != "1"
 # experimental packed bf16 operands between BN+binarizer and the next conv (round-2 groundwork, off by default)
 USE_PACKED = os.environ.get("MNB_PACKED_OPERANDS", "0") == "1"

@@ -162,7 +162,7 @@ static int make_plan(const mnb_conv_shape* s, int mode, int TA, int TBk, Plan& p
     const int last = (p.TH - 1) * p.BW + p.Wt;             // rows used by the last image of a tile
     p.TB = std::max(1, std::min(p.B, (128 - last) / (p.THH * p.BW) + 1));
   }
-  if (p.BW > 256 || p.THH > 256 || p.TB > 256) return unsupported("box dimension");
+  if (p.BW > 128 || p.THH > 256 || p.TB > 256) return unsupported("box dimension");
   p.npos = p.TB * p.THH * p.BW;
   p.row_tiles = ceil_div(p.OHr, p.TH);
   p.img_tiles = ceil_div(p.B, p.TB);
@@ -498,9 +498,9 @@ pk_conv_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_constant_
               const int r2 = tile / p.col_tiles;
               const int rt = r2 % p.row_tiles, bt = r2 / p.row_tiles;
               const int cw = ct * p.Wt - p.wlo, chh = rt * p.TH - p.hlo, cb = bt * p.TB;
-              tc::tma_load_5d(sbase + (size_t)(mt * p.TA) * p.a_bytes, &tmap0, &sh.full[slot], 0, cw, chh, cb, c8);
-              if (p.TA > 1) tc::tma_load_5d(sbase + (size_t)(mt * p.TA + 1) * p.a_bytes, &tmap1, &sh.full[slot], 0, cw, chh, cb, c8);
-              if (p.TA > 2) tc::tma_load_5d(sbase + (size_t)(mt * p.TA + 2) * p.a_bytes, &tmap2, &sh.full[slot], 0, cw, chh, cb, c8);
+              tc::tma_load_4d(sbase + (size_t)(mt * p.TA) * p.a_bytes, &tmap0, &sh.full[slot], 2 * cw, chh, cb, c8);
+              if (p.TA > 1) tc::tma_load_4d(sbase + (size_t)(mt * p.TA + 1) * p.a_bytes, &tmap1, &sh.full[slot], 2 * cw, chh, cb, c8);
+              if (p.TA > 2) tc::tma_load_4d(sbase + (size_t)(mt * p.TA + 2) * p.a_bytes, &tmap2, &sh.full[slot], 2 * cw, chh, cb, c8);
             }
             tc::bulk_load_1d(sbase + p.b_off, bsrc + (size_t)cc * blk, blk, &sh.full[slot]);
           }
@@ -513,6 +513,7 @@ pk_conv_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_constant_
     const uint32_t y = blockIdx.y;
     const uint64_t a_desc0 = tc::smem_desc_kmajor_noswz(tc::smem_u32(smem), p.m.a_lbo, 128);
     const uint64_t b_desc0 = tc::smem_desc_kmajor_noswz(tc::smem_u32(smem), p.m.b_lbo, 128) + (uint64_t)p.m.b_off16;
+    const uint32_t a_lo0 = (uint32_t)a_desc0, a_hi = (uint32_t)(a_desc0 >> 32), b_lo0 = (uint32_t)b_desc0, b_hi = (uint32_t)(b_desc0 >> 32);
     uint32_t sc = 0, accq = 0;   // accq counts accumulator hand-offs (one per segment)
     for (uint32_t it = blockIdx.x; it < p.m.n_items; it += gridDim.x) {
       uint32_t started = 0, seg_pos = 0, open = 0;
@@ -537,8 +538,8 @@ pk_conv_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_constant_
               for (uint32_t pr = 0; pr < p.m.npairs; ++pr) {
                 const uint32_t a2 = aoff + p.m.pair_a[pr] * p.m.a_term16, b2 = boff + p.m.pair_b[pr] * b_term16;
                 for (uint32_t j = 0; j < p.m.ksteps; ++j)
-                  tc::mma_f16_guarded(d, a_desc0 + (uint64_t)(a2 + j * p.m.a_k16), b_desc0 + (uint64_t)(b2 + j * p.m.b_k16),
-                                      p.m.idesc, (started | i | pr | j) != 0u, lead);
+                  tc::mma_f16_guarded_lh(d, a_lo0 + a2 + j * p.m.a_k16, a_hi, b_lo0 + b2 + j * p.m.b_k16, b_hi,
+                                         p.m.idesc, (started | i | pr | j) != 0u, lead);
               }
             }
           }
@@ -668,14 +669,18 @@ done:
   }
 }
 
-// 5-D map over term plane `t` of a packed tensor: box traversal order (8, w, h, b, octet)
+// Map over term plane `t` of a packed tensor [b][octet][h][w][8 x bf16].  The TMA unit's cost is per box ROW (~12 cycles
+// per row and SM whatever its length: with the 16-byte channel octet as innermost dimension a 170-position x 16-channel
+// box took 4000 cycles), so the 16-byte pixels of one image row are declared as ONE dimension of 8-byte elements:
+// dims (2*W, H, B, octets), box (2*BW, rows, images, octets) - same shared-memory image [octet][image][row][col][16 B],
+// halo columns still zero-filled (start coordinate -2*wlo: a multiple of 16 bytes).
 static int make_pk_tmap(CUtensorMap* m, const void* base, int64_t plane_bytes, int t, int B, int C8tot, int H, int W,
                         int bw, int bh, int bb, int bc8) {
   const uint64_t HW = (uint64_t)H * W;
-  uint64_t dims[5] = {8, (uint64_t)W, (uint64_t)H, (uint64_t)B, (uint64_t)C8tot};
-  uint64_t strides[4] = {16, (uint64_t)W * 16, (uint64_t)C8tot * HW * 16, HW * 16};
-  uint32_t box[5] = {8, (uint32_t)bw, (uint32_t)bh, (uint32_t)bb, (uint32_t)bc8};
-  return mnb_make_tmap_strided(m, reinterpret_cast<const uint8_t*>(base) + (int64_t)t * plane_bytes, 2, 5, dims, strides, box);
+  uint64_t dims[4] = {(uint64_t)W * 2, (uint64_t)H, (uint64_t)B, (uint64_t)C8tot};
+  uint64_t strides[3] = {(uint64_t)W * 16, (uint64_t)C8tot * HW * 16, HW * 16};
+  uint32_t box[4] = {(uint32_t)bw * 2, (uint32_t)bh, (uint32_t)bb, (uint32_t)bc8};
+  return mnb_make_tmap_strided(m, reinterpret_cast<const uint8_t*>(base) + (int64_t)t * plane_bytes, 8, 4, dims, strides, box);
 }
 
 template <typename K>
@@ -738,7 +743,7 @@ static int make_wg_plan(const mnb_conv_shape* s, int TA, int TX, WgPlan& p) {
   p.hlo = hlo; p.hhi = hhi; p.wlo = wlo; p.whi = whi;
   // raster: rows of BW >= Q + halo columns; TH * BW must be a multiple of 16 (MMA K-steps of 16 positions)
   const int need = p.Q + wlo + whi;
-  if (need > 256) return mnb_fail(MNB_E_UNSUPPORTED, "pk wgrad: row wider than 256 positions");
+  if (need > 128) return mnb_fail(MNB_E_UNSUPPORTED, "pk wgrad: row wider than 128 positions");
   // N tile over input channels: taps * Nc accumulator columns
   int nc = (512 / p.ntap) / 16 * 16;
   if (nc < 16) return mnb_fail(MNB_E_UNSUPPORTED, "pk wgrad: more than 32 taps");
@@ -763,7 +768,7 @@ static int make_wg_plan(const mnb_conv_shape* s, int TA, int TX, WgPlan& p) {
   double best_score = -1;
   for (int pass = 0; pass < 2 && !best_bw; ++pass) {
     const int limit = (kSmemBudget - 2048) / (pass == 0 ? 4 : 2);
-    for (int bw = need; bw <= std::min(256, need + 15); ++bw)
+    for (int bw = need; bw <= std::min(128, need + 15); ++bw)
       for (int th = 1; th <= p.P; ++th) {
         if ((th * bw) % 16) continue;
         if (th + hlo + hhi > 256 || sub_bytes_of(bw, th) > limit) continue;
@@ -874,14 +879,14 @@ pk_wgrad_kernel(const __grid_constant__ CUtensorMap dy0, const __grid_constant__
           const int b = sub / p.row_tiles, rt = sub - b * p.row_tiles;
           uint8_t* sb = smem + (size_t)slot * p.stage_bytes + (size_t)si * p.sub_bytes;
           const int h0 = rt * p.TH;
-          tc::tma_load_5d(sb, &dy0, &sh.full[slot], 0, 0, h0, b, k8);
-          if (p.TA > 1) tc::tma_load_5d(sb + p.dy_bytes, &dy1, &sh.full[slot], 0, 0, h0, b, k8);
-          if (p.TA > 2) tc::tma_load_5d(sb + 2 * p.dy_bytes, &dy2, &sh.full[slot], 0, 0, h0, b, k8);
+          tc::tma_load_4d(sb, &dy0, &sh.full[slot], 0, h0, b, k8);
+          if (p.TA > 1) tc::tma_load_4d(sb + p.dy_bytes, &dy1, &sh.full[slot], 0, h0, b, k8);
+          if (p.TA > 2) tc::tma_load_4d(sb + 2 * p.dy_bytes, &dy2, &sh.full[slot], 0, h0, b, k8);
           uint8_t* xb = sb + (size_t)p.TA * p.dy_bytes;
           for (int tx = 0; tx < p.TX; ++tx)
             for (int ks = 0; ks < p.nkph_used; ++ks) {
               const CUtensorMap* tm = tx == 0 ? &x0 : (tx == 1 ? &x1 : &x2);
-              tc::tma_load_5d(xb + (size_t)(tx * p.nkph_used + ks) * p.x_bytes, tm, &sh.full[slot], 0, -p.wlo, h0 - p.hlo, b,
+              tc::tma_load_4d(xb + (size_t)(tx * p.nkph_used + ks) * p.x_bytes, tm, &sh.full[slot], -2 * p.wlo, h0 - p.hlo, b,
                               p.kph_used[ks] * p.C8X + c8);
             }
         }
@@ -892,6 +897,7 @@ pk_wgrad_kernel(const __grid_constant__ CUtensorMap dy0, const __grid_constant__
     const uint32_t lead = lane == 0;
     const uint64_t a_desc0 = tc::smem_desc_mnmajor_noswz(tc::smem_u32(smem), 128, p.m.dy_sbo);
     const uint64_t b_desc0 = tc::smem_desc_mnmajor_noswz(tc::smem_u32(smem), 128, p.m.x_sbo) + (uint64_t)p.m.x_off16;
+    const uint32_t a_lo0 = (uint32_t)a_desc0, a_hi = (uint32_t)(a_desc0 >> 32), b_lo0 = (uint32_t)b_desc0, b_hi = (uint32_t)(b_desc0 >> 32);
     const uint32_t split_u = blockIdx.y;
     const uint32_t s0 = split_u * p.m.stg_per_split;
     const uint32_t s1 = min(p.m.nstg_total, s0 + p.m.stg_per_split);
@@ -906,11 +912,11 @@ pk_wgrad_kernel(const __grid_constant__ CUtensorMap dy0, const __grid_constant__
         for (uint32_t j = 0; j < p.m.ksteps; ++j) {
           const uint32_t arow = s16 + j * 16u, brow = s16 + j * 16u;
           for (uint32_t pr = 0; pr < p.m.npairs; ++pr) {
-            const uint64_t ad = a_desc0 + (uint64_t)(arow + p.m.pair_a[pr] * p.m.dy_term16);
-            const uint32_t b2 = brow + p.m.pair_b[pr] * p.m.x_term16;
+            const uint32_t ad = a_lo0 + arow + p.m.pair_a[pr] * p.m.dy_term16;
+            const uint32_t b2 = b_lo0 + brow + p.m.pair_b[pr] * p.m.x_term16;
             for (uint32_t t = 0; t < p.m.ntap; ++t)
-              tc::mma_f16_guarded(tmem + t * p.m.Nc, ad, b_desc0 + (uint64_t)(b2 + p.m.tap_off[t]), p.m.idesc,
-                                  (started | si | j | pr) != 0u, lead);
+              tc::mma_f16_guarded_lh(tmem + t * p.m.Nc, ad, a_hi, b2 + p.m.tap_off[t], b_hi, p.m.idesc,
+                                     (started | si | j | pr) != 0u, lead);
           }
         }
       }

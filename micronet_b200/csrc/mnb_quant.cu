@@ -802,3 +802,80 @@ extern "C" int mnb_adam_step(float* p, const float* g, float* m, float* v, int64
   MNB_LAUNCHED(1);
   return 0;
 }
+
+// ------------------------------------------------------------------ IAO QuantAdd (IAO:1441-1498), one pass
+// out = Q(a) + Q(b) with the shared (union-range) quantizer: one read of each addend, one write of the sum, the two
+// STE pass masks for the backward pass.  Replaces two fake-quant launches and the ATen add (5 launches with their
+// intermediate tensors); the arithmetic per element is that of act_quant_fwd_kernel followed by __fadd_rn.
+__global__ void __launch_bounds__(256) quant_add_fwd_kernel(const float* __restrict__ a, const float* __restrict__ b,
+                                                            int64_t n, mnb_act_qparams p, float* __restrict__ out,
+                                                            uint32_t* __restrict__ bits_a, uint32_t* __restrict__ bits_b) {
+  const MnbActQ q = mnb_load_actq(p);
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t base = warp * 128; base < n; base += nwarps * 128) {
+    float va[4], vb[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int64_t i = base + lane + 32 * j;
+      va[j] = (i < n) ? __ldg(a + i) : 0.f;
+      vb[j] = (i < n) ? __ldg(b + i) : 0.f;
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int64_t i = base + lane + 32 * j;
+      bool pa, pb;
+      const int ca = mnb_act_code_certified(q, va[j], pa), cb = mnb_act_code_certified(q, vb[j], pb);
+      float oa, ob;
+      if (q.mode == MNB_ACT_DOREFA) { oa = __fmul_rn((float)ca, q.s); ob = __fmul_rn((float)cb, q.s); }
+      else {
+        oa = __fmul_rn(__fadd_rn((float)(ca + q.qmin), q.zp), q.s);
+        ob = __fmul_rn(__fadd_rn((float)(cb + q.qmin), q.zp), q.s);
+      }
+      const bool live = i < n;
+      const uint32_t wa = __ballot_sync(0xffffffffu, live && pa), wb = __ballot_sync(0xffffffffu, live && pb);
+      if (live) out[i] = __fadd_rn(oa, ob);
+      if (lane == 0 && (base + 32 * j) < n) {
+        if (bits_a) bits_a[(base >> 5) + j] = wa;
+        if (bits_b) bits_b[(base >> 5) + j] = wb;
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) quant_add_bwd_kernel(const float* __restrict__ g, const uint32_t* __restrict__ bits_a,
+                                                            const uint32_t* __restrict__ bits_b, int64_t n,
+                                                            mnb_act_qparams p, float* __restrict__ da, float* __restrict__ db) {
+  const MnbActQ q = mnb_load_actq(p);
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) {
+    const float gv = __ldg(g + i);
+    if (da) da[i] = mnb_act_ste_one(q, gv, (__ldg(bits_a + (i >> 5)) >> (i & 31)) & 1u);
+    if (db) db[i] = mnb_act_ste_one(q, gv, (__ldg(bits_b + (i >> 5)) >> (i & 31)) & 1u);
+  }
+}
+
+extern "C" int mnb_quant_add_fwd(const float* a, const float* b, int64_t n, const mnb_act_qparams* qp, float* out,
+                                 uint32_t* pass_bits_a, uint32_t* pass_bits_b, mnb_stream_t stream) {
+  if (int e = check_actq(qp)) return e;
+  MNB_REQUIRE(qp->mode != MNB_ACT_SIGN, "QuantAdd takes a DoReFa or IAO quantizer");
+  MNB_REQUIRE(a && b && out && n >= 0, "NULL pointer");
+  if (n == 0) return 0;
+  int blocks = (int)std::min<int64_t>(mnb_ceil_div(n, 256 * 4), MNB_NUM_SMS * 8);
+  quant_add_fwd_kernel<<<blocks, 256, 0, S(stream)>>>(a, b, n, *qp, out, pass_bits_a, pass_bits_b);
+  MNB_LAUNCHED(1);
+  return 0;
+}
+
+extern "C" int mnb_quant_add_bwd(const float* g, const uint32_t* pass_bits_a, const uint32_t* pass_bits_b, int64_t n,
+                                 const mnb_act_qparams* qp, float* da, float* db, mnb_stream_t stream) {
+  if (int e = check_actq(qp)) return e;
+  MNB_REQUIRE(g && n >= 0 && (da == nullptr || pass_bits_a) && (db == nullptr || pass_bits_b), "NULL pointer");
+  if (n == 0) return 0;
+  int blocks = (int)std::min<int64_t>(mnb_ceil_div(n, 256 * 4), MNB_NUM_SMS * 8);
+  quant_add_bwd_kernel<<<blocks, 256, 0, S(stream)>>>(g, pass_bits_a, pass_bits_b, n, *qp, da, db);
+  MNB_LAUNCHED(1);
+  return 0;
+}

@@ -146,6 +146,18 @@ __device__ __forceinline__ void mma_f16_guarded(uint32_t d_tmem, uint64_t adesc,
       ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(guard)
       : "memory");
 }
+// Same, descriptors given as (low word, high word): only the 14-bit start-address field of the low word changes from
+// MMA to MMA, so issue loops carry 32-bit adds and the loop-invariant high words stay in uniform registers.
+__device__ __forceinline__ void mma_f16_guarded_lh(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo,
+                                                   uint32_t b_hi, uint32_t idesc, uint32_t accumulate, uint32_t guard) {
+  asm volatile(
+      "{\n\t.reg .pred p, q;\n\t.reg .b64 da, db;\n\t"
+      "setp.ne.b32 p, %6, 0;\n\tsetp.ne.b32 q, %7, 0;\n\t"
+      "mov.b64 da, {%1, %2};\n\tmov.b64 db, {%3, %4};\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t}"
+      ::"r"(d_tmem), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate), "r"(guard)
+      : "memory");
+}
 __device__ __forceinline__ void mma_i8(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
                                        uint32_t accumulate) {
   asm volatile(

@@ -63,6 +63,14 @@ class ActSpec:
         return L.ActQParams(self.mode, self.bits, self.qmin, self.qmax, self.q_type, L.ptr(self.scale),
                             L.ptr(self.zero_point), L.ptr(self.obs_min), L.ptr(self.obs_max))
 
+    def frozen(self):
+        """copy with private clones of the device scalars: what backward must see is the forward-time scale / range
+        (the reference uses self.scale.clone(), IAO:228-239), not whatever a later forward of the module wrote"""
+        if self.mode != L.ACT_IAO:
+            return self
+        snap = torch.cat([self.scale.reshape(1), self.zero_point.reshape(1), self.obs_min.reshape(1), self.obs_max.reshape(1)])
+        return ActSpec(self.mode, self.bits, self.qmin, self.qmax, self.q_type, snap[0:1], snap[1:2], snap[2:3], snap[3:4])
+
     # decoding of the u8 codes: effective integer e = code + offset (+ zero_point), value = e * scale
     @property
     def code_offset(self):
@@ -103,7 +111,7 @@ class ActQuantFn(Function):
     @staticmethod
     def forward(ctx, x, spec: ActSpec):
         _, bits, xq = act_quant_raw(x, spec, False, ctx.needs_input_grad[0], True)
-        ctx.spec, ctx.bits = spec, bits
+        ctx.spec, ctx.bits = (spec.frozen() if ctx.needs_input_grad[0] else spec), bits
         return xq
 
     @staticmethod
@@ -115,6 +123,38 @@ class ActQuantFn(Function):
         L.check(lib.mnb_act_quant_bwd(g.data_ptr(), ctx.bits.data_ptr(), g.numel(), C.byref(qp),
                                       dx.data_ptr(), L.stream()), "act_quant_bwd")
         return dx, None
+
+
+class QuantAddFn(Function):
+    """IAO QuantAdd (IAO:1441-1498): Q(res) + Q(shortcut) with the shared quantizer, one kernel each way"""
+
+    @staticmethod
+    def forward(ctx, a, b, spec: ActSpec):
+        L.require_cuda(a, b)
+        lib = L.load()
+        a, b = a.contiguous(), b.contiguous()
+        assert a.shape == b.shape, "QuantAdd: operand shapes differ"
+        n = a.numel()
+        out = torch.empty_like(a)
+        words = (n + 31) // 32
+        ba = torch.empty(words, dtype=torch.int32, device=a.device) if ctx.needs_input_grad[0] else None
+        bb = torch.empty(words, dtype=torch.int32, device=a.device) if ctx.needs_input_grad[1] else None
+        qp = spec.struct()
+        L.check(lib.mnb_quant_add_fwd(a.data_ptr(), b.data_ptr(), n, C.byref(qp), out.data_ptr(), L.ptr(ba), L.ptr(bb),
+                                      L.stream()), "quant_add_fwd")
+        ctx.spec, ctx.ba, ctx.bb = spec.frozen() if (ba is not None or bb is not None) else spec, ba, bb
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        lib = L.load()
+        g = g.contiguous()
+        da = torch.empty_like(g) if ctx.ba is not None else None
+        db = torch.empty_like(g) if ctx.bb is not None else None
+        qp = ctx.spec.struct()
+        L.check(lib.mnb_quant_add_bwd(g.data_ptr(), L.ptr(ctx.ba), L.ptr(ctx.bb), g.numel(), C.byref(qp), L.ptr(da),
+                                      L.ptr(db), L.stream()), "quant_add_bwd")
+        return da, db, None
 
 
 # --------------------------------------------------------------------------
@@ -264,11 +304,20 @@ def _pk_forward(ctx, x, wq, bias, w_int, w_scale, spec, sh, y, need_dx):
     qp = spec.struct() if spec is not None else None
     split = sh.stride_h == 2
     x_pk, bits8 = PK.pack_act(x, qp, ta, phase_split=split, want_bits=need_dx)
-    w_img = PK.pack_weight(sh, 0, ta, tw, w_int=w_int, w_f32=None if w_int is not None else wq)
+    # frozen (inference) modules hang a dict on their cached weight tensor: the packed image is then built once
+    src = w_int if w_int is not None else wq
+    cache = getattr(src, "_mnb_pk_cache", None)
+    ckey = (PK._key(sh), ta, tw)
+    w_img = cache.get(ckey) if cache is not None else None
+    if w_img is None:
+        w_img = PK.pack_weight(sh, 0, ta, tw, w_int=w_int, w_f32=None if w_int is not None else wq)
+        if cache is not None:
+            cache[ckey] = w_img
     a_scale, a_const = None, 1.0
     if spec is not None:
         if spec.mode == L.ACT_IAO:
-            a_scale = spec.scale.clone()      # backward must see the forward-time scale (the reference clones it too)
+            # backward must see the forward-time scale (the reference clones it too); no clone needed without autograd
+            a_scale = spec.scale.clone() if (need_dx or ctx.needs_input_grad[1]) else spec.scale
         elif spec.mode == L.ACT_DOREFA:
             a_const = 1.0 / float(2 ** spec.bits - 1)
     rc = _timed("fwd_pk", sh, lambda: PK.conv(sh, 0, x_pk, ta, w_img, tw, y, n_scale=w_scale if w_int is not None else None,
@@ -390,6 +439,10 @@ class QuantConv2dFn(Function):
             ops.bias = L.ptr(bias)
             L.check(_timed("fwd", sh, lambda: lib.mnb_conv2d_fwd(C.byref(sh), C.byref(ops), y.data_ptr(), L.stream())),
                     "conv2d_fwd")
+        if spec is not None and not ctx.pk and (ctx.needs_input_grad[0] or ctx.needs_input_grad[1]):
+            spec = spec.frozen()   # backward re-quantizes / masks with the forward-time parameters
+            if spec.mode == L.ACT_IAO:
+                a_scale = spec.scale
         ctx.sh, ctx.spec, ctx.a_scale = sh, spec, a_scale
         ctx.codes, ctx.bits = codes, bits
         ctx.x = x if (not ctx.pk and (codes is None or (L.USE_TC and w_int is not None))) else None

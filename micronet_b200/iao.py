@@ -257,10 +257,37 @@ class QuantConv2d(nn.Conv2d):
             wq, w_int, w_scale = self.weight_quantizer.quantize_weight(weight)
         else:
             wq, w_int, w_scale = weight, None, None
+        if L.KEEP_DEBUG:   # tests: the fake-quantized weight of this call (tie-excuse rule for BN-fused weights)
+            self.__dict__["_dbg_wq"] = wq.detach()
         return F_.quant_conv2d(input, wq, bias, w_int, w_scale, spec, self.stride, self.padding,
                                self.dilation, self.groups)
 
+    def _frozen_operands(self, make):
+        """inference fast path (freeze_inference): the quantized weights of an eval-mode module are computed once;
+        ``make`` returns (weight to quantize, bias).  Invalidated when any parameter / buffer is written in place."""
+        key = tuple(t._version for t in list(self.parameters()) + list(self.buffers()))
+        fr = self.__dict__.get("_frozen")
+        if fr is None or fr[0] != key:
+            weight, bias = make()
+            if not self.quant_inference:
+                wq, w_int, w_scale = self.weight_quantizer.quantize_weight(weight)
+            else:
+                wq, w_int, w_scale = weight, None, None
+            wq = wq.detach()
+            (w_int if w_int is not None else wq)._mnb_pk_cache = {}
+            fr = (key, wq, w_int, w_scale, None if bias is None else bias.detach())
+            self.__dict__["_frozen"] = fr
+        return fr[1:]
+
+    def _use_frozen(self):
+        return self.__dict__.get("_frozen_inference", False) and not self.training and not torch.is_grad_enabled()
+
     def forward(self, input):
+        if self._use_frozen():
+            wq, w_int, w_scale, bias = self._frozen_operands(lambda: (self.weight, self.bias))
+            spec = self.activation_quantizer.prepare_activation(input)
+            return F_.quant_conv2d(input, wq, bias, w_int, w_scale, spec, self.stride, self.padding, self.dilation,
+                                   self.groups)
         return self._quant_conv(input, self.weight, self.bias)
 
 
@@ -302,7 +329,20 @@ class QuantBNFuseConv2d(QuantConv2d):
         nn.init.uniform_(self.gamma)
         nn.init.zeros_(self.beta)
 
+    def _fold_running(self):
+        ratio = self.gamma / torch.sqrt(self.running_var + self.eps)
+        if self.bias is not None:
+            bias_fused = reshape_to_bias(self.beta + (self.bias - self.running_mean) * ratio)
+        else:
+            bias_fused = reshape_to_bias(self.beta - self.running_mean * ratio)
+        return self.weight * reshape_to_weight(ratio), bias_fused
+
     def forward(self, input):
+        if self._use_frozen():   # eval / running statistics (IAO:903-935), folded and quantized once
+            wq, w_int, w_scale, bias = self._frozen_operands(self._fold_running)
+            spec = self.activation_quantizer.prepare_activation(input)
+            return F_.quant_conv2d(input, wq, bias, w_int, w_scale, spec, self.stride, self.padding, self.dilation,
+                                   self.groups)
         use_batch = (not self.qaft) and self.training
         if use_batch:
             # un-quantised conv only to obtain the BN batch statistics (IAO:843-855)
@@ -434,12 +474,21 @@ class QuantAdd(nn.Module):
         self.activation_quantizer = _activation_quantizer(a_bits, q_type, qaft, ptq, percentile, union=True)
 
     def forward(self, res, shortcut):
-        self.observer_res(res)
-        self.observer_shortcut(shortcut)
-        obs = self.activation_quantizer.observer
-        obs.min_val = torch.min(self.observer_res.min_val, self.observer_shortcut.min_val)
-        obs.max_val = torch.max(self.observer_res.max_val, self.observer_shortcut.max_val)
-        return self.activation_quantizer(res) + self.activation_quantizer(shortcut)
+        q = self.activation_quantizer
+        frozen = self.__dict__.get("_frozen_inference", False) and not self.training
+        if not frozen:
+            # the reference refreshes the two observers on every call, eval included (IAO:1483-1494); in eval they only
+            # feed the STE range of a backward pass, so a frozen inference model (freeze_inference) skips them
+            self.observer_res(res)
+            self.observer_shortcut(shortcut)
+            obs = q.observer
+            obs.min_val = torch.min(self.observer_res.min_val, self.observer_shortcut.min_val)
+            obs.max_val = torch.max(self.observer_res.max_val, self.observer_shortcut.max_val)
+        if q.bits == 32:
+            return res + shortcut
+        q._check_bits()
+        q.refresh(res)          # union quantizer: update_qparams only (training, not QAFT)
+        return F_.QuantAddFn.apply(res, shortcut, q.act_spec())
 
 
 # ********************* prepare (IAO:1501-1824) *********************
@@ -511,6 +560,18 @@ def add_quant_op(module, a_bits=8, w_bits=8, q_type=0, q_level=0, weight_observe
             module._modules[name] = QuantAdd(**aq)
         else:
             add_quant_op(child, **kw)
+
+
+def freeze_inference(model, enable=True):
+    """Opt-in inference fast path for an IAO-prepared model in eval mode (BASELINE.json configs[4], iao/main.py:511-519):
+    every quant conv / linear folds + quantizes its weights and packs their tensor-core image ONCE (re-done when a
+    parameter or buffer is written), and QuantAdd stops refreshing its observers, which cannot influence an eval
+    forward.  Outputs are bit-identical to the un-frozen eval forward."""
+    for m in model.modules():
+        if isinstance(m, (QuantConv2d, QuantLinear, QuantAdd)):
+            m.__dict__["_frozen_inference"] = bool(enable)
+            m.__dict__.pop("_frozen", None)
+    return model
 
 
 def prepare(model, inplace=False, a_bits=8, w_bits=8, q_type=0, q_level=0, weight_observer=0, bn_fuse=False,

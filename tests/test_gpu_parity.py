@@ -262,8 +262,18 @@ def _teacher_forced(om, em, x, t, wtol=2e-5):
     """every engine module of the prepared model (quant conv / linear / bn-fuse conv, binarizer,
     quantized add / pool), fed the ORACLE's own inputs and output-gradient at that layer (captured
     with hooks during one oracle QAT step), must reproduce the oracle's output, input gradients and
-    parameter gradients to 1e-5 (parameter gradients: ``wtol``)."""
+    parameter gradients to 1e-5 (parameter gradients: ``wtol``).
+
+    Two quantities are not reproducible to 1e-5 even CPU <-> CPU and get the tie-excuse treatment of SURVEY §7.2.1:
+    * BN-fused weights are quantized AFTER folding batch statistics of an fp32 convolution into them: a different
+      summation order moves w_fused by ~1e-7 relative and flips the level of the few weights that sit on a rounding
+      tie (about 1e-5 of them).  The engine's fake-quantized weight is read back; it may differ from the oracle's by
+      ONE level on at most 1e-4 of the weights, and the comparison is made after removing conv(xq, w_e - w_o).
+    * DoReFa's weight gradient has one element (the arg-max of |tanh w|) that collects -sum(g t)/m^2 over the whole
+      tensor: a cancelling fp32 sum of 3e5 terms whose value depends on the summation order at the 1e-4 level on both
+      sides.  That element is compared at 1e-3."""
     import copy
+    from micronet_b200 import _lib as L
     pristine = copy.deepcopy(om)  # per-layer replay needs first-call observer state
     names = [n for n, mod in em.named_modules() if type(mod).__name__ in QUANT_TYPES
              and not n.endswith("activation_quantizer")]
@@ -283,37 +293,80 @@ def _teacher_forced(om, em, x, t, wtol=2e-5):
         h.remove()
     emods, pmods = dict(em.named_modules()), dict(pristine.named_modules())
     assert names, "no quantized layers found"
-    for n in names:
-        e, o, c = emods[n], pmods[n], cap[n]
-        # oracle layer replayed stand-alone on the captured inputs (a tensor hook on the model's
-        # activation would also collect the gradient of its other consumers, e.g. the residual add)
-        xo = [t.clone().requires_grad_(True) for t in c["x"]]
-        yo = o(*xo)
-        assert torch.equal(yo.detach(), c["y"]) or rel_err(yo.detach(), c["y"]) <= 1e-6
-        yo.backward(c["go"])
-        xin = [t.to(DEV).requires_grad_(True) for t in c["x"]]
-        y = e(*xin)
-        assert rel_err(y.detach(), c["y"]) <= TOL, f"{n}: fwd {rel_err(y.detach(), c['y'])}"
-        e.zero_grad()
-        y.backward(c["go"].to(DEV))
-        for i in range(len(xin)):
-            if xo[i].grad is None:
-                continue
-            assert rel_err(xin[i].grad, xo[i].grad) <= TOL, f"{n}: dx[{i}] {rel_err(xin[i].grad, xo[i].grad)}"
-        ograds = {k: p.grad for k, p in o.named_parameters()}
-        wscale = max((g.abs().max().item() for k, g in ograds.items() if g is not None and k != "bias"), default=1.0)
-        for k, p in e.named_parameters():
-            if ograds.get(k) is None:
-                continue
-            if k == "bias":
-                # a conv bias in front of a BatchNorm has a mathematically zero gradient: both sides
-                # hold round-off noise, compare on the scale of the layer's weight gradient instead
-                tol = max(1e-6, 2e-5 * max(wscale, ograds[k].abs().max().item()))
-                assert (p.grad.cpu() - ograds[k]).abs().max().item() <= tol, f"{n}.bias"
-                continue
-            assert rel_err(p.grad, ograds[k]) <= wtol, f"{n}.{k}: {rel_err(p.grad, ograds[k])}"
-    from micronet_b200 import _lib as L
+    bad = []
+
+    def check(ok, msg):
+        if not ok:
+            bad.append(msg)
+
+    L.KEEP_DEBUG = True
+    try:
+        for n in names:
+            e, o, c = emods[n], pmods[n], cap[n]
+            bnfuse = type(e).__name__ == "QuantBNFuseConv2d"
+            side = {}
+            hk = []
+            if bnfuse:   # the oracle's fake-quantized fused weight and quantized input of this call
+                hk.append(o.weight_quantizer.register_forward_hook(lambda m, i, out: side.__setitem__("wq", out.detach().clone())))
+                hk.append(o.activation_quantizer.register_forward_hook(lambda m, i, out: side.__setitem__("xq", out.detach().clone())))
+            # oracle layer replayed stand-alone on the captured inputs (a tensor hook on the model's
+            # activation would also collect the gradient of its other consumers, e.g. the residual add)
+            xo = [t.clone().requires_grad_(True) for t in c["x"]]
+            yo = o(*xo)
+            for h in hk:
+                h.remove()
+            assert torch.equal(yo.detach(), c["y"]) or rel_err(yo.detach(), c["y"]) <= 1e-6
+            yo.backward(c["go"])
+            xin = [t.to(DEV).requires_grad_(True) for t in c["x"]]
+            y = e(*xin)
+            ye = y.detach().cpu()
+            flips = 0
+            if bnfuse and "wq" in side and "_dbg_wq" in e.__dict__:
+                dw = e.__dict__["_dbg_wq"].cpu() - side["wq"]
+                step = e.weight_quantizer.scale.detach().cpu().reshape(-1, 1, 1, 1)
+                flips = int((dw.abs() > 0.5 * step).sum())
+                check(flips <= max(2, int(1e-4 * dw.numel())), f"{n}: {flips} weight levels differ")
+                check(bool((dw.abs() <= 1.01 * step + 1e-6 * side["wq"].abs()).all()), f"{n}: a weight differs by more than one level")
+                if flips:
+                    ye = ye - TF.conv2d(side["xq"], dw * (dw.abs() > 0.5 * step), None, e.stride, e.padding, e.dilation, e.groups)
+            err = rel_err(ye, c["y"])
+            check(err <= TOL, f"{n}: fwd {err:.2e} (flips {flips})")
+            e.zero_grad()
+            y.backward(c["go"].to(DEV))
+            gtol = TOL if flips == 0 else 5e-3     # gradients through flipped weights: one level of 1e-4 of the weights
+            for i in range(len(xin)):
+                if xo[i].grad is None:
+                    continue
+                err = rel_err(xin[i].grad, xo[i].grad)
+                check(err <= gtol, f"{n}: dx[{i}] {err:.2e} (flips {flips})")
+            ograds = {k: p.grad for k, p in o.named_parameters()}
+            wscale = max((g.abs().max().item() for k, g in ograds.items() if g is not None and k != "bias"), default=1.0)
+            dorefa = type(e).__module__.endswith("dorefa")
+            for k, p in e.named_parameters():
+                if ograds.get(k) is None:
+                    continue
+                ge, go_ = p.grad.detach().cpu(), ograds[k]
+                if k == "bias":
+                    # a conv bias in front of a BatchNorm has a mathematically zero gradient: both sides
+                    # hold round-off noise, compare on the scale of the layer's weight gradient instead
+                    tol = max(1e-6, 2e-5 * max(wscale, go_.abs().max().item()))
+                    check((ge - go_).abs().max().item() <= tol, f"{n}.bias {(ge - go_).abs().max().item():.2e}")
+                    continue
+                tol = wtol if flips == 0 else 5e-3
+                if dorefa and k == "weight":
+                    am = torch.tanh(dict(o.named_parameters())[k].detach()).abs().flatten().argmax()
+                    den = go_.abs().max().item()
+                    d = (ge - go_).abs().flatten()
+                    check(d[am].item() <= 1e-3 * den, f"{n}.{k}[argmax] {d[am].item() / den:.2e}")
+                    d[am] = 0
+                    check(d.max().item() <= tol * den, f"{n}.{k}: {d.max().item() / den:.2e}")
+                else:
+                    err = rel_err(ge, go_)
+                    check(err <= tol, f"{n}.{k}: {err:.2e} (flips {flips})")
+    finally:
+        L.KEEP_DEBUG = False
     L.tc_check()
+    assert not bad, "\n".join(bad)
 
 
 @pytest.mark.parametrize("case", MODEL_CASES, ids=[c["name"] for c in MODEL_CASES])
