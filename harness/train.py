@@ -83,6 +83,8 @@ class QatStepper:
         else:
             self.opt = make_optimizer(model, lr, wd)
         self.flat = flat
+        self.steps = 0
+        self.check_every = 50   # synchronising look at the tensor-core kernels' timeout flag (0: never)
 
     def step(self, x, t):
         self.model.train()
@@ -93,6 +95,10 @@ class QatStepper:
         if self.flat:
             self.opt.all_reduce()
         self.opt.step()
+        self.steps += 1
+        if self.flat and self.check_every and self.steps % self.check_every == 0:
+            from micronet_b200 import _lib as L
+            L.tc_check()   # a bounded pipeline wait that gave up means garbage results: raise instead of training on
         return loss
 
 

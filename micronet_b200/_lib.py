@@ -81,6 +81,7 @@ PROTOTYPES = {
     "mnb_adam_step": (C.c_int, [_P, _P, _P, _P, _L, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, _I, _P]),
     "mnb_pk_act_bytes": (_L, [_I, _I, _I, _I, _I]),
     "mnb_pk_pack_act": (C.c_int, [_P, _I, _I, _I, _I, _ACTQ, _I, _P, _I, _P, _P, _P]),
+    "mnb_bn_relu_quant_pack_fwd": (C.c_int, [_P, _I, _I, _I, _P, _P, _P, _P, _ACTQ, _I, _P, _P, _P]),
     "mnb_pk_conv_plan": (C.c_int, [_SHAPE, _I, _I, _I, _P]),
     "mnb_pk_wimage_bytes": (_L, [_SHAPE, _I, _I, _I]),
     "mnb_pk_pack_weight": (C.c_int, [_SHAPE, _I, _I, _I, _P, _P, _P, _P, _P]),
@@ -169,8 +170,8 @@ def tc_check(device=None):
 E_UNSUPPORTED = -2
 KEEP_DEBUG = False   # tests only: modules keep the fake-quantized weight of their last call
 USE_TC = os.environ.get("MNB_DISABLE_TC", "0") != "1"
-# experimental packed bf16 operands between BN+binarizer and the next conv (round-2 groundwork, off by default)
-USE_PACKED = os.environ.get("MNB_PACKED_OPERANDS", "0") == "1"
+# packed bf16 operands from the BN+binarizer producer to the next conv's forward (MNB_PACKED_OPERANDS=0 turns it off)
+USE_PACKED = os.environ.get("MNB_PACKED_OPERANDS", "1") == "1"
 # packed-operand tensor-core family (mnb_pk.cu): "auto" = wherever the fused kernels have no cover and for every fused-quantizer
 # layer; "all" = every conv it supports; "off" = never
 PK_MODE = os.environ.get("MNB_PK", "auto")

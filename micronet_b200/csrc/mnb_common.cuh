@@ -156,6 +156,41 @@ __device__ __forceinline__ int mnb_act_code_certified(const MnbActQ& q, float x,
   }
 }
 
+// Same decisions as mnb_act_code_certified, returning the effective integer level AS A FLOAT (level - qmin + a_off
+// arithmetic folded away: DoReFa -> k, IAO -> clamp(round(x/s - zp)), SIGN -> +-1) with no float <-> int conversions:
+// the operand packers of the tensor-core path are instruction-bound, not bandwidth-bound, on the quantizer.
+__device__ __forceinline__ float mnb_act_level_certified(const MnbActQ& q, float x, bool& pass) {
+  if (q.mode == MNB_ACT_DOREFA) {
+    const float t = __fmul_rn(x, 0.1f);
+    pass = (t >= 0.f) && (t <= 1.f);
+    const float c = fminf(fmaxf(t, 0.f), 1.f);
+    const float pa = c * q.rinv;
+    const float f = pa + 0.5f;
+    float r = floorf(f);
+    const float d = f - r, delta = 4e-7f * (pa + 1.f);
+    if (d < delta || d > 1.f - delta) r = floorf(__fadd_rn(__fdiv_rn(c, q.s), 0.5f));
+    return r;
+  } else if (q.mode == MNB_ACT_IAO) {
+    const float xa = x * q.rinv;
+    float v = xa - q.zp;
+    const float av = fabsf(v);
+    const float f = av + 0.5f;
+    float ra = floorf(f);
+    const float d = f - ra, delta = 4e-7f * (fabsf(xa) + fabsf(q.zp) + 1.f);
+    const bool near_edge = fabsf(v - q.hi) < delta || fabsf(v - q.lo) < delta;
+    if (d < delta || d > 1.f - delta || near_edge || av < delta) {
+      v = __fsub_rn(__fdiv_rn(x, q.s), q.zp);
+      ra = floorf(__fadd_rn(fabsf(v), 0.5f));
+    }
+    const float r = v > 0.f ? ra : (v < 0.f ? -ra : 0.f);
+    pass = !(v > q.hi) && !(v < q.lo) && (r >= (float)q.qmin) && (r <= (float)q.qmax);
+    return fminf(fmaxf(r, (float)q.qmin), (float)q.qmax);
+  } else {
+    pass = !(x >= 1.0f) && !(x <= -1.0f);
+    return !(x < 0.f) ? 1.f : -1.f;
+  }
+}
+
 __device__ __forceinline__ float mnb_act_ste_one(const MnbActQ& q, float g, bool pass) {
   if (q.mode == MNB_ACT_DOREFA) return __fmul_rn(pass ? __fdiv_rn(__fmul_rn(g, q.s), q.s) : 0.f, 0.1f);
   if (q.mode == MNB_ACT_IAO) return pass ? __fdiv_rn(__fmul_rn(g, q.s), q.s) : 0.f;

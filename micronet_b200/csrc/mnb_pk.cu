@@ -39,7 +39,7 @@ namespace pk {
 
 constexpr int NTHREADS = 256;      // warp 0 TMA, warp 1 MMA issue, warp 2 TMEM alloc, warps 4..7 epilogue
 constexpr int MAXST = 8;           // operand ring (power of two: ring index = counter & mask)
-constexpr int MAXTAP = 64, MAXTMPL = 16, MAXY = 4, MAXPAIR = 6;
+constexpr int MAXTAP = 64, MAXTMPL = 16, MAXY = 4, MAXPAIR = 6, MAXPROG = 384;
 constexpr int kSmemBudget = 227 * 1024 - 3072;   // dynamic shared memory the kernels may ask for
 
 // ---------------------------------------------------------------------------------------------------------
@@ -300,8 +300,8 @@ __global__ void __launch_bounds__(256) pack_act_kernel(const float* __restrict__
       float val = c < C ? __ldg(src + j * HW) : 0.f;
       if (QUANT) {
         bool pass;
-        const int code = mnb_act_code_certified(q, val, pass);
-        val = c < C ? (float)(code + a_off) + zp : 0.f;
+        const float lev = mnb_act_level_certified(q, val, pass);   // level itself (code + a_off), no int round trip
+        val = c < C ? lev + zp : 0.f;
         passbits |= (pass && c < C) ? (1u << j) : 0u;
       } else if (ch_scale) {
         val = c < C ? __fmul_rn(val, __ldg(ch_scale + c)) : 0.f;
@@ -326,6 +326,46 @@ __global__ void __launch_bounds__(256) pack_act_kernel(const float* __restrict__
       out[(int64_t)tm * plane_vecs + dst] = make_uint4(pk4[0], pk4[1], pk4[2], pk4[3]);
     }
     if (QUANT && bits8) bits8[idx] = (uint8_t)passbits;
+  }
+}
+
+// BatchNorm2d + ReLU + DoReFa activation quantizer + operand packing in ONE pass (SURVEY.md 8 f2 for the DoReFa blocks
+// conv -> nn.BatchNorm2d -> nn.ReLU -> [channel_shuffle] -> QuantConv2d, nin_gc.py:53-59 + DF:36-46): reads the conv output
+// once, writes the integer levels of the NEXT conv's activation quantizer as its packed bf16 plane (2 B / element, in the
+// output channel order of the folded shuffle) and the combined STE mask  relu'(bn) * [0.1 bn <= 1]  as flat NCHW bits in the
+// producer's own channel order - exactly what mnb_bn_sign_bwd consumes, so the backward needs no new kernel.  The fp32
+// BatchNorm / ReLU outputs and the separate quantize + pack pass never touch HBM.
+// one warp = 32 consecutive positions of one OUTPUT channel octet of one image
+__global__ void __launch_bounds__(256) bn_relu_quant_pack_kernel(const float* __restrict__ x, int batch, int channels, int hw,
+                                                                 int sg, const float* __restrict__ mean,
+                                                                 const float* __restrict__ invstd, const float* __restrict__ gamma,
+                                                                 const float* __restrict__ beta, mnb_act_qparams qp,
+                                                                 uint32_t* __restrict__ bits, uint4* __restrict__ xp) {
+  const int lane = threadIdx.x & 31;
+  const int c8n = channels / 8, p32n = hw / 32, cpg = channels / sg;
+  const int64_t items = (int64_t)batch * c8n * p32n;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  const MnbActQ q = mnb_load_actq(qp);
+  for (int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; w < items; w += nwarps) {
+    const int p32 = (int)(w % p32n);
+    const int64_t t = w / p32n;
+    const int oc8 = (int)(t % c8n), b = (int)(t / c8n);
+    const int pos = p32 * 32 + lane;
+    float lev[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int oc = oc8 * 8 + j;
+      const int c = sg > 1 ? (oc % sg) * cpg + oc / sg : oc;   // inverse of out[:, a*sg + b] = in[:, b*cpg + a]
+      const int64_t fi = ((int64_t)b * channels + c) * hw + pos;
+      const float bn = fmaf(__ldg(x + fi) - __ldg(mean + c), __ldg(gamma + c) * __ldg(invstd + c), __ldg(beta + c));
+      const float y = fmaxf(bn, 0.f);                          // nn.ReLU
+      bool pass;
+      lev[j] = mnb_act_level_certified(q, y, pass);            // DoReFa: pass = 0 <= 0.1 y <= 1
+      const uint32_t word = __ballot_sync(0xffffffffu, pass && bn > 0.f);   // relu'(0) = 0
+      if (lane == 0) bits[fi >> 5] = word;
+    }
+    xp[((int64_t)b * c8n + oc8) * hw + pos] = make_uint4(pack2(lev[0], lev[1]), pack2(lev[2], lev[3]), pack2(lev[4], lev[5]),
+                                                          pack2(lev[6], lev[7]));
   }
 }
 
@@ -400,10 +440,13 @@ struct ConvParams {
   struct Mma {
     uint32_t n_items, chunks, ksteps, MT, Nt, npairs, st_mask, st_log2, stage16, a_mt16, a_term16, a_k16, b_off16,
         b_tap16, b_k16, idesc, a_lbo, b_lbo, seg_len;
-    uint32_t pair_a[MAXPAIR], pair_b[MAXPAIR];
     uint32_t ntmpl[MAXY];
-    uint32_t tmpl_tap0[MAXY][MAXTMPL], tmpl_ntap[MAXY][MAXTMPL];
-    uint32_t tap_aoff[MAXY][MAXTAP];
+    // The MMA "program": one 32-bit word per (filter tap, piece pair) of a stage template = A offset | B offset << 16
+    // (16-byte units inside the stage); the issue loop is then  load word, two adds, MMA.  A single warp executes this
+    // loop serially, so every instruction in it costs MMA issue rate (measured: 45 uniform-datapath instructions per
+    // MMA = 420 cycles per MMA, tensor pipe 15 % busy).
+    uint16_t tmpl_begin[MAXY][MAXTMPL], tmpl_cnt[MAXY][MAXTMPL];
+    uint32_t prog[MAXPROG];
   } m;
   // TMA role
   int n_items, n_ntiles, G, MT, TA, chunks, CC8, C8A, kg8, stage_bytes, a_bytes, a_box_bytes, b_off, st_mask, st_log2;
@@ -509,7 +552,7 @@ pk_conv_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_constant_
     }
   } else if (warp == 1) {
     // ================================================================= MMA issuer (warp-converged, lane 0 issues)
-    const uint32_t lead = lane == 0;
+
     const uint32_t y = blockIdx.y;
     const uint64_t a_desc0 = tc::smem_desc_kmajor_noswz(tc::smem_u32(smem), p.m.a_lbo, 128);
     const uint64_t b_desc0 = tc::smem_desc_kmajor_noswz(tc::smem_u32(smem), p.m.b_lbo, 128) + (uint64_t)p.m.b_off16;
@@ -518,8 +561,7 @@ pk_conv_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_constant_
     for (uint32_t it = blockIdx.x; it < p.m.n_items; it += gridDim.x) {
       uint32_t started = 0, seg_pos = 0, open = 0;
       for (uint32_t t = 0; t < p.m.ntmpl[y]; ++t) {
-        const uint32_t tap0 = p.m.tmpl_tap0[y][t], ntap = p.m.tmpl_ntap[y][t];
-        const uint32_t b_term16 = ntap * p.m.b_tap16;
+        const uint32_t pb = p.m.tmpl_begin[y][t], pc = p.m.tmpl_cnt[y][t];
         for (uint32_t cc = 0; cc < p.m.chunks; ++cc, ++sc) {
           const uint32_t acc = accq & 1u, aph = (accq >> 1) & 1u;
           if (!open) {   // first stage of a segment: the accumulator must have been drained
@@ -532,22 +574,22 @@ pk_conv_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_constant_
           const uint32_t s16 = slot * p.m.stage16;
           for (uint32_t mt = 0; mt < p.m.MT; ++mt) {
             const uint32_t d = tmem + (acc * p.m.MT + mt) * p.m.Nt;
-            for (uint32_t i = 0; i < ntap; ++i) {
-              const uint32_t aoff = s16 + mt * p.m.a_mt16 + p.m.tap_aoff[y][tap0 + i];
-              const uint32_t boff = s16 + i * p.m.b_tap16;
-              for (uint32_t pr = 0; pr < p.m.npairs; ++pr) {
-                const uint32_t a2 = aoff + p.m.pair_a[pr] * p.m.a_term16, b2 = boff + p.m.pair_b[pr] * b_term16;
-                for (uint32_t j = 0; j < p.m.ksteps; ++j)
-                  tc::mma_f16_guarded_lh(d, a_lo0 + a2 + j * p.m.a_k16, a_hi, b_lo0 + b2 + j * p.m.b_k16, b_hi,
-                                         p.m.idesc, (started | i | pr | j) != 0u, lead);
+            const uint32_t a_base = a_lo0 + s16 + mt * p.m.a_mt16, b_base = b_lo0 + s16;
+            uint32_t accf = started;
+            for (uint32_t e = 0; e < pc; ++e) {
+              const uint32_t w = p.m.prog[pb + e];
+              uint32_t a = a_base + (w & 0xffffu), b = b_base + (w >> 16);
+              for (uint32_t j = 0; j < p.m.ksteps; ++j) {
+                tc::mma_f16_elect_lh(d, a, a_hi, b, b_hi, p.m.idesc, accf);
+                a += p.m.a_k16; b += p.m.b_k16; accf = 1u;
               }
             }
           }
-          if (lead) tc::mma_commit(&sh.empty[slot]);
+          tc::mma_commit_elect(&sh.empty[slot]);
           __syncwarp();
           started = 1;
           if (++seg_pos == p.m.seg_len) {   // segment complete: hand the accumulator to the epilogue
-            if (lead) tc::mma_commit(&sh.acc_full[acc]);
+            tc::mma_commit_elect(&sh.acc_full[acc]);
             __syncwarp();
             seg_pos = 0; open = 0; ++accq;
           }
@@ -556,7 +598,7 @@ pk_conv_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_constant_
       if (open || p.m.ntmpl[y] == 0) {      // last (partial) segment, or an output phase without any filter tap
         const uint32_t acc = accq & 1u, aph = (accq >> 1) & 1u;
         if (!open) tc::mbar_wait_soft(&sh.acc_empty[acc], aph ^ 1u, p.err, 702, &sh.abort);
-        if (lead) tc::mma_commit(&sh.acc_full[acc]);
+        tc::mma_commit_elect(&sh.acc_full[acc]);
         __syncwarp();
         ++accq;
       }
@@ -815,7 +857,7 @@ struct WgParams {
   struct Mma {
     uint32_t stg_per_split, nstg_total, NI, ksteps, ntap, Nc, npairs, st_mask, st_log2, stage16, sub16, dy_term16, x_off16,
         x_term16, x_kph16, idesc, dy_sbo, x_sbo, nsub;
-    uint32_t pair_a[MAXPAIR], pair_b[MAXPAIR];
+    uint32_t pair_a16[MAXPAIR], pair_b16[MAXPAIR];   // piece-plane offsets of the pairs (16-byte units)
     uint32_t tap_off[MAXTAP];       // x block start offset per tap (k-phase slot * x_kph16 + row offset), 16-byte units
   } m;
   int G, n_ktiles, n_ctiles, splits, stg_per_split, nstg_total, NI, nsub, row_tiles, TA, TX, nkph_used, kph_used[4];
@@ -894,14 +936,14 @@ pk_wgrad_kernel(const __grid_constant__ CUtensorMap dy0, const __grid_constant__
       }
     }
   } else if (warp == 1) {
-    const uint32_t lead = lane == 0;
+
     const uint64_t a_desc0 = tc::smem_desc_mnmajor_noswz(tc::smem_u32(smem), 128, p.m.dy_sbo);
     const uint64_t b_desc0 = tc::smem_desc_mnmajor_noswz(tc::smem_u32(smem), 128, p.m.x_sbo) + (uint64_t)p.m.x_off16;
     const uint32_t a_lo0 = (uint32_t)a_desc0, a_hi = (uint32_t)(a_desc0 >> 32), b_lo0 = (uint32_t)b_desc0, b_hi = (uint32_t)(b_desc0 >> 32);
     const uint32_t split_u = blockIdx.y;
     const uint32_t s0 = split_u * p.m.stg_per_split;
     const uint32_t s1 = min(p.m.nstg_total, s0 + p.m.stg_per_split);
-    uint32_t sc = 0, started = 0;
+    uint32_t sc = 0, accf = 0;
     for (uint32_t stg = s0; stg < s1; ++stg, ++sc) {
       const uint32_t slot = sc & p.m.st_mask, ph = (sc >> p.m.st_log2) & 1u;
       tc::mbar_wait_soft(&sh.full[slot], ph, p.err, 712, &sh.abort);
@@ -909,22 +951,21 @@ pk_wgrad_kernel(const __grid_constant__ CUtensorMap dy0, const __grid_constant__
       const uint32_t nsubs = min(p.m.NI, p.m.nsub - stg * p.m.NI);
       for (uint32_t si = 0; si < nsubs; ++si) {
         const uint32_t s16 = slot * p.m.stage16 + si * p.m.sub16;
-        for (uint32_t j = 0; j < p.m.ksteps; ++j) {
-          const uint32_t arow = s16 + j * 16u, brow = s16 + j * 16u;
+        uint32_t arow = a_lo0 + s16, brow = b_lo0 + s16;
+        for (uint32_t j = 0; j < p.m.ksteps; ++j, arow += 16u, brow += 16u) {
           for (uint32_t pr = 0; pr < p.m.npairs; ++pr) {
-            const uint32_t ad = a_lo0 + arow + p.m.pair_a[pr] * p.m.dy_term16;
-            const uint32_t b2 = b_lo0 + brow + p.m.pair_b[pr] * p.m.x_term16;
-            for (uint32_t t = 0; t < p.m.ntap; ++t)
-              tc::mma_f16_guarded_lh(tmem + t * p.m.Nc, ad, a_hi, b2 + p.m.tap_off[t], b_hi, p.m.idesc,
-                                     (started | si | j | pr) != 0u, lead);
+            const uint32_t ad = arow + p.m.pair_a16[pr], b2 = brow + p.m.pair_b16[pr];
+            uint32_t d = tmem;
+            for (uint32_t t = 0; t < p.m.ntap; ++t, d += p.m.Nc)
+              tc::mma_f16_elect_lh(d, ad, a_hi, b2 + p.m.tap_off[t], b_hi, p.m.idesc, accf);
           }
+          accf = 1u;
         }
       }
-      if (lead) tc::mma_commit(&sh.empty[slot]);
+      tc::mma_commit_elect(&sh.empty[slot]);
       __syncwarp();
-      started = 1;
     }
-    if (lead) tc::mma_commit(&sh.acc_full);
+    tc::mma_commit_elect(&sh.acc_full);
     __syncwarp();
   } else if (warp >= 4) {
     // partial[split][g][kt][ct][tap][c][k]: lanes = k -> coalesced
@@ -1012,6 +1053,26 @@ extern "C" int mnb_pk_pack_act(const float* x, int32_t batch, int32_t channels, 
   return 0;
 }
 
+extern "C" int mnb_bn_relu_quant_pack_fwd(const float* x, int32_t batch, int32_t channels, int32_t hw, const float* mean,
+                                          const float* invstd, const float* gamma, const float* beta,
+                                          const mnb_act_qparams* qp, int32_t out_shuffle_groups, void* x_packed,
+                                          uint32_t* pass_bits, mnb_stream_t stream) {
+  MNB_REQUIRE(x && mean && invstd && gamma && beta && qp && x_packed && pass_bits, "NULL bn_relu_quant_pack pointer");
+  MNB_REQUIRE(batch > 0 && channels > 0 && hw > 0, "bad bn_relu_quant_pack shape");
+  MNB_REQUIRE(qp->mode == MNB_ACT_DOREFA && qp->bits >= 2 && qp->bits <= 8, "the fused producer takes a DoReFa quantizer with 2..8 bits");
+  MNB_REQUIRE(out_shuffle_groups >= 1 && channels % out_shuffle_groups == 0, "shuffle groups %d do not divide %d channels",
+              out_shuffle_groups, channels);
+  if (channels % 8 || hw % 32 || (reinterpret_cast<uintptr_t>(x_packed) & 15))
+    return mnb_fail(MNB_E_UNSUPPORTED, "fused producer needs channels %% 8 == 0, H*W %% 32 == 0, 16-byte aligned output");
+  const int64_t warps = (int64_t)batch * (channels / 8) * (hw / 32);
+  const int blocks = (int)std::min<int64_t>(mnb_ceil_div(warps, 8), (int64_t)MNB_NUM_SMS * 16);
+  pk::bn_relu_quant_pack_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(x, batch, channels, hw, out_shuffle_groups, mean, invstd,
+                                                                       gamma, beta, *qp, pass_bits,
+                                                                       reinterpret_cast<uint4*>(x_packed));
+  MNB_LAUNCHED(1);
+  return 0;
+}
+
 // host only: out[16] = {wimg_bytes(lo), wimg_bytes(hi), Nt, n_ntiles, MT, CC, chunks, nstage, smem_bytes, tmem_cols, TH, TB,
 //                       BW, n_mtiles, n_items, ny}
 extern "C" int mnb_pk_conv_plan(const mnb_conv_shape* s, int32_t mode, int32_t terms_a, int32_t terms_w, int32_t* out16) {
@@ -1066,14 +1127,22 @@ extern "C" int mnb_pk_conv(const mnb_conv_shape* s, int32_t mode, const void* a_
   m.idesc = tc::make_idesc(1, 1, 1, 128, (uint32_t)pl.Nt);
   m.a_lbo = (uint32_t)pl.npos * 16u; m.b_lbo = (uint32_t)pl.Nt * 16u;
   m.seg_len = (uint32_t)pl.seg_len;
-  for (int i = 0; i < pl.npairs; ++i) { m.pair_a[i] = pl.pair_a[i]; m.pair_b[i] = pl.pair_b[i]; }
+  int nprog = 0;
   for (int y = 0; y < pl.ny; ++y) {
     m.ntmpl[y] = pl.ntmpl[y]; p.ntmpl[y] = pl.ntmpl[y];
     for (int t = 0; t < pl.ntmpl[y]; ++t) {
-      m.tmpl_tap0[y][t] = pl.tmpl[y][t].tap0; m.tmpl_ntap[y][t] = pl.tmpl[y][t].ntap;
-      p.tmpl_kph[y][t] = pl.tmpl[y][t].kph; p.tmpl_blk_off[y][t] = pl.tmpl[y][t].blk_off; p.tmpl_blk_bytes[y][t] = pl.tmpl[y][t].blk_bytes;
+      const Tmpl& tp = pl.tmpl[y][t];
+      p.tmpl_kph[y][t] = tp.kph; p.tmpl_blk_off[y][t] = tp.blk_off; p.tmpl_blk_bytes[y][t] = tp.blk_bytes;
+      m.tmpl_begin[y][t] = (uint16_t)nprog; m.tmpl_cnt[y][t] = (uint16_t)(tp.ntap * pl.npairs);
+      if (nprog + tp.ntap * pl.npairs > MAXPROG) return unsupported("MMA program longer than 384 entries");
+      for (int pr = 0; pr < pl.npairs; ++pr)          // piece pairs outermost: small products first
+        for (int i = 0; i < tp.ntap; ++i) {
+          const uint32_t a16 = (uint32_t)pl.tap_aoff[y][tp.tap0 + i] + (uint32_t)pl.pair_a[pr] * m.a_term16;
+          const uint32_t b16 = (uint32_t)i * m.b_tap16 + (uint32_t)pl.pair_b[pr] * (uint32_t)tp.ntap * m.b_tap16;
+          if (a16 > 0xffffu || b16 > 0xffffu) return mnb_fail(MNB_E_ARG, "pk conv: MMA program offset overflow");
+          m.prog[nprog++] = a16 | (b16 << 16);
+        }
     }
-    for (int i = 0; i < pl.ntap[y]; ++i) m.tap_aoff[y][i] = pl.tap_aoff[y][i];
     p.img_bytes[y] = pl.img_bytes[y]; p.y_off[y] = pl.y_off[y];
     p.zero_y[y] = pl.ntap[y] == 0;
     const int nstages = pl.ntmpl[y] * pl.chunks;
@@ -1134,7 +1203,7 @@ extern "C" int mnb_pk_wgrad(const mnb_conv_shape* s, const void* dy_pk, int32_t 
   m.x_term16 = (pl.nkph_used * pl.x_bytes) >> 4; m.x_kph16 = pl.x_bytes >> 4;
   m.idesc = tc::make_idesc_major(1, 1, 1, 128, (uint32_t)pl.Nc, 1, 1);
   m.dy_sbo = (uint32_t)pl.rows_dy * 16u; m.x_sbo = (uint32_t)pl.rows_x * 16u; m.nsub = pl.nsub;
-  for (int i = 0; i < pl.npairs; ++i) { m.pair_a[i] = pl.pair_a[i]; m.pair_b[i] = pl.pair_b[i]; }
+  for (int i = 0; i < pl.npairs; ++i) { m.pair_a16[i] = pl.pair_a[i] * m.dy_term16; m.pair_b16[i] = pl.pair_b[i] * m.x_term16; }
   for (int t = 0; t < pl.ntap; ++t) m.tap_off[t] = pl.kph_slot[pl.tap_kph[t]] * m.x_kph16 + pl.tap_off[t];
   p.G = pl.G; p.n_ktiles = pl.n_ktiles; p.n_ctiles = pl.n_ctiles; p.splits = pl.splits; p.stg_per_split = pl.stg_per_split;
   p.nstg_total = pl.nstg_total; p.NI = pl.NI; p.nsub = pl.nsub; p.row_tiles = pl.row_tiles; p.TA = pl.TA; p.TX = pl.TX;

@@ -158,6 +158,20 @@ __device__ __forceinline__ void mma_f16_guarded_lh(uint32_t d_tmem, uint32_t a_l
       ::"r"(d_tmem), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate), "r"(guard)
       : "memory");
 }
+// Warp-converged issue with the hardware election inside the instruction group: `elect.sync` tells ptxas that exactly
+// one lane issues, so no per-lane ELECT / BRA.U.ANY loop is generated around the UTCHMMA and uniform operands stay in
+// uniform registers.  All 32 lanes must execute this (converged).
+__device__ __forceinline__ void mma_f16_elect_lh(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
+                                                 uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p, q;\n\t.reg .b64 da, db;\n\t"
+      "elect.sync _|q, 0xffffffff;\n\t"
+      "setp.ne.b32 p, %6, 0;\n\t"
+      "mov.b64 da, {%1, %2};\n\tmov.b64 db, {%3, %4};\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t}"
+      ::"r"(d_tmem), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 __device__ __forceinline__ void mma_i8(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
                                        uint32_t accumulate) {
   asm volatile(
@@ -171,6 +185,16 @@ __device__ __forceinline__ void mma_i8(uint32_t d_tmem, uint64_t adesc, uint64_t
 __device__ __forceinline__ void mma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
                : "memory");
+}
+
+// commit issued by the SAME elected lane as mma_f16_elect_lh (elect.sync is deterministic for a given member mask): the
+// commit tracks the MMAs of the executing thread only.  Warp-converged.
+__device__ __forceinline__ void mma_commit_elect(uint64_t* bar) {
+  asm volatile(
+      "{\n\t.reg .pred q;\n\telect.sync _|q, 0xffffffff;\n\t"
+      "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}"
+      ::"r"(smem_u32(bar))
+      : "memory");
 }
 
 // TMEM -> registers: warp w (w % 4 selects the 32-lane quarter) reads 32 consecutive columns

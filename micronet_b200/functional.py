@@ -289,8 +289,9 @@ def _pk_terms(spec, w_int):
     return ta, (1 if w_int is not None else T)
 
 
-def _pk_forward(ctx, x, wq, bias, w_int, w_scale, spec, sh, y, need_dx):
-    """forward on the packed-operand tensor-core family; returns False when the shape is outside its cover"""
+def _pk_forward(ctx, x, wq, bias, w_int, w_scale, spec, sh, y, need_dx, prepacked=None):
+    """forward on the packed-operand tensor-core family; returns False when the shape is outside its cover.
+    ``prepacked``: the operand plane a fused producer (fused.BNReluQuantFn) already wrote - x itself holds no data then."""
     from . import pk as PK
     ta, tw = _pk_terms(spec, w_int)
     if not PK.supported(sh, 0, ta, tw):
@@ -303,7 +304,10 @@ def _pk_forward(ctx, x, wq, bias, w_int, w_scale, spec, sh, y, need_dx):
         return False
     qp = spec.struct() if spec is not None else None
     split = sh.stride_h == 2
-    x_pk, bits8 = PK.pack_act(x, qp, ta, phase_split=split, want_bits=need_dx)
+    if prepacked is not None:
+        x_pk, bits8 = prepacked, None      # the producer keeps the STE mask for its own backward
+    else:
+        x_pk, bits8 = PK.pack_act(x, qp, ta, phase_split=split, want_bits=need_dx)
     # frozen (inference) modules hang a dict on their cached weight tensor: the packed image is then built once
     src = w_int if w_int is not None else wq
     cache = getattr(src, "_mnb_pk_cache", None)
@@ -326,7 +330,7 @@ def _pk_forward(ctx, x, wq, bias, w_int, w_scale, spec, sh, y, need_dx):
         return False
     L.check(rc, "pk_conv fwd")
     ctx.pk = True
-    ctx.pk_x, ctx.pk_ta, ctx.pk_bits8, ctx.pk_a_scale = x_pk, ta, bits8, a_scale
+    ctx.pk_x, ctx.pk_ta, ctx.pk_bits8, ctx.pk_a_scale, ctx.pk_prepacked = x_pk, ta, bits8, a_scale, prepacked is not None
     return True
 
 
@@ -348,8 +352,10 @@ def _pk_backward(ctx, dy):
                                kzero=ctx.w_scale if int_w else None)
         dx = torch.empty((sh.batch, sh.in_c, sh.in_h, sh.in_w), dtype=torch.float32, device=dy.device)
         gain = 0.1 if (spec is not None and spec.mode == L.ACT_DOREFA) else 1.0
-        L.check(_timed("dgrad_pk", sh, lambda: PK.conv(sh, 1, dy_pk, T, w_img, tw, dx, bits8=ctx.pk_bits8, gain=gain)),
-                "pk_conv dgrad")
+        # a fused producer applies the STE mask itself (it owns the mask bits): plain data gradient times the quantizer's gain
+        plain_gain = gain if ctx.pk_prepacked else 1.0
+        L.check(_timed("dgrad_pk", sh, lambda: PK.conv(sh, 1, dy_pk, T, w_img, tw, dx, bits8=ctx.pk_bits8, gain=gain,
+                                                       a_scale_const=plain_gain)), "pk_conv dgrad")
     if need_dw:
         dwq = torch.empty_like(ctx.wq)
         a_scale = None
@@ -380,17 +386,28 @@ class QuantConv2dFn(Function):
             a_scale = spec.scale if spec.mode == L.ACT_IAO else _dorefa_scale_tensor(spec.bits, x.device)
         done = False
         ctx.pk = False
-        if L.PK_MODE != "off" and x.dtype == torch.float32 and (L.PK_MODE == "all" or spec is not None):
+        pkq = getattr(x, "_mnb_pk_q", None)   # operand plane written by a fused BN + ReLU + quantizer producer
+        if pkq is not None:
+            if spec is None or spec.mode != L.ACT_DOREFA or spec.bits != pkq[1] or w_int is None:
+                raise RuntimeError("micronet_b200: a fused producer's packed output reached a conv with another quantizer")
+            done = _pk_forward(ctx, x, wq, bias, w_int, w_scale, spec, sh, y, ctx.needs_input_grad[0], prepacked=pkq[0])
+            if not done:
+                raise RuntimeError("micronet_b200: fused producer output in front of a conv outside the packed-operand cover")
+        if not done and L.PK_MODE != "off" and x.dtype == torch.float32 and (L.PK_MODE == "all" or spec is not None):
             done = _pk_forward(ctx, x, wq, bias, w_int, w_scale, spec, sh, y, ctx.needs_input_grad[0])
-        if not done and packed is not None and spec is None and w_int is not None and packed.numel() == x.numel():
-            wpack = torch.empty(w_int.numel(), dtype=torch.int16, device=x.device)
-            rc = _timed("fwd_packed_tc", sh, lambda: lib.mnb_fq_conv2d_fwd_packed_tc(
-                C.byref(sh), packed.data_ptr(), w_int.data_ptr(), w_scale.data_ptr(), L.ptr(bias), y.data_ptr(),
-                wpack.data_ptr(), L.tc_err_flag(x.device).data_ptr(), L.stream()))
-            if rc == 0:
-                done = True
-            elif rc != L.E_UNSUPPORTED:
-                L.check(rc, "fq_conv2d_fwd_packed_tc")
+        if not done and packed is not None and spec is None and w_int is not None and packed.numel() == x.numel() \
+                and L.PK_MODE != "off" and sh.stride_h == 1:
+            # the BatchNorm + binarizer producer also wrote its +-1 output as the bf16 plane the packed-operand family
+            # reads (fused.BNSignFn): forward = TMA -> MMA -> epilogue on 2 B/element, no pack pass, no converter warps.
+            # The backward of this layer stays on the fused kernels below (they re-read the fp32 tensor).
+            from . import pk as PK
+            if PK.supported(sh, 0, 1, 1):
+                w_img = PK.pack_weight(sh, 0, 1, 1, w_int=w_int)
+                rc = _timed("fwd_pk", sh, lambda: PK.conv(sh, 0, packed, 1, w_img, 1, y, n_scale=w_scale, bias=bias))
+                if rc == 0:
+                    done = True
+                elif rc != L.E_UNSUPPORTED:
+                    L.check(rc, "pk_conv fwd (packed producer)")
         if not done and L.USE_TC and w_int is not None and x.dtype == torch.float32:
             # fused tcgen05 path: quantize inside the operand staging of the tensor-core conv
             qp = None

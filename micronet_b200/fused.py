@@ -134,6 +134,89 @@ class BatchNormBinarize2d(nn.BatchNorm2d):
         return super().extra_repr() + f", pool2={self.pool2}, out_shuffle_groups={self.out_shuffle_groups}"
 
 
+
+class BNReluQuantFn(Function):
+    """BatchNorm2d -> ReLU -> DoReFa activation quantizer of the NEXT conv, written as that conv's packed bf16 operand.
+    The returned fp32 tensor is a shape-carrying placeholder (never written, never read): its only consumer is the
+    engine QuantConv2d the rewrite pass found behind this block, which reads ``_mnb_pk_q`` instead."""
+
+    @staticmethod
+    def forward(ctx, x, gamma, beta, mean, invstd, training, shuffle_groups, a_bits):
+        from . import functional as F_
+        lib = L.load()
+        x = x.contiguous()
+        b, c = x.shape[0], x.shape[1]
+        hw = x.numel() // (b * c)
+        bits = torch.empty((x.numel() + 31) // 32, dtype=torch.int32, device=x.device)
+        packed = torch.empty(x.numel() * 2, dtype=torch.uint8, device=x.device)
+        qp = F_.ActSpec(L.ACT_DOREFA, bits=a_bits).struct()
+        L.check(lib.mnb_bn_relu_quant_pack_fwd(x.data_ptr(), b, c, hw, mean.data_ptr(), invstd.data_ptr(), gamma.data_ptr(),
+                                               beta.data_ptr(), C.byref(qp), shuffle_groups, packed.data_ptr(),
+                                               bits.data_ptr(), L.stream()), "bn_relu_quant_pack_fwd")
+        y = torch.empty_like(x)                      # placeholder: allocation only, no kernel
+        y._mnb_pk_q = (packed, a_bits)               # picked up by QuantConv2dFn.forward
+        ctx.save_for_backward(x, gamma, mean, invstd)
+        ctx.bits, ctx.training, ctx.shuffle_groups = bits, training, shuffle_groups
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        # g = d loss / d (quantized conv input) already multiplied by the quantizer's 0.1 (the conv's data-gradient epilogue);
+        # the combined mask relu'(bn) * [0.1 bn <= 1] and the BatchNorm backward are mnb_bn_sign_bwd's job
+        lib = L.load()
+        x, gamma, mean, invstd = ctx.saved_tensors
+        g = g.contiguous()
+        b, c = x.shape[0], x.shape[1]
+        hw = x.numel() // (b * c)
+        dx = torch.empty_like(x)
+        out = torch.empty(3 * c, dtype=torch.float32, device=x.device)
+        dgamma, dbeta, dx_sum = out[:c], out[c:2 * c], out[2 * c:]
+        L.check(lib.mnb_bn_sign_bwd(g.data_ptr(), ctx.bits.data_ptr(), x.data_ptr(), b, c, hw, mean.data_ptr(),
+                                    invstd.data_ptr(), gamma.data_ptr(), 1 if ctx.training else 0, ctx.shuffle_groups,
+                                    dx.data_ptr(), dgamma.data_ptr(), dbeta.data_ptr(), dx_sum.data_ptr(),
+                                    L.scratch(x.device, c).data_ptr(), L.stream()), "bn_sign_bwd")
+        dx._mnb_channel_sum = dx_sum
+        return dx, dgamma, dbeta, None, None, None, None, None
+
+
+class BatchNormReluQuant2d(nn.BatchNorm2d):
+    """nn.BatchNorm2d + nn.ReLU + the DoReFa activation quantizer (``a_bits``) of the QuantConv2d that consumes this block's
+    output, in one pass (SURVEY.md 8 f2).  Parameters, buffers and state_dict keys are those of the BatchNorm2d it replaces;
+    ``out_shuffle_groups`` as in BatchNormBinarize2d.  Planes outside the fused kernel's cover (C % 8, H*W % 32) fall back
+    to the un-fused sequence."""
+
+    out_shuffle_groups = 1
+    a_bits = 8
+
+    def forward(self, input):
+        L.require_cuda(input, self.weight)
+        L.require_f32(input, self.weight)
+        b, c = input.shape[0], input.shape[1]
+        hw = input.numel() // max(1, b * c)
+        sg = int(self.out_shuffle_groups)
+        if input.dim() != 4 or c % 8 or hw % 32:
+            y = TF.relu(super().forward(input))
+            if sg > 1:
+                y = y.view(b, sg, c // sg, *y.shape[2:]).transpose(1, 2).contiguous().view_as(y)
+            return y
+        if self.training:
+            lib = L.load()
+            x = input.detach().contiguous()
+            stats = torch.empty(2 * c, dtype=torch.float32, device=x.device)
+            L.check(lib.mnb_bn_batch_stats(x.data_ptr(), b, c, hw, float(self.eps), float(self.momentum),
+                                           self.running_mean.data_ptr(), self.running_var.data_ptr(),
+                                           self.num_batches_tracked.data_ptr(), stats.data_ptr(),
+                                           L.scratch(x.device, c).data_ptr(), L.stream()), "bn_batch_stats")
+            mean, invstd = stats[:c], stats[c:]
+        else:
+            mean = self.running_mean
+            invstd = torch.rsqrt(self.running_var + self.eps)
+        return BNReluQuantFn.apply(input, self.weight, self.bias, mean, invstd, self.training, sg, int(self.a_bits))
+
+    def extra_repr(self):
+        return super().extra_repr() + f", relu + dorefa a_bits={self.a_bits}, out_shuffle_groups={self.out_shuffle_groups}"
+
+
 class MaxPoolFn(Function):
     @staticmethod
     def forward(ctx, x, k, s, p, shuffle_groups):
@@ -280,11 +363,11 @@ def _fuse_pairs(module: nn.Module):
 
 def _tail_producer(m: nn.Module):
     """the module whose output IS ``m``'s output, if it is one of the shuffling producers"""
-    if isinstance(m, (BatchNormBinarize2d, EngineMaxPool2d)):
+    if isinstance(m, (BatchNormBinarize2d, BatchNormReluQuant2d, EngineMaxPool2d)):
         return m
     if hasattr(m, "channel_shuffle_flag"):  # the reference's conv-bn-act block: children run in order
         kids = [k for k in m.children() if not isinstance(k, nn.Identity)]
-        if kids and isinstance(kids[-1], BatchNormBinarize2d):
+        if kids and isinstance(kids[-1], (BatchNormBinarize2d, BatchNormReluQuant2d)):
             return kids[-1]
     return None
 
@@ -323,9 +406,55 @@ def _fold_shuffles(module: nn.Module):
         blk.channel_shuffle_flag = 0
 
 
+def _first_conv(m: nn.Module):
+    """the conv that consumes ``m``'s input first, if ``m`` is a conv or one of the reference's conv-bn-act blocks"""
+    if isinstance(m, nn.Conv2d):
+        return m
+    if hasattr(m, "channel_shuffle_flag"):
+        kids = [k for k in m.children() if not isinstance(k, nn.Identity)]
+        if kids and isinstance(kids[0], nn.Conv2d):
+            return kids[0]
+    return None
+
+
+def _fuse_dorefa_producers(module: nn.Module):
+    """conv-bn-relu block directly followed (in an nn.Sequential) by a block whose first conv is a DoReFa QuantConv2d with a
+    2..8-bit activation quantizer: BatchNorm2d + ReLU + that quantizer + operand packing become one producer"""
+    from .dorefa import QuantConv2d as DorefaConv
+    for child in module.children():
+        _fuse_dorefa_producers(child)
+    if not isinstance(module, nn.Sequential) or "mnb_bn_relu_quant_pack_fwd" not in L.PROTOTYPES:
+        return
+    kids = [k for k in module.children() if not isinstance(k, nn.Identity)]
+    for prev, nxt in zip(kids, kids[1:]):
+        conv = _first_conv(nxt)
+        a_bits = int(conv.activation_quantizer.a_bits) if isinstance(conv, DorefaConv) else 0
+        if not (2 <= a_bits <= 8) or conv.in_channels % 8 or tuple(conv.stride) != (1, 1) or conv.quant_inference:
+            continue
+        if not hasattr(prev, "channel_shuffle_flag"):
+            continue
+        names = [n for n, k in prev.named_children() if not isinstance(k, nn.Identity)]
+        if len(names) < 2:
+            continue
+        bn, act = prev._modules[names[-2]], prev._modules[names[-1]]
+        if type(bn) is not nn.BatchNorm2d or type(act) is not nn.ReLU:
+            continue
+        if not (bn.affine and bn.track_running_stats and bn.momentum is not None):
+            continue
+        fused = BatchNormReluQuant2d(bn.num_features, eps=bn.eps, momentum=bn.momentum)
+        fused.weight, fused.bias = bn.weight, bn.bias
+        fused.running_mean, fused.running_var = bn.running_mean, bn.running_var
+        fused.num_batches_tracked = bn.num_batches_tracked
+        fused.a_bits = a_bits
+        fused.train(bn.training)
+        prev._modules[names[-2]] = fused
+        prev._modules[names[-1]] = nn.Identity()
+
+
 def fuse_wbwtab_blocks(model: nn.Module, fold_shuffle: bool = True) -> nn.Module:
     _fuse_pairs(model)
     _fold_pools(model)
+    _fuse_dorefa_producers(model)
     if fold_shuffle:
         _fold_shuffles(model)
     return model

@@ -1,7 +1,7 @@
-"""EXPERIMENTAL packed-operand path (micronet_b200/csrc/mnb_conv_packed.cu): skipped unless MNB_PACKED_OPERANDS=1.
-The path is round-2 groundwork and has not run on hardware yet; these tests are its acceptance gate:
-
-    MNB_PACKED_OPERANDS=1 python -m pytest tests/test_gpu_packed_experimental.py -m gpu -x -q"""
+"""Packed operands from the BatchNorm + binarizer producer (fused.BNSignFn -> mnb_bn_sign_fwd_packed) to the forward of
+the next convolution on the packed-operand tensor-core family (mnb_pk.cu): the producer's bf16 plane must be exactly
+the +-1 output in [B][C/8][H][W][8] order (producer's OUTPUT channel order), and the convolution fed by it must equal
+an fp64 convolution of the fp32 tensor; the backward of such a layer must match the un-packed path."""
 import os
 
 import pytest
@@ -11,8 +11,7 @@ import torch.nn.functional as TF
 from tests.oracle_util import rel_err
 
 pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("MNB_PACKED_OPERANDS", "0") != "1",
-                                 reason="experimental path, enable with MNB_PACKED_OPERANDS=1")]
+              pytest.mark.skipif(os.environ.get("MNB_PACKED_OPERANDS", "1") != "1", reason="packed producer switched off")]
 DEV = "cuda"
 
 # B, C, H, W, K, R, groups, shuffle groups of the producer
@@ -52,3 +51,39 @@ def test_packed_producer_and_conv_match_the_unpacked_path(case):
     L.tc_check()
     ref = TF.conv2d(y.detach().double().cpu(), wq.double().cpu(), bias.double().cpu(), 1, R // 2, 1, G)
     assert rel_err(out.detach(), ref) < 2e-6
+
+
+@pytest.mark.parametrize("case", CASES[:5], ids=[str(c) for c in CASES[:5]])
+def test_block_with_packed_forward_has_the_same_gradients(case):
+    """BatchNorm+binarizer -> conv, forward through the packed plane, backward on the fused kernels: identical to the
+    un-packed path (same kernels in the backward, same +-1 operand in the forward)"""
+    from micronet_b200 import _lib as L, functional as F_
+    from micronet_b200.fused import BatchNormBinarize2d
+    B, C, H, W, K, R, G, sg = case
+    torch.manual_seed(sum(case) + 1)
+    x0 = (torch.randn(B, C, H, W) * 1.5).to(DEV)
+    w_int = torch.randint(-1, 2, (K, C // G, R, R), dtype=torch.int16).to(DEV)
+    w_scale = (torch.rand(K) * 0.02 + 0.001).to(DEV)
+    go = torch.randn(B, K, H, W).to(DEV)
+    res = {}
+    for flag in (True, False):
+        L.USE_PACKED = flag
+        try:
+            torch.manual_seed(5)
+            bn = BatchNormBinarize2d(C).to(DEV).train()
+            bn.out_shuffle_groups = sg
+            x = x0.clone().requires_grad_(True)
+            wq = (w_int.float() * w_scale.view(-1, 1, 1, 1)).requires_grad_(True)
+            F_.TIMER = F_.KernelTimer()
+            out = F_.quant_conv2d(bn(x), wq, None, w_int, w_scale, None, (1, 1), (R // 2, R // 2), (1, 1), G)
+            out.backward(go)
+            torch.cuda.synchronize()
+            kinds = {k for k, _, _, _ in F_.TIMER.records}
+            res[flag] = (out.detach(), x.grad, wq.grad, bn.weight.grad, kinds)
+        finally:
+            L.USE_PACKED = True
+            F_.TIMER = None
+    assert "fwd_pk" in res[True][4] and "fwd_pk" not in res[False][4], (res[True][4], res[False][4])
+    for a, b in zip(res[True][:4], res[False][:4]):
+        assert rel_err(a, b) <= 1e-6
+    L.tc_check()
