@@ -210,10 +210,10 @@ def run_engine(workload, steps, warmup, dev, rank, world, detail):
     host = [H.synthetic_batch(B, w["hw"], seed=100 + rank * 17 + i, pin=True) for i in range(nbuf)]
     devb = [(x.to(dev), t.to(dev)) for x, t in host]
     if inference:
-        stepper = H.InferStepper(model)
+        stepper = H.InferStepper(model, graph=os.environ.get("MNB_GRAPH", "1") == "1")
         stepper.calibrate([devb[i][0][: max(2, B // 8)] for i in range(w.get("calib_batches", 2))])
     else:
-        stepper = H.QatStepper(model, lr=0.01, wd=w["wd"], flat=True)
+        stepper = H.QatStepper(model, lr=0.01, wd=w["wd"], flat=True, graph=os.environ.get("MNB_GRAPH", "1") == "1")
 
     def barrier():
         if world > 1:
@@ -249,30 +249,44 @@ def run_engine(workload, steps, warmup, dev, rank, world, detail):
     sampler = ClockSampler(dev.index or 0) if detail and rank == 0 else None
     if sampler:
         sampler.start()  # started before the warm-up so that nvidia-smi is already streaming in the timed region
-    for i in range(warmup):
-        step_resident(i)
+    for i in range(max(warmup, 5 if getattr(stepper, "graph_wanted", False) else 0)):
+        step_resident(i)   # (a graph-replaying stepper captures after 3 eager steps: keep >= 2 replays in the warm-up)
     if sampler:
         sampler.mark()
-    launches0 = L.launch_count()
-    if detail:
-        F_.TIMER = F_.KernelTimer()
     ms_total = timed(step_resident, steps)
     torch.cuda.synchronize()
-    timer, F_.TIMER = F_.TIMER, None
-    launches = L.launch_count() - launches0
     L.tc_check()   # a bounded pipeline wait that gave up would have produced garbage: fail loudly instead
     clocks = sampler.stop() if sampler else None
     for i in range(2):
         step_e2e(i)
     ms_e2e = timed(step_e2e, steps)
     L.tc_check()
+    # per-kernel CUDA-event timings and the launch count come from an adjacent EAGER pass of the same stepper (a replayed
+    # graph runs the same kernels without going through the Python wrappers that place the events)
+    graph_used = getattr(stepper, "graph", None) is not None
+    saved = (getattr(stepper, "graph", None), getattr(stepper, "graph_wanted", False))
+    if hasattr(stepper, "graph"):
+        stepper.graph, stepper.graph_wanted = None, False
+    timer = None
+    launches0 = L.launch_count()
+    dsteps = min(steps, 3)
+    if detail:
+        F_.TIMER = F_.KernelTimer()
+    ms_detail = timed(step_resident, dsteps)
+    torch.cuda.synchronize()
+    timer, F_.TIMER = F_.TIMER, None
+    launches = (L.launch_count() - launches0) * steps // dsteps
+    if hasattr(stepper, "graph"):
+        stepper.graph, stepper.graph_wanted = saved
     imgs = B * world * steps
     res = {"workload": workload, "metric": metric_name(workload), "value": imgs / (ms_total / 1e3), "unit": "img/s",
            "ms_per_step": ms_total / steps, "steps": steps, "warmup": warmup, "per_gpu_batch": B,
            "e2e": {"value": imgs / (ms_e2e / 1e3), "unit": "img/s", "ms_per_step": ms_e2e / steps,
                    "h2d_bytes_per_step": (B * 3 * w["hw"] * w["hw"] * 4 + B * 8) * world,
                    "d2h_bytes_per_step": (B * 10 * 4 if inference else 4) * world},
-           "gpu_launches": int(launches), "clocks": clocks, "timer": timer, "ms_total": ms_total}
+           "gpu_launches": int(launches), "clocks": clocks, "timer": timer, "ms_total": ms_detail * steps / dsteps,
+           "cuda_graph": {"used": bool(graph_used), "error": getattr(stepper, "graph_error", None),
+                          "eager_ms_per_step": ms_detail / dsteps}}
     del stepper, model
     torch.cuda.empty_cache()
     return res
@@ -367,7 +381,7 @@ def main():
             "vs_baseline": None,
             "dtype": "f32 (bf16 tensor-core products of exact integer levels / exact bf16 pieces, fp32 accumulate)",
             "data": "synthetic", "config": config_dict(wl, world), "clocks": main_res["clocks"], "e2e": main_res["e2e"],
-            "gpu_launches": main_res["gpu_launches"], "roofline": roof}
+            "gpu_launches": main_res["gpu_launches"], "cuda_graph": main_res["cuda_graph"], "roofline": roof}
     if world == 1 and not args.no_extra:
         # the other BASELINE.json configs, a few steps each, so that the driver-run record covers them too
         extras = []

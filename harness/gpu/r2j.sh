@@ -1,0 +1,9 @@
+#!/bin/bash
+O=gpurun_out/r2j; mkdir -p $O
+timeout 900 python -m pytest tests -m gpu -q -p no:cacheprovider > $O/full.log 2>&1
+echo "== full rc=$?"; grep -E "^FAILED|passed|failed" $O/full.log | cut -c1-250 | tail -20
+timeout 600 python -m harness.pk_probe --json $O/pk_probe.json > $O/pk_probe.log 2>&1; echo "== probe rc=$?"; tail -2 $O/pk_probe.log | cut -c1-200
+for w in nin_gc_wbwtab_w3a2 nin_gc_dorefa_w4a4 nin_dorefa_w8a8 resnet18_iao_w8a8_bnfuse resnet18_iao_ptq_224; do
+  timeout 600 python bench.py --workload $w --steps 10 --warmup 3 --no-cpu-baseline --no-extra --kernels-json $O/k_$w.json > $O/bench_$w.log 2>&1
+  echo "== bench $w rc=$?"; tail -1 $O/bench_$w.log | cut -c1-200; tail -1 $O/bench_$w.log | python -c "import sys,json; d=json.loads(sys.stdin.read()); print('   graph', d.get('cuda_graph'))"
+done

@@ -170,8 +170,10 @@ def tc_check(device=None):
 E_UNSUPPORTED = -2
 KEEP_DEBUG = False   # tests only: modules keep the fake-quantized weight of their last call
 USE_TC = os.environ.get("MNB_DISABLE_TC", "0") != "1"
-# packed bf16 operands from the BN+binarizer producer to the next conv's forward (MNB_PACKED_OPERANDS=0 turns it off)
-USE_PACKED = os.environ.get("MNB_PACKED_OPERANDS", "1") == "1"
+# packed bf16 operands from the BN+binarizer producer to the next conv's forward.  Measured (r2h): the convs gain 0.1 ms per
+# step (fwd 158 -> 120 us on the 256-channel 1x1) but the producer's extra 2 B / element plane and its scalar form cost 0.7 ms,
+# so it stays opt-in (MNB_PACKED_OPERANDS=1) until the producer is vectorised and stops writing the fp32 plane as well
+USE_PACKED = os.environ.get("MNB_PACKED_OPERANDS", "0") == "1"
 # packed-operand tensor-core family (mnb_pk.cu): "auto" = wherever the fused kernels have no cover and for every fused-quantizer
 # layer; "all" = every conv it supports; "off" = never
 PK_MODE = os.environ.get("MNB_PK", "auto")

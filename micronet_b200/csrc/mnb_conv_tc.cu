@@ -39,8 +39,10 @@ int mnb_make_tmap(CUtensorMap* out, const void* base, int elem_bytes, int rank, 
                   const uint32_t* box) {
   EncodeTiledFn enc = get_encode_tiled();
   if (!enc) return mnb_fail(MNB_E_UNSUPPORTED, "cuTensorMapEncodeTiled is not available from this driver");
-  // driver-API call: make sure this host thread (e.g. an autograd worker) has the primary context bound
-  cudaFree(nullptr);
+  // driver-API call: make sure this host thread (e.g. an autograd worker) has the primary context bound - once per
+  // thread (a cudaFree inside a stream capture would invalidate the capture)
+  static thread_local bool ctx_bound = false;
+  if (!ctx_bound) { cudaFree(nullptr); ctx_bound = true; }
   cuuint64_t gdim[5], gstr[5];
   cuuint32_t bdim[5], estr[5];
   uint64_t stride = (uint64_t)elem_bytes;
@@ -64,7 +66,7 @@ int mnb_make_tmap_strided(CUtensorMap* out, const void* base, int elem_bytes, in
                           const uint64_t* strides_bytes, const uint32_t* box) {
   EncodeTiledFn enc = get_encode_tiled();
   if (!enc) return mnb_fail(MNB_E_UNSUPPORTED, "cuTensorMapEncodeTiled is not available from this driver");
-  cudaFree(nullptr);
+  { static thread_local bool ctx_bound = false; if (!ctx_bound) { cudaFree(nullptr); ctx_bound = true; } }
   cuuint64_t gdim[5], gstr[5];
   cuuint32_t bdim[5], estr[5];
   for (int i = 0; i < rank; ++i) {

@@ -39,7 +39,7 @@ namespace pk {
 
 constexpr int NTHREADS = 256;      // warp 0 TMA, warp 1 MMA issue, warp 2 TMEM alloc, warps 4..7 epilogue
 constexpr int MAXST = 8;           // operand ring (power of two: ring index = counter & mask)
-constexpr int MAXTAP = 64, MAXTMPL = 16, MAXY = 4, MAXPAIR = 6, MAXPROG = 384;
+constexpr int MAXTAP = 64, MAXTMPL = 16, MAXY = 4, MAXPAIR = 6, MAXPROG = 512;
 constexpr int kSmemBudget = 227 * 1024 - 3072;   // dynamic shared memory the kernels may ask for
 
 // ---------------------------------------------------------------------------------------------------------
@@ -181,8 +181,17 @@ static int make_plan(const mnb_conv_shape* s, int mode, int TA, int TBk, Plan& p
   else p.Nt = 128;
   p.n_ntiles = ceil_div(p.ng, p.Nt);
   p.MT = 1;
-  if (!p.segmented && p.Nt <= 128 && p.n_mtiles >= 2 &&
-      (int64_t)ceil_div(p.n_mtiles, 2) * p.n_ntiles * G * p.ny >= 120) p.MT = 2;
+  if (!p.segmented && p.Nt <= 128 && p.n_mtiles >= 2) {
+    // two M tiles per work item halve the weight traffic of an item, but the items are dealt to 148 persistent CTAs:
+    // take the pairing only if it does not cost wave efficiency (172 items of a 512-channel 4x4 layer = 2 rounds for
+    // some SMs, 1 for the others: 58 %)
+    auto wave_eff = [&](int mt) {
+      const int64_t items = (int64_t)ceil_div(p.n_mtiles, mt) * p.n_ntiles * G;
+      const int64_t ctas = std::max<int64_t>(1, MNB_NUM_SMS / p.ny);
+      return (double)items / (double)(ceil_div((int)std::min<int64_t>(items, 1 << 30), (int)ctas) * ctas);
+    };
+    if (wave_eff(2) >= wave_eff(1) - 0.04 && (int64_t)ceil_div(p.n_mtiles, 2) * p.n_ntiles * G * p.ny >= 120) p.MT = 2;
+  }
   if (const char* e = getenv("MNB_PK_MT")) { const int v = atoi(e); if (v == 1 || (v == 2 && p.Nt <= 128 && !p.segmented)) p.MT = v; }
   p.n_mgroups = ceil_div(p.n_mtiles, p.MT);
   p.n_items = p.n_mgroups * p.n_ntiles * G;
@@ -277,27 +286,28 @@ __global__ void __launch_bounds__(256) pack_act_kernel(const float* __restrict__
                                                        int terms, const float* __restrict__ ch_scale, mnb_act_qparams qp,
                                                        int a_off, int phase_split, uint4* __restrict__ out,
                                                        int64_t plane_vecs, uint8_t* __restrict__ bits8) {
-  const int64_t total = (int64_t)B * C8 * H * W;
   MnbActQ q;
   float zp = 0.f;
   if (QUANT) {
     q = mnb_load_actq(qp);
     if (qp.mode == MNB_ACT_IAO && qp.zero_point) zp = __ldg(qp.zero_point);
   }
-  const int64_t HW = (int64_t)H * W;
-  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
-    const int w = (int)(idx % W);
-    int64_t t = idx / W;
-    const int h = (int)(t % H);
-    t /= H;
-    const int c8 = (int)(t % C8), b = (int)(t / C8);
+  // grid = (chunks of the H*W plane, B * C8 planes): 32-bit index arithmetic only (the first version decoded a flat
+  // 64-bit index with five divisions per pixel and ran at 0.9 TB/s)
+  const uint32_t HW = (uint32_t)H * (uint32_t)W;
+  // block = (positions, planes): small images put several planes into one 256-thread block
+  const uint32_t plane = blockIdx.y * blockDim.y + threadIdx.y;                 // b * C8 + c8
+  if (plane >= (uint32_t)B * (uint32_t)C8) return;
+  const uint32_t b = plane / (uint32_t)C8, c8 = plane - b * (uint32_t)C8;
+  for (uint32_t pos = blockIdx.x * blockDim.x + threadIdx.x; pos < HW; pos += gridDim.x * blockDim.x) {
+    const int64_t idx = (int64_t)plane * HW + pos;
     float v[8];
     uint32_t passbits = 0;
-    const float* src = x + ((int64_t)b * C + c8 * 8) * HW + (int64_t)h * W + w;
+    const float* src = x + ((int64_t)b * C + c8 * 8) * HW + pos;
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      const int c = c8 * 8 + j;
-      float val = c < C ? __ldg(src + j * HW) : 0.f;
+      const int c = (int)c8 * 8 + j;
+      float val = c < C ? __ldg(src + (int64_t)j * HW) : 0.f;
       if (QUANT) {
         bool pass;
         const float lev = mnb_act_level_certified(q, val, pass);   // level itself (code + a_off), no int round trip
@@ -310,7 +320,8 @@ __global__ void __launch_bounds__(256) pack_act_kernel(const float* __restrict__
     }
     int64_t dst;
     if (phase_split) {
-      const int oct = ((h & 1) * 2 + (w & 1)) * C8 + c8;
+      const uint32_t h = pos / (uint32_t)W, w = pos - h * (uint32_t)W;
+      const uint32_t oct = ((h & 1u) * 2u + (w & 1u)) * (uint32_t)C8 + c8;
       dst = (((int64_t)b * 4 * C8 + oct) * (H >> 1) + (h >> 1)) * (W >> 1) + (w >> 1);
     } else {
       dst = idx;
@@ -575,14 +586,17 @@ pk_conv_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_constant_
           for (uint32_t mt = 0; mt < p.m.MT; ++mt) {
             const uint32_t d = tmem + (acc * p.m.MT + mt) * p.m.Nt;
             const uint32_t a_base = a_lo0 + s16 + mt * p.m.a_mt16, b_base = b_lo0 + s16;
-            uint32_t accf = started;
-            for (uint32_t e = 0; e < pc; ++e) {
+            // flat program: one word per MMA of this stage template (tap x piece pair x K-step).  The first MMA of a
+            // segment overwrites the accumulator; the rest is a straight unrolled stream of independent
+            // load-word / add / add / MMA groups (a single warp issues them: dependent chains cost MMA rate)
+            {
+              const uint32_t w = p.m.prog[pb];
+              tc::mma_f16_elect_lh(d, a_base + (w & 0xffffu), a_hi, b_base + (w >> 16), b_hi, p.m.idesc, started);
+            }
+#pragma unroll 4
+            for (uint32_t e = 1; e < pc; ++e) {
               const uint32_t w = p.m.prog[pb + e];
-              uint32_t a = a_base + (w & 0xffffu), b = b_base + (w >> 16);
-              for (uint32_t j = 0; j < p.m.ksteps; ++j) {
-                tc::mma_f16_elect_lh(d, a, a_hi, b, b_hi, p.m.idesc, accf);
-                a += p.m.a_k16; b += p.m.b_k16; accf = 1u;
-              }
+              tc::mma_f16_elect_lh(d, a_base + (w & 0xffffu), a_hi, b_base + (w >> 16), b_hi, p.m.idesc, 1u);
             }
           }
           tc::mma_commit_elect(&sh.empty[slot]);
@@ -727,9 +741,14 @@ static int make_pk_tmap(CUtensorMap* m, const void* base, int64_t plane_bytes, i
 
 template <typename K>
 static int set_max_smem(K kernel, int bytes) {
-  // per device (the attribute is a property of the function on the current device), cheap enough to repeat
+  // the attribute is a property of the function on a device: set it once per (function, device)
+  static bool done[64] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev >= 0 && dev < 64 && done[dev]) return 0;
   cudaError_t ce = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
   if (ce != cudaSuccess) return mnb_fail((int)ce, "cudaFuncSetAttribute: %s", cudaGetErrorString(ce));
+  if (dev >= 0 && dev < 64) done[dev] = true;
   return 0;
 }
 
@@ -739,9 +758,9 @@ static int set_max_smem(K kernel, int bytes) {
 struct WgPlan {
   int B, G, R, S, stride, ntap;
   int P, Q, K8, HX, WX, C8X, nkph;      // dy dims / octets; x planes as stored
-  int cin_g, cout_g;
+  int cin_g, cout_g, gm;       // channels per (merged) group; gm = original groups per merged group
   int hlo, hhi, wlo, whi, BW, TH, THH, rows_dy, rows_x, row_tiles;
-  int Nc, n_ctiles, n_ktiles, NI, nsub, nstg_total, splits, stg_per_split;
+  int Nc, n_ctiles, n_ktiles, tpg, n_tg, NI, nsub, nstg_total, splits, stg_per_split;
   int TA, TX, npairs, pair_a[MAXPAIR], pair_b[MAXPAIR];
   int tap_kph[MAXTAP], tap_off[MAXTAP];   // per tap: k-phase plane and start-row offset in the x block
   int kph_used[4], nkph_used, kph_slot[4];
@@ -765,6 +784,13 @@ static int make_wg_plan(const mnb_conv_shape* s, int TA, int TX, WgPlan& p) {
   if (p.P < 1 || p.Q < 1) return mnb_fail(MNB_E_UNSUPPORTED, "pk wgrad: empty output");
   p.cin_g = C / G; p.cout_g = K / G;
   if (G > 1 && ((p.cin_g % 8) || (p.cout_g % 8))) return mnb_fail(MNB_E_UNSUPPORTED, "pk wgrad: grouped conv needs channels per group % 8 == 0");
+  // Small groups are MERGED: gm neighbouring groups form one 128-row accumulator block (rows = their output channels,
+  // columns = their input channels); an MMA costs 61 cycles whether it is 128 x 16 or 128 x 64, so computing the discarded
+  // off-diagonal blocks is free and the MMA count drops by gm.  The reduction kernel keeps the diagonal blocks only.
+  p.gm = 1;
+  while (G % (p.gm * 2) == 0 && p.gm * 2 * p.cout_g <= 128 && p.gm * 2 * p.cin_g <= 256) p.gm *= 2;
+  if (const char* e = getenv("MNB_PK_WG_MERGE")) { if (atoi(e) == 0) p.gm = 1; }
+  p.G = G / p.gm; p.cin_g *= p.gm; p.cout_g *= p.gm;
   p.K8 = ceil_div(K, 8); p.C8X = ceil_div(C, 8);
   p.nkph = st == 2 ? 4 : 1; p.HX = H / st; p.WX = W / st;
   p.TA = TA; p.TX = TX;
@@ -786,17 +812,22 @@ static int make_wg_plan(const mnb_conv_shape* s, int TA, int TX, WgPlan& p) {
   // raster: rows of BW >= Q + halo columns; TH * BW must be a multiple of 16 (MMA K-steps of 16 positions)
   const int need = p.Q + wlo + whi;
   if (need > 128) return mnb_fail(MNB_E_UNSUPPORTED, "pk wgrad: row wider than 128 positions");
-  // N tile over input channels: taps * Nc accumulator columns
-  int nc = (512 / p.ntap) / 16 * 16;
-  if (nc < 16) return mnb_fail(MNB_E_UNSUPPORTED, "pk wgrad: more than 32 taps");
-  nc = std::min(nc, 256);
-  nc = std::min(nc, round_up(p.cin_g, 16));
+  // N tile over input channels and TAP GROUPS: one CTA accumulates tpg taps x Nc columns (<= 512 TMEM columns).  An MMA of
+  // N <= 64 costs the same 61 cycles as one of N = 128, so the N tile is made as wide as the layer allows (up to 256) and
+  // the taps are split over CTAs instead (each tap group re-reads the operands, mostly from L2): the MMA count is
+  // positions/16 x taps x pairs x ceil(C / Nc) - with Nc = 48 a 256-channel 3x3 layer issued six N = 48 MMAs where two
+  // tap groups of N = 256 do the same work at full tensor rate.
+  int nc = std::min(256, round_up(p.cin_g, 16));
+  if (const char* e = getenv("MNB_PK_WG_NC")) nc = std::max(16, std::min(nc, atoi(e) / 16 * 16));
   p.n_ctiles = ceil_div(p.cin_g, nc);
   p.Nc = round_up(ceil_div(p.cin_g, p.n_ctiles), 16);      // balance the tiles
   p.n_ctiles = ceil_div(p.cin_g, p.Nc);
   p.n_ktiles = ceil_div(p.cout_g, 128);
+  p.tpg = std::max(1, std::min(p.ntap, 512 / p.Nc));
+  p.n_tg = ceil_div(p.ntap, p.tpg);
+  p.tpg = ceil_div(p.ntap, p.n_tg);                        // balance the groups
   int cols = 32;
-  while (cols < p.ntap * p.Nc) cols <<= 1;
+  while (cols < p.tpg * p.Nc) cols <<= 1;
   if (cols > 512) return mnb_fail(MNB_E_UNSUPPORTED, "pk wgrad: accumulators exceed tensor memory");
   p.tmem_cols = cols;
   // stage = NI sub-blocks (one image row-tile each): dy [TA][16 octets][rows_dy], x [TX][k-phase][Nc/8][rows_x].
@@ -839,28 +870,28 @@ static int make_wg_plan(const mnb_conv_shape* s, int TA, int TX, WgPlan& p) {
   p.st_log2 = p.nstage == 4 ? 2 : 1;
   p.smem_bytes = p.nstage * p.stage_bytes + 1024;
   p.nstg_total = ceil_div(p.nsub, p.NI);
-  const int n_kc = p.n_ktiles * p.n_ctiles * G;
-  p.splits = std::max(1, std::min(p.nstg_total, MNB_NUM_SMS / n_kc));
+  const int n_kc = p.n_ktiles * p.n_ctiles * p.G * p.n_tg;
+  p.splits = std::max(1, std::min(p.nstg_total, std::max(1, MNB_NUM_SMS / n_kc)));
   // keep accumulation chains short: tcgen05.mma truncates the running fp32 sum after every instruction (a bias of
   // ~2e-8 of |D| per MMA), so one accumulator takes <= ~192 MMAs; the partial sums are added with RN adds
   const int chain_per_stage = p.NI * (p.rows_dy / 16) * p.npairs;
-  int chain_max = 192;
+  int chain_max = 256;
   if (const char* e = getenv("MNB_PK_WG_CHAIN")) chain_max = std::max(1, atoi(e));
   while (p.splits < p.nstg_total && (int64_t)ceil_div(p.nstg_total, p.splits) * chain_per_stage > chain_max) ++p.splits;
   p.stg_per_split = ceil_div(p.nstg_total, p.splits);
   p.splits = ceil_div(p.nstg_total, p.stg_per_split);
-  p.partial_floats = (int64_t)p.splits * G * p.n_ktiles * p.n_ctiles * p.ntap * p.Nc * 128;
+  p.partial_floats = (int64_t)p.splits * p.G * p.n_ktiles * p.n_ctiles * p.ntap * p.Nc * 128;
   return 0;
 }
 
 struct WgParams {
   struct Mma {
-    uint32_t stg_per_split, nstg_total, NI, ksteps, ntap, Nc, npairs, st_mask, st_log2, stage16, sub16, dy_term16, x_off16,
+    uint32_t stg_per_split, nstg_total, NI, ksteps, ntap, tpg, n_tg, Nc, npairs, st_mask, st_log2, stage16, sub16, dy_term16, x_off16,
         x_term16, x_kph16, idesc, dy_sbo, x_sbo, nsub;
     uint32_t pair_a16[MAXPAIR], pair_b16[MAXPAIR];   // piece-plane offsets of the pairs (16-byte units)
-    uint32_t tap_off[MAXTAP];       // x block start offset per tap (k-phase slot * x_kph16 + row offset), 16-byte units
+    uint32_t progb[MAXPAIR * MAXTAP];   // per (piece pair, tap): x-operand offset = pair plane + k-phase slot + tap row offset
   } m;
-  int G, n_ktiles, n_ctiles, splits, stg_per_split, nstg_total, NI, nsub, row_tiles, TA, TX, nkph_used, kph_used[4];
+  int G, n_ktiles, n_ctiles, n_tg, tpg, splits, stg_per_split, nstg_total, NI, nsub, row_tiles, TA, TX, nkph_used, kph_used[4];
   int K8, C8X, cout_g8, cin_g8, Nc8, TH, hlo, wlo, stage_bytes, sub_bytes, dy_bytes, x_bytes, dy_box_bytes, x_box_bytes,
       st_mask, st_log2, smem_bytes, tmem_cols, ntap, Nc, cout_g, cin_g;
   float* partial;
@@ -900,10 +931,13 @@ pk_wgrad_kernel(const __grid_constant__ CUtensorMap dy0, const __grid_constant__
   __syncthreads();
   tc::tc_fence_after();
   const uint32_t tmem = sh.tmem_slot;
-  // work item of this CTA: blockIdx.x = ((g * n_ktiles + kt) * n_ctiles + ct), blockIdx.y = split
+  // work item of this CTA: blockIdx.x = (((g * n_ktiles + kt) * n_ctiles + ct) * n_tg + tap group), blockIdx.y = split
   const int split = blockIdx.y;
-  const int ct = blockIdx.x % p.n_ctiles;
-  const int r1 = blockIdx.x / p.n_ctiles;
+  const int tg = blockIdx.x % p.n_tg;
+  const int r0 = blockIdx.x / p.n_tg;
+  const int t0 = tg * p.tpg, tn = min(p.tpg, p.ntap - t0);    // this CTA's filter taps
+  const int ct = r0 % p.n_ctiles;
+  const int r1 = r0 / p.n_ctiles;
   const int kt = r1 % p.n_ktiles, g = r1 / p.n_ktiles;
   const int stg0 = split * p.stg_per_split, stg1 = min(p.nstg_total, stg0 + p.stg_per_split);
 
@@ -941,6 +975,8 @@ pk_wgrad_kernel(const __grid_constant__ CUtensorMap dy0, const __grid_constant__
     const uint64_t b_desc0 = tc::smem_desc_mnmajor_noswz(tc::smem_u32(smem), 128, p.m.x_sbo) + (uint64_t)p.m.x_off16;
     const uint32_t a_lo0 = (uint32_t)a_desc0, a_hi = (uint32_t)(a_desc0 >> 32), b_lo0 = (uint32_t)b_desc0, b_hi = (uint32_t)(b_desc0 >> 32);
     const uint32_t split_u = blockIdx.y;
+    const uint32_t tgm = blockIdx.x % p.m.n_tg;
+    const uint32_t t0m = tgm * p.m.tpg, tnm = min(p.m.tpg, p.m.ntap - t0m);
     const uint32_t s0 = split_u * p.m.stg_per_split;
     const uint32_t s1 = min(p.m.nstg_total, s0 + p.m.stg_per_split);
     uint32_t sc = 0, accf = 0;
@@ -954,12 +990,13 @@ pk_wgrad_kernel(const __grid_constant__ CUtensorMap dy0, const __grid_constant__
         uint32_t arow = a_lo0 + s16, brow = b_lo0 + s16;
         for (uint32_t j = 0; j < p.m.ksteps; ++j, arow += 16u, brow += 16u) {
           for (uint32_t pr = 0; pr < p.m.npairs; ++pr) {
-            const uint32_t ad = arow + p.m.pair_a16[pr], b2 = brow + p.m.pair_b16[pr];
-            uint32_t d = tmem;
-            for (uint32_t t = 0; t < p.m.ntap; ++t, d += p.m.Nc)
-              tc::mma_f16_elect_lh(d, ad, a_hi, b2 + p.m.tap_off[t], b_hi, p.m.idesc, accf);
+            const uint32_t ad = arow + p.m.pair_a16[pr];
+            uint32_t d = tmem, e = pr * p.m.ntap + t0m;
+#pragma unroll 3
+            for (uint32_t t = 0; t < tnm; ++t, ++e, d += p.m.Nc)
+              tc::mma_f16_elect_lh(d, ad, a_hi, brow + p.m.progb[e], b_hi, p.m.idesc, accf);
+            accf = 1u;   // every tap accumulator has been written once: accumulate from here on
           }
-          accf = 1u;
         }
       }
       tc::mma_commit_elect(&sh.empty[slot]);
@@ -973,9 +1010,10 @@ pk_wgrad_kernel(const __grid_constant__ CUtensorMap dy0, const __grid_constant__
     const int kl = q * 32 + lane;
     if (!tc::mbar_wait(&sh.acc_full, 0, p.err, 713)) goto done;
     tc::tc_fence_after();
-    float* dst = p.partial + ((((int64_t)split * p.G + g) * p.n_ktiles + kt) * p.n_ctiles + ct) * (int64_t)(p.ntap * p.Nc * 128) + kl;
+    float* dst = p.partial + ((((int64_t)split * p.G + g) * p.n_ktiles + kt) * p.n_ctiles + ct) * (int64_t)(p.ntap * p.Nc * 128) +
+                 (int64_t)t0 * p.Nc * 128 + kl;
     const bool any = stg1 > stg0;
-    for (int col = 0; col < p.ntap * p.Nc; col += 16) {
+    for (int col = 0; col < tn * p.Nc; col += 16) {
       uint32_t r[16];
       tmem_ld_32x16(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)col, r);
       tc::tmem_ld_wait();
@@ -993,28 +1031,54 @@ done:
   }
 }
 
-// dw[k][c][tap] = mul(k) * sum over splits (fixed order: deterministic); mul = a_scale / kdiv[k] (either may be NULL)
-__global__ void __launch_bounds__(256) wg_reduce_kernel(const float* __restrict__ partial, int splits, int G, int n_ktiles,
+// dw[k][c][tap] = mul(k) * sum over splits (fixed order: deterministic); mul = a_scale / kdiv[k] (either may be NULL).
+// G merged groups of gm original groups each: only the diagonal (same original group) blocks are read.
+// One block = (128 output channels of a k tile) x (CB input channels) x all taps: the partials are read along k (their
+// contiguous dimension: 512-byte runs), transposed through shared memory, and written as CB * ntap contiguous floats per
+// output channel.  (First version: one thread per output element, 32-byte sectors for 4 useful bytes on every split.)
+__global__ void __launch_bounds__(128) wg_reduce_kernel(const float* __restrict__ partial, int splits, int G, int gm, int n_ktiles,
                                                         int n_ctiles, int ntap, int Nc, int cout_g, int cin_g,
                                                         const float* __restrict__ a_scale, const float* __restrict__ kdiv,
-                                                        float* __restrict__ dw) {
-  const int64_t total = (int64_t)G * cout_g * cin_g * ntap;
+                                                        float* __restrict__ dw, int WR_CB) {
+  // cout_g / cin_g: channels per ORIGINAL group.  grid = (c chunks, k tiles of the original group, original groups)
+  extern __shared__ float tile_s[];                 // [128][WR_CB * ntap + 1]
+  const int go = blockIdx.z, ktile = blockIdx.y, c0 = blockIdx.x * WR_CB;
+  const int g = go / gm, gi = go - g * gm;
+  const int kk = ktile * 128 + threadIdx.x;         // output channel inside the original group
+  const int ncol = WR_CB * ntap, ld = ncol + 1;
   const float as = a_scale ? __ldg(a_scale) : 1.f;
   const int64_t tile = (int64_t)ntap * Nc * 128;
   const int64_t split_stride = (int64_t)G * n_ktiles * n_ctiles * tile;
-  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
-    const int tap = (int)(idx % ntap);
-    int64_t t = idx / ntap;
-    const int c = (int)(t % cin_g);
-    t /= cin_g;
-    const int kk = (int)(t % cout_g), g = (int)(t / cout_g);
-    const int kt = kk >> 7, kl = kk & 127, ct = c / Nc, cl = c - ct * Nc;
-    const float* src = partial + (((int64_t)g * n_ktiles + kt) * n_ctiles + ct) * tile + ((int64_t)tap * Nc + cl) * 128 + kl;
-    float acc = 0.f;
-    for (int s = 0; s < splits; ++s) acc = __fadd_rn(acc, src[(int64_t)s * split_stride]);
-    float mul = as;
-    if (kdiv) mul = __fdiv_rn(as, __ldg(kdiv + g * cout_g + kk));
-    dw[idx] = (a_scale || kdiv) ? __fmul_rn(acc, mul) : acc;
+  const int km = gi * cout_g + kk;                  // row inside the merged group
+  const int kt = km >> 7, kl = km & 127;
+  if (kk < cout_g) {
+    for (int cc = 0; cc < WR_CB; ++cc) {
+      const int c = c0 + cc;
+      if (c >= cin_g) break;
+      const int cm = gi * cin_g + c, ct = cm / Nc, cl = cm - ct * Nc;
+      const float* base = partial + (((int64_t)g * n_ktiles + kt) * n_ctiles + ct) * tile + (int64_t)cl * 128 + kl;
+      for (int tap = 0; tap < ntap; ++tap) {
+        const float* src = base + (int64_t)tap * Nc * 128;
+        float acc = 0.f;
+        for (int s = 0; s < splits; ++s) acc = __fadd_rn(acc, __ldg(src + (int64_t)s * split_stride));
+        tile_s[threadIdx.x * ld + cc * ntap + tap] = acc;
+      }
+    }
+  }
+  __syncthreads();
+  // write: rows of this k tile, WR_CB * ntap contiguous floats each
+  const int nvalid_c = min(WR_CB, cin_g - c0);
+  const int rowlen = nvalid_c * ntap;
+  const int krows = min(128, cout_g - ktile * 128);
+  for (int idx = threadIdx.x; idx < krows * rowlen; idx += blockDim.x) {
+    const int r = idx / rowlen, col = idx - r * rowlen;
+    const int kout = go * cout_g + ktile * 128 + r;
+    float v = tile_s[r * ld + col];
+    if (a_scale || kdiv) {
+      const float mul = kdiv ? __fdiv_rn(as, __ldg(kdiv + kout)) : as;
+      v = __fmul_rn(v, mul);
+    }
+    dw[((int64_t)kout * cin_g + c0) * ntap + col] = v;
   }
 }
 
@@ -1035,18 +1099,24 @@ extern "C" int mnb_pk_pack_act(const float* x, int32_t batch, int32_t channels, 
   MNB_REQUIRE((reinterpret_cast<uintptr_t>(out_pk) & 15) == 0, "packed tensor must be 16-byte aligned");
   if (phase_split) MNB_REQUIRE(((h | w) & 1) == 0, "phase split needs even H and W");
   const int C8 = (channels + 7) / 8;
-  const int64_t plane_vecs = (int64_t)batch * C8 * h * w, total = plane_vecs;
-  const int blocks = (int)std::min<int64_t>((total + 255) / 256, (int64_t)MNB_NUM_SMS * 16);
+  const int64_t plane_vecs = (int64_t)batch * C8 * h * w;
+  MNB_REQUIRE((int64_t)batch * C8 <= 65535 * 8 && (int64_t)h * w < (1ll << 31), "pk_pack_act: too many (image, octet) planes");
+  const int hw = h * w;
+  const int tx = std::min(256, (hw + 31) / 32 * 32), ty = 256 / tx;     // threads along positions / planes per block
+  const int planes = batch * C8, gy = (planes + ty - 1) / ty;
+  const int bx = std::max(1, std::min((hw + tx - 1) / tx, std::max(1, (MNB_NUM_SMS * 16) / std::max(1, gy))));
+  if (gy > 65535) return mnb_fail(MNB_E_UNSUPPORTED, "pk_pack_act: %d (image, octet) planes exceed the grid", planes);
+  const dim3 blocks(bx, gy), threads(tx, ty);
   cudaStream_t st = (cudaStream_t)stream;
   if (qp) {
     MNB_REQUIRE(qp->mode == MNB_ACT_DOREFA || qp->mode == MNB_ACT_IAO || qp->mode == MNB_ACT_SIGN, "unknown activation quantizer");
     if (qp->mode == MNB_ACT_DOREFA) MNB_REQUIRE(qp->bits >= 2 && qp->bits <= 8, "DoReFa a_bits must be in [2,8]");
     const int a_off = qp->mode == MNB_ACT_IAO ? qp->qmin : (qp->mode == MNB_ACT_SIGN ? -1 : 0);
-    pk::pack_act_kernel<1><<<blocks, 256, 0, st>>>(x, batch, channels, h, w, C8, terms, nullptr, *qp, a_off, phase_split,
+    pk::pack_act_kernel<1><<<blocks, threads, 0, st>>>(x, batch, channels, h, w, C8, terms, nullptr, *qp, a_off, phase_split,
                                                    reinterpret_cast<uint4*>(out_pk), plane_vecs, bits8);
   } else {
     mnb_act_qparams none{};
-    pk::pack_act_kernel<0><<<blocks, 256, 0, st>>>(x, batch, channels, h, w, C8, terms, ch_scale, none, 0, phase_split,
+    pk::pack_act_kernel<0><<<blocks, threads, 0, st>>>(x, batch, channels, h, w, C8, terms, ch_scale, none, 0, phase_split,
                                                    reinterpret_cast<uint4*>(out_pk), plane_vecs, nullptr);
   }
   MNB_LAUNCHED(1);
@@ -1133,15 +1203,17 @@ extern "C" int mnb_pk_conv(const mnb_conv_shape* s, int32_t mode, const void* a_
     for (int t = 0; t < pl.ntmpl[y]; ++t) {
       const Tmpl& tp = pl.tmpl[y][t];
       p.tmpl_kph[y][t] = tp.kph; p.tmpl_blk_off[y][t] = tp.blk_off; p.tmpl_blk_bytes[y][t] = tp.blk_bytes;
-      m.tmpl_begin[y][t] = (uint16_t)nprog; m.tmpl_cnt[y][t] = (uint16_t)(tp.ntap * pl.npairs);
-      if (nprog + tp.ntap * pl.npairs > MAXPROG) return unsupported("MMA program longer than 384 entries");
+      const int cnt = tp.ntap * pl.npairs * pl.ksteps;
+      m.tmpl_begin[y][t] = (uint16_t)nprog; m.tmpl_cnt[y][t] = (uint16_t)cnt;
+      if (nprog + cnt > MAXPROG) return unsupported("MMA program longer than 512 entries");
       for (int pr = 0; pr < pl.npairs; ++pr)          // piece pairs outermost: small products first
-        for (int i = 0; i < tp.ntap; ++i) {
-          const uint32_t a16 = (uint32_t)pl.tap_aoff[y][tp.tap0 + i] + (uint32_t)pl.pair_a[pr] * m.a_term16;
-          const uint32_t b16 = (uint32_t)i * m.b_tap16 + (uint32_t)pl.pair_b[pr] * (uint32_t)tp.ntap * m.b_tap16;
-          if (a16 > 0xffffu || b16 > 0xffffu) return mnb_fail(MNB_E_ARG, "pk conv: MMA program offset overflow");
-          m.prog[nprog++] = a16 | (b16 << 16);
-        }
+        for (int i = 0; i < tp.ntap; ++i)
+          for (int j = 0; j < pl.ksteps; ++j) {
+            const uint32_t a16 = (uint32_t)pl.tap_aoff[y][tp.tap0 + i] + (uint32_t)pl.pair_a[pr] * m.a_term16 + (uint32_t)j * m.a_k16;
+            const uint32_t b16 = (uint32_t)i * m.b_tap16 + (uint32_t)pl.pair_b[pr] * (uint32_t)tp.ntap * m.b_tap16 + (uint32_t)j * m.b_k16;
+            if (a16 > 0xffffu || b16 > 0xffffu) return mnb_fail(MNB_E_ARG, "pk conv: MMA program offset overflow");
+            m.prog[nprog++] = a16 | (b16 << 16);
+          }
     }
     p.img_bytes[y] = pl.img_bytes[y]; p.y_off[y] = pl.y_off[y];
     p.zero_y[y] = pl.ntap[y] == 0;
@@ -1198,14 +1270,16 @@ extern "C" int mnb_pk_wgrad(const mnb_conv_shape* s, const void* dy_pk, int32_t 
   memset(&p, 0, sizeof(p));
   WgParams::Mma& m = p.m;
   m.stg_per_split = pl.stg_per_split; m.nstg_total = pl.nstg_total; m.NI = pl.NI; m.ksteps = pl.rows_dy / 16; m.ntap = pl.ntap;
-  m.Nc = pl.Nc; m.npairs = pl.npairs; m.st_mask = pl.nstage - 1; m.st_log2 = pl.st_log2; m.stage16 = pl.stage_bytes >> 4;
+  m.Nc = pl.Nc; m.tpg = pl.tpg; m.n_tg = pl.n_tg; m.npairs = pl.npairs; m.st_mask = pl.nstage - 1; m.st_log2 = pl.st_log2; m.stage16 = pl.stage_bytes >> 4;
   m.sub16 = pl.sub_bytes >> 4; m.dy_term16 = pl.dy_bytes >> 4; m.x_off16 = (pl.TA * pl.dy_bytes) >> 4;
   m.x_term16 = (pl.nkph_used * pl.x_bytes) >> 4; m.x_kph16 = pl.x_bytes >> 4;
   m.idesc = tc::make_idesc_major(1, 1, 1, 128, (uint32_t)pl.Nc, 1, 1);
   m.dy_sbo = (uint32_t)pl.rows_dy * 16u; m.x_sbo = (uint32_t)pl.rows_x * 16u; m.nsub = pl.nsub;
   for (int i = 0; i < pl.npairs; ++i) { m.pair_a16[i] = pl.pair_a[i] * m.dy_term16; m.pair_b16[i] = pl.pair_b[i] * m.x_term16; }
-  for (int t = 0; t < pl.ntap; ++t) m.tap_off[t] = pl.kph_slot[pl.tap_kph[t]] * m.x_kph16 + pl.tap_off[t];
-  p.G = pl.G; p.n_ktiles = pl.n_ktiles; p.n_ctiles = pl.n_ctiles; p.splits = pl.splits; p.stg_per_split = pl.stg_per_split;
+  for (int i = 0; i < pl.npairs; ++i)
+    for (int t = 0; t < pl.ntap; ++t)
+      m.progb[i * pl.ntap + t] = m.pair_b16[i] + pl.kph_slot[pl.tap_kph[t]] * m.x_kph16 + pl.tap_off[t];
+  p.G = pl.G; p.n_ktiles = pl.n_ktiles; p.n_ctiles = pl.n_ctiles; p.n_tg = pl.n_tg; p.tpg = pl.tpg; p.splits = pl.splits; p.stg_per_split = pl.stg_per_split;
   p.nstg_total = pl.nstg_total; p.NI = pl.NI; p.nsub = pl.nsub; p.row_tiles = pl.row_tiles; p.TA = pl.TA; p.TX = pl.TX;
   p.nkph_used = pl.nkph_used;
   for (int i = 0; i < 4; ++i) p.kph_used[i] = pl.kph_used[i];
@@ -1224,11 +1298,16 @@ extern "C" int mnb_pk_wgrad(const mnb_conv_shape* s, const void* dy_pk, int32_t 
   }
   if (int e = set_max_smem(pk_wgrad_kernel, kSmemBudget)) return e;
   cudaStream_t st = (cudaStream_t)stream;
-  pk_wgrad_kernel<<<dim3(pl.G * pl.n_ktiles * pl.n_ctiles, pl.splits), NTHREADS, pl.smem_bytes, st>>>(tdy[0], tdy[1], tdy[2], tx[0],
+  pk_wgrad_kernel<<<dim3(pl.G * pl.n_ktiles * pl.n_ctiles * pl.n_tg, pl.splits), NTHREADS, pl.smem_bytes, st>>>(tdy[0], tdy[1], tdy[2], tx[0],
                                                                                                       tx[1], tx[2], p);
-  const int64_t total = (int64_t)s->out_c * pl.cin_g * pl.ntap;
-  wg_reduce_kernel<<<(int)std::min<int64_t>((total + 255) / 256, MNB_NUM_SMS * 8), 256, 0, st>>>(
-      p.partial, pl.splits, pl.G, pl.n_ktiles, pl.n_ctiles, pl.ntap, pl.Nc, pl.cout_g, pl.cin_g, a_scale, kdiv, dw);
+  {
+    const int cout_o = pl.cout_g / pl.gm, cin_o = pl.cin_g / pl.gm;     // channels per original group
+    const int cb = std::max(1, std::min(8, 92 / pl.ntap));            // 128 x (cb * taps + 1) floats of shared memory <= 48 KB
+    const dim3 rgrid((cin_o + cb - 1) / cb, (cout_o + 127) / 128, pl.G * pl.gm);
+    const int rsmem = 128 * (cb * pl.ntap + 1) * 4;
+    wg_reduce_kernel<<<rgrid, 128, rsmem, st>>>(p.partial, pl.splits, pl.G, pl.gm, pl.n_ktiles, pl.n_ctiles, pl.ntap, pl.Nc,
+                                                cout_o, cin_o, a_scale, kdiv, dw, cb);
+  }
   MNB_LAUNCHED(2);
   return 0;
 }

@@ -219,11 +219,13 @@ def test_fused_model_step_matches_unfused_engine_model():
     assert cos > 0.98, float(cos)
 
 
-def test_dorefa_fuse_option_changes_no_number():
-    """pool kernels are bit-identical to ATen and a folded shuffle is only an addressing change: the fused DoReFa
-    model must reproduce the unfused engine model exactly.  The one exception is the un-quantized first
-    convolution (DF leaves it a plain nn.Conv2d): ATen/cuDNN there, the fp32 tensor-core kernel here, so that
-    block agrees to fp32 rounding."""
+def test_dorefa_fuse_option_agrees_with_the_unfused_engine():
+    """pool kernels are bit-identical to ATen and a folded shuffle is only an addressing change; since round 2 the fuse
+    option also merges BatchNorm2d + ReLU + the next conv's activation quantizer into one producer
+    (fused.BatchNormReluQuant2d), whose BatchNorm arithmetic (one fma, statistics from mnb_bn_batch_stats) differs from
+    ATen's in the last bit: a few activation levels land on the other side of a rounding tie, so the fused model agrees
+    with the unfused engine model in direction and loss, not bit for bit (the strict per-module checks are
+    tests/test_gpu_fused_dorefa.py)."""
     import micronet_b200 as E
     from harness import models as zoo
     torch.manual_seed(2)
@@ -237,13 +239,9 @@ def test_dorefa_fuse_option_changes_no_number():
         loss = nn.functional.cross_entropy(m(x), t)
         loss.backward()
         out[name] = (loss.detach().clone(), {n: p.grad.clone() for n, p in m.named_parameters()})
-    assert torch.equal(out["plain"][0], out["fused"][0])
+    assert abs(out["plain"][0].item() - out["fused"][0].item()) <= 2e-3 * max(1.0, abs(out["plain"][0].item()))
     for n, g in out["plain"][1].items():
-        if n.startswith("model.0."):
-            # A training-mode BN makes its input's gradient orthogonal to that input, so the first conv's weight
-            # gradient is a ~1000x cancelling sum and its bias gradient pure rounding noise: compare by direction.
-            if not n.endswith("conv.bias"):
-                a, b = out["fused"][1][n].flatten().double(), g.flatten().double()
-                assert torch.dot(a, b) / (a.norm() * b.norm()) > 0.9999, n
-        else:
-            assert torch.equal(g, out["fused"][1][n]), n
+        if n.endswith("conv.bias"):
+            continue      # a conv bias in front of a training-mode BatchNorm has a mathematically zero gradient: noise
+        a, b = out["fused"][1][n].flatten().double(), g.flatten().double()
+        assert torch.dot(a, b) / (a.norm() * b.norm()) > 0.99, n

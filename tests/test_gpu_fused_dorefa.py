@@ -101,6 +101,8 @@ def test_fused_blocks_match_the_unfused_engine(a_bits):
     assert cos > 0.9995, cos
     gp = dict(plain.named_parameters())
     for n, p in fused.named_parameters():
+        if n.endswith("conv.bias"):
+            continue      # bias in front of a training-mode BatchNorm: mathematically zero gradient, both sides hold noise
         c = TF.cosine_similarity(p.grad.flatten(), gp[n].grad.flatten(), dim=0).item()
         assert c > 0.995, (n, c)
     assert plain.state_dict().keys() == fused.state_dict().keys()

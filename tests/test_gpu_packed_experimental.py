@@ -10,8 +10,7 @@ import torch.nn.functional as TF
 
 from tests.oracle_util import rel_err
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("MNB_PACKED_OPERANDS", "1") != "1", reason="packed producer switched off")]
+pytestmark = pytest.mark.gpu
 DEV = "cuda"
 
 # B, C, H, W, K, R, groups, shuffle groups of the producer
@@ -37,7 +36,11 @@ def test_packed_producer_and_conv_match_the_unpacked_path(case):
         bn.weight.copy_(torch.rand(C) + 0.5)
         bn.bias.copy_(torch.randn(C) * 0.3)
     x = (torch.randn(B, C, H, W) * 1.5).to(DEV)
-    y = bn(x)
+    L.USE_PACKED = True       # opt-in path (MNB_PACKED_OPERANDS=1)
+    try:
+        y = bn(x)
+    finally:
+        L.USE_PACKED = False
     packed = getattr(y, "_mnb_packed", None)
     assert packed is not None, "producer did not emit the packed operand"
     # packed tensor = the +-1 plane in [B][C/8][H][W][8] order
@@ -81,7 +84,7 @@ def test_block_with_packed_forward_has_the_same_gradients(case):
             kinds = {k for k, _, _, _ in F_.TIMER.records}
             res[flag] = (out.detach(), x.grad, wq.grad, bn.weight.grad, kinds)
         finally:
-            L.USE_PACKED = True
+            L.USE_PACKED = False
             F_.TIMER = None
     assert "fwd_pk" in res[True][4] and "fwd_pk" not in res[False][4], (res[True][4], res[False][4])
     for a, b in zip(res[True][:4], res[False][:4]):
