@@ -268,6 +268,9 @@ def run_engine(workload, steps, warmup, dev, rank, world, detail):
     if hasattr(stepper, "graph"):
         stepper.graph, stepper.graph_wanted = None, False
     timer = None
+    for i in range(2):
+        step_resident(i)   # eager allocations after a capture come from the non-graph pool: let the caching allocator fill it
+    torch.cuda.synchronize()
     launches0 = L.launch_count()
     dsteps = min(steps, 3)
     if detail:

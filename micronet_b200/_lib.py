@@ -43,6 +43,9 @@ PROTOTYPES = {
     "mnb_launch_count": (_L, []),
     "mnb_act_quant_fwd": (C.c_int, [_P, _L, _ACTQ, _P, _P, _P, _P]),
     "mnb_act_quant_bwd": (C.c_int, [_P, _P, _L, _ACTQ, _P, _P]),
+    "mnb_bn_fold_fwd": (C.c_int, [_P, _I, _I, _P, _P, _P, _P, _P, _D, _P, _P, _P]),
+    "mnb_bn_fold_bwd": (C.c_int, [_P, _P, _P, _I, _I, _P, _P, _P, _P, _D, _P, _P, _P]),
+    "mnb_bn_fold_running": (C.c_int, [_P, _P, _P, _P, _I, _D, _I, _P]),
     "mnb_quant_add_fwd": (C.c_int, [_P, _P, _L, _ACTQ, _P, _P, _P, _P]),
     "mnb_quant_add_bwd": (C.c_int, [_P, _P, _P, _L, _ACTQ, _P, _P, _P]),
     "mnb_observe_scratch_bytes": (_L, [_L, _I]),

@@ -741,14 +741,18 @@ static int make_pk_tmap(CUtensorMap* m, const void* base, int64_t plane_bytes, i
 
 template <typename K>
 static int set_max_smem(K kernel, int bytes) {
-  // the attribute is a property of the function on a device: set it once per (function, device)
-  static bool done[64] = {};
+  // the attribute is a property of the function on a device: set it once per (function, device).  Keyed by the function
+  // ADDRESS (instantiations of one template share their pointer TYPE, so a per-type static would cover only the first)
+  static const void* seen_fn[32];
+  static int seen_dev[32], nseen = 0;
   int dev = 0;
   cudaGetDevice(&dev);
-  if (dev >= 0 && dev < 64 && done[dev]) return 0;
+  const void* fn = reinterpret_cast<const void*>(kernel);
+  for (int i = 0; i < nseen; ++i)
+    if (seen_fn[i] == fn && seen_dev[i] == dev) return 0;
   cudaError_t ce = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
   if (ce != cudaSuccess) return mnb_fail((int)ce, "cudaFuncSetAttribute: %s", cudaGetErrorString(ce));
-  if (dev >= 0 && dev < 64) done[dev] = true;
+  if (nseen < 32) { seen_fn[nseen] = fn; seen_dev[nseen] = dev; ++nseen; }
   return 0;
 }
 
@@ -768,7 +772,7 @@ struct WgPlan {
   int64_t partial_floats;
 };
 
-static int make_wg_plan(const mnb_conv_shape* s, int TA, int TX, WgPlan& p) {
+static int make_wg_plan_nc(const mnb_conv_shape* s, int TA, int TX, WgPlan& p, int nc_cap) {
   MNB_REQUIRE(s != nullptr, "conv shape is NULL");
   memset(&p, 0, sizeof(p));
   const int C = s->in_c, K = s->out_c, G = s->groups, H = s->in_h, W = s->in_w, R = s->ker_h, S = s->ker_w;
@@ -817,7 +821,7 @@ static int make_wg_plan(const mnb_conv_shape* s, int TA, int TX, WgPlan& p) {
   // the taps are split over CTAs instead (each tap group re-reads the operands, mostly from L2): the MMA count is
   // positions/16 x taps x pairs x ceil(C / Nc) - with Nc = 48 a 256-channel 3x3 layer issued six N = 48 MMAs where two
   // tap groups of N = 256 do the same work at full tensor rate.
-  int nc = std::min(256, round_up(p.cin_g, 16));
+  int nc = std::min(nc_cap, round_up(p.cin_g, 16));
   if (const char* e = getenv("MNB_PK_WG_NC")) nc = std::max(16, std::min(nc, atoi(e) / 16 * 16));
   p.n_ctiles = ceil_div(p.cin_g, nc);
   p.Nc = round_up(ceil_div(p.cin_g, p.n_ctiles), 16);      // balance the tiles
@@ -850,7 +854,7 @@ static int make_wg_plan(const mnb_conv_shape* s, int TA, int TX, WgPlan& p) {
         if (score > best_score) { best_score = score; best_bw = bw; best_th = th; }
       }
   }
-  if (!best_bw) return mnb_fail(MNB_E_UNSUPPORTED, "pk wgrad: no raster fits shared memory");
+  if (!best_bw) return mnb_fail(MNB_E_UNSUPPORTED, "pk wgrad: no raster fits shared memory (N tile %d)", p.Nc);
   p.BW = best_bw; p.TH = best_th; p.THH = p.TH + hlo + hhi;
   p.rows_dy = p.TH * p.BW; p.rows_x = p.THH * p.BW;
   p.row_tiles = ceil_div(p.P, p.TH);
@@ -882,6 +886,17 @@ static int make_wg_plan(const mnb_conv_shape* s, int TA, int TX, WgPlan& p) {
   p.splits = ceil_div(p.nstg_total, p.stg_per_split);
   p.partial_floats = (int64_t)p.splits * p.G * p.n_ktiles * p.n_ctiles * p.ntap * p.Nc * 128;
   return 0;
+}
+
+// the widest N tile whose operand blocks fit shared memory next to the dy planes (split fp32 x and stride-2 phase planes are
+// several times larger than one plane of integer levels)
+static int make_wg_plan(const mnb_conv_shape* s, int TA, int TX, WgPlan& p) {
+  int rc = MNB_E_UNSUPPORTED;
+  for (int cap = 256; cap >= 16; cap /= 2) {
+    rc = make_wg_plan_nc(s, TA, TX, p, cap);
+    if (rc != MNB_E_UNSUPPORTED) return rc;
+  }
+  return rc;
 }
 
 struct WgParams {
@@ -1033,53 +1048,37 @@ done:
 
 // dw[k][c][tap] = mul(k) * sum over splits (fixed order: deterministic); mul = a_scale / kdiv[k] (either may be NULL).
 // G merged groups of gm original groups each: only the diagonal (same original group) blocks are read.
-// One block = (128 output channels of a k tile) x (CB input channels) x all taps: the partials are read along k (their
-// contiguous dimension: 512-byte runs), transposed through shared memory, and written as CB * ntap contiguous floats per
-// output channel.  (First version: one thread per output element, 32-byte sectors for 4 useful bytes on every split.)
+// One block = the 128 output channels of a k tile for ONE (input channel, tap): the partials are read along k, their
+// contiguous dimension (512-byte runs per warp), four splits in flight per thread; |W| threads in total.
 __global__ void __launch_bounds__(128) wg_reduce_kernel(const float* __restrict__ partial, int splits, int G, int gm, int n_ktiles,
                                                         int n_ctiles, int ntap, int Nc, int cout_g, int cin_g,
                                                         const float* __restrict__ a_scale, const float* __restrict__ kdiv,
-                                                        float* __restrict__ dw, int WR_CB) {
-  // cout_g / cin_g: channels per ORIGINAL group.  grid = (c chunks, k tiles of the original group, original groups)
-  extern __shared__ float tile_s[];                 // [128][WR_CB * ntap + 1]
-  const int go = blockIdx.z, ktile = blockIdx.y, c0 = blockIdx.x * WR_CB;
+                                                        float* __restrict__ dw) {
+  // cout_g / cin_g: channels per ORIGINAL group.  grid = (cin_g * ntap, k tiles of the original group, original groups)
+  const int go = blockIdx.z, ktile = blockIdx.y;
+  const int c = blockIdx.x / ntap, tap = blockIdx.x - c * ntap;
   const int g = go / gm, gi = go - g * gm;
   const int kk = ktile * 128 + threadIdx.x;         // output channel inside the original group
-  const int ncol = WR_CB * ntap, ld = ncol + 1;
-  const float as = a_scale ? __ldg(a_scale) : 1.f;
+  if (kk >= cout_g) return;
   const int64_t tile = (int64_t)ntap * Nc * 128;
   const int64_t split_stride = (int64_t)G * n_ktiles * n_ctiles * tile;
-  const int km = gi * cout_g + kk;                  // row inside the merged group
-  const int kt = km >> 7, kl = km & 127;
-  if (kk < cout_g) {
-    for (int cc = 0; cc < WR_CB; ++cc) {
-      const int c = c0 + cc;
-      if (c >= cin_g) break;
-      const int cm = gi * cin_g + c, ct = cm / Nc, cl = cm - ct * Nc;
-      const float* base = partial + (((int64_t)g * n_ktiles + kt) * n_ctiles + ct) * tile + (int64_t)cl * 128 + kl;
-      for (int tap = 0; tap < ntap; ++tap) {
-        const float* src = base + (int64_t)tap * Nc * 128;
-        float acc = 0.f;
-        for (int s = 0; s < splits; ++s) acc = __fadd_rn(acc, __ldg(src + (int64_t)s * split_stride));
-        tile_s[threadIdx.x * ld + cc * ntap + tap] = acc;
-      }
-    }
+  const int km = gi * cout_g + kk, cm = gi * cin_g + c;     // row / column inside the merged group
+  const int kt = km >> 7, kl = km & 127, ct = cm / Nc, cl = cm - ct * Nc;
+  const float* src = partial + (((int64_t)g * n_ktiles + kt) * n_ctiles + ct) * tile + ((int64_t)tap * Nc + cl) * 128 + kl;
+  float acc = 0.f;
+  int s = 0;
+  for (; s + 4 <= splits; s += 4) {
+    const float v0 = __ldg(src + (int64_t)s * split_stride), v1 = __ldg(src + (int64_t)(s + 1) * split_stride),
+                v2 = __ldg(src + (int64_t)(s + 2) * split_stride), v3 = __ldg(src + (int64_t)(s + 3) * split_stride);
+    acc = __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(acc, v0), v1), v2), v3);
   }
-  __syncthreads();
-  // write: rows of this k tile, WR_CB * ntap contiguous floats each
-  const int nvalid_c = min(WR_CB, cin_g - c0);
-  const int rowlen = nvalid_c * ntap;
-  const int krows = min(128, cout_g - ktile * 128);
-  for (int idx = threadIdx.x; idx < krows * rowlen; idx += blockDim.x) {
-    const int r = idx / rowlen, col = idx - r * rowlen;
-    const int kout = go * cout_g + ktile * 128 + r;
-    float v = tile_s[r * ld + col];
-    if (a_scale || kdiv) {
-      const float mul = kdiv ? __fdiv_rn(as, __ldg(kdiv + kout)) : as;
-      v = __fmul_rn(v, mul);
-    }
-    dw[((int64_t)kout * cin_g + c0) * ntap + col] = v;
+  for (; s < splits; ++s) acc = __fadd_rn(acc, __ldg(src + (int64_t)s * split_stride));
+  const int kout = go * cout_g + kk;
+  if (a_scale || kdiv) {
+    const float as = a_scale ? __ldg(a_scale) : 1.f;
+    acc = __fmul_rn(acc, kdiv ? __fdiv_rn(as, __ldg(kdiv + kout)) : as);
   }
+  dw[((int64_t)kout * cin_g + c) * ntap + tap] = acc;
 }
 
 }  // namespace pk
@@ -1302,11 +1301,9 @@ extern "C" int mnb_pk_wgrad(const mnb_conv_shape* s, const void* dy_pk, int32_t 
                                                                                                       tx[1], tx[2], p);
   {
     const int cout_o = pl.cout_g / pl.gm, cin_o = pl.cin_g / pl.gm;     // channels per original group
-    const int cb = std::max(1, std::min(8, 92 / pl.ntap));            // 128 x (cb * taps + 1) floats of shared memory <= 48 KB
-    const dim3 rgrid((cin_o + cb - 1) / cb, (cout_o + 127) / 128, pl.G * pl.gm);
-    const int rsmem = 128 * (cb * pl.ntap + 1) * 4;
-    wg_reduce_kernel<<<rgrid, 128, rsmem, st>>>(p.partial, pl.splits, pl.G, pl.gm, pl.n_ktiles, pl.n_ctiles, pl.ntap, pl.Nc,
-                                                cout_o, cin_o, a_scale, kdiv, dw, cb);
+    const dim3 rgrid(cin_o * pl.ntap, (cout_o + 127) / 128, pl.G * pl.gm);
+    wg_reduce_kernel<<<rgrid, 128, 0, st>>>(p.partial, pl.splits, pl.G, pl.gm, pl.n_ktiles, pl.n_ctiles, pl.ntap, pl.Nc, cout_o,
+                                            cin_o, a_scale, kdiv, dw);
   }
   MNB_LAUNCHED(2);
   return 0;

@@ -879,3 +879,104 @@ extern "C" int mnb_quant_add_bwd(const float* g, const uint32_t* pass_bits_a, co
   MNB_LAUNCHED(1);
   return 0;
 }
+
+// ------------------------------------------------------------------ IAO BN-fuse: fold BatchNorm into (weight, bias)
+// IAO:903-945 (QuantBNFuseConv2d.forward):  ratio = gamma / sqrt(var + eps);  w_f = w * ratio[k];
+// b_f = beta + (bias - mean) * ratio   (bias may be absent: beta - mean * ratio).  The reference composes this from ~10
+// ATen launches per layer forward and ~25 backward (broadcast multiplies, reshapes, reductions); here it is one launch each
+// way, one block per output channel.  Same operation order and roundings as the ATen composition.
+__global__ void __launch_bounds__(256) bn_fold_fwd_kernel(const float* __restrict__ w, int n, const float* __restrict__ gamma,
+                                                          const float* __restrict__ beta, const float* __restrict__ bias,
+                                                          const float* __restrict__ mean, const float* __restrict__ var,
+                                                          float eps, float* __restrict__ w_f, float* __restrict__ b_f) {
+  const int k = blockIdx.x;
+  const float ratio = __fdiv_rn(__ldg(gamma + k), __fsqrt_rn(__fadd_rn(__ldg(var + k), eps)));
+  if (threadIdx.x == 0) {
+    const float m = __ldg(mean + k);
+    b_f[k] = bias ? __fadd_rn(__ldg(beta + k), __fmul_rn(__fsub_rn(__ldg(bias + k), m), ratio))
+                  : __fsub_rn(__ldg(beta + k), __fmul_rn(m, ratio));
+  }
+  const float* wk = w + (int64_t)k * n;
+  float* ok = w_f + (int64_t)k * n;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) ok[i] = __fmul_rn(__ldg(wk + i), ratio);
+}
+
+// backward of the fold: dw = dw_f * ratio;  dratio = sum_i dw_f * w + db_f * (bias - mean);  dgamma = dratio / sqrt(var + eps);
+// dvar = -0.5 * dratio * gamma * (var + eps)^-1.5;  dmean = -db_f * ratio;  dbeta = db_f;  dbias = db_f * ratio.
+// out6[k*6 ..] = {dgamma, dbeta, dbias, dmean, dvar, -}
+__global__ void __launch_bounds__(256) bn_fold_bwd_kernel(const float* __restrict__ dw_f, const float* __restrict__ db_f,
+                                                          const float* __restrict__ w, int n, const float* __restrict__ gamma,
+                                                          const float* __restrict__ bias, const float* __restrict__ mean,
+                                                          const float* __restrict__ var, float eps, float* __restrict__ dw,
+                                                          float* __restrict__ out6) {
+  __shared__ double red[32];
+  const int k = blockIdx.x;
+  const float ve = __fadd_rn(__ldg(var + k), eps);
+  const float sq = __fsqrt_rn(ve);
+  const float g = __ldg(gamma + k);
+  const float ratio = __fdiv_rn(g, sq);
+  const float* dk = dw_f + (int64_t)k * n;
+  const float* wk = w + (int64_t)k * n;
+  float* ok = dw ? dw + (int64_t)k * n : nullptr;
+  double s = 0.0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const float d = __ldg(dk + i);
+    s += (double)d * (double)__ldg(wk + i);
+    if (ok) ok[i] = __fmul_rn(d, ratio);
+  }
+  s = mnb_block_reduce(s, MnbSum(), 0.0, red);
+  if (threadIdx.x == 0) {
+    const float db = db_f ? __ldg(db_f + k) : 0.f;
+    const float m = __ldg(mean + k);
+    const float diff = bias ? __fsub_rn(__ldg(bias + k), m) : -m;
+    const float dratio = (float)(s + (double)db * (double)diff);
+    float* o = out6 + (int64_t)k * 6;
+    o[0] = __fdiv_rn(dratio, sq);                               // dgamma
+    o[1] = db;                                                  // dbeta
+    o[2] = db * ratio;                                          // dbias
+    o[3] = -db * ratio;                                         // dmean
+    o[4] = -0.5f * dratio * g / (ve * sq);                      // dvar
+    o[5] = 0.f;
+  }
+}
+
+// running_mean / running_var update of QuantBNFuseConv2d (IAO:858-876): first call copies the batch statistics, later calls
+// r = (1 - momentum) * r + momentum * batch   (Python doubles cast to fp32 by ATen, then mul, mul, add)
+__global__ void __launch_bounds__(256) bn_fold_running_kernel(float* __restrict__ rm, float* __restrict__ rv,
+                                                              const float* __restrict__ bm, const float* __restrict__ bv, int n,
+                                                              float keep, float mom, int first) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  if (first) { rm[i] = __ldg(bm + i); rv[i] = __ldg(bv + i); }
+  else {
+    rm[i] = __fadd_rn(__fmul_rn(keep, rm[i]), __fmul_rn(mom, __ldg(bm + i)));
+    rv[i] = __fadd_rn(__fmul_rn(keep, rv[i]), __fmul_rn(mom, __ldg(bv + i)));
+  }
+}
+
+extern "C" int mnb_bn_fold_fwd(const float* w, int32_t out_c, int32_t per_channel, const float* gamma, const float* beta,
+                               const float* bias, const float* mean, const float* var, double eps, float* w_fused,
+                               float* b_fused, mnb_stream_t stream) {
+  MNB_REQUIRE(w && gamma && beta && mean && var && w_fused && b_fused && out_c > 0 && per_channel > 0, "bad bn_fold_fwd arguments");
+  bn_fold_fwd_kernel<<<out_c, 256, 0, S(stream)>>>(w, per_channel, gamma, beta, bias, mean, var, (float)eps, w_fused, b_fused);
+  MNB_LAUNCHED(1);
+  return 0;
+}
+
+extern "C" int mnb_bn_fold_bwd(const float* dw_fused, const float* db_fused, const float* w, int32_t out_c, int32_t per_channel,
+                               const float* gamma, const float* bias, const float* mean, const float* var, double eps, float* dw,
+                               float* out6, mnb_stream_t stream) {
+  MNB_REQUIRE(dw_fused && w && gamma && mean && var && out6 && out_c > 0 && per_channel > 0, "bad bn_fold_bwd arguments");
+  bn_fold_bwd_kernel<<<out_c, 256, 0, S(stream)>>>(dw_fused, db_fused, w, per_channel, gamma, bias, mean, var, (float)eps, dw, out6);
+  MNB_LAUNCHED(1);
+  return 0;
+}
+
+extern "C" int mnb_bn_fold_running(float* running_mean, float* running_var, const float* batch_mean, const float* batch_var,
+                                   int32_t n, double momentum, int32_t first, mnb_stream_t stream) {
+  MNB_REQUIRE(running_mean && running_var && batch_mean && batch_var && n > 0, "bad bn_fold_running arguments");
+  bn_fold_running_kernel<<<mnb_ceil_div(n, 256), 256, 0, S(stream)>>>(running_mean, running_var, batch_mean, batch_var, n,
+                                                                      (float)(1.0 - momentum), (float)momentum, first);
+  MNB_LAUNCHED(1);
+  return 0;
+}

@@ -559,6 +559,43 @@ def quant_linear(x, wq, bias, w_int, w_scale, spec):
     return y.reshape(*lead, wq.shape[0])
 
 
+class BNFoldFn(Function):
+    """IAO:903-945: (weight, bias) with the BatchNorm statistics folded in, one kernel each way"""
+
+    @staticmethod
+    def forward(ctx, weight, bias, gamma, beta, mean, var, eps):
+        L.require_cuda(weight, gamma)
+        lib = L.load()
+        weight = weight.contiguous()
+        k, n = weight.shape[0], weight.numel() // weight.shape[0]
+        mean, var = mean.contiguous(), var.contiguous()
+        w_f = torch.empty_like(weight)
+        b_f = torch.empty(k, dtype=torch.float32, device=weight.device)
+        L.check(lib.mnb_bn_fold_fwd(weight.data_ptr(), k, n, gamma.data_ptr(), beta.data_ptr(), L.ptr(bias), mean.data_ptr(),
+                                    var.data_ptr(), float(eps), w_f.data_ptr(), b_f.data_ptr(), L.stream()), "bn_fold_fwd")
+        ctx.save_for_backward(weight, bias, gamma, mean, var)
+        ctx.eps = eps
+        return w_f, b_f
+
+    @staticmethod
+    def backward(ctx, dw_f, db_f):
+        lib = L.load()
+        weight, bias, gamma, mean, var = ctx.saved_tensors
+        k, n = weight.shape[0], weight.numel() // weight.shape[0]
+        if dw_f is None:
+            dw_f = torch.zeros_like(weight)
+        dw_f = dw_f.contiguous()
+        db_f = None if db_f is None else db_f.contiguous()
+        dw = torch.empty_like(weight) if ctx.needs_input_grad[0] else None
+        out6 = torch.empty((k, 6), dtype=torch.float32, device=weight.device)
+        L.check(lib.mnb_bn_fold_bwd(dw_f.data_ptr(), L.ptr(db_f), weight.data_ptr(), k, n, gamma.data_ptr(), L.ptr(bias),
+                                    mean.data_ptr(), var.data_ptr(), float(ctx.eps), L.ptr(dw), out6.data_ptr(), L.stream()),
+                "bn_fold_bwd")
+        g = ctx.needs_input_grad
+        return (dw, out6[:, 2] if (bias is not None and g[1]) else None, out6[:, 0] if g[2] else None,
+                out6[:, 1] if g[3] else None, out6[:, 3] if g[4] else None, out6[:, 4] if g[5] else None, None)
+
+
 # --------------------------------------------------------------------------
 # per-channel batch statistics (BN-fuse training path, IAO:853-855)
 # --------------------------------------------------------------------------

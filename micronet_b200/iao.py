@@ -349,26 +349,26 @@ class QuantBNFuseConv2d(QuantConv2d):
             pre = F_.quant_conv2d(input, self.weight, self.bias, None, None, None, self.stride, self.padding,
                                   self.dilation, self.groups)
             batch_mean, batch_var = F_.channel_mean_var(pre)
-            with torch.no_grad():
-                if (not self.pretrained_model) and self.num_flag == 0:
-                    self.num_flag += 1
-                    self.running_mean.copy_(batch_mean)
-                    self.running_var.copy_(batch_var)
-                else:
-                    self.running_mean.copy_((1 - self.momentum) * self.running_mean + self.momentum * batch_mean)
-                    self.running_var.copy_((1 - self.momentum) * self.running_var + self.momentum * batch_var)
+            first = (not self.pretrained_model) and self.num_flag == 0
+            if first:
+                self.num_flag += 1
+            L.check(L.load().mnb_bn_fold_running(self.running_mean.data_ptr(), self.running_var.data_ptr(),
+                                                 batch_mean.detach().contiguous().data_ptr(),
+                                                 batch_var.detach().contiguous().data_ptr(), self.running_mean.numel(),
+                                                 float(self.momentum), 1 if first else 0, L.stream()), "bn_fold_running")
             mean, var = batch_mean, batch_var
         else:
             mean, var = self.running_mean, self.running_var
-        ratio = self.gamma / torch.sqrt(var + self.eps)
-        if self.bias is not None:
-            bias_fused = reshape_to_bias(self.beta + (self.bias - mean) * ratio)
-        else:
-            bias_fused = reshape_to_bias(self.beta - mean * ratio)
         if use_batch and self.bn_fuse_calib:
+            # calibration variant (IAO:936-945): the weight is folded with the RUNNING variance, the bias with the batch one
+            ratio = self.gamma / torch.sqrt(var + self.eps)
+            if self.bias is not None:
+                bias_fused = reshape_to_bias(self.beta + (self.bias - mean) * ratio)
+            else:
+                bias_fused = reshape_to_bias(self.beta - mean * ratio)
             weight_fused = self.weight * reshape_to_weight(self.gamma / torch.sqrt(self.running_var + self.eps))
         else:
-            weight_fused = self.weight * reshape_to_weight(ratio)
+            weight_fused, bias_fused = F_.BNFoldFn.apply(self.weight, self.bias, self.gamma, self.beta, mean, var, self.eps)
         if use_batch and self.bn_fuse_calib:  # IAO:957-972
             output = self._quant_conv(input, weight_fused, None)
             output = output * reshape_to_activation(
