@@ -468,6 +468,7 @@ struct ConvParams {
   // epilogue
   int B, THH, BW, OHr, OWr, OH, OW, omul, ny, ng, Nt, NOUT, C8O, smem_bytes, tmem_cols, mode, zero_y[MAXY];
   int nseg[MAXY];           // accumulation segments per work item (1 unless segmented)
+  int dbg;                  // MNB_PK_DEBUG (timing experiments only): 1 no epilogue stores, 2 no MMAs, 4 no TMEM loads
   const float* n_scale;     // [NOUT] per-output-channel scale or NULL
   const float* a_scale;     // device scalar multiplied into n_scale, or NULL
   float a_scale_const;
@@ -589,12 +590,12 @@ pk_conv_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_constant_
             // flat program: one word per MMA of this stage template (tap x piece pair x K-step).  The first MMA of a
             // segment overwrites the accumulator; the rest is a straight unrolled stream of independent
             // load-word / add / add / MMA groups (a single warp issues them: dependent chains cost MMA rate)
-            {
+            if (!(p.dbg & 2)) {
               const uint32_t w = p.m.prog[pb];
               tc::mma_f16_elect_lh(d, a_base + (w & 0xffffu), a_hi, b_base + (w >> 16), b_hi, p.m.idesc, started);
             }
 #pragma unroll 4
-            for (uint32_t e = 1; e < pc; ++e) {
+            for (uint32_t e = 1; e < ((p.dbg & 2) ? 0u : pc); ++e) {
               const uint32_t w = p.m.prog[pb + e];
               tc::mma_f16_elect_lh(d, a_base + (w & 0xffffu), a_hi, b_base + (w >> 16), b_hi, p.m.idesc, 1u);
             }
@@ -667,7 +668,7 @@ pk_conv_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_constant_
             const int n0 = c16 * 16;
             if (n0 >= p.Nt) break;
             uint32_t r[16];
-            if (!p.zero_y[y]) {
+            if (!p.zero_y[y] && !(p.dbg & 4)) {
               tmem_ld_32x16(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)((acc * p.MT + mt) * p.Nt + n0), r);
               tc::tmem_ld_wait();
             } else {
@@ -683,7 +684,7 @@ pk_conv_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_constant_
               }
               if (!last) continue;
             }
-            if (!valid || n0 >= n_cnt) continue;
+            if (!valid || n0 >= n_cnt || (p.dbg & 1)) continue;
             float sc[16], bs[16];
 #pragma unroll
             for (int v = 0; v < 4; ++v) {
@@ -1230,6 +1231,7 @@ extern "C" int mnb_pk_conv(const mnb_conv_shape* s, int32_t mode, const void* a_
   p.mode = mode;
   p.n_scale = n_scale; p.a_scale = a_scale; p.a_scale_const = a_scale_const; p.bias = bias; p.bits8 = bits8; p.gain = gain;
   p.out = out; p.err = err_flag;
+  { static const int dbg = [] { const char* e = getenv("MNB_PK_DEBUG"); return e ? atoi(e) : 0; }(); p.dbg = dbg; }
   CUtensorMap tm[3];
   const int C8tot = pl.nkph * pl.C8A;
   const int64_t plane_bytes = (int64_t)pl.B * C8tot * pl.HA * pl.WA * 16;
