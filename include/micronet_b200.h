@@ -92,7 +92,8 @@ int mnb_bn_fold_running(float* running_mean, float* running_var, const float* ba
 /* IAO QuantAdd (IAO:1441-1498) in one pass: out = Q(a) + Q(b) with the shared union-range quantizer (read both addends
  * once, write the sum; pass masks for the backward pass, either may be NULL).  Backward: da = STE_a(g), db = STE_b(g). */
 int mnb_quant_add_fwd(const float* a, const float* b, int64_t n, const mnb_act_qparams* qp, float* out,
-                      uint32_t* pass_bits_a, uint32_t* pass_bits_b, mnb_stream_t stream);
+                      uint32_t* pass_bits_a, uint32_t* pass_bits_b, int32_t relu /* out = max(., 0): inference graphs */,
+                      mnb_stream_t stream);
 int mnb_quant_add_bwd(const float* g, const uint32_t* pass_bits_a, const uint32_t* pass_bits_b, int64_t n,
                       const mnb_act_qparams* qp, float* da, float* db, mnb_stream_t stream);
 
@@ -329,6 +330,10 @@ int mnb_pk_pack_act(const float* x, int32_t batch, int32_t channels, int32_t h, 
 int mnb_bn_relu_quant_pack_fwd(const float* x, int32_t batch, int32_t channels, int32_t hw, const float* mean,
                                const float* invstd, const float* gamma, const float* beta, const mnb_act_qparams* qp,
                                int32_t out_shuffle_groups, void* x_packed, uint32_t* pass_bits, mnb_stream_t stream);
+/* mnb_pk_pack_act with a preceding nn.ReLU folded in (relu != 0: x is clamped at 0 before it is quantized / split) */
+int mnb_pk_pack_act_relu(const float* x, int32_t batch, int32_t channels, int32_t h, int32_t w, const mnb_act_qparams* qp,
+                         int32_t terms, const float* ch_scale, int32_t phase_split, int32_t relu, void* out_pk,
+                         uint8_t* bits8, mnb_stream_t stream);
 int mnb_pk_conv_plan(const mnb_conv_shape* s, int32_t mode, int32_t terms_a, int32_t terms_w, int32_t* out16); /* host only */
 int64_t mnb_pk_wimage_bytes(const mnb_conv_shape* s, int32_t mode, int32_t terms_a, int32_t terms_w);
 int mnb_pk_pack_weight(const mnb_conv_shape* s, int32_t mode, int32_t terms_a, int32_t terms_w, const int16_t* w_int,

@@ -180,19 +180,29 @@ static int make_plan(const mnb_conv_shape* s, int mode, int TA, int TBk, Plan& p
   else if (ng16 <= 256) p.Nt = round_up(ceil_div(p.ng, 2), 16);
   else p.Nt = 128;
   p.n_ntiles = ceil_div(p.ng, p.Nt);
+  // M tiles per work item: every item streams the WHOLE weight block of its (N tile, group) from L2 - measured floor of the
+  // 64 -> 64 3x3 layer with the MMAs switched off (MNB_PK_DEBUG=2): 190 us for the split-fp32 forward at MT = 1, i.e. L2 ->
+  // shared-memory bandwidth on the re-fetched weights.  MT M tiles share one weight fetch (TMEM: 2 x MT x Nt <= 512 columns;
+  // segmented mode keeps MT x Nt <= 128 running sums per thread in registers).  The items are dealt to 148 persistent
+  // CTAs, so a larger MT is taken only while it costs no wave efficiency.
   p.MT = 1;
-  if (!p.segmented && p.Nt <= 128 && p.n_mtiles >= 2) {
-    // two M tiles per work item halve the weight traffic of an item, but the items are dealt to 148 persistent CTAs:
-    // take the pairing only if it does not cost wave efficiency (172 items of a 512-channel 4x4 layer = 2 rounds for
-    // some SMs, 1 for the others: 58 %)
+  {
     auto wave_eff = [&](int mt) {
       const int64_t items = (int64_t)ceil_div(p.n_mtiles, mt) * p.n_ntiles * G;
       const int64_t ctas = std::max<int64_t>(1, MNB_NUM_SMS / p.ny);
       return (double)items / (double)(ceil_div((int)std::min<int64_t>(items, 1 << 30), (int)ctas) * ctas);
     };
-    if (wave_eff(2) >= wave_eff(1) - 0.04 && (int64_t)ceil_div(p.n_mtiles, 2) * p.n_ntiles * G * p.ny >= 120) p.MT = 2;
+    const int cap = p.segmented ? std::max(1, 128 / p.Nt) : std::max(1, 256 / p.Nt);
+    for (int mt = 2; mt <= std::min(4, cap); mt *= 2) {
+      if (p.n_mtiles < mt) break;
+      if ((int64_t)ceil_div(p.n_mtiles, mt) * p.n_ntiles * G * p.ny < 120) break;
+      if (wave_eff(mt) >= wave_eff(1) - 0.04) p.MT = mt;
+    }
   }
-  if (const char* e = getenv("MNB_PK_MT")) { const int v = atoi(e); if (v == 1 || (v == 2 && p.Nt <= 128 && !p.segmented)) p.MT = v; }
+  if (const char* e = getenv("MNB_PK_MT")) {
+    const int v = atoi(e);
+    if ((v == 1 || v == 2 || v == 4) && v * p.Nt <= (p.segmented ? 128 : 256)) p.MT = v;
+  }
   p.n_mgroups = ceil_div(p.n_mtiles, p.MT);
   p.n_items = p.n_mgroups * p.n_ntiles * G;
   // ---- K chunking and tap groups: one stage = MT * TA boxes of CC channels + the weights of (chunk, tap group)
@@ -285,7 +295,7 @@ template <int QUANT>
 __global__ void __launch_bounds__(256) pack_act_kernel(const float* __restrict__ x, int B, int C, int H, int W, int C8,
                                                        int terms, const float* __restrict__ ch_scale, mnb_act_qparams qp,
                                                        int a_off, int phase_split, uint4* __restrict__ out,
-                                                       int64_t plane_vecs, uint8_t* __restrict__ bits8) {
+                                                       int64_t plane_vecs, uint8_t* __restrict__ bits8, int relu) {
   MnbActQ q;
   float zp = 0.f;
   if (QUANT) {
@@ -308,6 +318,7 @@ __global__ void __launch_bounds__(256) pack_act_kernel(const float* __restrict__
     for (int j = 0; j < 8; ++j) {
       const int c = (int)c8 * 8 + j;
       float val = c < C ? __ldg(src + (int64_t)j * HW) : 0.f;
+      if (relu) val = fmaxf(val, 0.f);          // a preceding nn.ReLU folded into the packer (inference graphs)
       if (QUANT) {
         bool pass;
         const float lev = mnb_act_level_certified(q, val, pass);   // level itself (code + a_off), no int round trip
@@ -647,68 +658,76 @@ pk_conv_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_constant_
       }
       epi_bar_sync();
       const int nseg = SEG ? p.nseg[y] : 1;
-      float rs[SEG ? 8 : 1][16];   // running sums of the N tile (segmented mode only: Nt <= 128, MT = 1)
+      // running sums of the item's accumulator columns (segmented mode only: MT * Nt <= 128 -> 8 slots of 16 columns;
+      // slot = mt * (Nt / 16) + column chunk).  The slot loop is fully unrolled so that rs[][] stays in registers.
+      float rs[SEG ? 8 : 1][16];
+      const int nc16 = p.Nt >> 4, nslots = p.MT * nc16;
       for (int seg = 0; seg < nseg; ++seg, ++accq) {
         const uint32_t acc = accq & 1u, aph = (accq >> 1) & 1u;
         if (!tc::mbar_wait(&sh.acc_full[acc], aph, p.err, 704)) goto done;
         tc::tc_fence_after();
         const bool last = seg == nseg - 1;
-        for (int mt = 0; mt < p.MT; ++mt) {
-          const int tile = mg * p.MT + mt;
-          const int ct = tile % p.col_tiles;
-          const int r2 = tile / p.col_tiles;
-          const int rt = r2 % p.row_tiles, bt = r2 / p.row_tiles;
-          const int b = bt * p.TB + tb, i = rt * p.TH + th, j = ct * p.Wt + wc;
-          const bool valid = row_ok && tile < p.n_mtiles && b < p.B && i < p.OHr && j < p.OWr;
-          const int oh = i * p.omul + ya, ow = j * p.omul + yb;
-          float* orow = p.out + ((int64_t)b * p.NOUT + n_base) * plane + (int64_t)oh * p.OW + ow;
-          const uint8_t* brow = p.bits8 ? p.bits8 + (int64_t)b * p.C8O * plane + (int64_t)oh * p.OW + ow : nullptr;
+        int mt_cur = -1;
+        bool valid = false;
+        float* orow = nullptr;
+        const uint8_t* brow = nullptr;
 #pragma unroll
-          for (int c16 = 0; c16 < (SEG ? 8 : 16); ++c16) {
-            const int n0 = c16 * 16;
-            if (n0 >= p.Nt) break;
-            uint32_t r[16];
-            if (!p.zero_y[y] && !(p.dbg & 4)) {
-              tmem_ld_32x16(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)((acc * p.MT + mt) * p.Nt + n0), r);
-              tc::tmem_ld_wait();
-            } else {
+        for (int slot = 0; slot < (SEG ? 8 : 32); ++slot) {
+          if (slot >= nslots) break;
+          const int mt = slot / nc16, c16 = slot - mt * nc16, n0 = c16 * 16;
+          if (mt != mt_cur) {   // output row of this thread in M tile mt
+            mt_cur = mt;
+            const int tile = mg * p.MT + mt;
+            const int ct = tile % p.col_tiles;
+            const int r2 = tile / p.col_tiles;
+            const int rt = r2 % p.row_tiles, bt = r2 / p.row_tiles;
+            const int b = bt * p.TB + tb, i = rt * p.TH + th, j = ct * p.Wt + wc;
+            valid = row_ok && tile < p.n_mtiles && b < p.B && i < p.OHr && j < p.OWr;
+            const int oh = i * p.omul + ya, ow = j * p.omul + yb;
+            orow = p.out + ((int64_t)b * p.NOUT + n_base) * plane + (int64_t)oh * p.OW + ow;
+            brow = p.bits8 ? p.bits8 + (int64_t)b * p.C8O * plane + (int64_t)oh * p.OW + ow : nullptr;
+          }
+          uint32_t r[16];
+          if (!p.zero_y[y] && !(p.dbg & 4)) {
+            tmem_ld_32x16(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)((acc * p.MT + mt) * p.Nt + n0), r);
+            tc::tmem_ld_wait();
+          } else {
 #pragma unroll
-              for (int k = 0; k < 16; ++k) r[k] = 0u;
+            for (int k = 0; k < 16; ++k) r[k] = 0u;
+          }
+          if (SEG) {   // accumulate the segment (round-to-nearest fp32 adds), write only after the last one
+#pragma unroll
+            for (int k = 0; k < 16; ++k) {
+              const float v = seg == 0 ? __uint_as_float(r[k]) : __fadd_rn(rs[SEG ? slot : 0][k], __uint_as_float(r[k]));
+              rs[SEG ? slot : 0][k] = v;
+              r[k] = __float_as_uint(v);
             }
-            if (SEG) {   // accumulate the segment (round-to-nearest fp32 adds), write only after the last one
+            if (!last) continue;
+          }
+          if (!valid || n0 >= n_cnt || (p.dbg & 1)) continue;
+          float sc[16], bs[16];
 #pragma unroll
-              for (int k = 0; k < 16; ++k) {
-                const float v = seg == 0 ? __uint_as_float(r[k]) : __fadd_rn(rs[SEG ? c16 : 0][k], __uint_as_float(r[k]));
-                rs[SEG ? c16 : 0][k] = v;
-                r[k] = __float_as_uint(v);
-              }
-              if (!last) continue;
-            }
-            if (!valid || n0 >= n_cnt || (p.dbg & 1)) continue;
-            float sc[16], bs[16];
+          for (int v = 0; v < 4; ++v) {
+            const float4 a = *reinterpret_cast<const float4*>(&sh.epi_scale[n0 + 4 * v]);
+            const float4 c = *reinterpret_cast<const float4*>(&sh.epi_bias[n0 + 4 * v]);
+            sc[4 * v] = a.x; sc[4 * v + 1] = a.y; sc[4 * v + 2] = a.z; sc[4 * v + 3] = a.w;
+            bs[4 * v] = c.x; bs[4 * v + 1] = c.y; bs[4 * v + 2] = c.z; bs[4 * v + 3] = c.w;
+          }
+          float* op = orow + (int64_t)n0 * plane;
+          if (p.mode == 0 || !brow) {
 #pragma unroll
-            for (int v = 0; v < 4; ++v) {
-              const float4 a = *reinterpret_cast<const float4*>(&sh.epi_scale[n0 + 4 * v]);
-              const float4 c = *reinterpret_cast<const float4*>(&sh.epi_bias[n0 + 4 * v]);
-              sc[4 * v] = a.x; sc[4 * v + 1] = a.y; sc[4 * v + 2] = a.z; sc[4 * v + 3] = a.w;
-              bs[4 * v] = c.x; bs[4 * v + 1] = c.y; bs[4 * v + 2] = c.z; bs[4 * v + 3] = c.w;
-            }
-            float* op = orow + (int64_t)n0 * plane;
-            if (p.mode == 0 || !brow) {
+            for (int k = 0; k < 16; ++k, op += plane)
+              if (n0 + k < n_cnt) *op = fmaf(__uint_as_float(r[k]), sc[k], bs[k]);
+          } else {
+            // STE of the activation quantizer that fed the forward conv: the reference computes ((g*s)*pass)/s (IAO) or
+            // (((g*s)/s)*pass)*0.1 (DoReFa); (g*s)/s is g to within one ulp, so g itself is passed
+            const int oc0 = (n_base + n0) >> 3;     // n_base + n0 is a multiple of 8 (checked on the host)
+            const uint32_t m0 = __ldg(brow + (int64_t)oc0 * plane);
+            const uint32_t m1 = (n0 + 8 < n_cnt) ? __ldg(brow + (int64_t)(oc0 + 1) * plane) : 0u;
+            const uint32_t mask = m0 | (m1 << 8);
 #pragma unroll
-              for (int k = 0; k < 16; ++k, op += plane)
-                if (n0 + k < n_cnt) *op = fmaf(__uint_as_float(r[k]), sc[k], bs[k]);
-            } else {
-              // STE of the activation quantizer that fed the forward conv: the reference computes ((g*s)*pass)/s (IAO) or
-              // (((g*s)/s)*pass)*0.1 (DoReFa); (g*s)/s is g to within one ulp, so g itself is passed
-              const int oc0 = (n_base + n0) >> 3;     // n_base + n0 is a multiple of 8 (checked on the host)
-              const uint32_t m0 = __ldg(brow + (int64_t)oc0 * plane);
-              const uint32_t m1 = (n0 + 8 < n_cnt) ? __ldg(brow + (int64_t)(oc0 + 1) * plane) : 0u;
-              const uint32_t mask = m0 | (m1 << 8);
-#pragma unroll
-              for (int k = 0; k < 16; ++k, op += plane)
-                if (n0 + k < n_cnt) *op = ((mask >> k) & 1u) ? __uint_as_float(r[k]) * p.gain : 0.f;
-            }
+            for (int k = 0; k < 16; ++k, op += plane)
+              if (n0 + k < n_cnt) *op = ((mask >> k) & 1u) ? __uint_as_float(r[k]) * p.gain : 0.f;
           }
         }
         tc::tc_fence_before();
@@ -1094,6 +1113,12 @@ extern "C" int64_t mnb_pk_act_bytes(int32_t batch, int32_t channels, int32_t h, 
 extern "C" int mnb_pk_pack_act(const float* x, int32_t batch, int32_t channels, int32_t h, int32_t w,
                                const mnb_act_qparams* qp, int32_t terms, const float* ch_scale, int32_t phase_split,
                                void* out_pk, uint8_t* bits8, mnb_stream_t stream) {
+  return mnb_pk_pack_act_relu(x, batch, channels, h, w, qp, terms, ch_scale, phase_split, 0, out_pk, bits8, stream);
+}
+
+extern "C" int mnb_pk_pack_act_relu(const float* x, int32_t batch, int32_t channels, int32_t h, int32_t w,
+                                    const mnb_act_qparams* qp, int32_t terms, const float* ch_scale, int32_t phase_split,
+                                    int32_t relu, void* out_pk, uint8_t* bits8, mnb_stream_t stream) {
   MNB_REQUIRE(x && out_pk, "NULL pk_pack_act pointer");
   MNB_REQUIRE(batch > 0 && channels > 0 && h > 0 && w > 0 && terms >= 1 && terms <= 3, "bad pk_pack_act arguments");
   MNB_REQUIRE((reinterpret_cast<uintptr_t>(out_pk) & 15) == 0, "packed tensor must be 16-byte aligned");
@@ -1113,11 +1138,11 @@ extern "C" int mnb_pk_pack_act(const float* x, int32_t batch, int32_t channels, 
     if (qp->mode == MNB_ACT_DOREFA) MNB_REQUIRE(qp->bits >= 2 && qp->bits <= 8, "DoReFa a_bits must be in [2,8]");
     const int a_off = qp->mode == MNB_ACT_IAO ? qp->qmin : (qp->mode == MNB_ACT_SIGN ? -1 : 0);
     pk::pack_act_kernel<1><<<blocks, threads, 0, st>>>(x, batch, channels, h, w, C8, terms, nullptr, *qp, a_off, phase_split,
-                                                   reinterpret_cast<uint4*>(out_pk), plane_vecs, bits8);
+                                                   reinterpret_cast<uint4*>(out_pk), plane_vecs, bits8, relu);
   } else {
     mnb_act_qparams none{};
     pk::pack_act_kernel<0><<<blocks, threads, 0, st>>>(x, batch, channels, h, w, C8, terms, ch_scale, none, 0, phase_split,
-                                                   reinterpret_cast<uint4*>(out_pk), plane_vecs, nullptr);
+                                                   reinterpret_cast<uint4*>(out_pk), plane_vecs, nullptr, relu);
   }
   MNB_LAUNCHED(1);
   return 0;
@@ -1241,7 +1266,7 @@ extern "C" int mnb_pk_conv(const mnb_conv_shape* s, int32_t mode, const void* a_
   }
   const int gx = std::max(1, std::min(pl.n_items, MNB_NUM_SMS / pl.ny));
   if (pl.segmented) {
-    if (pl.Nt > 128 || pl.MT != 1) return mnb_fail(MNB_E_ARG, "pk conv: segmented plan with Nt %d, MT %d", pl.Nt, pl.MT);
+    if (pl.MT * pl.Nt > 128) return mnb_fail(MNB_E_ARG, "pk conv: segmented plan with Nt %d, MT %d", pl.Nt, pl.MT);
     if (int e = set_max_smem(pk_conv_kernel<true>, kSmemBudget)) return e;
     pk_conv_kernel<true><<<dim3(gx, pl.ny), NTHREADS, pl.smem_bytes, (cudaStream_t)stream>>>(tm[0], tm[1], tm[2], p);
   } else {

@@ -631,6 +631,10 @@ __global__ void __launch_bounds__(256) channel_stats_kernel(const float* __restr
   const int c = blockIdx.x, sp = blockIdx.y, nsp = gridDim.y;
   const int64_t per = (int64_t)batch * hw;
   double s1 = 0.0, s2 = 0.0;
+  // Sums are taken of (x - pivot), pivot = the channel's first value: sum(x^2) - N mean^2 in fp32 partials cancels
+  // catastrophically when |mean| >> std (a conv with a large bias); the shifted form is exact to fp32 rounding of the
+  // deviations (as_mean_var == 0, plain sums for bias gradients, keeps pivot 0).
+  const float pivot = as_mean_var ? __ldg(x + (int64_t)c * hw) : 0.f;
   // images [b_lo, b_hi) of this split.  The (image, offset) pairs of the split are walked as one flat index
   // space so that small planes (8x8) still keep every thread loading; fp32 partials per thread, fp64 across.
   const int b_lo = (int)((int64_t)batch * sp / nsp), b_hi = (int)((int64_t)batch * (sp + 1) / nsp);
@@ -645,7 +649,8 @@ __global__ void __launch_bounds__(256) channel_stats_kernel(const float* __restr
         const uint32_t t = t0 + u * blockDim.x;
         if (t < total) {
           const uint32_t b = t / hw4, i = t - b * hw4;
-          const float4 v = __ldg(base + ((int64_t)(b_lo + b) * channels + c) * hw4 + i);
+          float4 v = __ldg(base + ((int64_t)(b_lo + b) * channels + c) * hw4 + i);
+          v.x -= pivot; v.y -= pivot; v.z -= pivot; v.w -= pivot;
           f1[u] += (v.x + v.y) + (v.z + v.w);
           f2[u] += (v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w);
         }
@@ -658,7 +663,7 @@ __global__ void __launch_bounds__(256) channel_stats_kernel(const float* __restr
       const float* plane = x + ((int64_t)b * channels + c) * hw;
       float f1 = 0.f, f2 = 0.f;
       for (int i = threadIdx.x; i < hw; i += blockDim.x) {
-        const float v = __ldg(plane + i);
+        const float v = __ldg(plane + i) - pivot;
         f1 += v; f2 += v * v;
       }
       s1 += (double)f1;
@@ -679,8 +684,9 @@ __global__ void __launch_bounds__(256) channel_stats_kernel(const float* __restr
   s1 = 0.0; s2 = 0.0;
   for (int j = 0; j < nsp; ++j) { s1 += partial[((int64_t)c * nsp + j) * 2]; s2 += partial[((int64_t)c * nsp + j) * 2 + 1]; }
   if (as_mean_var) {
-    double mean = s1 / (double)per;
-    double ss = s2 - (double)per * mean * mean;
+    const double dmean = s1 / (double)per;          // mean of the deviations from the pivot
+    double mean = (double)pivot + dmean;
+    double ss = s2 - (double)per * dmean * dmean;
     if (ss < 0.0) ss = 0.0;
     double var = ss / (double)(per - 1);  // unbiased (torch.var default)
     stats[c] = (float)mean;
@@ -809,7 +815,8 @@ extern "C" int mnb_adam_step(float* p, const float* g, float* m, float* v, int64
 // intermediate tensors); the arithmetic per element is that of act_quant_fwd_kernel followed by __fadd_rn.
 __global__ void __launch_bounds__(256) quant_add_fwd_kernel(const float* __restrict__ a, const float* __restrict__ b,
                                                             int64_t n, mnb_act_qparams p, float* __restrict__ out,
-                                                            uint32_t* __restrict__ bits_a, uint32_t* __restrict__ bits_b) {
+                                                            uint32_t* __restrict__ bits_a, uint32_t* __restrict__ bits_b,
+                                                            int relu) {
   const MnbActQ q = mnb_load_actq(p);
   const int lane = threadIdx.x & 31;
   const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -835,7 +842,7 @@ __global__ void __launch_bounds__(256) quant_add_fwd_kernel(const float* __restr
       }
       const bool live = i < n;
       const uint32_t wa = __ballot_sync(0xffffffffu, live && pa), wb = __ballot_sync(0xffffffffu, live && pb);
-      if (live) out[i] = __fadd_rn(oa, ob);
+      if (live) { const float sum = __fadd_rn(oa, ob); out[i] = relu ? fmaxf(sum, 0.f) : sum; }
       if (lane == 0 && (base + 32 * j) < n) {
         if (bits_a) bits_a[(base >> 5) + j] = wa;
         if (bits_b) bits_b[(base >> 5) + j] = wb;
@@ -858,13 +865,13 @@ __global__ void __launch_bounds__(256) quant_add_bwd_kernel(const float* __restr
 }
 
 extern "C" int mnb_quant_add_fwd(const float* a, const float* b, int64_t n, const mnb_act_qparams* qp, float* out,
-                                 uint32_t* pass_bits_a, uint32_t* pass_bits_b, mnb_stream_t stream) {
+                                 uint32_t* pass_bits_a, uint32_t* pass_bits_b, int32_t relu, mnb_stream_t stream) {
   if (int e = check_actq(qp)) return e;
   MNB_REQUIRE(qp->mode != MNB_ACT_SIGN, "QuantAdd takes a DoReFa or IAO quantizer");
   MNB_REQUIRE(a && b && out && n >= 0, "NULL pointer");
   if (n == 0) return 0;
   int blocks = (int)std::min<int64_t>(mnb_ceil_div(n, 256 * 4), MNB_NUM_SMS * 8);
-  quant_add_fwd_kernel<<<blocks, 256, 0, S(stream)>>>(a, b, n, *qp, out, pass_bits_a, pass_bits_b);
+  quant_add_fwd_kernel<<<blocks, 256, 0, S(stream)>>>(a, b, n, *qp, out, pass_bits_a, pass_bits_b, relu);
   MNB_LAUNCHED(1);
   return 0;
 }

@@ -129,7 +129,7 @@ class QuantAddFn(Function):
     """IAO QuantAdd (IAO:1441-1498): Q(res) + Q(shortcut) with the shared quantizer, one kernel each way"""
 
     @staticmethod
-    def forward(ctx, a, b, spec: ActSpec):
+    def forward(ctx, a, b, spec: ActSpec, relu=False):
         L.require_cuda(a, b)
         lib = L.load()
         a, b = a.contiguous(), b.contiguous()
@@ -140,8 +140,9 @@ class QuantAddFn(Function):
         ba = torch.empty(words, dtype=torch.int32, device=a.device) if ctx.needs_input_grad[0] else None
         bb = torch.empty(words, dtype=torch.int32, device=a.device) if ctx.needs_input_grad[1] else None
         qp = spec.struct()
+        assert not (relu and (ba is not None or bb is not None)), "the folded ReLU is an inference-only fusion"
         L.check(lib.mnb_quant_add_fwd(a.data_ptr(), b.data_ptr(), n, C.byref(qp), out.data_ptr(), L.ptr(ba), L.ptr(bb),
-                                      L.stream()), "quant_add_fwd")
+                                      1 if relu else 0, L.stream()), "quant_add_fwd")
         ctx.spec, ctx.ba, ctx.bb = spec.frozen() if (ba is not None or bb is not None) else spec, ba, bb
         return out
 
@@ -154,7 +155,7 @@ class QuantAddFn(Function):
         qp = ctx.spec.struct()
         L.check(lib.mnb_quant_add_bwd(g.data_ptr(), L.ptr(ctx.ba), L.ptr(ctx.bb), g.numel(), C.byref(qp), L.ptr(da),
                                       L.ptr(db), L.stream()), "quant_add_bwd")
-        return da, db, None
+        return da, db, None, None
 
 
 # --------------------------------------------------------------------------
@@ -289,7 +290,7 @@ def _pk_terms(spec, w_int):
     return ta, (1 if w_int is not None else T)
 
 
-def _pk_forward(ctx, x, wq, bias, w_int, w_scale, spec, sh, y, need_dx, prepacked=None):
+def _pk_forward(ctx, x, wq, bias, w_int, w_scale, spec, sh, y, need_dx, prepacked=None, pre_relu=False):
     """forward on the packed-operand tensor-core family; returns False when the shape is outside its cover.
     ``prepacked``: the operand plane a fused producer (fused.BNReluQuantFn) already wrote - x itself holds no data then."""
     from . import pk as PK
@@ -297,17 +298,17 @@ def _pk_forward(ctx, x, wq, bias, w_int, w_scale, spec, sh, y, need_dx, prepacke
     if not PK.supported(sh, 0, ta, tw):
         return False
     # the backward of a layer stays in the family its forward ran in (saved operands are packed): check its cover now
-    T = L.PK_TERMS
-    if need_dx and not PK.supported(sh, 1, T, 1 if w_int is not None else T):
+    Tb = min(L.PK_TERMS, L.PK_TERMS_BWD)
+    if need_dx and not PK.supported(sh, 1, Tb, 1 if w_int is not None else Tb):
         return False
-    if ctx.needs_input_grad[1] and not PK.wgrad_supported(sh, T, ta):
+    if ctx.needs_input_grad[1] and not PK.wgrad_supported(sh, Tb, min(ta, Tb)):
         return False
     qp = spec.struct() if spec is not None else None
     split = sh.stride_h == 2
     if prepacked is not None:
         x_pk, bits8 = prepacked, None      # the producer keeps the STE mask for its own backward
     else:
-        x_pk, bits8 = PK.pack_act(x, qp, ta, phase_split=split, want_bits=need_dx)
+        x_pk, bits8 = PK.pack_act(x, qp, ta, phase_split=split, want_bits=need_dx, relu=pre_relu)
     # frozen (inference) modules hang a dict on their cached weight tensor: the packed image is then built once
     src = w_int if w_int is not None else wq
     cache = getattr(src, "_mnb_pk_cache", None)
@@ -338,7 +339,7 @@ def _pk_backward(ctx, dy):
     """data and weight gradients of a layer whose forward ran on the packed-operand path"""
     from . import pk as PK
     sh, spec = ctx.sh, ctx.spec
-    T = L.PK_TERMS
+    T = min(L.PK_TERMS, L.PK_TERMS_BWD)     # pieces of dy and of an fp32 second operand (see _lib.PK_TERMS_BWD)
     int_w = ctx.w_int is not None
     need_dx, need_dw = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
     # dy is packed once for both gradients; the data gradient wants the per-channel weight scale folded in (it sits on
@@ -361,7 +362,8 @@ def _pk_backward(ctx, dy):
         a_scale = None
         if spec is not None:
             a_scale = ctx.pk_a_scale if spec.mode == L.ACT_IAO else _dorefa_scale_tensor(spec.bits, dy.device)
-        L.check(_timed("wgrad_pk", sh, lambda: PK.wgrad(sh, dy_pk, T, ctx.pk_x, ctx.pk_ta, dwq, a_scale=a_scale,
+        tx = min(ctx.pk_ta, T)     # a 3-piece saved input contributes its two leading pieces
+        L.check(_timed("wgrad_pk", sh, lambda: PK.wgrad(sh, dy_pk, T, ctx.pk_x, tx, dwq, a_scale=a_scale,
                                                         kdiv=ctx.w_scale if fold else None)), "pk_wgrad")
     return dx, dwq
 
@@ -371,8 +373,9 @@ class QuantConv2dFn(Function):
     and the clip-STE fused into dgrad.  ``spec`` None => x is used as fp32 (wbwtab, a_bits=32)."""
 
     @staticmethod
-    def forward(ctx, x, wq, bias, w_int, w_scale, spec, stride, padding, dilation, groups):
+    def forward(ctx, x, wq, bias, w_int, w_scale, spec, stride, padding, dilation, groups, pre_relu=False):
         L.require_cuda(x, wq)
+        assert not (pre_relu and any(ctx.needs_input_grad)), "the folded ReLU is an inference-only fusion"
         lib = L.load()
         packed = getattr(x, "_mnb_packed", None) if L.USE_PACKED else None   # experimental, see fused.BNSignFn
         x = x.contiguous()
@@ -394,7 +397,9 @@ class QuantConv2dFn(Function):
             if not done:
                 raise RuntimeError("micronet_b200: fused producer output in front of a conv outside the packed-operand cover")
         if not done and L.PK_MODE != "off" and x.dtype == torch.float32 and (L.PK_MODE == "all" or spec is not None):
-            done = _pk_forward(ctx, x, wq, bias, w_int, w_scale, spec, sh, y, ctx.needs_input_grad[0])
+            done = _pk_forward(ctx, x, wq, bias, w_int, w_scale, spec, sh, y, ctx.needs_input_grad[0], pre_relu=pre_relu)
+        if not done and pre_relu:
+            x = torch.relu(x)     # outside the packed-operand cover: the folded ReLU as its own pass
         if not done and packed is not None and spec is None and w_int is not None and packed.numel() == x.numel() \
                 and L.PK_MODE != "off" and sh.stride_h == 1:
             # the BatchNorm + binarizer producer also wrote its +-1 output as the bf16 plane the packed-operand family
@@ -480,7 +485,7 @@ class QuantConv2dFn(Function):
             db = presummed if presummed is not None and presummed.numel() == dy.shape[1] else channel_sums(dy)
         if ctx.pk:
             dx, dwq = _pk_backward(ctx, dy)
-            return dx, dwq, db, None, None, None, None, None, None, None
+            return dx, dwq, db, None, None, None, None, None, None, None, None
         if ctx.needs_input_grad[0]:
             dx = torch.empty((sh.batch, sh.in_c, sh.in_h, sh.in_w), dtype=torch.float32, device=dy.device)
             qp = spec.struct() if spec is not None else None
@@ -541,12 +546,12 @@ class QuantConv2dFn(Function):
                 L.check(_timed("wgrad", sh, lambda: lib.mnb_conv2d_wgrad(
                     C.byref(sh), dy.data_ptr(), C.byref(ops), dwq.data_ptr(), ws.data_ptr(), L.stream())),
                     "conv2d_wgrad")
-        return dx, dwq, db, None, None, None, None, None, None, None
+        return dx, dwq, db, None, None, None, None, None, None, None, None
 
 
-def quant_conv2d(x, wq, bias, w_int, w_scale, spec, stride, padding, dilation, groups):
+def quant_conv2d(x, wq, bias, w_int, w_scale, spec, stride, padding, dilation, groups, pre_relu=False):
     return QuantConv2dFn.apply(x, wq, bias, w_int, w_scale, spec, tuple(stride), tuple(padding),
-                               tuple(dilation), groups)
+                               tuple(dilation), groups, pre_relu)
 
 
 def quant_linear(x, wq, bias, w_int, w_scale, spec):

@@ -287,7 +287,7 @@ class QuantConv2d(nn.Conv2d):
             wq, w_int, w_scale, bias = self._frozen_operands(lambda: (self.weight, self.bias))
             spec = self.activation_quantizer.prepare_activation(input)
             return F_.quant_conv2d(input, wq, bias, w_int, w_scale, spec, self.stride, self.padding, self.dilation,
-                                   self.groups)
+                                   self.groups, pre_relu=self.__dict__.get("_pre_relu", False))
         return self._quant_conv(input, self.weight, self.bias)
 
 
@@ -342,7 +342,7 @@ class QuantBNFuseConv2d(QuantConv2d):
             wq, w_int, w_scale, bias = self._frozen_operands(self._fold_running)
             spec = self.activation_quantizer.prepare_activation(input)
             return F_.quant_conv2d(input, wq, bias, w_int, w_scale, spec, self.stride, self.padding, self.dilation,
-                                   self.groups)
+                                   self.groups, pre_relu=self.__dict__.get("_pre_relu", False))
         use_batch = (not self.qaft) and self.training
         if use_batch:
             # un-quantised conv only to obtain the BN batch statistics (IAO:843-855)
@@ -488,7 +488,7 @@ class QuantAdd(nn.Module):
             return res + shortcut
         q._check_bits()
         q.refresh(res)          # union quantizer: update_qparams only (training, not QAFT)
-        return F_.QuantAddFn.apply(res, shortcut, q.act_spec())
+        return F_.QuantAddFn.apply(res, shortcut, q.act_spec(), bool(frozen and self.__dict__.get("_fuse_relu", False)))
 
 
 # ********************* prepare (IAO:1501-1824) *********************
@@ -564,13 +564,37 @@ def add_quant_op(module, a_bits=8, w_bits=8, q_type=0, q_level=0, weight_observe
 
 def freeze_inference(model, enable=True):
     """Opt-in inference fast path for an IAO-prepared model in eval mode (BASELINE.json configs[4], iao/main.py:511-519):
-    every quant conv / linear folds + quantizes its weights and packs their tensor-core image ONCE (re-done when a
-    parameter or buffer is written), and QuantAdd stops refreshing its observers, which cannot influence an eval
-    forward.  Outputs are bit-identical to the un-frozen eval forward."""
+    * every quant conv folds + quantizes its weights and packs their tensor-core image ONCE (re-done when a parameter or
+      buffer is written in place);
+    * QuantAdd stops refreshing its observers, which cannot influence an eval forward;
+    * an nn.ReLU whose only consumer is the next quant conv of an nn.Sequential is folded into that conv's operand packer,
+      and the nn.ReLU behind a residual QuantAdd (``self.act(self.add(res, shortcut))`` blocks) into the add kernel.
+    Outputs are bit-identical to the un-frozen eval forward; ``enable=False`` restores the modules."""
     for m in model.modules():
         if isinstance(m, (QuantConv2d, QuantLinear, QuantAdd)):
             m.__dict__["_frozen_inference"] = bool(enable)
             m.__dict__.pop("_frozen", None)
+            m.__dict__.pop("_pre_relu", None)
+            m.__dict__.pop("_fuse_relu", None)
+    for m in model.modules():
+        saved = m.__dict__.setdefault("_mnb_saved_relus", {})
+        for name, relu in list(saved.items()):       # undo an earlier rewrite first
+            m._modules[name] = relu
+        saved.clear()
+        if not enable:
+            continue
+        if isinstance(m, nn.Sequential):
+            kids = [(n, k) for n, k in m.named_children() if not isinstance(k, nn.Identity)]
+            for (n0, k0), (n1, k1) in zip(kids, kids[1:]):
+                if type(k0) is nn.ReLU and isinstance(k1, QuantConv2d) and not k1.quant_inference:
+                    k1.__dict__["_pre_relu"] = True
+                    saved[n0] = k0
+                    m._modules[n0] = nn.Identity()
+        add, act = m._modules.get("add"), m._modules.get("act")
+        if isinstance(add, QuantAdd) and type(act) is nn.ReLU:
+            add.__dict__["_fuse_relu"] = True
+            saved["act"] = act
+            m._modules["act"] = nn.Identity()
     return model
 
 

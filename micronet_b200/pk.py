@@ -40,7 +40,7 @@ def wgrad_supported(sh, terms_dy, terms_x):
     return _plan_cache[k] >= 0
 
 
-def pack_act(x, qp, terms, ch_scale=None, phase_split=False, want_bits=False):
+def pack_act(x, qp, terms, ch_scale=None, phase_split=False, want_bits=False, relu=False):
     """-> (planes u8[terms * B * ceil(C/8) * H * W * 16], bits8 u8[B, ceil(C/8), H, W] or None)"""
     lib = L.load()
     b, c, h, w = x.shape
@@ -49,8 +49,9 @@ def pack_act(x, qp, terms, ch_scale=None, phase_split=False, want_bits=False):
     bits = None
     if qp is not None and want_bits:
         bits = torch.empty((b, (c + 7) // 8, h, w), dtype=torch.uint8, device=x.device)
-    L.check(lib.mnb_pk_pack_act(x.data_ptr(), b, c, h, w, None if qp is None else C.byref(qp), terms, L.ptr(ch_scale),
-                                1 if phase_split else 0, out.data_ptr(), L.ptr(bits), L.stream()), "pk_pack_act")
+    L.check(lib.mnb_pk_pack_act_relu(x.data_ptr(), b, c, h, w, None if qp is None else C.byref(qp), terms, L.ptr(ch_scale),
+                                     1 if phase_split else 0, 1 if relu else 0, out.data_ptr(), L.ptr(bits), L.stream()),
+            "pk_pack_act")
     return out, bits
 
 
