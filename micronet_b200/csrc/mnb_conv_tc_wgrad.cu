@@ -29,6 +29,7 @@ struct Params {
   int npos_x, npos_d, ksteps, row_tiles, n_tiles;   // npos_d: gradient positions per tile (multiple of 16)
   int op_buf_bytes, nbuf;                            // one {activation, 3 x gradient} operand buffer; nbuf (1|2) are cycled
   int Gb, nsplit, n_block, n_slabs, ranks;
+  int seg_tiles;         // tiles per accumulation segment (tcgen05.mma truncates the running fp32 sum: bounded chains)
   int tap_groups, tpc;   // filter taps are split over `tap_groups` CTA sets of `tpc` taps (TMEM holds tpc * n_block columns)
   int quant_mode, a_offset, tmem_cols;
   int slot_bytes, stage_x_bytes, stage_d_bytes, xop_bytes, dop_term_bytes, off_stage, off_xop, off_dop;
@@ -102,6 +103,43 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
   tc::tc_fence_after();
   const uint32_t tmem = sh.tmem_slot;
 
+  // TMEM -> partial dW of this CTA (warps 4..7; `first`: plain stores, later segments add to the CTA's own earlier stores
+  // with round-to-nearest adds - the reason the K loop is cut into segments, see Params::seg_tiles)
+  auto drain = [&](bool have, bool first) {
+    const int q = warp - 4, m = q * 32 + lane;
+    const int64_t wsize = (int64_t)p.K * p.Cg * RS;
+    float* mine = p.partial + (int64_t)rank * wsize;
+    const int k_abs = dy_ch0 + m;
+    const int k_group = k_abs / p.Ng;
+    for (int tap = tap0; tap < tap1; ++tap) {
+      for (int n0 = 0; n0 < p.n_block; n0 += 32) {
+        uint32_t r[32];
+        if (have) {
+          tc::tmem_ld_32x32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)((tap - tap0) * p.n_block + n0), r);
+          tc::tmem_ld_wait();
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) r[j] = 0u;
+        }
+        if (m < m_real) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const int n = n0 + j;
+            if (n < p.n_block) {
+              const int xg = (x_ch0 + n) / p.Cg;           // group of this activation channel
+              if (xg == k_group) {
+                const int c = (x_ch0 + n) - xg * p.Cg;
+                float* dst = mine + ((int64_t)k_abs * p.Cg + c) * RS + tap;
+                *dst = first ? __uint_as_float(r[j]) : __fadd_rn(*dst, __uint_as_float(r[j]));
+              }
+            }
+          }
+        }
+      }
+    }
+    tc::tc_fence_before();
+  };
+
   if (warp == 0) {
     // ================================================================= TMA producer
     if (lane == 0) {
@@ -136,7 +174,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
       const uint64_t a_desc0 = tc::smem_desc_mnmajor_noswz(tc::smem_u32(dop), 128, (uint32_t)p.npos_d * 16u);
       const uint32_t buf16 = (uint32_t)p.op_buf_bytes >> 4;
       const uint32_t a_term = (uint32_t)p.dop_term_bytes >> 4;
-      uint32_t t = 0;
+      uint32_t t = 0, tseg = 0;
       for (int tile = rank; tile < p.n_tiles; tile += p.ranks, ++t) {
         const uint32_t ob = p.nbuf == 2 ? (t & 1u) : 0u, oph = p.nbuf == 2 ? ((t >> 1) & 1u) : (t & 1u);
         tc::mbar_wait_soft(&sh.op_full[ob], oph, p.err, 402, &sh.abort);
@@ -149,13 +187,20 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
           for (int ps = 0; ps < p.ksteps; ++ps) {
             const uint64_t bd = b_tap + (uint64_t)(ps * 16);   // 16 positions x 16 bytes = 256 B
             const uint64_t ad = a_desc0 + (uint64_t)(ob * buf16 + (uint32_t)(ps * 16));
-            tc::mma_f16_guarded(d_tmem, ad, bd, idesc, (t | (uint32_t)ps) != 0, lead);
+            tc::mma_f16_guarded(d_tmem, ad, bd, idesc, (tseg | (uint32_t)ps) != 0, lead);
             tc::mma_f16_guarded(d_tmem, ad + a_term, bd, idesc, 1, lead);
             tc::mma_f16_guarded(d_tmem, ad + 2 * a_term, bd, idesc, 1, lead);
           }
         }
         if (lead) tc::mma_commit(&sh.op_empty[ob]);
         __syncwarp();
+        if (++tseg == (uint32_t)p.seg_tiles && (int)(t + 1) < my_tiles) {
+          // segment complete: warps 4..7 drain the accumulators into the partial before they convert the next tile
+          // (their op_full arrival for that tile orders the drain before the overwriting MMA below)
+          if (lead) tc::mma_commit(&sh.done);
+          __syncwarp();
+          tseg = 0;
+        }
       }
       if (lead) tc::mma_commit(&sh.done);
       __syncwarp();
@@ -209,6 +254,12 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
       const int bt = tile / p.row_tiles, rt = tile - bt * p.row_tiles;
       const int b0 = bt * p.TB, h0 = rt * p.TH;
       const uint32_t ob = p.nbuf == 2 ? (t & 1u) : 0u, oph = p.nbuf == 2 ? ((t >> 1) & 1u) : (t & 1u);
+      if (warp < 8 && warp >= 4 && t > 0 && t % (uint32_t)p.seg_tiles == 0) {
+        const uint32_t seg = t / (uint32_t)p.seg_tiles - 1;
+        if (!tc::mbar_wait(&sh.done, seg & 1u, p.err, 406)) goto done;
+        tc::tc_fence_after();
+        drain(true, seg == 0);
+      }
       if (!tc::mbar_wait(&sh.op_empty[ob], oph ^ 1, p.err, 404)) goto done;  // MMAs of the tile two back retired
       uint8_t* xop_b = xop + (size_t)ob * p.op_buf_bytes;
       uint8_t* dop_b = dop + (size_t)ob * p.op_buf_bytes;
@@ -277,43 +328,14 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
     }
   }
   if (warp >= 4 && warp < 8) {
-    // ================================================================= final epilogue: TMEM -> partial dW
-    const int q = warp - 4, m = q * 32 + lane;
-    const int64_t wsize = (int64_t)p.K * p.Cg * RS;
-    float* mine = p.partial + (int64_t)rank * wsize;
-    bool have = my_tiles > 0;
+    // ================================================================= final epilogue: last segment -> partial dW
+    const bool have = my_tiles > 0;
+    const uint32_t last_seg = have ? (uint32_t)((my_tiles - 1) / p.seg_tiles) : 0u;
     if (have) {
-      if (!tc::mbar_wait(&sh.done, 0, p.err, 403)) goto done;
+      if (!tc::mbar_wait(&sh.done, last_seg & 1u, p.err, 403)) goto done;
       tc::tc_fence_after();
     }
-    const int k_abs = dy_ch0 + m;
-    const int k_group = k_abs / p.Ng;
-    for (int tap = tap0; tap < tap1; ++tap) {
-      for (int n0 = 0; n0 < p.n_block; n0 += 32) {
-        uint32_t r[32];
-        if (have) {
-          tc::tmem_ld_32x32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)((tap - tap0) * p.n_block + n0), r);
-          tc::tmem_ld_wait();
-        } else {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) r[j] = 0u;
-        }
-        if (m < m_real) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const int n = n0 + j;
-            if (n < p.n_block) {
-              const int xg = (x_ch0 + n) / p.Cg;           // group of this activation channel
-              if (xg == k_group) {
-                const int c = (x_ch0 + n) - xg * p.Cg;
-                mine[((int64_t)k_abs * p.Cg + c) * RS + tap] = __uint_as_float(r[j]);
-              }
-            }
-          }
-        }
-      }
-    }
-    tc::tc_fence_before();
+    drain(have, last_seg == 0);
   }
 done:
   tc::tc_fence_before();
@@ -437,6 +459,10 @@ static int plan(const mnb_conv_shape* s, int quant_mode, Params& p, int& smem_by
   p.row_tiles = (p.H + p.TH - 1) / p.TH;
   p.n_tiles = ((p.B + p.TB - 1) / p.TB) * p.row_tiles;
   p.ranks = std::max(1, std::min(p.n_tiles, MNB_NUM_SMS / p.n_slabs));  // one wave of CTAs
+  // chains of at most ~256 MMAs per accumulator (measured truncation bias of tcgen05.mma: 1.8e-8 |D| per instruction)
+  int chain = 256;
+  if (const char* e = getenv("MNB_WG_CHAIN")) chain = std::max(1, atoi(e));
+  p.seg_tiles = std::max(1, chain / (3 * p.ksteps));
   p.quant_mode = quant_mode;
   int cols = 32;
   while (cols < p.tpc * p.n_block) cols <<= 1;

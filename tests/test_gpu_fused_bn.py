@@ -85,8 +85,8 @@ def test_fused_bn_binarize_matches_bn_then_oracle_binarizer(shape, training, shu
     # the by-product handed to the producing convolution: channel sums of dx
 
     assert torch.equal(y.detach().cpu().double(), y_r)
-    assert rel_err(xg.grad, dx_r) < 2e-5
-    assert rel_err(fused.weight.grad, dg_r) < 2e-5 and rel_err(fused.bias.grad, db_r) < 2e-5
+    assert rel_err(xg.grad, dx_r) < 1e-5
+    assert rel_err(fused.weight.grad, dg_r) < 1e-5 and rel_err(fused.bias.grad, db_r) < 1e-5
     if training:
         assert rel_err(fused.running_mean, ref.running_mean) < 1e-6
         assert rel_err(fused.running_var, ref.running_var) < 1e-6
@@ -128,8 +128,8 @@ def test_fused_bn_binarize_pool_matches_reference_chain(shape, training, shuffle
     y = fused(xg)
     y.backward(go.to(DEV))
     assert torch.equal(y.detach().cpu().double(), y_r)
-    assert rel_err(xg.grad, dx_r) < 2e-5
-    assert rel_err(fused.weight.grad, dg_r) < 2e-5 and rel_err(fused.bias.grad, db_r) < 2e-5
+    assert rel_err(xg.grad, dx_r) < 1e-5
+    assert rel_err(fused.weight.grad, dg_r) < 1e-5 and rel_err(fused.bias.grad, db_r) < 1e-5
     if training:
         assert rel_err(fused.running_mean, ref.running_mean) < 1e-6 and rel_err(fused.running_var, ref.running_var) < 1e-6
 
