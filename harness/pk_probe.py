@@ -45,6 +45,7 @@ def main():
     ap.add_argument("--json", default=None)
     ap.add_argument("--batch", type=int, default=256)
     ap.add_argument("--only", default=None)
+    ap.add_argument("--compact", action="store_true", help="also print one short line per layer on stderr")
     args = ap.parse_args()
     from micronet_b200 import _lib as L, pk as PK
     dev = torch.device("cuda:0")
@@ -89,6 +90,17 @@ def main():
         rec["fwd_3x3"] = timeit(lambda i=0: L.check(PK.conv(sh, 0, xr[i % nb], 3, img33, 3, y), "c"))
         rec["dgrad_3x1"] = timeit(lambda i=0: L.check(PK.conv(sh, 1, dyp[i % nb], 3, imgd, 1, dx), "c"))
         rec["dgrad_3x3"] = timeit(lambda i=0: L.check(PK.conv(sh, 1, dyp[i % nb], 3, imgd3, 3, dx), "c"))
+        # what the QAT backward actually runs since round 2 (L.PK_TERMS_BWD = 2 pieces)
+        xr2 = [PK.pack_act(x, None, 2, phase_split=split)[0] for x in xs]
+        dyp2 = [PK.pack_act(d, None, 2)[0] for d in dys]
+        imgd2 = PK.pack_weight(sh, 1, 2, 2, w_f32=w_f)
+        imgd21 = PK.pack_weight(sh, 1, 2, 1, w_int=w_int)
+        rec["dgrad_2x1"] = timeit(lambda i=0: L.check(PK.conv(sh, 1, dyp2[i % nb], 2, imgd21, 1, dx), "c"))
+        rec["dgrad_2x2"] = timeit(lambda i=0: L.check(PK.conv(sh, 1, dyp2[i % nb], 2, imgd2, 2, dx), "c"))
+        if PK.wgrad_supported(sh, 2, 1):
+            rec["wgrad_2x1"] = timeit(lambda i=0: L.check(PK.wgrad(sh, dyp2[i % nb], 2, xq[i % nb], 1, dw), "w"))
+            rec["wgrad_2x2"] = timeit(lambda i=0: L.check(PK.wgrad(sh, dyp2[i % nb], 2, xr2[i % nb], 2, dw), "w"))
+        del xr2, dyp2
         if PK.wgrad_supported(sh, 3, 1):
             rec["wgrad_3x1"] = timeit(lambda i=0: L.check(PK.wgrad(sh, dyp[i % nb], 3, xq[i % nb], 1, dw), "w"))
             rec["wgrad_3x3"] = timeit(lambda i=0: L.check(PK.wgrad(sh, dyp[i % nb], 3, xr[i % nb], 3, dw), "w"))
@@ -98,6 +110,9 @@ def main():
         L.tc_check()
         rows.append(rec)
         print(json.dumps(rec))
+        if args.compact:
+            print("  " + name + ": " + " ".join(f"{k}={v:.0f}" for k, v in rec.items() if isinstance(v, float) and k not in ("GFLOP", "MB")),
+                  file=sys.stderr)
         del xs, dys, xq, xr, dyp
         torch.cuda.empty_cache()
     if args.json:

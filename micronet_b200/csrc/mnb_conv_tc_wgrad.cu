@@ -29,6 +29,7 @@ struct Params {
   int npos_x, npos_d, ksteps, row_tiles, n_tiles;   // npos_d: gradient positions per tile (multiple of 16)
   int op_buf_bytes, nbuf;                            // one {activation, 3 x gradient} operand buffer; nbuf (1|2) are cycled
   int Gb, nsplit, n_block, n_slabs, ranks;
+  int nseg_max;          // accumulation segments of the CTA with the most tiles (= partial slots per CTA)
   int seg_tiles;         // tiles per accumulation segment (tcgen05.mma truncates the running fp32 sum: bounded chains)
   int tap_groups, tpc;   // filter taps are split over `tap_groups` CTA sets of `tpc` taps (TMEM holds tpc * n_block columns)
   int quant_mode, a_offset, tmem_cols;
@@ -103,12 +104,13 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
   tc::tc_fence_after();
   const uint32_t tmem = sh.tmem_slot;
 
-  // TMEM -> partial dW of this CTA (warps 4..7; `first`: plain stores, later segments add to the CTA's own earlier stores
-  // with round-to-nearest adds - the reason the K loop is cut into segments, see Params::seg_tiles)
-  auto drain = [&](bool have, bool first) {
+  // TMEM -> the partial dW of (segment, CTA) (warps 4..7; plain stores: every accumulation segment has its own slot and the
+  // reduce kernel adds them in a fixed order with round-to-nearest adds - the reason the K loop is cut into segments,
+  // see Params::seg_tiles)
+  auto drain = [&](bool have, int seg) {
     const int q = warp - 4, m = q * 32 + lane;
     const int64_t wsize = (int64_t)p.K * p.Cg * RS;
-    float* mine = p.partial + (int64_t)rank * wsize;
+    float* mine = p.partial + ((int64_t)seg * p.ranks + rank) * wsize;
     const int k_abs = dy_ch0 + m;
     const int k_group = k_abs / p.Ng;
     for (int tap = tap0; tap < tap1; ++tap) {
@@ -129,8 +131,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
               const int xg = (x_ch0 + n) / p.Cg;           // group of this activation channel
               if (xg == k_group) {
                 const int c = (x_ch0 + n) - xg * p.Cg;
-                float* dst = mine + ((int64_t)k_abs * p.Cg + c) * RS + tap;
-                *dst = first ? __uint_as_float(r[j]) : __fadd_rn(*dst, __uint_as_float(r[j]));
+                mine[((int64_t)k_abs * p.Cg + c) * RS + tap] = __uint_as_float(r[j]);
               }
             }
           }
@@ -258,7 +259,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
         const uint32_t seg = t / (uint32_t)p.seg_tiles - 1;
         if (!tc::mbar_wait(&sh.done, seg & 1u, p.err, 406)) goto done;
         tc::tc_fence_after();
-        drain(true, seg == 0);
+        drain(true, (int)seg);
       }
       if (!tc::mbar_wait(&sh.op_empty[ob], oph ^ 1, p.err, 404)) goto done;  // MMAs of the tile two back retired
       uint8_t* xop_b = xop + (size_t)ob * p.op_buf_bytes;
@@ -335,7 +336,8 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
       if (!tc::mbar_wait(&sh.done, last_seg & 1u, p.err, 403)) goto done;
       tc::tc_fence_after();
     }
-    drain(have, last_seg == 0);
+    drain(have, (int)last_seg);
+    for (int seg = have ? (int)last_seg + 1 : 1; seg < p.nseg_max; ++seg) drain(false, seg);   // ranks with fewer tiles: zeros
   }
 done:
   tc::tc_fence_before();
@@ -353,9 +355,16 @@ __global__ void __launch_bounds__(256) wgrad_tc_reduce_kernel(const float* __res
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (; i < n; i += stride) {
-    float s = 0.f;
-    for (int j = 0; j < ranks; ++j) s += partial[(int64_t)j * n + i];
-    dwq[i] = __fmul_rn(s, sc);
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;   // four chains in flight, fixed order: deterministic
+    int j = 0;
+    for (; j + 4 <= ranks; j += 4) {
+      s0 += partial[(int64_t)j * n + i];
+      s1 += partial[(int64_t)(j + 1) * n + i];
+      s2 += partial[(int64_t)(j + 2) * n + i];
+      s3 += partial[(int64_t)(j + 3) * n + i];
+    }
+    for (; j < ranks; ++j) s0 += partial[(int64_t)j * n + i];
+    dwq[i] = __fmul_rn((s0 + s1) + (s2 + s3), sc);
   }
 }
 
@@ -463,6 +472,7 @@ static int plan(const mnb_conv_shape* s, int quant_mode, Params& p, int& smem_by
   int chain = 256;
   if (const char* e = getenv("MNB_WG_CHAIN")) chain = std::max(1, atoi(e));
   p.seg_tiles = std::max(1, chain / (3 * p.ksteps));
+  p.nseg_max = mnb_ceil_div(mnb_ceil_div(p.n_tiles, p.ranks), p.seg_tiles);
   p.quant_mode = quant_mode;
   int cols = 32;
   while (cols < p.tpc * p.n_block) cols <<= 1;
@@ -476,7 +486,7 @@ extern "C" int64_t mnb_wgrad_tc_scratch_bytes(const mnb_conv_shape* s) {
   tcwgrad::Params p{};
   int smem = 0;
   if (tcwgrad::plan(s, 0, p, smem)) return -1;
-  return (int64_t)p.ranks * p.K * p.Cg * p.R * p.S * 4;
+  return (int64_t)p.nseg_max * p.ranks * p.K * p.Cg * p.R * p.S * 4;
 }
 
 extern "C" int mnb_conv2d_wgrad_tc(const mnb_conv_shape* s, const float* dy, const float* x, const mnb_act_qparams* qp,
@@ -521,7 +531,7 @@ extern "C" int mnb_conv2d_wgrad_tc(const mnb_conv_shape* s, const float* dy, con
   const float a_const = (qp && qp->mode == MNB_ACT_DOREFA) ? (float)(1.0 / (double)((1 << qp->bits) - 1)) : 1.f;
   const float* a_ptr = (qp && qp->mode == MNB_ACT_IAO) ? qp->scale : nullptr;
   int blocks = (int)std::min<int64_t>(mnb_ceil_div(n, 256), MNB_NUM_SMS * 8);
-  wgrad_tc_reduce_kernel<<<blocks, 256, 0, st>>>(p.partial, n, p.ranks, a_ptr, a_const, dwq);
+  wgrad_tc_reduce_kernel<<<blocks, 256, 0, st>>>(p.partial, n, p.ranks * p.nseg_max, a_ptr, a_const, dwq);
   MNB_LAUNCHED(2);
   return 0;
 }

@@ -555,10 +555,12 @@ pk_conv_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_constant_
           for (int cc = 0; cc < p.chunks; ++cc, ++sc) {
             const uint32_t slot = sc & (uint32_t)p.st_mask, ph = (sc >> p.st_log2) & 1u;
             if (!tc::mbar_wait(&sh.empty[slot], ph ^ 1u, p.err, 701)) goto done;
-            tc::mbar_arrive_expect_tx(&sh.full[slot], (uint32_t)(p.MT * p.TA * p.a_box_bytes) + blk);
+            // MNB_PK_DEBUG bits 8 / 16 (timing experiments only): leave out the activation boxes / the weight block
+            const bool ld_a = !(p.dbg & 8), ld_b = !(p.dbg & 16);
+            tc::mbar_arrive_expect_tx(&sh.full[slot], (ld_a ? (uint32_t)(p.MT * p.TA * p.a_box_bytes) : 0u) + (ld_b ? blk : 0u));
             uint8_t* sbase = smem + (size_t)slot * p.stage_bytes;
             const int c8 = kph * p.C8A + g * p.kg8 + cc * p.CC8;
-            for (int mt = 0; mt < p.MT; ++mt) {
+            for (int mt = 0; mt < (ld_a ? p.MT : 0); ++mt) {
               const int tile = mg * p.MT + mt;
               const int ct = tile % p.col_tiles;
               const int r2 = tile / p.col_tiles;
@@ -568,7 +570,7 @@ pk_conv_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_constant_
               if (p.TA > 1) tc::tma_load_4d(sbase + (size_t)(mt * p.TA + 1) * p.a_bytes, &tmap1, &sh.full[slot], 2 * cw, chh, cb, c8);
               if (p.TA > 2) tc::tma_load_4d(sbase + (size_t)(mt * p.TA + 2) * p.a_bytes, &tmap2, &sh.full[slot], 2 * cw, chh, cb, c8);
             }
-            tc::bulk_load_1d(sbase + p.b_off, bsrc + (size_t)cc * blk, blk, &sh.full[slot]);
+            if (ld_b) tc::bulk_load_1d(sbase + p.b_off, bsrc + (size_t)cc * blk, blk, &sh.full[slot]);
           }
         }
       }

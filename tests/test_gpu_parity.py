@@ -258,6 +258,18 @@ QUANT_TYPES = ("QuantConv2d", "QuantBNFuseConv2d", "QuantLinear", "QuantAdd", "Q
                "QuantMaxPool2d", "QuantAvgPool2d", "ActivationQuantizer")
 
 
+_ERRLOG = []   # every comparison made by _teacher_forced ("name: kind value"); dumped when MNB_TEST_ERRLOG names a file
+
+
+def _dump_errlog():
+    import os
+    path = os.environ.get("MNB_TEST_ERRLOG")
+    if path:
+        with open(path, "a") as f:
+            f.write("\n".join(_ERRLOG) + "\n")
+    _ERRLOG.clear()
+
+
 def _teacher_forced(om, em, x, t, wtol=TOL):
     """every engine module of the prepared model (quant conv / linear / bn-fuse conv, binarizer,
     quantized add / pool), fed the ORACLE's own inputs and output-gradient at that layer (captured
@@ -296,6 +308,7 @@ def _teacher_forced(om, em, x, t, wtol=TOL):
     bad = []
 
     def check(ok, msg):
+        _ERRLOG.append(msg)
         if not ok:
             bad.append(msg)
 
@@ -365,6 +378,7 @@ def _teacher_forced(om, em, x, t, wtol=TOL):
                     check(err <= tol, f"{n}.{k}: {err:.2e} (flips {flips})")
     finally:
         L.KEEP_DEBUG = False
+        _dump_errlog()
     L.tc_check()
     assert not bad, "\n".join(bad)
 
@@ -486,6 +500,7 @@ def test_fused_headline_graph_blocks_teacher_forced(batch):
         if xe.grad is not None and j > 0:
             want_dx = xo.grad if in_g == 1 else _shuffle(xo.grad, in_g)
             err = rel_err(xe.grad, want_dx)
+            _ERRLOG.append(f"fused {n}: dx {err:.2e}")
             if err > TOL:
                 bad.append(f"{n}: dx {err:.2e}")
         ograds = {k: p.grad for k, p in ob.named_parameters()}
@@ -498,14 +513,16 @@ def test_fused_headline_graph_blocks_teacher_forced(batch):
                     bad.append(f"{n}.{k}: {d:.2e}")
                 continue
             err = rel_err(ge, go_)
+            _ERRLOG.append(f"fused {n}.{k}: {err:.2e}")
             if err > TOL:
                 bad.append(f"{n}.{k}: {err:.2e}")
         for k in ("running_mean", "running_var"):
             err = rel_err(getattr(e.bn, k), getattr(ob.bn, k))
             if err > TOL:
                 bad.append(f"{n}.bn.{k}: {err:.2e}")
+    _dump_errlog()
     L.tc_check()
-    assert nblocks == 10, nblocks
+    assert nblocks == 8, nblocks
     assert not bad, "\n".join(bad)
 
 
