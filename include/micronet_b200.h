@@ -341,6 +341,26 @@ int mnb_pk_pack_weight(const mnb_conv_shape* s, int32_t mode, int32_t terms_a, i
 int mnb_pk_conv(const mnb_conv_shape* s, int32_t mode, const void* a_pk, int32_t terms_a, const void* w_img, int32_t terms_w,
                 const float* n_scale, const float* a_scale, float a_scale_const, const float* bias, const uint8_t* bits8,
                 float gain, float* out, int32_t* err_flag, mnb_stream_t stream);
+/* Inference graphs with frozen quantizers (BASELINE.json configs[4], iao/main.py:511-519: eval forward of a calibrated model):
+ * the producer writes the operand plane of its consumer, so the fp32 activation between two quantized convs is neither
+ * written nor re-read nor packed in a separate pass.
+ *   mnb_pk_conv_post        : forward conv (mode 0 of mnb_pk_conv) whose epilogue also computes
+ *                             level = Q_consumer([ReLU](y)) (IAO:214-240 / DF:36-46 of the NEXT layer's activation quantizer)
+ *                             and stores it as that layer's bf16 plane; out may be NULL (plane only).
+ *   mnb_quant_add_pack_fwd  : IAO QuantAdd (IAO:1441-1498: out = Q(a) + Q(b) [-> ReLU]) that additionally quantizes its
+ *                             result for the consuming conv and writes that conv's plane (a, b, out: fp32 [B, C, H, W]).
+ * phase_split: the consumer is a stride-2 conv (space-to-depth plane order of mnb_pk_pack_act). */
+typedef struct mnb_pk_post {
+  const mnb_act_qparams* q; /* the consumer's activation quantizer, 2..8 bits, DoReFa or IAO */
+  int32_t relu;             /* an nn.ReLU sits between producer and consumer */
+  int32_t phase_split;
+  void* out_pk;             /* mnb_pk_act_bytes(B, C_out, OH, OW, 1) bytes, 16-byte aligned */
+} mnb_pk_post;
+int mnb_pk_conv_post(const mnb_conv_shape* s, const void* a_pk, int32_t terms_a, const void* w_img, int32_t terms_w,
+                     const float* n_scale, const float* a_scale, float a_scale_const, const float* bias, float* out,
+                     const mnb_pk_post* post, int32_t* err_flag, mnb_stream_t stream);
+int mnb_quant_add_pack_fwd(const float* a, const float* b, int32_t batch, int32_t channels, int32_t h, int32_t w,
+                           const mnb_act_qparams* qp, int32_t relu, float* out, const mnb_pk_post* post, mnb_stream_t stream);
 int64_t mnb_pk_wgrad_scratch_bytes(const mnb_conv_shape* s, int32_t terms_dy, int32_t terms_x);
 int mnb_pk_wgrad(const mnb_conv_shape* s, const void* dy_pk, int32_t terms_dy, const void* x_pk, int32_t terms_x,
                  const float* a_scale, const float* kdiv, float* dw, void* scratch, int32_t* err_flag, mnb_stream_t stream);

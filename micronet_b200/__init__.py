@@ -7,7 +7,7 @@
 All arithmetic runs in hand-written CUDA kernels exported through the C-ABI in
 ``include/micronet_b200.h`` (``micronet_b200/lib/libmicronet_b200.so``); there is no CPU path."""
 from . import _lib, functional  # noqa: F401
-from . import dorefa, fused, iao, wbwtab  # noqa: F401
+from . import bn_fuse, dorefa, fused, iao, wbwtab  # noqa: F401
 from .parallel import FlatAdam, FlatGradBucket  # noqa: F401
 
 __version__ = "0.1.0"

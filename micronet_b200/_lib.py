@@ -27,6 +27,11 @@ class ActQParams(C.Structure):
                 ("obs_min", C.c_void_p), ("obs_max", C.c_void_p)]
 
 
+class PkPost(C.Structure):
+    """mnb_pk_post: the consumer of a frozen-inference producer (its quantizer and operand plane)"""
+    _fields_ = [("q", C.POINTER(ActQParams)), ("relu", C.c_int32), ("phase_split", C.c_int32), ("out_pk", C.c_void_p)]
+
+
 class ConvOperands(C.Structure):
     _fields_ = [("a_codes", C.c_void_p), ("a_f32", C.c_void_p), ("a_offset", C.c_int32),
                 ("a_offset_zp", C.c_void_p), ("a_scale", C.c_void_p), ("w_int", C.c_void_p),
@@ -90,6 +95,8 @@ PROTOTYPES = {
     "mnb_pk_wimage_bytes": (_L, [_SHAPE, _I, _I, _I]),
     "mnb_pk_pack_weight": (C.c_int, [_SHAPE, _I, _I, _I, _P, _P, _P, _P, _P]),
     "mnb_pk_conv": (C.c_int, [_SHAPE, _I, _P, _I, _P, _I, _P, _P, C.c_float, _P, _P, C.c_float, _P, _P, _P]),
+    "mnb_pk_conv_post": (C.c_int, [_SHAPE, _P, _I, _P, _I, _P, _P, C.c_float, _P, _P, C.POINTER(PkPost), _P, _P]),
+    "mnb_quant_add_pack_fwd": (C.c_int, [_P, _P, _I, _I, _I, _I, _ACTQ, _I, _P, C.POINTER(PkPost), _P]),
     "mnb_pk_wgrad_scratch_bytes": (_L, [_SHAPE, _I, _I]),
     "mnb_pk_wgrad": (C.c_int, [_SHAPE, _P, _I, _P, _I, _P, _P, _P, _P, _P, _P]),
     "mnb_set_tc_profile_buffer": (None, [_P]),

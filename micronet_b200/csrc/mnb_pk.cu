@@ -391,6 +391,57 @@ __global__ void __launch_bounds__(256) bn_relu_quant_pack_kernel(const float* __
   }
 }
 
+// IAO QuantAdd of a frozen inference graph + the consuming conv's quantizer and operand packing in one pass (see
+// mnb_quant_add_pack_fwd): one thread = one pixel of one channel octet, same arithmetic as quant_add_fwd_kernel
+// (mnb_quant.cu) followed by pack_act_kernel<1>.
+__global__ void __launch_bounds__(256) quant_add_pack_kernel(const float* __restrict__ a, const float* __restrict__ b, int B, int C,
+                                                             int H, int W, int C8, mnb_act_qparams qadd, int relu,
+                                                             float* __restrict__ out, mnb_act_qparams qnext, int next_relu,
+                                                             int phase_split, uint4* __restrict__ out_pk) {
+  const MnbActQ q = mnb_load_actq(qadd), qn = mnb_load_actq(qnext);
+  const float zpn = (qnext.mode == MNB_ACT_IAO && qnext.zero_point) ? __ldg(qnext.zero_point) : 0.f;
+  const uint32_t HW = (uint32_t)H * (uint32_t)W;
+  const uint32_t plane = blockIdx.y * blockDim.y + threadIdx.y;                 // b * C8 + c8
+  if (plane >= (uint32_t)B * (uint32_t)C8) return;
+  const uint32_t bi = plane / (uint32_t)C8, c8 = plane - bi * (uint32_t)C8;
+  for (uint32_t pos = blockIdx.x * blockDim.x + threadIdx.x; pos < HW; pos += gridDim.x * blockDim.x) {
+    const int64_t base = ((int64_t)bi * C + c8 * 8) * HW + pos;
+    float va[8], vb[8], lev[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const bool live = (int)c8 * 8 + j < C;
+      va[j] = live ? __ldg(a + base + (int64_t)j * HW) : 0.f;
+      vb[j] = live ? __ldg(b + base + (int64_t)j * HW) : 0.f;
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const bool live = (int)c8 * 8 + j < C;
+      bool pa, pb;
+      const int ca = mnb_act_code_certified(q, va[j], pa), cb = mnb_act_code_certified(q, vb[j], pb);
+      float oa, ob;
+      if (q.mode == MNB_ACT_DOREFA) { oa = __fmul_rn((float)ca, q.s); ob = __fmul_rn((float)cb, q.s); }
+      else {
+        oa = __fmul_rn(__fadd_rn((float)(ca + q.qmin), q.zp), q.s);
+        ob = __fmul_rn(__fadd_rn((float)(cb + q.qmin), q.zp), q.s);
+      }
+      float sum = __fadd_rn(oa, ob);
+      if (relu) sum = fmaxf(sum, 0.f);
+      if (live) out[base + (int64_t)j * HW] = sum;
+      bool pass;
+      lev[j] = live ? mnb_act_level_certified(qn, next_relu ? fmaxf(sum, 0.f) : sum, pass) + zpn : 0.f;
+    }
+    int64_t dst;
+    if (phase_split) {
+      const uint32_t h = pos / (uint32_t)W, w = pos - h * (uint32_t)W;
+      const uint32_t oct = ((h & 1u) * 2u + (w & 1u)) * (uint32_t)C8 + c8;
+      dst = (((int64_t)bi * 4 * C8 + oct) * (H >> 1) + (h >> 1)) * (W >> 1) + (w >> 1);
+    } else {
+      dst = (int64_t)plane * HW + pos;
+    }
+    out_pk[dst] = make_uint4(pack2(lev[0], lev[1]), pack2(lev[2], lev[3]), pack2(lev[4], lev[5]), pack2(lev[6], lev[7]));
+  }
+}
+
 struct PackWParams {
   Plan pl;
   const int16_t* w_int; const float* w_f32; const float* kzero;   // kzero[k] == 0 -> the weights of channel k read as 0 (dgrad)
@@ -486,7 +537,12 @@ struct ConvParams {
   const float* bias;        // [NOUT] or NULL
   const uint8_t* bits8;     // dgrad STE mask [B][C8O][OH][OW] or NULL
   float gain;               // dgrad: factor on passed gradients (DoReFa 0.1)
-  float* out;
+  float* out;               // fp32 NCHW result, or NULL when only the packed output below is wanted
+  // fused consumer (inference graphs): the epilogue also applies [ReLU +] the NEXT conv's activation quantizer and writes
+  // that conv's operand plane [b][c/8][h][w][8] bf16 (space-to-depth phase planes for a stride-2 consumer)
+  uint4* post_out;
+  mnb_act_qparams post_q;
+  int post_relu, post_split;
   int* err;
 };
 
@@ -642,6 +698,12 @@ pk_conv_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_constant_
     const int y = blockIdx.y, ya = p.ny == 4 ? (y >> 1) : 0, yb = p.ny == 4 ? (y & 1) : 0;
     const int64_t plane = (int64_t)p.OH * p.OW;
     const float a_sc = p.a_scale ? __ldg(p.a_scale) : p.a_scale_const;
+    MnbActQ pq;
+    float pzp = 0.f;
+    if (p.post_out) {
+      pq = mnb_load_actq(p.post_q);
+      if (p.post_q.mode == MNB_ACT_IAO && p.post_q.zero_point) pzp = __ldg(p.post_q.zero_point);
+    }
     uint32_t accq = 0;
     for (int it = blockIdx.x; it < p.n_items; it += gridDim.x) {
       const int nt = it % p.n_ntiles;
@@ -673,6 +735,7 @@ pk_conv_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_constant_
         bool valid = false;
         float* orow = nullptr;
         const uint8_t* brow = nullptr;
+        int64_t prow = 0;      // vector index of this thread's position in octet 0 of the consumer's operand plane
 #pragma unroll
         for (int slot = 0; slot < (SEG ? 8 : 32); ++slot) {
           if (slot >= nslots) break;
@@ -686,8 +749,14 @@ pk_conv_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_constant_
             const int b = bt * p.TB + tb, i = rt * p.TH + th, j = ct * p.Wt + wc;
             valid = row_ok && tile < p.n_mtiles && b < p.B && i < p.OHr && j < p.OWr;
             const int oh = i * p.omul + ya, ow = j * p.omul + yb;
-            orow = p.out + ((int64_t)b * p.NOUT + n_base) * plane + (int64_t)oh * p.OW + ow;
+            orow = p.out ? p.out + ((int64_t)b * p.NOUT + n_base) * plane + (int64_t)oh * p.OW + ow : nullptr;
             brow = p.bits8 ? p.bits8 + (int64_t)b * p.C8O * plane + (int64_t)oh * p.OW + ow : nullptr;
+            if (p.post_out) {
+              if (p.post_split)   // octet index (h%2 * 2 + w%2) * C8 + c/8 of a [.., OH/2, OW/2] plane
+                prow = (((int64_t)b * 4 * p.C8O + ((oh & 1) * 2 + (ow & 1)) * p.C8O) * (p.OH >> 1) + (oh >> 1)) * (p.OW >> 1) + (ow >> 1);
+              else
+                prow = ((int64_t)b * p.C8O * p.OH + oh) * p.OW + ow;
+            }
           }
           uint32_t r[16];
           if (!p.zero_y[y] && !(p.dbg & 4)) {
@@ -716,7 +785,24 @@ pk_conv_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_constant_
             bs[4 * v] = c.x; bs[4 * v + 1] = c.y; bs[4 * v + 2] = c.z; bs[4 * v + 3] = c.w;
           }
           float* op = orow + (int64_t)n0 * plane;
-          if (p.mode == 0 || !brow) {
+          if (p.post_out) {
+            // forward conv of a frozen inference graph: y = acc * scale + bias [-> ReLU] -> consumer's quantizer -> bf16 levels
+            float lev[16];
+#pragma unroll
+            for (int k = 0; k < 16; ++k) {
+              float v = fmaf(__uint_as_float(r[k]), sc[k], bs[k]);
+              if (orow && n0 + k < n_cnt) op[(int64_t)k * plane] = v;
+              if (p.post_relu) v = fmaxf(v, 0.f);
+              bool pass;
+              lev[k] = n0 + k < n_cnt ? mnb_act_level_certified(pq, v, pass) + pzp : 0.f;
+            }
+            const int64_t oct_stride = p.post_split ? (int64_t)(p.OH >> 1) * (p.OW >> 1) : plane;
+            const int oc8 = (n_base + n0) >> 3;
+            uint4* dst = p.post_out + prow + (int64_t)oc8 * oct_stride;
+            dst[0] = make_uint4(pack2(lev[0], lev[1]), pack2(lev[2], lev[3]), pack2(lev[4], lev[5]), pack2(lev[6], lev[7]));
+            if (n0 + 8 < n_cnt)
+              dst[oct_stride] = make_uint4(pack2(lev[8], lev[9]), pack2(lev[10], lev[11]), pack2(lev[12], lev[13]), pack2(lev[14], lev[15]));
+          } else if (p.mode == 0 || !brow) {
 #pragma unroll
             for (int k = 0; k < 16; ++k, op += plane)
               if (n0 + k < n_cnt) *op = fmaf(__uint_as_float(r[k]), sc[k], bs[k]);
@@ -1150,6 +1236,29 @@ extern "C" int mnb_pk_pack_act_relu(const float* x, int32_t batch, int32_t chann
   return 0;
 }
 
+extern "C" int mnb_quant_add_pack_fwd(const float* a, const float* b, int32_t batch, int32_t channels, int32_t h, int32_t w,
+                                      const mnb_act_qparams* qp, int32_t relu, float* out, const mnb_pk_post* post,
+                                      mnb_stream_t stream) {
+  MNB_REQUIRE(a && b && qp && out && post && post->q && post->out_pk, "NULL quant_add_pack pointer");
+  MNB_REQUIRE(batch > 0 && channels > 0 && h > 0 && w > 0, "bad quant_add_pack shape");
+  MNB_REQUIRE(qp->mode == MNB_ACT_DOREFA || qp->mode == MNB_ACT_IAO, "QuantAdd takes a DoReFa or IAO quantizer");
+  MNB_REQUIRE(post->q->mode == MNB_ACT_DOREFA || post->q->mode == MNB_ACT_IAO, "consumer quantizer must be DoReFa or IAO");
+  MNB_REQUIRE(post->q->bits >= 2 && post->q->bits <= 8 && qp->bits >= 2 && qp->bits <= 8, "quantizers must have 2..8 bits");
+  MNB_REQUIRE((reinterpret_cast<uintptr_t>(post->out_pk) & 15) == 0, "packed tensor must be 16-byte aligned");
+  if (post->phase_split) MNB_REQUIRE(((h | w) & 1) == 0, "phase split needs even H and W");
+  const int C8 = (channels + 7) / 8;
+  const int hw = h * w;
+  const int tx = std::min(256, (hw + 31) / 32 * 32), ty = 256 / tx;
+  const int planes = batch * C8, gy = (planes + ty - 1) / ty;
+  const int bx = std::max(1, std::min((hw + tx - 1) / tx, std::max(1, (MNB_NUM_SMS * 16) / std::max(1, gy))));
+  if (gy > 65535) return mnb_fail(MNB_E_UNSUPPORTED, "quant_add_pack: %d (image, octet) planes exceed the grid", planes);
+  pk::quant_add_pack_kernel<<<dim3(bx, gy), dim3(tx, ty), 0, (cudaStream_t)stream>>>(
+      a, b, batch, channels, h, w, C8, *qp, relu, out, *post->q, post->relu, post->phase_split,
+      reinterpret_cast<uint4*>(post->out_pk));
+  MNB_LAUNCHED(1);
+  return 0;
+}
+
 extern "C" int mnb_bn_relu_quant_pack_fwd(const float* x, int32_t batch, int32_t channels, int32_t hw, const float* mean,
                                           const float* invstd, const float* gamma, const float* beta,
                                           const mnb_act_qparams* qp, int32_t out_shuffle_groups, void* x_packed,
@@ -1205,14 +1314,22 @@ extern "C" int mnb_pk_pack_weight(const mnb_conv_shape* s, int32_t mode, int32_t
   return 0;
 }
 
-extern "C" int mnb_pk_conv(const mnb_conv_shape* s, int32_t mode, const void* a_pk, int32_t terms_a, const void* w_img,
-                           int32_t terms_w, const float* n_scale, const float* a_scale, float a_scale_const,
-                           const float* bias, const uint8_t* bits8, float gain, float* out, int32_t* err_flag,
-                           mnb_stream_t stream) {
+static int pk_conv_impl(const mnb_conv_shape* s, int32_t mode, const void* a_pk, int32_t terms_a, const void* w_img,
+                        int32_t terms_w, const float* n_scale, const float* a_scale, float a_scale_const,
+                        const float* bias, const uint8_t* bits8, float gain, float* out, const mnb_pk_post* post,
+                        int32_t* err_flag, mnb_stream_t stream) {
   using namespace pk;
-  MNB_REQUIRE(s && a_pk && w_img && out && err_flag, "NULL pk_conv pointer");
+  MNB_REQUIRE(s && a_pk && w_img && (out || post) && err_flag, "NULL pk_conv pointer");
   Plan pl;
   if (int e = make_plan(s, mode, terms_a, terms_w, pl)) return e;
+  if (post) {
+    MNB_REQUIRE(mode == 0 && !bits8, "pk conv: a fused consumer is a forward-only (inference) option");
+    MNB_REQUIRE(post->q && post->out_pk && (reinterpret_cast<uintptr_t>(post->out_pk) & 15) == 0, "pk conv: consumer plane / quantizer");
+    MNB_REQUIRE(post->q->mode == MNB_ACT_DOREFA || post->q->mode == MNB_ACT_IAO, "pk conv: consumer quantizer must be DoReFa or IAO");
+    MNB_REQUIRE(post->q->bits >= 2 && post->q->bits <= 8, "pk conv: consumer levels must fit one bf16 piece (2..8 bits)");
+    if (pl.G > 1 && (pl.ng % 8)) return unsupported("fused consumer of a grouped conv needs channels per group % 8 == 0");
+    if (post->phase_split && ((pl.OH | pl.OW) & 1)) return unsupported("stride-2 consumer of an odd-sized plane");
+  }
   if (bits8 && pl.G > 1 && (pl.ng % 8)) return unsupported("STE mask of a grouped conv needs channels per group % 8 == 0");
   static ConvParams p;   // large POD: filled per call (single host thread per process)
   memset(&p, 0, sizeof(p));
@@ -1258,6 +1375,9 @@ extern "C" int mnb_pk_conv(const mnb_conv_shape* s, int32_t mode, const void* a_
   p.mode = mode;
   p.n_scale = n_scale; p.a_scale = a_scale; p.a_scale_const = a_scale_const; p.bias = bias; p.bits8 = bits8; p.gain = gain;
   p.out = out; p.err = err_flag;
+  if (post) {
+    p.post_out = reinterpret_cast<uint4*>(post->out_pk); p.post_q = *post->q; p.post_relu = post->relu; p.post_split = post->phase_split;
+  }
   { static const int dbg = [] { const char* e = getenv("MNB_PK_DEBUG"); return e ? atoi(e) : 0; }(); p.dbg = dbg; }
   CUtensorMap tm[3];
   const int C8tot = pl.nkph * pl.C8A;
@@ -1277,6 +1397,23 @@ extern "C" int mnb_pk_conv(const mnb_conv_shape* s, int32_t mode, const void* a_
   }
   MNB_LAUNCHED(1);
   return 0;
+}
+
+extern "C" int mnb_pk_conv(const mnb_conv_shape* s, int32_t mode, const void* a_pk, int32_t terms_a, const void* w_img,
+                           int32_t terms_w, const float* n_scale, const float* a_scale, float a_scale_const,
+                           const float* bias, const uint8_t* bits8, float gain, float* out, int32_t* err_flag,
+                           mnb_stream_t stream) {
+  MNB_REQUIRE(out, "NULL pk_conv output");
+  return pk_conv_impl(s, mode, a_pk, terms_a, w_img, terms_w, n_scale, a_scale, a_scale_const, bias, bits8, gain, out, nullptr,
+                      err_flag, stream);
+}
+
+extern "C" int mnb_pk_conv_post(const mnb_conv_shape* s, const void* a_pk, int32_t terms_a, const void* w_img, int32_t terms_w,
+                                const float* n_scale, const float* a_scale, float a_scale_const, const float* bias,
+                                float* out, const mnb_pk_post* post, int32_t* err_flag, mnb_stream_t stream) {
+  MNB_REQUIRE(post, "NULL consumer description");
+  return pk_conv_impl(s, 0, a_pk, terms_a, w_img, terms_w, n_scale, a_scale, a_scale_const, bias, nullptr, 1.f, out, post,
+                      err_flag, stream);
 }
 
 extern "C" int64_t mnb_pk_wgrad_scratch_bytes(const mnb_conv_shape* s, int32_t terms_dy, int32_t terms_x) {

@@ -554,6 +554,115 @@ def quant_conv2d(x, wq, bias, w_int, w_scale, spec, stride, padding, dilation, g
                                tuple(dilation), groups, pre_relu)
 
 
+# --------------------------------------------------------------------------
+# frozen inference graphs (iao.freeze_inference): producer -> consumer hand-off of packed operand planes
+# --------------------------------------------------------------------------
+class Consumer:
+    """the quantized conv that reads a producer's output next (set up by iao.freeze_inference): its frozen activation
+    quantizer, the nn.ReLU in between (folded away), its geometry, and whether anybody else needs the fp32 tensor"""
+
+    def __init__(self, module, spec, relu, only, w_shape, stride, padding, dilation, groups, int_weights):
+        self.module, self.spec, self.relu, self.only = module, spec, bool(relu), bool(only)
+        self.w_shape, self.stride, self.padding, self.dilation, self.groups = w_shape, stride, padding, dilation, groups
+        self.int_weights = int_weights
+
+    def accepts(self, act_shape):
+        """will the consumer's forward run on the packed-operand family with a one-piece plane of this activation?"""
+        from . import pk as PK
+        sp = self.spec
+        if sp is None or not self.int_weights or not (2 <= sp.bits <= 8) or _pk_terms(sp, True)[0] != 1:
+            return False
+        if act_shape[1] != self.w_shape[1] * self.groups:
+            return False
+        sh = _shape_struct(act_shape, self.w_shape, self.stride, self.padding, self.dilation, self.groups)
+        if sh.stride_h == 2 and ((act_shape[2] | act_shape[3]) & 1):
+            return False
+        return L.PK_MODE != "off" and PK.supported(sh, 0, 1, 1)
+
+    @property
+    def split(self):
+        return self.stride[0] == 2
+
+
+def handed_plane(module, x):
+    """the operand plane a producer wrote for ``module`` (None if ``x`` does not carry one that is still valid)"""
+    pre = getattr(x, "_mnb_pk_pre", None)
+    if pre is not None and pre[0] is module and (x.device.type == "meta" or x._version == pre[2]):
+        return pre[1]
+    if x.device.type == "meta":
+        raise RuntimeError("micronet_b200: a plane-only producer output reached a module it was not produced for")
+    return None
+
+
+def _tag(y, consumer, plane):
+    y._mnb_pk_pre = (consumer.module, plane, y._version)
+    return y
+
+
+@torch.no_grad()
+def frozen_conv(x, plane, wq, bias, w_int, w_scale, spec, stride, padding, dilation, groups, pre_relu=False, consumer=None):
+    """eval forward of a frozen quantized conv.  ``plane``: operand plane its producer already wrote (x holds no data
+    then); ``consumer``: write the next conv's plane from the epilogue (mnb_pk_conv_post)."""
+    from . import pk as PK
+    stride, padding, dilation = tuple(stride), tuple(padding), tuple(dilation)
+    sh = _shape_struct(x.shape, wq.shape, stride, padding, dilation, groups)
+    p, q = _out_hw(sh)
+    out_shape = (x.shape[0], wq.shape[0], p, q)
+    fused = consumer is not None and consumer.accepts(out_shape)
+    ta, tw = _pk_terms(spec, w_int)
+    if (plane is None and not fused) or spec is None or w_int is None or L.PK_MODE == "off" or not PK.supported(sh, 0, ta, tw):
+        if plane is not None:
+            raise RuntimeError("micronet_b200: handed-over plane in front of a conv outside the packed-operand cover")
+        return quant_conv2d(x, wq, bias, w_int, w_scale, spec, stride, padding, dilation, groups, pre_relu=pre_relu)
+    dev = wq.device
+    if plane is None:
+        L.require_cuda(x, wq)
+        plane, _ = PK.pack_act(x.contiguous(), spec.struct(), ta, phase_split=sh.stride_h == 2, relu=pre_relu)
+    cache = getattr(w_int, "_mnb_pk_cache", None)
+    ckey = (PK._key(sh), ta, tw)
+    w_img = cache.get(ckey) if cache is not None else None
+    if w_img is None:
+        w_img = PK.pack_weight(sh, 0, ta, tw, w_int=w_int)
+        if cache is not None:
+            cache[ckey] = w_img
+    a_scale = spec.scale if spec.mode == L.ACT_IAO else None
+    a_const = 1.0 / float(2 ** spec.bits - 1) if spec.mode == L.ACT_DOREFA else 1.0
+    if not fused:
+        y = torch.empty(out_shape, dtype=torch.float32, device=dev)
+        L.check(_timed("fwd_pk", sh, lambda: PK.conv(sh, 0, plane, ta, w_img, tw, y, n_scale=w_scale, a_scale=a_scale,
+                                                     a_scale_const=a_const, bias=bias)), "pk_conv fwd")
+        return y
+    y = None if consumer.only else torch.empty(out_shape, dtype=torch.float32, device=dev)
+    cplane = PK.consumer_plane(*out_shape, dev)
+    cqp = consumer.spec.struct()
+    L.check(_timed("fwd_pk", sh, lambda: PK.conv_post(sh, plane, ta, w_img, tw, y, cqp, cplane, consumer.relu, consumer.split,
+                                                      n_scale=w_scale, a_scale=a_scale, a_scale_const=a_const, bias=bias)),
+            "pk_conv_post")
+    if y is None:
+        y = torch.empty(out_shape, dtype=torch.float32, device="meta")   # shape only: the data lives in the consumer's plane
+    return _tag(y, consumer, cplane)
+
+
+@torch.no_grad()
+def frozen_quant_add(a, b, spec, relu, consumer=None):
+    """eval forward of a frozen QuantAdd; with a ``consumer`` the kernel also writes the next conv's operand plane"""
+    if consumer is None or not consumer.accepts(tuple(a.shape)) or a.dim() != 4:
+        return QuantAddFn.apply(a, b, spec, relu)
+    from . import pk as PK
+    L.require_cuda(a, b)
+    lib = L.load()
+    a, b = a.contiguous(), b.contiguous()
+    assert a.shape == b.shape, "QuantAdd: operand shapes differ"
+    out = torch.empty_like(a)
+    cplane = PK.consumer_plane(*a.shape, a.device)
+    qp, cqp = spec.struct(), consumer.spec.struct()
+    post = L.PkPost(C.pointer(cqp), 1 if (consumer.relu and not relu) else 0, 1 if consumer.split else 0, cplane.data_ptr())
+    L.check(lib.mnb_quant_add_pack_fwd(a.data_ptr(), b.data_ptr(), a.shape[0], a.shape[1], a.shape[2], a.shape[3],
+                                       C.byref(qp), 1 if relu else 0, out.data_ptr(), C.byref(post), L.stream()),
+            "quant_add_pack_fwd")
+    return _tag(out, consumer, cplane)
+
+
 def quant_linear(x, wq, bias, w_int, w_scale, spec):
     """F.linear on the same kernels: [*, C] -> 1x1 conv on a [N, C, 1, 1] view."""
     lead = x.shape[:-1]

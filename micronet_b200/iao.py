@@ -239,6 +239,21 @@ def _weight_quantizer(w_bits, q_type, q_level, weight_observer, out_channels, qa
     return cls(bits=w_bits, observer=observer, activation_weight_flag=0, qaft=qaft)
 
 
+def _consumer_of(producer):
+    """F_.Consumer for the conv that freeze_inference linked behind ``producer`` (None without a link)"""
+    link = producer.__dict__.get("_post_consumer")
+    if link is None:
+        return None
+    nxt, only = link
+    if not nxt._use_frozen() or nxt.quant_inference:
+        return None
+    aq, wq = nxt.activation_quantizer, nxt.weight_quantizer
+    if aq.bits == 32 or wq.bits == 32 or not wq.symmetric:
+        return None
+    return F_.Consumer(nxt, aq.act_spec(), nxt.__dict__.get("_pre_relu", False), only, tuple(nxt.weight.shape), tuple(nxt.stride),
+                       tuple(nxt.padding), tuple(nxt.dilation), nxt.groups, True)
+
+
 # ********************* quantized conv / linear *********************
 class QuantConv2d(nn.Conv2d):
     def __init__(self, in_channels, out_channels, kernel_size, stride=1, padding=0, dilation=1, groups=1,
@@ -282,12 +297,20 @@ class QuantConv2d(nn.Conv2d):
     def _use_frozen(self):
         return self.__dict__.get("_frozen_inference", False) and not self.training and not torch.is_grad_enabled()
 
+    def _frozen_forward(self, input, make):
+        """eval forward of a frozen module: cached quantized weights, the operand plane its producer may have written
+        (F_.handed_plane) and the plane it writes for its own consumer (freeze_inference's ``_post_consumer``)"""
+        wq, w_int, w_scale, bias = self._frozen_operands(make)
+        plane = F_.handed_plane(self, input)
+        aq = self.activation_quantizer
+        spec = aq.act_spec() if plane is not None else aq.prepare_activation(input)
+        return F_.frozen_conv(input, plane, wq, bias, w_int, w_scale, spec, self.stride, self.padding, self.dilation,
+                              self.groups, pre_relu=self.__dict__.get("_pre_relu", False),
+                              consumer=_consumer_of(self))
+
     def forward(self, input):
         if self._use_frozen():
-            wq, w_int, w_scale, bias = self._frozen_operands(lambda: (self.weight, self.bias))
-            spec = self.activation_quantizer.prepare_activation(input)
-            return F_.quant_conv2d(input, wq, bias, w_int, w_scale, spec, self.stride, self.padding, self.dilation,
-                                   self.groups, pre_relu=self.__dict__.get("_pre_relu", False))
+            return self._frozen_forward(input, lambda: (self.weight, self.bias))
         return self._quant_conv(input, self.weight, self.bias)
 
 
@@ -339,10 +362,7 @@ class QuantBNFuseConv2d(QuantConv2d):
 
     def forward(self, input):
         if self._use_frozen():   # eval / running statistics (IAO:903-935), folded and quantized once
-            wq, w_int, w_scale, bias = self._frozen_operands(self._fold_running)
-            spec = self.activation_quantizer.prepare_activation(input)
-            return F_.quant_conv2d(input, wq, bias, w_int, w_scale, spec, self.stride, self.padding, self.dilation,
-                                   self.groups, pre_relu=self.__dict__.get("_pre_relu", False))
+            return self._frozen_forward(input, self._fold_running)
         use_batch = (not self.qaft) and self.training
         if use_batch:
             # un-quantised conv only to obtain the BN batch statistics (IAO:843-855)
@@ -488,7 +508,10 @@ class QuantAdd(nn.Module):
             return res + shortcut
         q._check_bits()
         q.refresh(res)          # union quantizer: update_qparams only (training, not QAFT)
-        return F_.QuantAddFn.apply(res, shortcut, q.act_spec(), bool(frozen and self.__dict__.get("_fuse_relu", False)))
+        relu = bool(frozen and self.__dict__.get("_fuse_relu", False))
+        if frozen and not torch.is_grad_enabled():
+            return F_.frozen_quant_add(res, shortcut, q.act_spec(), relu, consumer=_consumer_of(self))
+        return F_.QuantAddFn.apply(res, shortcut, q.act_spec(), relu)
 
 
 # ********************* prepare (IAO:1501-1824) *********************
@@ -562,13 +585,16 @@ def add_quant_op(module, a_bits=8, w_bits=8, q_type=0, q_level=0, weight_observe
             add_quant_op(child, **kw)
 
 
-def freeze_inference(model, enable=True):
+def freeze_inference(model, enable=True, handoff=True):
     """Opt-in inference fast path for an IAO-prepared model in eval mode (BASELINE.json configs[4], iao/main.py:511-519):
     * every quant conv folds + quantizes its weights and packs their tensor-core image ONCE (re-done when a parameter or
       buffer is written in place);
     * QuantAdd stops refreshing its observers, which cannot influence an eval forward;
     * an nn.ReLU whose only consumer is the next quant conv of an nn.Sequential is folded into that conv's operand packer,
       and the nn.ReLU behind a residual QuantAdd (``self.act(self.add(res, shortcut))`` blocks) into the add kernel.
+    * ``handoff``: producers write the bf16 operand plane of the conv that consumes them (conv epilogue -> next conv of an
+      nn.Sequential, QuantAdd -> first conv of the next residual block; mnb_pk_conv_post / mnb_quant_add_pack_fwd), so those
+      convs need no separate quantize + pack pass and the Sequential intermediates are never written as fp32.
     Outputs are bit-identical to the un-frozen eval forward; ``enable=False`` restores the modules."""
     for m in model.modules():
         if isinstance(m, (QuantConv2d, QuantLinear, QuantAdd)):
@@ -576,6 +602,7 @@ def freeze_inference(model, enable=True):
             m.__dict__.pop("_frozen", None)
             m.__dict__.pop("_pre_relu", None)
             m.__dict__.pop("_fuse_relu", None)
+            m.__dict__.pop("_post_consumer", None)
     for m in model.modules():
         saved = m.__dict__.setdefault("_mnb_saved_relus", {})
         for name, relu in list(saved.items()):       # undo an earlier rewrite first
@@ -595,7 +622,36 @@ def freeze_inference(model, enable=True):
             add.__dict__["_fuse_relu"] = True
             saved["act"] = act
             m._modules["act"] = nn.Identity()
+    if enable and handoff:
+        _link_consumers(model)
     return model
+
+
+def _first_quant_conv(seq):
+    kids = [k for k in seq.children() if not isinstance(k, nn.Identity)] if isinstance(seq, nn.Sequential) else []
+    return kids[0] if kids and isinstance(kids[0], QuantConv2d) else None
+
+
+def _link_consumers(model):
+    """producer -> consumer links of the frozen graph (the consumer's operand plane is then written by the producer):
+    * two quant convs that are adjacent in an nn.Sequential (the nn.ReLU between them already folded away): the first
+      one's epilogue writes the second one's plane and no fp32 tensor at all - nobody else can read a Sequential's
+      intermediate;
+    * a residual block's QuantAdd (with its trailing ReLU folded in) -> the first conv of the NEXT block's
+      ``residual_function``: the add kernel writes fp32 (next shortcut) and that conv's plane.
+    A link is only a hint: the consumer takes the plane only if the tensor it receives is the tagged, unmodified producer
+    output (F_.handed_plane), so a wrong guess about the data flow costs a wasted write, never a wrong result."""
+    for m in model.modules():
+        if isinstance(m, nn.Sequential):
+            kids = [k for k in m.children() if not isinstance(k, nn.Identity)]
+            for k0, k1 in zip(kids, kids[1:]):
+                if isinstance(k0, QuantConv2d) and isinstance(k1, QuantConv2d):
+                    k0.__dict__["_post_consumer"] = (k1, True)
+    blocks = [m for m in model.modules() if isinstance(m._modules.get("add"), QuantAdd)
+              and _first_quant_conv(m._modules.get("residual_function")) is not None]
+    for b0, b1 in zip(blocks, blocks[1:]):
+        if b0._modules["add"].__dict__.get("_fuse_relu", False):
+            b0._modules["add"].__dict__["_post_consumer"] = (_first_quant_conv(b1._modules["residual_function"]), False)
 
 
 def prepare(model, inplace=False, a_bits=8, w_bits=8, q_type=0, q_level=0, weight_observer=0, bn_fuse=False,

@@ -75,6 +75,21 @@ def conv(sh, mode, a_pk, terms_a, w_img, terms_w, out, n_scale=None, a_scale=Non
                            L.tc_err_flag(out.device).data_ptr(), L.stream())
 
 
+def consumer_plane(b, c, h, w, device):
+    """empty operand plane (one bf16 piece) of a conv that reads a [b, c, h, w] activation"""
+    return torch.empty(int(L.load().mnb_pk_act_bytes(b, c, h, w, 1)), dtype=torch.uint8, device=device)
+
+
+def conv_post(sh, a_pk, terms_a, w_img, terms_w, out, post_qp, post_plane, post_relu, post_split, n_scale=None, a_scale=None,
+              a_scale_const=1.0, bias=None):
+    """forward conv whose epilogue also writes the consumer's operand plane (frozen inference graphs); out may be None"""
+    lib = L.load()
+    post = L.PkPost(C.pointer(post_qp), 1 if post_relu else 0, 1 if post_split else 0, post_plane.data_ptr())
+    return lib.mnb_pk_conv_post(C.byref(sh), a_pk.data_ptr(), terms_a, w_img.data_ptr(), terms_w, L.ptr(n_scale), L.ptr(a_scale),
+                                float(a_scale_const), L.ptr(bias), L.ptr(out), C.byref(post),
+                                L.tc_err_flag(a_pk.device).data_ptr(), L.stream())
+
+
 def wgrad(sh, dy_pk, terms_dy, x_pk, terms_x, dw, a_scale=None, kdiv=None):
     lib = L.load()
     nbytes = int(lib.mnb_pk_wgrad_scratch_bytes(C.byref(sh), terms_dy, terms_x))

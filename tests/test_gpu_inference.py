@@ -38,14 +38,76 @@ def test_frozen_inference_is_bit_identical_and_graph_safe():
     with torch.no_grad():
         eng.train(); eng(calib.to(DEV)); eng.eval()
         plain = eng(x.to(DEV)).clone()
-        iao.freeze_inference(eng)
+        lib = L.load()
+        iao.freeze_inference(eng, handoff=False)
+        eng(x.to(DEV))
+        n0 = lib.mnb_launch_count()
+        nohand = eng(x.to(DEV)).clone()
+        launches_nohand = lib.mnb_launch_count() - n0
+        iao.freeze_inference(eng)                  # producers write their consumer's operand plane
         n_identity = sum(isinstance(m, torch.nn.Identity) for m in eng.modules())
         frozen1 = eng(x.to(DEV)).clone()
+        n0 = lib.mnb_launch_count()
         frozen2 = eng(x.to(DEV)).clone()          # second call: cached weights / images
+        launches_hand = lib.mnb_launch_count() - n0
         iao.freeze_inference(eng, enable=False)
         back = eng(x.to(DEV)).clone()
+    assert torch.equal(plain, nohand)
     assert torch.equal(plain, frozen1) and torch.equal(plain, frozen2) and torch.equal(plain, back)
     assert n_identity > sum(isinstance(m, torch.nn.Identity) for m in eng.modules())   # the ReLUs came back
+    # 8 residual blocks: conv1 -> conv2 hand-offs (8 pack launches gone) and 7 QuantAdd -> next conv1 hand-offs
+    assert launches_hand <= launches_nohand - 15, (launches_hand, launches_nohand)
+    L.tc_check()
+
+
+def test_conv_epilogue_writes_the_consumers_plane():
+    """mnb_pk_conv_post / mnb_quant_add_pack_fwd against the separate kernels: same fp32 result, same operand plane"""
+    import ctypes as C
+    from micronet_b200 import _lib as L, functional as F_, pk as PK
+    torch.manual_seed(5)
+    B, Cc, H, W, K = 4, 64, 16, 16, 128
+    x = torch.randn(B, Cc, H, W, device=DEV) * 3
+    w_int = torch.randint(-127, 128, (K, Cc, 3, 3), dtype=torch.int16, device=DEV)
+    w_scale = torch.rand(K, device=DEV) * 0.01 + 0.001
+    bias = torch.randn(K, device=DEV)
+
+    def iao_spec(scale):
+        bufs = dict(scale=torch.tensor([scale]), zero_point=torch.zeros(1), obs_min=torch.tensor([-127.5 * scale]),
+                    obs_max=torch.tensor([127.5 * scale]))
+        return F_.ActSpec(L.ACT_IAO, qmin=-128, qmax=127, q_type=0, **{k: v.to(DEV) for k, v in bufs.items()})
+
+    spec, nxt = iao_spec(0.05), iao_spec(0.11)
+    sh = L.ConvShape(B, Cc, H, W, K, 3, 3, 1, 1, 1, 1, 1, 1, 1)
+    x_pk, _ = PK.pack_act(x, spec.struct(), 1)
+    w_img = PK.pack_weight(sh, 0, 1, 1, w_int=w_int)
+    y_ref = torch.empty(B, K, H, W, device=DEV)
+    L.check(PK.conv(sh, 0, x_pk, 1, w_img, 1, y_ref, n_scale=w_scale, a_scale=spec.scale, bias=bias), "conv")
+    for relu in (False, True):
+        for split in (False, True):
+            want, _ = PK.pack_act(y_ref, nxt.struct(), 1, phase_split=split, relu=relu)
+            for with_out in (True, False):
+                y = torch.empty_like(y_ref) if with_out else None
+                plane = PK.consumer_plane(B, K, H, W, DEV)
+                L.check(PK.conv_post(sh, x_pk, 1, w_img, 1, y, nxt.struct(), plane, relu, split, n_scale=w_scale,
+                                     a_scale=spec.scale, bias=bias), "conv_post")
+                assert torch.equal(plane, want), (relu, split, with_out)
+                if with_out:
+                    assert torch.equal(y, y_ref)
+    # QuantAdd + pack
+    a, b = torch.randn(B, K, H, W, device=DEV) * 4, torch.randn(B, K, H, W, device=DEV) * 4
+    add = iao_spec(0.07)
+    lib = L.load()
+    for relu in (False, True):
+        ref = F_.QuantAddFn.apply(a, b, add, relu)
+        for split in (False, True):
+            want, _ = PK.pack_act(ref, nxt.struct(), 1, phase_split=split)
+            out = torch.empty_like(a)
+            plane = PK.consumer_plane(B, K, H, W, DEV)
+            qp, cqp = add.struct(), nxt.struct()
+            post = L.PkPost(C.pointer(cqp), 0, 1 if split else 0, plane.data_ptr())
+            L.check(lib.mnb_quant_add_pack_fwd(a.data_ptr(), b.data_ptr(), B, K, H, W, C.byref(qp), 1 if relu else 0,
+                                               out.data_ptr(), C.byref(post), L.stream()), "quant_add_pack")
+            assert torch.equal(out, ref) and torch.equal(plane, want), (relu, split)
     L.tc_check()
 
 
