@@ -191,6 +191,72 @@ __device__ __forceinline__ float mnb_act_level_certified(const MnbActQ& q, float
   }
 }
 
+// Branch-free first half of mnb_act_level_certified: the provisional level / pass flag from the reciprocal product, and
+// `exact` = this element sits within `delta` of a decision boundary and must be redone with the IEEE division
+// (mnb_act_level_certified does that).  Callers evaluate a whole vector of elements with this straight-line code and
+// take ONE rarely-taken branch for the flagged ones: with the fallback branch inside every element (first version) a
+// lone epilogue warp could not overlap the elements' dependent chains - 360 cycles per element in pk_conv's fused
+// consumer epilogue, ncu r2q/r2r.
+__device__ __forceinline__ float mnb_act_level_fast(const MnbActQ& q, float x, bool& pass, bool& exact) {
+  if (q.mode == MNB_ACT_DOREFA) {
+    const float t = __fmul_rn(x, 0.1f);
+    pass = (t >= 0.f) && (t <= 1.f);
+    const float c = fminf(fmaxf(t, 0.f), 1.f);
+    const float pa = c * q.rinv;
+    const float f = pa + 0.5f;
+    const float r = floorf(f);
+    const float d = f - r, delta = 4e-7f * (pa + 1.f);
+    exact = d < delta || d > 1.f - delta;
+    return r;
+  } else if (q.mode == MNB_ACT_IAO) {
+    const float xa = x * q.rinv;
+    const float v = xa - q.zp;
+    const float av = fabsf(v);
+    const float f = av + 0.5f;
+    const float ra = floorf(f);
+    const float d = f - ra, delta = 4e-7f * (fabsf(xa) + fabsf(q.zp) + 1.f);
+    exact = d < delta || d > 1.f - delta || fabsf(v - q.hi) < delta || fabsf(v - q.lo) < delta || av < delta;
+    const float r = v > 0.f ? ra : (v < 0.f ? -ra : 0.f);
+    pass = !(v > q.hi) && !(v < q.lo) && (r >= (float)q.qmin) && (r <= (float)q.qmax);
+    return fminf(fmaxf(r, (float)q.qmin), (float)q.qmax);
+  } else {
+    exact = false;
+    pass = !(x >= 1.0f) && !(x <= -1.0f);
+    return !(x < 0.f) ? 1.f : -1.f;
+  }
+}
+
+// N levels at once: straight-line fast path for all, one branch for the (about 1e-4 of the) elements that need the exact
+// division.  lev[k] = effective level as a float (see mnb_act_level_certified), passbits bit k = STE pass flag.
+template <int N>
+__device__ __forceinline__ void mnb_act_levels(const MnbActQ& q, const float (&x)[N], float (&lev)[N], uint32_t& passbits) {
+  uint32_t redo = 0;
+  passbits = 0;
+#pragma unroll
+  for (int k = 0; k < N; ++k) {
+    bool pass, exact;
+    lev[k] = mnb_act_level_fast(q, x[k], pass, exact);
+    passbits |= pass ? (1u << k) : 0u;
+    redo |= exact ? (1u << k) : 0u;
+  }
+  if (redo) {
+#pragma unroll 1
+    for (int k = 0; k < N; ++k) {
+      if (!((redo >> k) & 1u)) continue;
+      bool pass;
+      float xv = 0.f;            // register arrays: dynamic element k through select chains, no local memory
+#pragma unroll
+      for (int j = 0; j < N; ++j)
+        if (j == k) xv = x[j];
+      const float l = mnb_act_level_certified(q, xv, pass);
+#pragma unroll
+      for (int j = 0; j < N; ++j)
+        if (j == k) lev[j] = l;
+      passbits = (passbits & ~(1u << k)) | (pass ? (1u << k) : 0u);
+    }
+  }
+}
+
 __device__ __forceinline__ float mnb_act_ste_one(const MnbActQ& q, float g, bool pass) {
   if (q.mode == MNB_ACT_DOREFA) return __fmul_rn(pass ? __fdiv_rn(__fmul_rn(g, q.s), q.s) : 0.f, 0.1f);
   if (q.mode == MNB_ACT_IAO) return pass ? __fdiv_rn(__fmul_rn(g, q.s), q.s) : 0.f;

@@ -319,15 +319,20 @@ __global__ void __launch_bounds__(256) pack_act_kernel(const float* __restrict__
       const int c = (int)c8 * 8 + j;
       float val = c < C ? __ldg(src + (int64_t)j * HW) : 0.f;
       if (relu) val = fmaxf(val, 0.f);          // a preceding nn.ReLU folded into the packer (inference graphs)
-      if (QUANT) {
-        bool pass;
-        const float lev = mnb_act_level_certified(q, val, pass);   // level itself (code + a_off), no int round trip
-        val = c < C ? lev + zp : 0.f;
-        passbits |= (pass && c < C) ? (1u << j) : 0u;
-      } else if (ch_scale) {
-        val = c < C ? __fmul_rn(val, __ldg(ch_scale + c)) : 0.f;
-      }
+      if (!QUANT && ch_scale) val = c < C ? __fmul_rn(val, __ldg(ch_scale + c)) : 0.f;
       v[j] = val;
+    }
+    if (QUANT) {   // level itself (code + a_off) as a float, eight channels in straight-line code
+      float lev[8];
+      mnb_act_levels<8>(q, v, lev, passbits);
+      uint32_t live = 0;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const bool in = (int)c8 * 8 + j < C;
+        v[j] = in ? lev[j] + zp : 0.f;
+        live |= in ? (1u << j) : 0u;
+      }
+      passbits &= live;
     }
     int64_t dst;
     if (phase_split) {
@@ -373,17 +378,23 @@ __global__ void __launch_bounds__(256) bn_relu_quant_pack_kernel(const float* __
     const int64_t t = w / p32n;
     const int oc8 = (int)(t % c8n), b = (int)(t / c8n);
     const int pos = p32 * 32 + lane;
-    float lev[8];
+    float lev[8], yv[8], bnv[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const int oc = oc8 * 8 + j;
       const int c = sg > 1 ? (oc % sg) * cpg + oc / sg : oc;   // inverse of out[:, a*sg + b] = in[:, b*cpg + a]
       const int64_t fi = ((int64_t)b * channels + c) * hw + pos;
-      const float bn = fmaf(__ldg(x + fi) - __ldg(mean + c), __ldg(gamma + c) * __ldg(invstd + c), __ldg(beta + c));
-      const float y = fmaxf(bn, 0.f);                          // nn.ReLU
-      bool pass;
-      lev[j] = mnb_act_level_certified(q, y, pass);            // DoReFa: pass = 0 <= 0.1 y <= 1
-      const uint32_t word = __ballot_sync(0xffffffffu, pass && bn > 0.f);   // relu'(0) = 0
+      bnv[j] = fmaf(__ldg(x + fi) - __ldg(mean + c), __ldg(gamma + c) * __ldg(invstd + c), __ldg(beta + c));
+      yv[j] = fmaxf(bnv[j], 0.f);                              // nn.ReLU
+    }
+    uint32_t passbits;
+    mnb_act_levels<8>(q, yv, lev, passbits);                   // DoReFa: pass = 0 <= 0.1 y <= 1
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int oc = oc8 * 8 + j;
+      const int c = sg > 1 ? (oc % sg) * cpg + oc / sg : oc;
+      const int64_t fi = ((int64_t)b * channels + c) * hw + pos;
+      const uint32_t word = __ballot_sync(0xffffffffu, ((passbits >> j) & 1u) && bnv[j] > 0.f);   // relu'(0) = 0
       if (lane == 0) bits[fi >> 5] = word;
     }
     xp[((int64_t)b * c8n + oc8) * hw + pos] = make_uint4(pack2(lev[0], lev[1]), pack2(lev[2], lev[3]), pack2(lev[4], lev[5]),
@@ -413,23 +424,25 @@ __global__ void __launch_bounds__(256) quant_add_pack_kernel(const float* __rest
       va[j] = live ? __ldg(a + base + (int64_t)j * HW) : 0.f;
       vb[j] = live ? __ldg(b + base + (int64_t)j * HW) : 0.f;
     }
+    // Q(a), Q(b): the level as a float (IAO: clamp(round(x/s - zp)), value = (level + zp) * s; DoReFa: value = level * s)
+    float la[8], lb[8], sum[8];
+    uint32_t pbits;
+    mnb_act_levels<8>(q, va, la, pbits);
+    mnb_act_levels<8>(q, vb, lb, pbits);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const bool live = (int)c8 * 8 + j < C;
-      bool pa, pb;
-      const int ca = mnb_act_code_certified(q, va[j], pa), cb = mnb_act_code_certified(q, vb[j], pb);
       float oa, ob;
-      if (q.mode == MNB_ACT_DOREFA) { oa = __fmul_rn((float)ca, q.s); ob = __fmul_rn((float)cb, q.s); }
-      else {
-        oa = __fmul_rn(__fadd_rn((float)(ca + q.qmin), q.zp), q.s);
-        ob = __fmul_rn(__fadd_rn((float)(cb + q.qmin), q.zp), q.s);
-      }
-      float sum = __fadd_rn(oa, ob);
-      if (relu) sum = fmaxf(sum, 0.f);
-      if (live) out[base + (int64_t)j * HW] = sum;
-      bool pass;
-      lev[j] = live ? mnb_act_level_certified(qn, next_relu ? fmaxf(sum, 0.f) : sum, pass) + zpn : 0.f;
+      if (q.mode == MNB_ACT_DOREFA) { oa = __fmul_rn(la[j], q.s); ob = __fmul_rn(lb[j], q.s); }
+      else { oa = __fmul_rn(__fadd_rn(la[j], q.zp), q.s); ob = __fmul_rn(__fadd_rn(lb[j], q.zp), q.s); }
+      float t = __fadd_rn(oa, ob);
+      if (relu) t = fmaxf(t, 0.f);
+      if (live) out[base + (int64_t)j * HW] = t;
+      sum[j] = next_relu ? fmaxf(t, 0.f) : t;
     }
+    mnb_act_levels<8>(qn, sum, lev, pbits);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) lev[j] = ((int)c8 * 8 + j < C) ? lev[j] + zpn : 0.f;
     int64_t dst;
     if (phase_split) {
       const uint32_t h = pos / (uint32_t)W, w = pos - h * (uint32_t)W;
@@ -518,8 +531,8 @@ struct ConvParams {
     // (16-byte units inside the stage); the issue loop is then  load word, two adds, MMA.  A single warp executes this
     // loop serially, so every instruction in it costs MMA issue rate (measured: 45 uniform-datapath instructions per
     // MMA = 420 cycles per MMA, tensor pipe 15 % busy).
-    uint16_t tmpl_begin[MAXY][MAXTMPL], tmpl_cnt[MAXY][MAXTMPL];
-    uint32_t prog[MAXPROG];
+    uint16_t tmpl_begin[MAXY][MAXTMPL], tmpl_cnt[MAXY][MAXTMPL];   // in groups of four words
+    alignas(16) uint4 prog4[MAXPROG / 4];                          // padded with 0xffffffff to whole groups
   } m;
   // TMA role
   int n_items, n_ntiles, G, MT, TA, chunks, CC8, C8A, kg8, stage_bytes, a_bytes, a_box_bytes, b_off, st_mask, st_log2;
@@ -660,13 +673,10 @@ pk_conv_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_constant_
             // segment overwrites the accumulator; the rest is a straight unrolled stream of independent
             // load-word / add / add / MMA groups (a single warp issues them: dependent chains cost MMA rate)
             if (!(p.dbg & 2)) {
-              const uint32_t w = p.m.prog[pb];
-              tc::mma_f16_elect_lh(d, a_base + (w & 0xffffu), a_hi, b_base + (w >> 16), b_hi, p.m.idesc, started);
-            }
-#pragma unroll 4
-            for (uint32_t e = 1; e < ((p.dbg & 2) ? 0u : pc); ++e) {
-              const uint32_t w = p.m.prog[pb + e];
-              tc::mma_f16_elect_lh(d, a_base + (w & 0xffffu), a_hi, b_base + (w >> 16), b_hi, p.m.idesc, 1u);
+              tc::mma_f16_x4(d, a_base, a_hi, b_base, b_hi, p.m.idesc, p.m.prog4[pb], started);
+#pragma unroll 2
+              for (uint32_t e = 1; e < pc; ++e)
+                tc::mma_f16_x4(d, a_base, a_hi, b_base, b_hi, p.m.idesc, p.m.prog4[pb + e], 1u);
             }
           }
           tc::mma_commit_elect(&sh.empty[slot]);
@@ -736,9 +746,10 @@ pk_conv_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_constant_
         float* orow = nullptr;
         const uint8_t* brow = nullptr;
         int64_t prow = 0;      // vector index of this thread's position in octet 0 of the consumer's operand plane
-#pragma unroll
-        for (int slot = 0; slot < (SEG ? 8 : 32); ++slot) {
-          if (slot >= nslots) break;
+        // one slot = 16 accumulator columns of one M tile.  Segmented kernels need rs[slot] with a compile-time index (8 slots,
+        // unrolled); the others run a ROLLED loop: unrolled 32 x, this body was 1 MB of SASS and the epilogue warps stalled
+        // on instruction fetch
+        auto do_slot = [&](const int slot, float (&rsl)[16]) {
           const int mt = slot / nc16, c16 = slot - mt * nc16, n0 = c16 * 16;
           if (mt != mt_cur) {   // output row of this thread in M tile mt
             mt_cur = mt;
@@ -751,7 +762,7 @@ pk_conv_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_constant_
             const int oh = i * p.omul + ya, ow = j * p.omul + yb;
             orow = p.out ? p.out + ((int64_t)b * p.NOUT + n_base) * plane + (int64_t)oh * p.OW + ow : nullptr;
             brow = p.bits8 ? p.bits8 + (int64_t)b * p.C8O * plane + (int64_t)oh * p.OW + ow : nullptr;
-            if (p.post_out) {
+            if (!SEG && p.post_out) {
               if (p.post_split)   // octet index (h%2 * 2 + w%2) * C8 + c/8 of a [.., OH/2, OW/2] plane
                 prow = (((int64_t)b * 4 * p.C8O + ((oh & 1) * 2 + (ow & 1)) * p.C8O) * (p.OH >> 1) + (oh >> 1)) * (p.OW >> 1) + (ow >> 1);
               else
@@ -769,13 +780,13 @@ pk_conv_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_constant_
           if (SEG) {   // accumulate the segment (round-to-nearest fp32 adds), write only after the last one
 #pragma unroll
             for (int k = 0; k < 16; ++k) {
-              const float v = seg == 0 ? __uint_as_float(r[k]) : __fadd_rn(rs[SEG ? slot : 0][k], __uint_as_float(r[k]));
-              rs[SEG ? slot : 0][k] = v;
+              const float v = seg == 0 ? __uint_as_float(r[k]) : __fadd_rn(rsl[k], __uint_as_float(r[k]));
+              rsl[k] = v;
               r[k] = __float_as_uint(v);
             }
-            if (!last) continue;
+            if (!last) return;
           }
-          if (!valid || n0 >= n_cnt || (p.dbg & 1)) continue;
+          if (!valid || n0 >= n_cnt || (p.dbg & 1)) return;
           float sc[16], bs[16];
 #pragma unroll
           for (int v = 0; v < 4; ++v) {
@@ -785,17 +796,19 @@ pk_conv_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_constant_
             bs[4 * v] = c.x; bs[4 * v + 1] = c.y; bs[4 * v + 2] = c.z; bs[4 * v + 3] = c.w;
           }
           float* op = orow + (int64_t)n0 * plane;
-          if (p.post_out) {
+          if (!SEG && p.post_out) {
             // forward conv of a frozen inference graph: y = acc * scale + bias [-> ReLU] -> consumer's quantizer -> bf16 levels
-            float lev[16];
+            float lev[16], yv[16];
 #pragma unroll
             for (int k = 0; k < 16; ++k) {
-              float v = fmaf(__uint_as_float(r[k]), sc[k], bs[k]);
+              const float v = fmaf(__uint_as_float(r[k]), sc[k], bs[k]);
               if (orow && n0 + k < n_cnt) op[(int64_t)k * plane] = v;
-              if (p.post_relu) v = fmaxf(v, 0.f);
-              bool pass;
-              lev[k] = n0 + k < n_cnt ? mnb_act_level_certified(pq, v, pass) + pzp : 0.f;
+              yv[k] = p.post_relu ? fmaxf(v, 0.f) : v;
             }
+            uint32_t passbits;
+            mnb_act_levels<16>(pq, yv, lev, passbits);
+#pragma unroll
+            for (int k = 0; k < 16; ++k) lev[k] = n0 + k < n_cnt ? lev[k] + pzp : 0.f;
             const int64_t oct_stride = p.post_split ? (int64_t)(p.OH >> 1) * (p.OW >> 1) : plane;
             const int oc8 = (n_base + n0) >> 3;
             uint4* dst = p.post_out + prow + (int64_t)oc8 * oct_stride;
@@ -817,6 +830,14 @@ pk_conv_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_constant_
             for (int k = 0; k < 16; ++k, op += plane)
               if (n0 + k < n_cnt) *op = ((mask >> k) & 1u) ? __uint_as_float(r[k]) * p.gain : 0.f;
           }
+                };
+        if (SEG) {
+#pragma unroll
+          for (int slot = 0; slot < 8; ++slot)
+            if (slot < nslots) do_slot(slot, rs[SEG ? slot : 0]);
+        } else {
+#pragma unroll 1
+          for (int slot = 0; slot < nslots; ++slot) do_slot(slot, rs[0]);
         }
         tc::tc_fence_before();
         tc::mbar_arrive(&sh.acc_empty[acc]);
@@ -1342,21 +1363,24 @@ static int pk_conv_impl(const mnb_conv_shape* s, int32_t mode, const void* a_pk,
   m.a_lbo = (uint32_t)pl.npos * 16u; m.b_lbo = (uint32_t)pl.Nt * 16u;
   m.seg_len = (uint32_t)pl.seg_len;
   int nprog = 0;
+  uint32_t* prog = reinterpret_cast<uint32_t*>(m.prog4);
+  for (int i = 0; i < MAXPROG; ++i) prog[i] = 0xffffffffu;    // padding words: no MMA
   for (int y = 0; y < pl.ny; ++y) {
     m.ntmpl[y] = pl.ntmpl[y]; p.ntmpl[y] = pl.ntmpl[y];
     for (int t = 0; t < pl.ntmpl[y]; ++t) {
       const Tmpl& tp = pl.tmpl[y][t];
       p.tmpl_kph[y][t] = tp.kph; p.tmpl_blk_off[y][t] = tp.blk_off; p.tmpl_blk_bytes[y][t] = tp.blk_bytes;
       const int cnt = tp.ntap * pl.npairs * pl.ksteps;
-      m.tmpl_begin[y][t] = (uint16_t)nprog; m.tmpl_cnt[y][t] = (uint16_t)cnt;
-      if (nprog + cnt > MAXPROG) return unsupported("MMA program longer than 512 entries");
+      nprog = (nprog + 3) & ~3;                       // every template starts on a group of four words
+      m.tmpl_begin[y][t] = (uint16_t)(nprog / 4); m.tmpl_cnt[y][t] = (uint16_t)((cnt + 3) / 4);
+      if (nprog + ((cnt + 3) & ~3) > MAXPROG) return unsupported("MMA program longer than 512 entries");
       for (int pr = 0; pr < pl.npairs; ++pr)          // piece pairs outermost: small products first
         for (int i = 0; i < tp.ntap; ++i)
           for (int j = 0; j < pl.ksteps; ++j) {
             const uint32_t a16 = (uint32_t)pl.tap_aoff[y][tp.tap0 + i] + (uint32_t)pl.pair_a[pr] * m.a_term16 + (uint32_t)j * m.a_k16;
             const uint32_t b16 = (uint32_t)i * m.b_tap16 + (uint32_t)pl.pair_b[pr] * (uint32_t)tp.ntap * m.b_tap16 + (uint32_t)j * m.b_k16;
             if (a16 > 0xffffu || b16 > 0xffffu) return mnb_fail(MNB_E_ARG, "pk conv: MMA program offset overflow");
-            m.prog[nprog++] = a16 | (b16 << 16);
+            prog[nprog++] = a16 | (b16 << 16);
           }
     }
     p.img_bytes[y] = pl.img_bytes[y]; p.y_off[y] = pl.y_off[y];

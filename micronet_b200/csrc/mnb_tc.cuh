@@ -172,6 +172,37 @@ __device__ __forceinline__ void mma_f16_elect_lh(uint32_t d_tmem, uint32_t a_lo,
       ::"r"(d_tmem), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// FOUR MMAs of a host-built issue program in one instruction group: w.x .. w.w = (A offset | B offset << 16) in 16-byte
+// units relative to a_base / b_base, 0xffffffff = no MMA (padding of the program to a multiple of four).  One election
+// and one 128-bit constant load per four MMAs; the first MMA takes `accumulate_first`, the others accumulate.
+// (Measured on the one-word-per-iteration loop, ncu source view: ~105 issue cycles per MMA against 61 of tensor time -
+// the indexed constant load sat on the critical path of every MMA, plus ELECT / VOTEU / 4 x R2UR each.)
+__device__ __forceinline__ void mma_f16_x4(uint32_t d_tmem, uint32_t a_base, uint32_t a_hi, uint32_t b_base, uint32_t b_hi,
+                                           uint32_t idesc, uint4 w, uint32_t accumulate_first) {
+  asm volatile(
+      "{\n\t.reg .pred q, p0, e1, e2, e3, pt;\n\t.reg .b64 da, db;\n\t.reg .b32 al, bl;\n\t"
+      "elect.sync _|q, 0xffffffff;\n\t"
+      "setp.ne.b32 p0, %10, 0;\n\t"
+      "setp.eq.b32 pt, %5, %5;\n\t"
+      "setp.ne.and.b32 e1, %7, 0xffffffff, q;\n\t"
+      "setp.ne.and.b32 e2, %8, 0xffffffff, q;\n\t"
+      "setp.ne.and.b32 e3, %9, 0xffffffff, q;\n\t"
+      "and.b32 al, %6, 0xffff;\n\tadd.u32 al, al, %1;\n\tshr.u32 bl, %6, 16;\n\tadd.u32 bl, bl, %3;\n\t"
+      "mov.b64 da, {al, %2};\n\tmov.b64 db, {bl, %4};\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p0;\n\t"
+      "and.b32 al, %7, 0xffff;\n\tadd.u32 al, al, %1;\n\tshr.u32 bl, %7, 16;\n\tadd.u32 bl, bl, %3;\n\t"
+      "mov.b64 da, {al, %2};\n\tmov.b64 db, {bl, %4};\n\t"
+      "@e1 tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, pt;\n\t"
+      "and.b32 al, %8, 0xffff;\n\tadd.u32 al, al, %1;\n\tshr.u32 bl, %8, 16;\n\tadd.u32 bl, bl, %3;\n\t"
+      "mov.b64 da, {al, %2};\n\tmov.b64 db, {bl, %4};\n\t"
+      "@e2 tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, pt;\n\t"
+      "and.b32 al, %9, 0xffff;\n\tadd.u32 al, al, %1;\n\tshr.u32 bl, %9, 16;\n\tadd.u32 bl, bl, %3;\n\t"
+      "mov.b64 da, {al, %2};\n\tmov.b64 db, {bl, %4};\n\t"
+      "@e3 tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, pt;\n\t}"
+      ::"r"(d_tmem), "r"(a_base), "r"(a_hi), "r"(b_base), "r"(b_hi), "r"(idesc), "r"(w.x), "r"(w.y), "r"(w.z), "r"(w.w),
+        "r"(accumulate_first)
+      : "memory");
+}
 __device__ __forceinline__ void mma_i8(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
                                        uint32_t accumulate) {
   asm volatile(
