@@ -215,7 +215,9 @@ __device__ __forceinline__ float mnb_act_level_fast(const MnbActQ& q, float x, b
     const float f = av + 0.5f;
     const float ra = floorf(f);
     const float d = f - ra, delta = 4e-7f * (fabsf(xa) + fabsf(q.zp) + 1.f);
-    exact = d < delta || d > 1.f - delta || fabsf(v - q.hi) < delta || fabsf(v - q.lo) < delta || av < delta;
+    // (no `av < delta` test here: it guards the SIGN of v, which only matters when ra >= 1, i.e. av >= 0.5 - and a
+    // ReLU output is exactly 0 for half of its elements, every one of which would take the slow path)
+    exact = d < delta || d > 1.f - delta || fabsf(v - q.hi) < delta || fabsf(v - q.lo) < delta;
     const float r = v > 0.f ? ra : (v < 0.f ? -ra : 0.f);
     pass = !(v > q.hi) && !(v < q.lo) && (r >= (float)q.qmin) && (r <= (float)q.qmax);
     return fminf(fmaxf(r, (float)q.qmin), (float)q.qmax);
