@@ -14,3 +14,5 @@ for mt in 1 2; do
   MNB_PK_MT=$mt timeout 300 python -m harness.pk_probe --only conv2_x --compact > $O/probe_mt$mt.log 2> $O/probe_mt$mt.txt
   echo "== probe mt=$mt"; grep "^  resnet" $O/probe_mt$mt.txt | cut -c1-330
 done
+timeout 900 python -m pytest tests/test_gpu_parity.py -m gpu -q -p no:cacheprovider > $O/parity.log 2>&1
+echo "== parity rc=$?"; grep -E "^FAILED|passed|failed" $O/parity.log | cut -c1-200 | tail -8; grep -E "^E   " $O/parity.log | cut -c1-250 | head -12

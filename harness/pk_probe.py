@@ -22,6 +22,8 @@ LAYERS = [
     ("resnet conv4_x 256->256 3x3 @8", 256, 8, 8, 256, 3, 1, 1, 1),
     ("resnet conv5_x 512->512 3x3 @4", 512, 4, 4, 512, 3, 1, 1, 1),
     ("nin 5x5 96->192 @16", 96, 16, 16, 192, 5, 1, 2, 1),
+    ("ptq224 conv2_x 64->64 3x3 @224 (use --batch 64)", 64, 224, 224, 64, 3, 1, 1, 1),
+    ("ptq224 conv3_x 128->128 3x3 @112 (use --batch 64)", 128, 112, 112, 128, 3, 1, 1, 1),
     ("nin-gc 1x1 g2 256->256 @32", 256, 32, 32, 256, 1, 1, 0, 2),
     ("nin-gc 3x3 g16 256->512 @16", 256, 16, 16, 512, 3, 1, 1, 16),
     ("nin-gc 1x1 g4 512->512 @16", 512, 16, 16, 512, 1, 1, 0, 4),

@@ -152,10 +152,30 @@ static int make_plan(const mnb_conv_shape* s, int mode, int TA, int TBk, Plan& p
   // ---- M tile: 128 consecutive positions of the zero-padded tile raster (tb, row, col)
   const int halo_w = wlo + whi;
   if (halo_w >= 96) return unsupported("filter too wide");
-  p.col_tiles = ceil_div(p.OWr, 128 - halo_w);
-  p.Wt = ceil_div(p.OWr, p.col_tiles);
-  p.BW = p.Wt + halo_w;
-  p.TH = std::max(1, std::min(p.OHr, 128 / p.BW));
+  // Column tiling: a tile is TH rows of Wt columns, rastered with the row pitch BW = Wt + halo, and its last valid position
+  // must be < 128.  Narrower tiles often hold MORE valid positions (224 wide: 1 x 112 = 112 vs 4 x 28 = 112 with a third
+  // of the halo rows; 32 wide: 3 x 32 = 96 vs 7 x 16 = 112) - every tile costs the same MMAs, and the halo rows are re-read
+  // (THH * BW) / (TH * Wt) times.  cost = tiles per image * (1 + 0.25 * read amplification) * (1 + 3.2 / Wt)
+  {
+    const int ct_min = ceil_div(p.OWr, 128 - halo_w);
+    double best = 1e30;
+    for (int ct = ct_min; ct <= std::min(p.OWr, ct_min + 14); ++ct) {
+      const int wt = ceil_div(p.OWr, ct), bw = wt + halo_w;
+      if (ceil_div(p.OWr, wt) != ct) continue;                       // same tiling as a smaller ct
+      const int th = std::max(1, std::min(p.OHr, (128 - wt) / bw + 1));
+      const double amp = (double)((th + hlo + hhi) * bw) / (double)(th * wt);
+      // (+ a mild preference for long rows: the epilogue's fp32 stores cover Wt * 4 contiguous bytes per channel and row)
+      const double cost = (double)ct * ceil_div(p.OHr, th) * (1.0 + 0.25 * amp) * (1.0 + 3.2 / wt);
+      if (cost < best - 1e-9) { best = cost; p.col_tiles = ct; p.Wt = wt; p.BW = bw; p.TH = th; }
+    }
+    if (const char* e = getenv("MNB_PK_COLTILES")) {                 // experiments: force the number of column tiles
+      const int ct = atoi(e);
+      if (ct >= ct_min && ct <= p.OWr) {
+        p.col_tiles = ct; p.Wt = ceil_div(p.OWr, ct); p.col_tiles = ceil_div(p.OWr, p.Wt); p.BW = p.Wt + halo_w;
+        p.TH = std::max(1, std::min(p.OHr, (128 - p.Wt) / p.BW + 1));
+      }
+    }
+  }
   p.THH = p.TH + hlo + hhi;
   p.TB = 1;
   if (p.TH == p.OHr && p.col_tiles == 1) {

@@ -497,7 +497,9 @@ def test_fused_headline_graph_blocks_teacher_forced(batch):
         # ---- the oracle's span, replayed on its own captured input
         side = {}
         hk = ob.bn.register_forward_hook(lambda m, i, out: side.__setitem__("bn", out.detach().clone()))
-        hk2 = ob.conv.register_forward_hook(lambda m, i, out: out.register_hook(lambda g: side.__setitem__("go_conv", g.detach().clone())))
+        def conv_hook(m, i, out):
+            out.register_hook(lambda g: side.__setitem__("go_conv", g.detach().clone()))
+        hk2 = ob.conv.register_forward_hook(conv_hook)
         xo = cap[n]["x"].clone().requires_grad_(True)
         yo = xo
         for s_ in span:
