@@ -27,6 +27,8 @@ LAYERS = [
     ("nin-gc 1x1 g2 256->256 @32", 256, 32, 32, 256, 1, 1, 0, 2),
     ("nin-gc 3x3 g16 256->512 @16", 256, 16, 16, 512, 3, 1, 1, 16),
     ("nin-gc 1x1 g4 512->512 @16", 512, 16, 16, 512, 1, 1, 0, 4),
+    ("nin-gc 3x3 g32 512->1024 @8", 512, 8, 8, 1024, 3, 1, 1, 32),
+    ("nin-gc 1x1 g8 1024->1024 @8", 1024, 8, 8, 1024, 1, 1, 0, 8),
 ]
 
 

@@ -95,6 +95,7 @@ PROTOTYPES = {
     "mnb_pk_wimage_bytes": (_L, [_SHAPE, _I, _I, _I]),
     "mnb_pk_pack_weight": (C.c_int, [_SHAPE, _I, _I, _I, _P, _P, _P, _P, _P]),
     "mnb_pk_conv": (C.c_int, [_SHAPE, _I, _P, _I, _P, _I, _P, _P, C.c_float, _P, _P, C.c_float, _P, _P, _P]),
+    "mnb_bn_sign_bwd_pack": (C.c_int, [_P, _P, _P, _I, _I, _I, _P, _P, _P, _P, _P, _I, _P, _I, _P, _P, _P]),
     "mnb_pk_conv_post": (C.c_int, [_SHAPE, _P, _I, _P, _I, _P, _P, C.c_float, _P, _P, C.POINTER(PkPost), _P, _P]),
     "mnb_quant_add_pack_fwd": (C.c_int, [_P, _P, _I, _I, _I, _I, _ACTQ, _I, _P, C.POINTER(PkPost), _P]),
     "mnb_pk_wgrad_scratch_bytes": (_L, [_SHAPE, _I, _I]),
@@ -196,6 +197,10 @@ PK_TERMS = int(os.environ.get("MNB_PK_TERMS", "3"))
 # decides an integer level depends on them.  The forward statistics conv keeps PK_TERMS (its mean / variance decide the
 # quantized weight levels).  MNB_PK_TERMS_BWD=3 restores the exact split.
 PK_TERMS_BWD = int(os.environ.get("MNB_PK_TERMS_BWD", "2"))
+# wbwtab layers between two fused BatchNorm + binarizer producers (fused.BatchNormBinarize2d) take the packed-operand family
+# with BOTH operands written by the producers: +-1 planes forward (mnb_bn_sign_fwd_packed), gradient pieces backward
+# (mnb_bn_sign_bwd_pack); 3x3 layers take it in any case.  MNB_PK_WBWTAB=0 keeps every wbwtab layer on the fused kernels.
+PK_WBWTAB = os.environ.get("MNB_PK_WBWTAB", "1") == "1"
 
 _scratch = {}
 

@@ -283,7 +283,7 @@ __global__ void __launch_bounds__(256) bn_sign_packed_fwd_kernel(const float* __
       const int64_t fi = ((int64_t)b * channels + c) * hw + pos;
       const float bn = fmaf(__ldg(x + fi) - __ldg(mean + c), __ldg(gamma + c) * __ldg(invstd + c), __ldg(beta + c));
       const bool neg = bn < 0.f;
-      y[((int64_t)b * channels + oc) * hw + pos] = neg ? -1.f : 1.f;
+      if (y) y[((int64_t)b * channels + oc) * hw + pos] = neg ? -1.f : 1.f;
       const uint32_t word = __ballot_sync(0xffffffffu, fabsf(bn) < 1.f);
       if (lane == 0) bits[fi >> 5] = word;
       h[j] = neg ? 0xBF80u : 0x3F80u;   // bf16 -1 / +1
@@ -298,7 +298,7 @@ __global__ void __launch_bounds__(256) bn_sign_packed_fwd_kernel(const float* __
 extern "C" int mnb_bn_sign_fwd_packed(const float* x, int32_t batch, int32_t channels, int32_t hw, const float* mean,
                                       const float* invstd, const float* gamma, const float* beta, int32_t out_shuffle_groups,
                                       float* y, uint32_t* pass_bits, void* x_packed, mnb_stream_t stream) {
-  MNB_REQUIRE(x && mean && invstd && gamma && beta && y && pass_bits && x_packed, "NULL bn_sign_fwd_packed pointer");
+  MNB_REQUIRE(x && mean && invstd && gamma && beta && pass_bits && x_packed, "NULL bn_sign_fwd_packed pointer");   // y may be NULL
   MNB_REQUIRE(batch > 0 && channels > 0 && hw > 0, "bad bn_sign_fwd_packed shape");
   MNB_REQUIRE(out_shuffle_groups >= 1 && channels % out_shuffle_groups == 0, "shuffle groups %d do not divide %d channels",
               out_shuffle_groups, channels);

@@ -288,12 +288,14 @@ extern "C" int mnb_bn_sign_bwd(const float* g, const uint32_t* pass_bits, const 
   if (planes_vectorizable(n, hw, x, g, dx)) {
     bn_sign_bwd_reduce_kernel<true><<<grid, 256, 0, S(stream)>>>(g, pass_bits, x, batch, channels, hw, out_shuffle_groups, mean,
                                                                  invstd, dgamma, dbeta, counters, partial);
+    if (training == 2) { MNB_LAUNCHED(1); return 0; }   // reduce pass only: the caller applies (mnb_bn_sign_bwd_pack)
     bn_sign_bwd_apply_kernel<true><<<grid, 256, 0, S(stream)>>>(g, pass_bits, x, batch, channels, hw, out_shuffle_groups,
                                                                 inv_count, mean, invstd, gamma, dgamma, dbeta, training, dx,
                                                                 dx_channel_sum, counters, partial);
   } else {
     bn_sign_bwd_reduce_kernel<false><<<grid, 256, 0, S(stream)>>>(g, pass_bits, x, batch, channels, hw, out_shuffle_groups, mean,
                                                                   invstd, dgamma, dbeta, counters, partial);
+    if (training == 2) { MNB_LAUNCHED(1); return 0; }
     bn_sign_bwd_apply_kernel<false><<<grid, 256, 0, S(stream)>>>(g, pass_bits, x, batch, channels, hw, out_shuffle_groups,
                                                                  inv_count, mean, invstd, gamma, dgamma, dbeta, training, dx,
                                                                  dx_channel_sum, counters, partial);

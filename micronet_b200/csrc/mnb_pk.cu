@@ -159,7 +159,16 @@ static int make_plan(const mnb_conv_shape* s, int mode, int TA, int TBk, Plan& p
   {
     const int ct_min = ceil_div(p.OWr, 128 - halo_w);
     double best = 1e30;
-    for (int ct = ct_min; ct <= std::min(p.OWr, ct_min + 14); ++ct) {
+    // (measured, r2w / r2x: the single-product kernels gain from narrower tiles - 64 -> 64 3x3 @32: 62 -> 53 us - while the
+    // segmented split-fp32 kernels lose 10 - 15 % unless the widest tiling re-reads its halo rows more than ~2.2 x, as on
+    // 112- and 224-wide planes)
+    int ct_max = std::min(p.OWr, ct_min + 14);
+    if (p.npairs > 1) {
+      const int wt0 = ceil_div(p.OWr, ct_min), bw0 = wt0 + halo_w;
+      const int th0 = std::max(1, std::min(p.OHr, (128 - wt0) / bw0 + 1));
+      if ((double)((th0 + hlo + hhi) * bw0) / (double)(th0 * wt0) <= 2.2) ct_max = ct_min;
+    }
+    for (int ct = ct_min; ct <= ct_max; ++ct) {
       const int wt = ceil_div(p.OWr, ct), bw = wt + halo_w;
       if (ceil_div(p.OWr, wt) != ct) continue;                       // same tiling as a smaller ct
       const int th = std::max(1, std::min(p.OHr, (128 - wt) / bw + 1));
@@ -475,6 +484,59 @@ __global__ void __launch_bounds__(256) quant_add_pack_kernel(const float* __rest
   }
 }
 
+// Second pass of the fused BatchNorm + binarizer backward (mnb_bn_sign_bwd: dgamma / dbeta already reduced) that writes the
+// gradient of the PRODUCING convolution's output directly as that convolution's packed operand: `terms` exact bf16 pieces
+// of  dx * ch_scale[c]  in the plane layout [t][b][c/8][h][w][8] (and, optionally, plain fp32 dx).  The conv's data- and
+// weight-gradient kernels then start from TMA loads; the separate pack pass (read 4 B, write 4 B per element) is gone.
+//   dx = gamma * invstd * (g * pass - dbeta / N - xhat * dgamma / N)            (training-mode BatchNorm, saturate STE)
+// one thread = one pixel of one channel octet (the conv's own channel order; g is read in the shuffled order)
+__global__ void __launch_bounds__(256) bn_sign_bwd_pack_kernel(const float* __restrict__ g, const uint32_t* __restrict__ bits,
+                                                               const float* __restrict__ x, int batch, int channels, int hw,
+                                                               int sg, float inv_count, const float* __restrict__ mean,
+                                                               const float* __restrict__ invstd, const float* __restrict__ gamma,
+                                                               const float* __restrict__ dgamma, const float* __restrict__ dbeta,
+                                                               const float* __restrict__ ch_scale, int terms,
+                                                               float* __restrict__ dx, uint4* __restrict__ out, int64_t plane_vecs) {
+  const int c8n = channels / 8, cpg = channels / sg;
+  const uint32_t plane = blockIdx.y * blockDim.y + threadIdx.y;                 // b * c8n + c8
+  if (plane >= (uint32_t)batch * (uint32_t)c8n) return;
+  const uint32_t b = plane / (uint32_t)c8n, c8 = plane - b * (uint32_t)c8n;
+  float k[8], db[8], dg[8], mu[8], is[8], sc[8];
+  int oc[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int c = (int)c8 * 8 + j;
+    mu[j] = __ldg(mean + c); is[j] = __ldg(invstd + c); k[j] = __ldg(gamma + c) * is[j];
+    db[j] = __ldg(dbeta + c) * inv_count; dg[j] = __ldg(dgamma + c) * inv_count;
+    sc[j] = ch_scale ? __ldg(ch_scale + c) : 1.f;
+    oc[j] = sg > 1 ? (c % cpg) * sg + c / cpg : c;      // out[:, a*sg + b] = in[:, b*cpg + a]
+  }
+  for (uint32_t pos = blockIdx.x * blockDim.x + threadIdx.x; pos < (uint32_t)hw; pos += gridDim.x * blockDim.x) {
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int64_t fi = ((int64_t)b * channels + (int64_t)c8 * 8 + j) * hw + pos;
+      const bool pass = (__ldg(bits + (fi >> 5)) >> (fi & 31)) & 1u;
+      float t = pass ? __ldg(g + ((int64_t)b * channels + oc[j]) * hw + pos) : 0.f;
+      t = t - db[j] - ((__ldg(x + fi) - mu[j]) * is[j]) * dg[j];
+      t = k[j] * t;
+      if (dx) dx[fi] = t;
+      v[j] = ch_scale ? __fmul_rn(t, sc[j]) : t;
+    }
+    const int64_t dst = (int64_t)plane * hw + pos;
+    for (int tm = 0; tm < terms; ++tm) {
+      uint32_t pk4[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        pk4[j] = pack2(v[2 * j], v[2 * j + 1]);
+        v[2 * j] -= __uint_as_float(pk4[j] << 16);
+        v[2 * j + 1] -= __uint_as_float(pk4[j] & 0xffff0000u);
+      }
+      out[(int64_t)tm * plane_vecs + dst] = make_uint4(pk4[0], pk4[1], pk4[2], pk4[3]);
+    }
+  }
+}
+
 struct PackWParams {
   Plan pl;
   const int16_t* w_int; const float* w_f32; const float* kzero;   // kzero[k] == 0 -> the weights of channel k read as 0 (dgrad)
@@ -699,11 +761,12 @@ pk_conv_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_constant_
                 tc::mma_f16_x4(d, a_base, a_hi, b_base, b_hi, p.m.idesc, p.m.prog4[pb + e], 1u);
             }
           }
-          tc::mma_commit_elect(&sh.empty[slot]);
+          // MNB_PK_DEBUG bit 32 (with bit 2, timing experiments): plain mbarrier arrivals instead of tcgen05.commit
+          if (p.dbg & 32) { if (lane == 0) tc::mbar_arrive(&sh.empty[slot]); } else tc::mma_commit_elect(&sh.empty[slot]);
           __syncwarp();
           started = 1;
           if (++seg_pos == p.m.seg_len) {   // segment complete: hand the accumulator to the epilogue
-            tc::mma_commit_elect(&sh.acc_full[acc]);
+            if (p.dbg & 32) { if (lane == 0) tc::mbar_arrive(&sh.acc_full[acc]); } else tc::mma_commit_elect(&sh.acc_full[acc]);
             __syncwarp();
             seg_pos = 0; open = 0; ++accq;
           }
@@ -712,7 +775,7 @@ pk_conv_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_constant_
       if (open || p.m.ntmpl[y] == 0) {      // last (partial) segment, or an output phase without any filter tap
         const uint32_t acc = accq & 1u, aph = (accq >> 1) & 1u;
         if (!open) tc::mbar_wait_soft(&sh.acc_empty[acc], aph ^ 1u, p.err, 702, &sh.abort);
-        tc::mma_commit_elect(&sh.acc_full[acc]);
+        if (p.dbg & 32) { if (lane == 0) tc::mbar_arrive(&sh.acc_full[acc]); } else tc::mma_commit_elect(&sh.acc_full[acc]);
         __syncwarp();
         ++accq;
       }
@@ -769,8 +832,8 @@ pk_conv_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_constant_
         // one slot = 16 accumulator columns of one M tile.  Segmented kernels need rs[slot] with a compile-time index (8 slots,
         // unrolled); the others run a ROLLED loop: unrolled 32 x, this body was 1 MB of SASS and the epilogue warps stalled
         // on instruction fetch
-        auto do_slot = [&](const int slot, float (&rsl)[16]) {
-          const int mt = slot / nc16, c16 = slot - mt * nc16, n0 = c16 * 16;
+        auto do_slot = [&](const int slot, const int mt, const int c16, float (&rsl)[16]) {
+          const int n0 = c16 * 16;
           if (mt != mt_cur) {   // output row of this thread in M tile mt
             mt_cur = mt;
             const int tile = mg * p.MT + mt;
@@ -852,12 +915,17 @@ pk_conv_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_constant_
           }
                 };
         if (SEG) {
+          int mt = 0, c16 = 0;
 #pragma unroll
-          for (int slot = 0; slot < 8; ++slot)
-            if (slot < nslots) do_slot(slot, rs[SEG ? slot : 0]);
+          for (int slot = 0; slot < 8; ++slot) {
+            if (slot < nslots) do_slot(slot, mt, c16, rs[SEG ? slot : 0]);
+            if (++c16 == nc16) { c16 = 0; ++mt; }
+          }
         } else {
 #pragma unroll 1
-          for (int slot = 0; slot < nslots; ++slot) do_slot(slot, rs[0]);
+          for (int mt = 0, slot = 0; mt < p.MT; ++mt)
+#pragma unroll 1
+            for (int c16 = 0; c16 < nc16; ++c16, ++slot) do_slot(slot, mt, c16, rs[0]);
         }
         tc::tc_fence_before();
         tc::mbar_arrive(&sh.acc_empty[acc]);
@@ -1053,7 +1121,10 @@ struct WgParams {
     uint32_t stg_per_split, nstg_total, NI, ksteps, ntap, tpg, n_tg, Nc, npairs, st_mask, st_log2, stage16, sub16, dy_term16, x_off16,
         x_term16, x_kph16, idesc, dy_sbo, x_sbo, nsub;
     uint32_t pair_a16[MAXPAIR], pair_b16[MAXPAIR];   // piece-plane offsets of the pairs (16-byte units)
-    uint32_t progb[MAXPAIR * MAXTAP];   // per (piece pair, tap): x-operand offset = pair plane + k-phase slot + tap row offset
+    // per (piece pair, tap group of this CTA, four taps): x-operand offsets = pair plane + k-phase slot + tap row offset,
+    // 0xffffffff behind the last tap of a group (one 128-bit constant load and one election per four MMAs)
+    alignas(16) uint4 progb4[MAXPAIR * MAXTAP / 4 + MAXPAIR * 16];
+    uint32_t g4;                        // uint4 entries per (pair, tap group) = ceil(tpg / 4)
   } m;
   int G, n_ktiles, n_ctiles, n_tg, tpg, splits, stg_per_split, nstg_total, NI, nsub, row_tiles, TA, TX, nkph_used, kph_used[4];
   int K8, C8X, cout_g8, cin_g8, Nc8, TH, hlo, wlo, stage_bytes, sub_bytes, dy_bytes, x_bytes, dy_box_bytes, x_box_bytes,
@@ -1155,10 +1226,10 @@ pk_wgrad_kernel(const __grid_constant__ CUtensorMap dy0, const __grid_constant__
         for (uint32_t j = 0; j < p.m.ksteps; ++j, arow += 16u, brow += 16u) {
           for (uint32_t pr = 0; pr < p.m.npairs; ++pr) {
             const uint32_t ad = arow + p.m.pair_a16[pr];
-            uint32_t d = tmem, e = pr * p.m.ntap + t0m;
-#pragma unroll 3
-            for (uint32_t t = 0; t < tnm; ++t, ++e, d += p.m.Nc)
-              tc::mma_f16_elect_lh(d, ad, a_hi, brow + p.m.progb[e], b_hi, p.m.idesc, accf);
+            uint32_t d = tmem, e = (pr * p.m.n_tg + tgm) * p.m.g4;
+#pragma unroll 2
+            for (uint32_t t = 0; t < tnm; t += 4u, ++e, d += 4u * p.m.Nc)
+              tc::mma_f16_x4_taps(d, p.m.Nc, ad, a_hi, brow, b_hi, p.m.idesc, p.m.progb4[e], accf);
             accf = 1u;   // every tap accumulator has been written once: accumulate from here on
           }
         }
@@ -1273,6 +1344,28 @@ extern "C" int mnb_pk_pack_act_relu(const float* x, int32_t batch, int32_t chann
     pk::pack_act_kernel<0><<<blocks, threads, 0, st>>>(x, batch, channels, h, w, C8, terms, ch_scale, none, 0, phase_split,
                                                    reinterpret_cast<uint4*>(out_pk), plane_vecs, nullptr, relu);
   }
+  MNB_LAUNCHED(1);
+  return 0;
+}
+
+extern "C" int mnb_bn_sign_bwd_pack(const float* g, const uint32_t* pass_bits, const float* x, int32_t batch, int32_t channels,
+                                    int32_t hw, const float* mean, const float* invstd, const float* gamma, const float* dgamma,
+                                    const float* dbeta, int32_t out_shuffle_groups, const float* ch_scale, int32_t terms,
+                                    float* dx, void* dy_packed, mnb_stream_t stream) {
+  MNB_REQUIRE(g && pass_bits && x && mean && invstd && gamma && dgamma && dbeta && dy_packed, "NULL bn_sign_bwd_pack pointer");
+  MNB_REQUIRE(batch > 0 && channels > 0 && hw > 0 && terms >= 1 && terms <= 3, "bad bn_sign_bwd_pack arguments");
+  MNB_REQUIRE(out_shuffle_groups >= 1 && channels % out_shuffle_groups == 0, "shuffle groups %d do not divide %d channels",
+              out_shuffle_groups, channels);
+  if (channels % 8 || (reinterpret_cast<uintptr_t>(dy_packed) & 15))
+    return mnb_fail(MNB_E_UNSUPPORTED, "packed BatchNorm backward needs channels %% 8 == 0 and a 16-byte aligned output");
+  const int c8n = channels / 8;
+  const int tx = std::min(256, (hw + 31) / 32 * 32), ty = 256 / tx;
+  const int planes = batch * c8n, gy = (planes + ty - 1) / ty;
+  const int bx = std::max(1, std::min((hw + tx - 1) / tx, std::max(1, (MNB_NUM_SMS * 16) / std::max(1, gy))));
+  if (gy > 65535) return mnb_fail(MNB_E_UNSUPPORTED, "bn_sign_bwd_pack: %d (image, octet) planes exceed the grid", planes);
+  pk::bn_sign_bwd_pack_kernel<<<dim3(bx, gy), dim3(tx, ty), 0, (cudaStream_t)stream>>>(
+      g, pass_bits, x, batch, channels, hw, out_shuffle_groups, 1.f / (float)((int64_t)batch * hw), mean, invstd, gamma, dgamma,
+      dbeta, ch_scale, terms, dx, reinterpret_cast<uint4*>(dy_packed), (int64_t)batch * c8n * hw);
   MNB_LAUNCHED(1);
   return 0;
 }
@@ -1485,9 +1578,18 @@ extern "C" int mnb_pk_wgrad(const mnb_conv_shape* s, const void* dy_pk, int32_t 
   m.idesc = tc::make_idesc_major(1, 1, 1, 128, (uint32_t)pl.Nc, 1, 1);
   m.dy_sbo = (uint32_t)pl.rows_dy * 16u; m.x_sbo = (uint32_t)pl.rows_x * 16u; m.nsub = pl.nsub;
   for (int i = 0; i < pl.npairs; ++i) { m.pair_a16[i] = pl.pair_a[i] * m.dy_term16; m.pair_b16[i] = pl.pair_b[i] * m.x_term16; }
-  for (int i = 0; i < pl.npairs; ++i)
-    for (int t = 0; t < pl.ntap; ++t)
-      m.progb[i * pl.ntap + t] = m.pair_b16[i] + pl.kph_slot[pl.tap_kph[t]] * m.x_kph16 + pl.tap_off[t];
+  {
+    m.g4 = (uint32_t)ceil_div(pl.tpg, 4);
+    if ((size_t)pl.npairs * pl.n_tg * m.g4 > sizeof(m.progb4) / sizeof(uint4)) return unsupported("wgrad issue program too long");
+    uint32_t* prog = reinterpret_cast<uint32_t*>(m.progb4);
+    for (size_t i = 0; i < sizeof(m.progb4) / 4; ++i) prog[i] = 0xffffffffu;
+    for (int i = 0; i < pl.npairs; ++i)
+      for (int tg = 0; tg < pl.n_tg; ++tg)
+        for (int tt = 0; tt < pl.tpg && tg * pl.tpg + tt < pl.ntap; ++tt) {
+          const int t = tg * pl.tpg + tt;
+          prog[((size_t)(i * pl.n_tg + tg) * m.g4) * 4 + tt] = m.pair_b16[i] + pl.kph_slot[pl.tap_kph[t]] * m.x_kph16 + pl.tap_off[t];
+        }
+  }
   p.G = pl.G; p.n_ktiles = pl.n_ktiles; p.n_ctiles = pl.n_ctiles; p.n_tg = pl.n_tg; p.tpg = pl.tpg; p.splits = pl.splits; p.stg_per_split = pl.stg_per_split;
   p.nstg_total = pl.nstg_total; p.NI = pl.NI; p.nsub = pl.nsub; p.row_tiles = pl.row_tiles; p.TA = pl.TA; p.TX = pl.TX;
   p.nkph_used = pl.nkph_used;

@@ -203,6 +203,32 @@ __device__ __forceinline__ void mma_f16_x4(uint32_t d_tmem, uint32_t a_base, uin
         "r"(accumulate_first)
       : "memory");
 }
+// Up to four MMAs that share the A operand and the accumulate flag and differ in the B offset and the accumulator
+// (weight gradient: one accumulator per filter tap, d_tmem + i * d_step): boff.x .. boff.w are added to b_row,
+// 0xffffffff = no MMA.  One election / one 128-bit program load per group, see mma_f16_x4.
+__device__ __forceinline__ void mma_f16_x4_taps(uint32_t d_tmem, uint32_t d_step, uint32_t a_lo, uint32_t a_hi, uint32_t b_row,
+                                                uint32_t b_hi, uint32_t idesc, uint4 boff, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred q, p, e0, e1, e2, e3;\n\t.reg .b64 da, db;\n\t.reg .b32 bl, dd;\n\t"
+      "elect.sync _|q, 0xffffffff;\n\t"
+      "setp.ne.b32 p, %11, 0;\n\t"
+      "setp.ne.and.b32 e0, %7, 0xffffffff, q;\n\t"
+      "setp.ne.and.b32 e1, %8, 0xffffffff, q;\n\t"
+      "setp.ne.and.b32 e2, %9, 0xffffffff, q;\n\t"
+      "setp.ne.and.b32 e3, %10, 0xffffffff, q;\n\t"
+      "mov.b64 da, {%2, %3};\n\t"
+      "add.u32 bl, %4, %7;\n\tmov.b64 db, {bl, %5};\n\t"
+      "@e0 tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %6, p;\n\t"
+      "add.u32 bl, %4, %8;\n\tmov.b64 db, {bl, %5};\n\tadd.u32 dd, %0, %1;\n\t"
+      "@e1 tcgen05.mma.cta_group::1.kind::f16 [dd], da, db, %6, p;\n\t"
+      "add.u32 bl, %4, %9;\n\tmov.b64 db, {bl, %5};\n\tadd.u32 dd, dd, %1;\n\t"
+      "@e2 tcgen05.mma.cta_group::1.kind::f16 [dd], da, db, %6, p;\n\t"
+      "add.u32 bl, %4, %10;\n\tmov.b64 db, {bl, %5};\n\tadd.u32 dd, dd, %1;\n\t"
+      "@e3 tcgen05.mma.cta_group::1.kind::f16 [dd], da, db, %6, p;\n\t}"
+      ::"r"(d_tmem), "r"(d_step), "r"(a_lo), "r"(a_hi), "r"(b_row), "r"(b_hi), "r"(idesc), "r"(boff.x), "r"(boff.y), "r"(boff.z),
+        "r"(boff.w), "r"(accumulate)
+      : "memory");
+}
 __device__ __forceinline__ void mma_i8(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
                                        uint32_t accumulate) {
   asm volatile(

@@ -280,21 +280,22 @@ def channel_sums(x4):
 
 
 
-def _pk_terms(spec, w_int):
-    """(terms of the activation operand, terms of the weight operand) on the packed-operand path"""
+def _pk_terms(spec, w_int, pm1=False):
+    """(terms of the activation operand, terms of the weight operand) on the packed-operand path; ``pm1``: the raw input is
+    known to hold only +-1 (output of a binarizer): one bf16 piece is exact"""
     T = L.PK_TERMS
     if spec is None:
-        ta = T
+        ta = 1 if pm1 else T
     else:
         ta = 2 if (spec.mode == L.ACT_IAO and spec.q_type == 1) else 1   # asymmetric: |level + zero_point| may exceed 256
     return ta, (1 if w_int is not None else T)
 
 
-def _pk_forward(ctx, x, wq, bias, w_int, w_scale, spec, sh, y, need_dx, prepacked=None, pre_relu=False):
+def _pk_forward(ctx, x, wq, bias, w_int, w_scale, spec, sh, y, need_dx, prepacked=None, pre_relu=False, pm1=False):
     """forward on the packed-operand tensor-core family; returns False when the shape is outside its cover.
     ``prepacked``: the operand plane a fused producer (fused.BNReluQuantFn) already wrote - x itself holds no data then."""
     from . import pk as PK
-    ta, tw = _pk_terms(spec, w_int)
+    ta, tw = _pk_terms(spec, w_int, pm1)
     if not PK.supported(sh, 0, ta, tw):
         return False
     # the backward of a layer stays in the family its forward ran in (saved operands are packed): check its cover now
@@ -345,7 +346,13 @@ def _pk_backward(ctx, dy):
     # dy is packed once for both gradients; the data gradient wants the per-channel weight scale folded in (it sits on
     # the reduction dimension there), the weight gradient divides it out again (mnb_pk_wgrad's kdiv)
     fold = int_w and need_dx
-    dy_pk, _ = PK.pack_act(dy, None, T, ch_scale=ctx.w_scale if fold else None)
+    pre = getattr(dy, "_mnb_pk_dy", None)     # written by the consumer's fused BatchNorm backward (fused.BNSignFn): dy holds no data
+    if pre is not None:
+        if pre[1] != T or (pre[2] is not None) != fold:
+            raise RuntimeError("micronet_b200: packed gradient operand does not match this layer's backward configuration")
+        dy_pk = pre[0]
+    else:
+        dy_pk, _ = PK.pack_act(dy, None, T, ch_scale=ctx.w_scale if fold else None)
     dx = dwq = None
     if need_dx:
         tw = 1 if int_w else T
@@ -398,6 +405,16 @@ class QuantConv2dFn(Function):
                 raise RuntimeError("micronet_b200: fused producer output in front of a conv outside the packed-operand cover")
         if not done and L.PK_MODE != "off" and x.dtype == torch.float32 and (L.PK_MODE == "all" or spec is not None):
             done = _pk_forward(ctx, x, wq, bias, w_int, w_scale, spec, sh, y, ctx.needs_input_grad[0], pre_relu=pre_relu)
+        pm1_plane = getattr(x, "_mnb_pk_pm1", None)
+        if (not done and L.PK_WBWTAB and L.PK_MODE != "off" and spec is None and w_int is not None and x.dtype == torch.float32
+                and getattr(x, "_mnb_pm1", False) and (pm1_plane is not None or sh.ker_h * sh.ker_w > 1)):
+            # wbwtab layer behind a fused BatchNorm + binarizer: +-1 input (one exact bf16 piece).  With the producer's plane
+            # the layer is pure TMA -> MMA; 3x3 layers win on the packed-operand family even when they pack themselves
+            # (measured per layer).  Falls through to the fused kernels when the shape is outside the cover.
+            if pm1_plane is not None and pm1_plane.numel() != x.numel() * 2:
+                pm1_plane = None
+            done = _pk_forward(ctx, x, wq, bias, w_int, w_scale, None, sh, y, ctx.needs_input_grad[0], prepacked=pm1_plane,
+                               pm1=True)
         if not done and pre_relu:
             x = torch.relu(x)     # outside the packed-operand cover: the folded ReLU as its own pass
         if not done and packed is not None and spec is None and w_int is not None and packed.numel() == x.numel() \
@@ -471,6 +488,9 @@ class QuantConv2dFn(Function):
         ctx.wq = wq
         ctx.w_int, ctx.w_scale = (w_int, w_scale) if w_int is not None else (None, None)
         ctx.has_bias = bias is not None
+        if ctx.pk and spec is None and w_int is not None and ctx.needs_input_grad[1]:
+            # a fused BatchNorm + binarizer consuming y may write this layer's gradient operand itself (fused.BNSignFn)
+            y._mnb_pk_conv = (w_scale if ctx.needs_input_grad[0] else None, min(L.PK_TERMS, L.PK_TERMS_BWD))
         return y
 
     @staticmethod

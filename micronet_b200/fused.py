@@ -50,7 +50,19 @@ class BNSignFn(Function):
         else:
             y = torch.empty_like(x)
             packed = None
-            if L.USE_PACKED and c % 8 == 0 and hw % 32 == 0:
+            if L.PK_WBWTAB and not L.USE_PACKED and c % 8 == 0 and hw % 32 == 0 and x.dim() == 4 and L.PK_MODE != "off":
+                # the +-1 output also as the operand plane of the consuming conv (packed-operand family): 2 extra bytes per
+                # element here save that conv's 4-byte read and its pack pass
+                plane = torch.empty(x.numel() * 2, dtype=torch.uint8, device=x.device)
+                rc = lib.mnb_bn_sign_fwd_packed(x.data_ptr(), b, c, hw, mean.data_ptr(), invstd.data_ptr(), gamma.data_ptr(),
+                                                beta.data_ptr(), shuffle_groups, y.data_ptr(), bits.data_ptr(),
+                                                plane.data_ptr(), L.stream())
+                if rc == 0:
+                    y._mnb_pk_pm1 = plane
+                    packed = False          # done (not the experimental bf16 tensor of MNB_PACKED_OPERANDS)
+                elif rc != L.E_UNSUPPORTED:
+                    L.check(rc, "bn_sign_fwd_packed")
+            if packed is None and L.USE_PACKED and c % 8 == 0 and hw % 32 == 0:
                 # experimental (MNB_PACKED_OPERANDS=1): also emit the bf16 position-major operand of the next conv
                 packed = torch.empty(x.numel(), dtype=torch.bfloat16, device=x.device)
                 rc = lib.mnb_bn_sign_fwd_packed(x.data_ptr(), b, c, hw, mean.data_ptr(), invstd.data_ptr(), gamma.data_ptr(),
@@ -64,10 +76,14 @@ class BNSignFn(Function):
                 L.check(lib.mnb_bn_sign_fwd(x.data_ptr(), b, c, hw, mean.data_ptr(), invstd.data_ptr(), gamma.data_ptr(),
                                             beta.data_ptr(), shuffle_groups, y.data_ptr(), bits.data_ptr(), L.stream()),
                         "bn_sign_fwd")
-            else:
+            elif packed is not False:
                 y._mnb_packed = packed   # picked up by QuantConv2dFn.forward when y is its input
+        y._mnb_pm1 = True        # exactly +-1: a consuming conv may pack it as ONE bf16 piece
         ctx.save_for_backward(x, gamma, mean, invstd)
         ctx.bits, ctx.arg, ctx.training, ctx.shuffle_groups = bits, arg, training, shuffle_groups
+        # the conv that produced x ran on the packed-operand family (functional.QuantConv2dFn tags its output): its
+        # gradient operand is written by this backward, pre-multiplied with the conv's per-channel weight scale
+        ctx.pk_conv = getattr(x, "_mnb_pk_conv", None)
         return y
 
     @staticmethod
@@ -87,6 +103,22 @@ class BNSignFn(Function):
                                              1 if ctx.training else 0, ctx.shuffle_groups, dx.data_ptr(), dgamma.data_ptr(),
                                              dbeta.data_ptr(), dx_sum.data_ptr(), scratch.data_ptr(), L.stream()),
                     "bn_sign_pool_bwd")
+        elif ctx.pk_conv is not None and ctx.training and c % 8 == 0 and "mnb_bn_sign_bwd_pack" in L.PROTOTYPES:
+            # reduce pass of mnb_bn_sign_bwd (dgamma, dbeta), then the apply pass that writes dx as the producing conv's packed
+            # gradient operand.  The channel sums of dx (that conv's bias gradient) are exactly zero behind a training-mode
+            # BatchNorm; the reference's value is the rounding noise of that sum.
+            w_scale, T = ctx.pk_conv
+            L.check(lib.mnb_bn_sign_bwd(g.data_ptr(), ctx.bits.data_ptr(), x.data_ptr(), b, c, hw, mean.data_ptr(),
+                                        invstd.data_ptr(), gamma.data_ptr(), 2, ctx.shuffle_groups,
+                                        dx.data_ptr(), dgamma.data_ptr(), dbeta.data_ptr(), None,
+                                        scratch.data_ptr(), L.stream()), "bn_sign_bwd (reduce)")
+            dy_pk = torch.empty(T * x.numel() * 2, dtype=torch.uint8, device=x.device)
+            L.check(lib.mnb_bn_sign_bwd_pack(g.data_ptr(), ctx.bits.data_ptr(), x.data_ptr(), b, c, hw, mean.data_ptr(),
+                                             invstd.data_ptr(), gamma.data_ptr(), dgamma.data_ptr(), dbeta.data_ptr(),
+                                             ctx.shuffle_groups, L.ptr(w_scale), T, None, dy_pk.data_ptr(), L.stream()),
+                    "bn_sign_bwd_pack")
+            dx_sum.zero_()
+            dx._mnb_pk_dy = (dy_pk, T, w_scale)     # dx itself is NOT written: its only reader is that conv's backward
         else:
             L.check(lib.mnb_bn_sign_bwd(g.data_ptr(), ctx.bits.data_ptr(), x.data_ptr(), b, c, hw, mean.data_ptr(),
                                         invstd.data_ptr(), gamma.data_ptr(), 1 if ctx.training else 0, ctx.shuffle_groups,

@@ -245,3 +245,50 @@ def test_dorefa_fuse_option_agrees_with_the_unfused_engine():
             continue      # a conv bias in front of a training-mode BatchNorm has a mathematically zero gradient: noise
         a, b = out["fused"][1][n].flatten().double(), g.flatten().double()
         assert torch.dot(a, b) / (a.norm() * b.norm()) > 0.99, n
+
+
+@pytest.mark.parametrize("cfg", [(8, 256, 256, 32, 1, 2, 2), (8, 256, 512, 16, 3, 16, 1), (4, 512, 512, 16, 1, 4, 4)],
+                         ids=["1x1g2", "3x3g16", "1x1g4"])
+def test_wbwtab_layer_between_two_fused_producers_on_the_packed_operand_family(cfg):
+    """BatchNormBinarize2d -> wbwtab QuantConv2d -> BatchNormBinarize2d with both conv operands written by the producers
+    (+-1 plane forward: mnb_bn_sign_fwd_packed, gradient pieces backward: mnb_bn_sign_bwd_pack) against the same chain on the
+    fused kernels (MNB_PK_WBWTAB=0), which the oracle tests pin: identical +-1 outputs, gradients to 1e-5 (weight gradient:
+    plus the cancellation allowance of tests/test_gpu_parity.py)."""
+    import micronet_b200 as E
+    from micronet_b200 import _lib as L
+    from micronet_b200.fused import BatchNormBinarize2d
+    from tests.test_gpu_parity import _cancellation_allowance
+    B, C, K, H, R, G, sg = cfg
+    torch.manual_seed(sum(cfg))
+    x = torch.randn(B, C, H, H) * 1.3
+    go = torch.randn(B, K, H, H)
+    bn0, bn1 = _pair(C, 3), _pair(K, 4)
+    conv = E.wbwtab.QuantConv2d(C, K, R, padding=R // 2, groups=G, W=3)
+    res = {}
+    for mode in (False, True):
+        L.PK_WBWTAB = mode
+        try:
+            p0 = BatchNormBinarize2d(C); p0.load_state_dict(bn0.state_dict()); p0.out_shuffle_groups = sg
+            p1 = BatchNormBinarize2d(K); p1.load_state_dict(bn1.state_dict())
+            cv = copy.deepcopy(conv)
+            net = nn.Sequential(p0, cv, p1).to(DEV).train()
+            captured = {}
+            cv.register_forward_hook(lambda m, i, o: captured.__setitem__("y", o.detach().clone()))
+            xg = x.to(DEV).requires_grad_(True)
+            out = net(xg)
+            out.backward(go.to(DEV))
+            torch.cuda.synchronize()
+            res[mode] = dict(out=out.detach().cpu(), conv=captured["y"].cpu(), dx=xg.grad.cpu(), dw=cv.weight.grad.cpu(),
+                             db=cv.bias.grad.cpu(), dg1=p1.weight.grad.cpu(), db1=p1.bias.grad.cpu(), dg0=p0.weight.grad.cpu())
+        finally:
+            L.PK_WBWTAB = True
+    a, b = res[False], res[True]
+    assert rel_err(b["conv"], a["conv"]) <= 1e-6                      # integer-level products: exact up to the bias add
+    flips = (a["out"] != b["out"]).float().mean().item()
+    assert flips <= 1e-4, flips                                         # sign of bn values within rounding of 0
+    for k in ("dx", "dg1", "db1", "dg0"):
+        assert rel_err(b[k], a[k]) <= 2e-5 if flips else rel_err(b[k], a[k]) <= 1e-5, (k, rel_err(b[k], a[k]))
+    allow = _cancellation_allowance(go, 1.0) / a["dw"].abs().max().item()
+    assert rel_err(b["dw"], a["dw"]) <= 1e-5 + 50 * allow, (rel_err(b["dw"], a["dw"]), allow)
+    assert b["db"].abs().max().item() <= 1e-4 * a["dw"].abs().max().item() + a["db"].abs().max().item() * 2 + 1e-6
+    L.tc_check()
