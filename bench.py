@@ -287,7 +287,8 @@ def run_engine(workload, steps, warmup, dev, rank, world, detail):
            "e2e": {"value": imgs / (ms_e2e / 1e3), "unit": "img/s", "ms_per_step": ms_e2e / steps,
                    "h2d_bytes_per_step": (B * 3 * w["hw"] * w["hw"] * 4 + B * 8) * world,
                    "d2h_bytes_per_step": (B * 10 * 4 if inference else 4) * world},
-           "gpu_launches": int(launches), "clocks": clocks, "timer": timer, "ms_total": ms_detail * steps / dsteps,
+           "gpu_launches": int(launches), "clocks": clocks, "timer": timer,
+           "ms_total": ms_detail,   # the eager detail pass the per-kernel events were recorded in (dsteps steps)
            "cuda_graph": {"used": bool(graph_used), "error": getattr(stepper, "graph_error", None),
                           "eager_ms_per_step": ms_detail / dsteps}}
     del stepper, model

@@ -273,17 +273,12 @@ int mnb_maxpool2d_bwd(const float* g, const uint8_t* argmax, int32_t batch, int3
                       int32_t kernel, int32_t stride, int32_t pad, int32_t out_shuffle_groups, float* dx,
                       mnb_stream_t stream);
 
-/* EXPERIMENTAL, not enabled by default (MNB_PACKED_OPERANDS=1) and not yet validated on hardware: packed bf16
- * activations between the BatchNorm + binarizer producer and the tensor-core forward convolution (DESIGN.md 6,
- * "Plan for the next round").  x_packed: bf16 [B][C/8][H][W][8] in the OUTPUT channel order (B*C*H*W*2 bytes,
- * 16-byte aligned); needs C % 8 == 0 and H*W % 32 == 0.  The convolution takes the same geometry cover as
- * mnb_fq_conv2d_fwd_tc with qp == NULL and reads only x_packed.                                              */
+/* mnb_bn_sign_fwd that additionally writes its +-1 output as the bf16 operand plane of the packed-operand tensor-core
+ * family (below): x_packed = bf16 [B][C/8][H][W][8] in the OUTPUT channel order (B*C*H*W*2 bytes, 16-byte aligned); needs
+ * C % 8 == 0 and H*W % 32 == 0, else MNB_E_UNSUPPORTED.  y may be NULL (the consumer reads only the plane).           */
 int mnb_bn_sign_fwd_packed(const float* x, int32_t batch, int32_t channels, int32_t hw, const float* mean,
                            const float* invstd, const float* gamma, const float* beta, int32_t out_shuffle_groups, float* y,
                            uint32_t* pass_bits, void* x_packed, mnb_stream_t stream);
-int mnb_fq_conv2d_fwd_packed_plan(const mnb_conv_shape* s, int32_t* out8); /* host only: {slab_groups, n_slabs, nbuf, smem_bytes, tmem_cols, TH, TB, n_tiles} */
-int mnb_fq_conv2d_fwd_packed_tc(const mnb_conv_shape* s, const void* x_packed, const int16_t* w_int, const float* w_scale,
-                                const float* bias, float* y, void* wpack_scratch, int32_t* err_flag, mnb_stream_t stream);
 
 /* fp32 convolution with few input channels on the tensor-core path: the un-quantized first layer of the QAT
  * models (plain nn.Conv2d in the reference: nin_gc.py:82, nin.py:60, resnet.py first conv; WB:300-317 leaves it
@@ -374,6 +369,25 @@ int mnb_quant_add_pack_fwd(const float* a, const float* b, int32_t batch, int32_
 int64_t mnb_pk_wgrad_scratch_bytes(const mnb_conv_shape* s, int32_t terms_dy, int32_t terms_x);
 int mnb_pk_wgrad(const mnb_conv_shape* s, const void* dy_pk, int32_t terms_dy, const void* x_pk, int32_t terms_x,
                  const float* a_scale, const float* kdiv, float* dw, void* scratch, int32_t* err_flag, mnb_stream_t stream);
+
+/* ------------------------------------------------------------------------
+ * Bit-packed XNOR-popcount forward for wbwtab layers (mnb_xnor.cu): binary activations (WB:11-36, sign with 0 -> +1)
+ * times binary / ternary weights (WB:40-75, 98-146) as sum = popc(N) - 2 popc(N & (A ^ S)) on 1-bit planes; the integer
+ * sum is exact, y = fmaf(sum, alpha[k], bias[k]) equals mnb_pk_conv's result bit for bit.  Forward only (the gradients
+ * of a QAT step multiply real-valued dy).  functional.py picks it per layer from the measured table of
+ * profiles/r2_xnor_vs_tc.md (north_star: "picked when ncu shows it beating the tensor-core path").
+ *   a_bits : u32 [B][G][ceil(C/g / 32)][H][W], bit j of word n = [x[b][g*C/g + 32 n + j][h][w] is not < 0]
+ *   w_img  : mnb_xnor_wimage_bytes() bytes, built from the i16 levels {-1, 0, +1} [K][C/g][R][S] of mnb_wb_weight_fwd
+ * Cover: square filter 1/3/5, equal strides / pads, dilation 1, C/g <= 128 (3x3), <= 64 (5x5), <= 256 (1x1); else
+ * MNB_E_UNSUPPORTED (mnb_xnor_supported: 1 / 0).                                                                      */
+int mnb_xnor_supported(const mnb_conv_shape* s);
+int64_t mnb_xnor_act_bytes(int32_t batch, int32_t channels, int32_t h, int32_t w, int32_t groups);
+int mnb_xnor_pack_act(const float* x, int32_t batch, int32_t channels, int32_t h, int32_t w, int32_t groups, void* out_bits,
+                      mnb_stream_t stream);
+int64_t mnb_xnor_wimage_bytes(const mnb_conv_shape* s);
+int mnb_xnor_pack_weight(const mnb_conv_shape* s, const int16_t* w_int, void* w_img, mnb_stream_t stream);
+int mnb_xnor_conv_fwd(const mnb_conv_shape* s, const void* a_bits, const void* w_img, const float* alpha, const float* bias,
+                      float* y, mnb_stream_t stream);
 
 /* Optimizer step of the QAT loop (torch.optim.Adam semantics, L2 weight decay, no amsgrad;
  * wbwtab/main.py:84,331-339) over one flat fp32 parameter / gradient bucket: a single launch. */

@@ -79,8 +79,6 @@ PROTOTYPES = {
     "mnb_bn_sign_pool_fwd": (C.c_int, [_P, _I, _I, _I, _I, _P, _P, _P, _P, _I, _P, _P, _P, _P]),
     "mnb_bn_sign_pool_bwd": (C.c_int, [_P, _P, _P, _P, _I, _I, _I, _I, _P, _P, _P, _I, _I, _P, _P, _P, _P, _P, _P]),
     "mnb_bn_sign_fwd_packed": (C.c_int, [_P, _I, _I, _I, _P, _P, _P, _P, _I, _P, _P, _P, _P]),
-    "mnb_fq_conv2d_fwd_packed_plan": (C.c_int, [_SHAPE, _P]),
-    "mnb_fq_conv2d_fwd_packed_tc": (C.c_int, [_SHAPE, _P, _P, _P, _P, _P, _P, _P, _P]),
     "mnb_fconv2d_fwd_tc": (C.c_int, [_SHAPE, _P, _P, _P, _P, _P, _P]),
     "mnb_fconv2d_wgrad_tc_scratch_bytes": (_L, [_SHAPE]),
     "mnb_fconv2d_wgrad_tc": (C.c_int, [_SHAPE, _P, _P, _P, _P, _P, _P]),
@@ -100,6 +98,12 @@ PROTOTYPES = {
     "mnb_quant_add_pack_fwd": (C.c_int, [_P, _P, _I, _I, _I, _I, _ACTQ, _I, _P, C.POINTER(PkPost), _P]),
     "mnb_pk_wgrad_scratch_bytes": (_L, [_SHAPE, _I, _I]),
     "mnb_pk_wgrad": (C.c_int, [_SHAPE, _P, _I, _P, _I, _P, _P, _P, _P, _P, _P]),
+    "mnb_xnor_supported": (C.c_int, [_SHAPE]),
+    "mnb_xnor_act_bytes": (_L, [_I, _I, _I, _I, _I]),
+    "mnb_xnor_pack_act": (C.c_int, [_P, _I, _I, _I, _I, _I, _P, _P]),
+    "mnb_xnor_wimage_bytes": (_L, [_SHAPE]),
+    "mnb_xnor_pack_weight": (C.c_int, [_SHAPE, _P, _P, _P]),
+    "mnb_xnor_conv_fwd": (C.c_int, [_SHAPE, _P, _P, _P, _P, _P, _P]),
     "mnb_set_tc_profile_buffer": (None, [_P]),
     "mnb_selftest_mma_rate": (C.c_int, [_I, _I, _I, _I, _I, _P, _P, _P]),
     "mnb_selftest_umma": (C.c_int, [_P, _P, _P, _I, _I, _I, _P, _P]),
@@ -201,6 +205,10 @@ PK_TERMS_BWD = int(os.environ.get("MNB_PK_TERMS_BWD", "2"))
 # with BOTH operands written by the producers: +-1 planes forward (mnb_bn_sign_fwd_packed), gradient pieces backward
 # (mnb_bn_sign_bwd_pack); 3x3 layers take it in any case.  MNB_PK_WBWTAB=0 keeps every wbwtab layer on the fused kernels.
 PK_WBWTAB = os.environ.get("MNB_PK_WBWTAB", "1") == "1"
+
+# bit-packed XNOR-popcount forward for wbwtab inference (mnb_xnor.cu): "auto" = the layers where it was measured to beat the
+# tensor-core forward (functional.xnor_preferred), "all" = wherever it has cover, "off" = never
+XNOR_MODE = os.environ.get("MNB_XNOR", "auto")
 
 _scratch = {}
 

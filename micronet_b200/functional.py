@@ -280,6 +280,16 @@ def channel_sums(x4):
 
 
 
+def xnor_preferred(sh):
+    """MNB_XNOR=auto: take the XNOR-popcount forward for this layer?  Decided from the layer-by-layer measurement of
+    harness/xnor_probe.py on B200 (profiles/r2_xnor_vs_tc.md): rule = the measured winners, nothing extrapolated."""
+    return _XNOR_RULE(sh)
+
+
+def _XNOR_RULE(sh):
+    return False     # filled from the measurement (see profiles/r2_xnor_vs_tc.md)
+
+
 def _pk_terms(spec, w_int, pm1=False):
     """(terms of the activation operand, terms of the weight operand) on the packed-operand path; ``pm1``: the raw input is
     known to hold only +-1 (output of a binarizer): one bf16 piece is exact"""
@@ -396,8 +406,22 @@ class QuantConv2dFn(Function):
             a_scale = spec.scale if spec.mode == L.ACT_IAO else _dorefa_scale_tensor(spec.bits, x.device)
         done = False
         ctx.pk = False
+        if (L.XNOR_MODE != "off" and spec is None and w_int is not None and getattr(x, "_mnb_pm1", False)
+                and not any(ctx.needs_input_grad[:3]) and x.dtype == torch.float32 and not pre_relu):
+            # wbwtab inference forward on +-1 activations: bit-packed XNOR-popcount kernel where it was measured to beat the
+            # tensor-core forward (north_star; table: profiles/r2_xnor_vs_tc.md).  Same integer sums, same fmaf epilogue:
+            # bit-identical to the packed-operand path.  Training steps never come here (their backward multiplies real-valued
+            # gradients and wants the bf16 operand plane the forward already read).
+            from . import xnor as XN
+            if XN.supported(sh) and (L.XNOR_MODE == "all" or xnor_preferred(sh)):
+                a_bits = XN.pack_act(x, groups)
+                rc = _timed("fwd_xnor", sh, lambda: XN.conv(sh, a_bits, XN.pack_weight(sh, w_int), y, alpha=w_scale, bias=bias))
+                if rc == 0:
+                    done = True
+                elif rc != L.E_UNSUPPORTED:
+                    L.check(rc, "xnor_conv_fwd")
         pkq = getattr(x, "_mnb_pk_q", None)   # operand plane written by a fused BN + ReLU + quantizer producer
-        if pkq is not None:
+        if pkq is not None and not done:
             if spec is None or spec.mode != L.ACT_DOREFA or spec.bits != pkq[1] or w_int is None:
                 raise RuntimeError("micronet_b200: a fused producer's packed output reached a conv with another quantizer")
             done = _pk_forward(ctx, x, wq, bias, w_int, w_scale, spec, sh, y, ctx.needs_input_grad[0], prepacked=pkq[0])

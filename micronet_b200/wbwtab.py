@@ -21,7 +21,9 @@ class ActivationQuantizer(nn.Module):
         self.relu = nn.ReLU(inplace=True)
 
     def binary(self, input):
-        return F_.ActQuantFn.apply(input, F_.ActSpec(L.ACT_SIGN))
+        y = F_.ActQuantFn.apply(input, F_.ActSpec(L.ACT_SIGN))
+        y._mnb_pm1 = True     # exactly +-1: a consuming conv may read it as one bf16 piece / one bit per value
+        return y
 
     def forward(self, input):
         return self.binary(input) if self.A == 2 else self.relu(input)

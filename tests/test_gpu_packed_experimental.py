@@ -58,8 +58,10 @@ def test_packed_producer_and_conv_match_the_unpacked_path(case):
 
 @pytest.mark.parametrize("case", CASES[:5], ids=[str(c) for c in CASES[:5]])
 def test_block_with_packed_forward_has_the_same_gradients(case):
-    """BatchNorm+binarizer -> conv, forward through the packed plane, backward on the fused kernels: identical to the
-    un-packed path (same kernels in the backward, same +-1 operand in the forward)"""
+    """BatchNorm+binarizer -> conv three ways: (base) everything on the fused kernels, (fwd) forward through the producer's
+    packed plane and backward on the fused kernels (MNB_PACKED_OPERANDS=1), (both) the default since round 2 - forward AND
+    backward on the packed-operand family with producer-written operands (MNB_PK_WBWTAB=1).  Same +-1 operand in the
+    forward: identical outputs; gradients agree to the accuracy of the backward's operand split."""
     from micronet_b200 import _lib as L, functional as F_
     from micronet_b200.fused import BatchNormBinarize2d
     B, C, H, W, K, R, G, sg = case
@@ -69,8 +71,9 @@ def test_block_with_packed_forward_has_the_same_gradients(case):
     w_scale = (torch.rand(K) * 0.02 + 0.001).to(DEV)
     go = torch.randn(B, K, H, W).to(DEV)
     res = {}
-    for flag in (True, False):
-        L.USE_PACKED = flag
+    saved = (L.USE_PACKED, L.PK_WBWTAB)
+    for name, packed, wb in (("base", False, False), ("fwd", True, False), ("both", False, True)):
+        L.USE_PACKED, L.PK_WBWTAB = packed, wb
         try:
             torch.manual_seed(5)
             bn = BatchNormBinarize2d(C).to(DEV).train()
@@ -82,11 +85,17 @@ def test_block_with_packed_forward_has_the_same_gradients(case):
             out.backward(go)
             torch.cuda.synchronize()
             kinds = {k for k, _, _, _ in F_.TIMER.records}
-            res[flag] = (out.detach(), x.grad, wq.grad, bn.weight.grad, kinds)
+            res[name] = (out.detach(), x.grad, wq.grad, bn.weight.grad, kinds)
         finally:
-            L.USE_PACKED = False
+            L.USE_PACKED, L.PK_WBWTAB = saved
             F_.TIMER = None
-    assert "fwd_pk" in res[True][4] and "fwd_pk" not in res[False][4], (res[True][4], res[False][4])
-    for a, b in zip(res[True][:4], res[False][:4]):
+    if R == 1:   # (3x3 layers take the packed-operand family in every configuration: they win there even when they pack themselves)
+        assert "fwd_pk" not in res["base"][4], res["base"][4]
+    assert "fwd_pk" in res["fwd"][4] and {"fwd_pk", "dgrad_pk", "wgrad_pk"} <= res["both"][4], (res["fwd"][4], res["both"][4])
+    assert torch.equal(res["fwd"][0], res["base"][0]) or rel_err(res["fwd"][0], res["base"][0]) <= 1e-6
+    assert rel_err(res["both"][0], res["base"][0]) <= 1e-6
+    for a, b in zip(res["fwd"][1:4], res["base"][1:4]):
         assert rel_err(a, b) <= 1e-6
+    for a, b in zip(res["both"][1:4], res["base"][1:4]):
+        assert rel_err(a, b) <= 1e-5     # two-piece dy operand (MNB_PK_TERMS_BWD=2): ~3e-6, inside the 1e-5 contract
     L.tc_check()

@@ -218,31 +218,3 @@ def test_flat_bucket_allreduce_gloo_world2(tmp_path):
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=240)
     assert out.returncode == 0, out.stdout + out.stderr
     assert out.stdout.count("ok") == 2
-
-
-def test_packed_conv_index_arithmetic_model():
-    """numpy replay of the staged packed-operand forward conv (TMA box layout, UMMA descriptor offsets per group / tap /
-    k-step, epilogue row mapping) against a plain grouped correlation: the arithmetic of mnb_conv_packed.cu"""
-    from harness import packed_conv_model as M
-    M.run(3, 32, 32, 8, 8, 1, 2)
-    M.run(2, 32, 32, 8, 8, 3, 2)
-
-
-def test_packed_conv_plan_covers_the_headline_layers():
-    """host-side plan of the staged packed-operand conv for every quantized NIN-GC layer at batch 256: supported,
-    inside shared / tensor memory, power-of-two operand ring"""
-    import ctypes as C
-    from micronet_b200 import _lib as L
-    lib = L.load()
-    layers = [(256, 32, 32, 256, 1, 2), (256, 16, 16, 512, 3, 16), (512, 16, 16, 512, 1, 4), (512, 8, 8, 1024, 3, 32),
-              (1024, 8, 8, 1024, 1, 8)]
-    for (c, h, w, k, r, g) in layers:
-        sh = L.ConvShape(256, c, h, w, k, r, r, 1, 1, r // 2, r // 2, 1, 1, g)
-        out = (C.c_int32 * 8)()
-        assert lib.mnb_fq_conv2d_fwd_packed_plan(C.byref(sh), out) == 0, lib.mnb_last_error()
-        slab, n_slabs, nbuf, smem, tmem, th, tb, n_tiles = list(out)
-        assert slab * n_slabs == g and nbuf in (2, 4) and smem <= 227 * 1024 - 4096 and tmem <= 512
-        assert 2 * slab * (k // g) <= tmem and th * tb * (w + r - 1) <= 128 + (r - 1) * 2   # rows of one MMA
-        assert n_tiles == -(-256 // tb) * -(-h // th)
-    big = L.ConvShape(256, 128, 16, 16, 128, 3, 3, 1, 1, 1, 1, 1, 1, 1)   # ResNet-size weights: not resident
-    assert lib.mnb_fq_conv2d_fwd_packed_plan(C.byref(big), (C.c_int32 * 8)()) == L.E_UNSUPPORTED
