@@ -202,7 +202,17 @@ static int make_plan(const mnb_conv_shape* s, int mode, int TA, int TBk, Plan& p
   // fp32 accumulator after every instruction (a bias of ~2e-8 of |D| per MMA, measured: 3e-5 after 1700 chained MMAs),
   // so the K loop is cut into segments of <= ~64 MMAs, each into a fresh TMEM accumulator, and the epilogue warps add
   // the segments in registers with round-to-nearest adds.  That needs the whole N tile in registers: Nt <= 128, MT = 1.
-  p.segmented = p.npairs > 1;
+  // A K loop that is short anyway needs no segments: the whole chain of one accumulator (taps x piece pairs x K-steps) is
+  // then no longer than a segment would be, and the kernel keeps the rolled epilogue, MT > 1 and N tiles up to 256 (the
+  // data gradients of NIN-GC's grouped layers: 16 / 36 MMAs per accumulator; r2z: the segmented form of the 256-channel 1x1
+  // data gradient took 226 us against 95 us for the forward of the same tile shape).
+  {
+    int seg_target = 64;
+    if (const char* e = getenv("MNB_PK_SEG_MMAS")) seg_target = std::max(1, atoi(e));
+    int chain = 0;
+    for (int y = 0; y < p.ny; ++y) chain = std::max(chain, p.ntap[y] * p.npairs * ceil_div(p.kg, 16));
+    p.segmented = p.npairs > 1 && chain > seg_target;
+  }
   if (ng16 <= 128) p.Nt = ng16;
   else if (ng16 % 128 == 0) p.Nt = 128;
   else if (ng16 <= 256 && !p.segmented) p.Nt = ng16;
@@ -484,12 +494,21 @@ __global__ void __launch_bounds__(256) quant_add_pack_kernel(const float* __rest
   }
 }
 
+template <int VEC> struct PkVec;
+template <> struct PkVec<1> { typedef float type; };
+template <> struct PkVec<2> { typedef float2 type; };
+template <> struct PkVec<4> { typedef float4 type; };
+
 // Second pass of the fused BatchNorm + binarizer backward (mnb_bn_sign_bwd: dgamma / dbeta already reduced) that writes the
 // gradient of the PRODUCING convolution's output directly as that convolution's packed operand: `terms` exact bf16 pieces
 // of  dx * ch_scale[c]  in the plane layout [t][b][c/8][h][w][8] (and, optionally, plain fp32 dx).  The conv's data- and
 // weight-gradient kernels then start from TMA loads; the separate pack pass (read 4 B, write 4 B per element) is gone.
 //   dx = gamma * invstd * (g * pass - dbeta / N - xhat * dgamma / N)            (training-mode BatchNorm, saturate STE)
-// one thread = one pixel of one channel octet (the conv's own channel order; g is read in the shuffled order)
+// One warp = 32 * VEC consecutive pixels of one channel octet (the conv's own channel order; g is read in the shuffled
+// order); a lane owns VEC consecutive pixels: 16-byte loads of g and x (VEC = 4), one word of pass bits per channel, VEC
+// consecutive 16-byte pixels per piece plane.  (First version: one pixel per thread, 4-byte loads with the g load predicated
+// on the bits load - 2.0 TB/s of its 12 B per element, 1.0 ms of the 6.6 ms headline step in the r2z launch list.)
+template <int VEC>
 __global__ void __launch_bounds__(256) bn_sign_bwd_pack_kernel(const float* __restrict__ g, const uint32_t* __restrict__ bits,
                                                                const float* __restrict__ x, int batch, int channels, int hw,
                                                                int sg, float inv_count, const float* __restrict__ mean,
@@ -497,42 +516,61 @@ __global__ void __launch_bounds__(256) bn_sign_bwd_pack_kernel(const float* __re
                                                                const float* __restrict__ dgamma, const float* __restrict__ dbeta,
                                                                const float* __restrict__ ch_scale, int terms,
                                                                float* __restrict__ dx, uint4* __restrict__ out, int64_t plane_vecs) {
-  const int c8n = channels / 8, cpg = channels / sg;
-  const uint32_t plane = blockIdx.y * blockDim.y + threadIdx.y;                 // b * c8n + c8
-  if (plane >= (uint32_t)batch * (uint32_t)c8n) return;
-  const uint32_t b = plane / (uint32_t)c8n, c8 = plane - b * (uint32_t)c8n;
-  float k[8], db[8], dg[8], mu[8], is[8], sc[8];
-  int oc[8];
-#pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    const int c = (int)c8 * 8 + j;
-    mu[j] = __ldg(mean + c); is[j] = __ldg(invstd + c); k[j] = __ldg(gamma + c) * is[j];
-    db[j] = __ldg(dbeta + c) * inv_count; dg[j] = __ldg(dgamma + c) * inv_count;
-    sc[j] = ch_scale ? __ldg(ch_scale + c) : 1.f;
-    oc[j] = sg > 1 ? (c % cpg) * sg + c / cpg : c;      // out[:, a*sg + b] = in[:, b*cpg + a]
-  }
-  for (uint32_t pos = blockIdx.x * blockDim.x + threadIdx.x; pos < (uint32_t)hw; pos += gridDim.x * blockDim.x) {
-    float v[8];
+  typedef typename PkVec<VEC>::type T;
+  const int lane = threadIdx.x & 31;
+  const int c8n = channels / 8, cpg = channels / sg, chunks = hw / (32 * VEC);
+  const int64_t items = (int64_t)batch * c8n * chunks;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; w < items; w += nwarps) {
+    const int ch = (int)(w % chunks);
+    const int64_t pl = w / chunks;                                // b * c8n + c8
+    const int c8 = (int)(pl % c8n), b = (int)(pl / c8n);
+    const int pos = (ch * 32 + lane) * VEC;
+    T gv[8], xv[8];
+    uint32_t bw[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      const int64_t fi = ((int64_t)b * channels + (int64_t)c8 * 8 + j) * hw + pos;
-      const bool pass = (__ldg(bits + (fi >> 5)) >> (fi & 31)) & 1u;
-      float t = pass ? __ldg(g + ((int64_t)b * channels + oc[j]) * hw + pos) : 0.f;
-      t = t - db[j] - ((__ldg(x + fi) - mu[j]) * is[j]) * dg[j];
-      t = k[j] * t;
-      if (dx) dx[fi] = t;
-      v[j] = ch_scale ? __fmul_rn(t, sc[j]) : t;
+      const int c = c8 * 8 + j;
+      const int oc = sg > 1 ? (c % cpg) * sg + c / cpg : c;      // out[:, a*sg + b] = in[:, b*cpg + a]
+      const int64_t fi = ((int64_t)b * channels + c) * hw + pos;
+      gv[j] = __ldg(reinterpret_cast<const T*>(g + ((int64_t)b * channels + oc) * hw + pos));
+      xv[j] = __ldg(reinterpret_cast<const T*>(x + fi));
+      bw[j] = __ldg(bits + (fi >> 5)) >> (fi & 31);              // bit i = pass flag of pixel pos + i
     }
-    const int64_t dst = (int64_t)plane * hw + pos;
-    for (int tm = 0; tm < terms; ++tm) {
-      uint32_t pk4[4];
+    float v[VEC][8];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        pk4[j] = pack2(v[2 * j], v[2 * j + 1]);
-        v[2 * j] -= __uint_as_float(pk4[j] << 16);
-        v[2 * j + 1] -= __uint_as_float(pk4[j] & 0xffff0000u);
+    for (int j = 0; j < 8; ++j) {
+      const int c = c8 * 8 + j;
+      const float mu = __ldg(mean + c), is = __ldg(invstd + c), k = __ldg(gamma + c) * is;
+      const float db = __ldg(dbeta + c) * inv_count, dg = __ldg(dgamma + c) * inv_count;
+      const float sc = ch_scale ? __ldg(ch_scale + c) : 1.f;
+      const float* gf = reinterpret_cast<const float*>(&gv[j]);
+      const float* xf = reinterpret_cast<const float*>(&xv[j]);
+      T dv;
+      float* df = reinterpret_cast<float*>(&dv);
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) {
+        float t = ((bw[j] >> i) & 1u) ? gf[i] : 0.f;
+        t = t - db - ((xf[i] - mu) * is) * dg;
+        t = k * t;
+        df[i] = t;
+        v[i][j] = ch_scale ? __fmul_rn(t, sc) : t;
       }
-      out[(int64_t)tm * plane_vecs + dst] = make_uint4(pk4[0], pk4[1], pk4[2], pk4[3]);
+      if (dx) *reinterpret_cast<T*>(dx + ((int64_t)b * channels + c) * hw + pos) = dv;
+    }
+    const int64_t dst = pl * hw + pos;
+    for (int tm = 0; tm < terms; ++tm) {
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) {
+        uint32_t pk4[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          pk4[j] = pack2(v[i][2 * j], v[i][2 * j + 1]);
+          v[i][2 * j] -= __uint_as_float(pk4[j] << 16);
+          v[i][2 * j + 1] -= __uint_as_float(pk4[j] & 0xffff0000u);
+        }
+        out[(int64_t)tm * plane_vecs + dst + i] = make_uint4(pk4[0], pk4[1], pk4[2], pk4[3]);
+      }
     }
   }
 }
@@ -1358,14 +1396,21 @@ extern "C" int mnb_bn_sign_bwd_pack(const float* g, const uint32_t* pass_bits, c
               out_shuffle_groups, channels);
   if (channels % 8 || (reinterpret_cast<uintptr_t>(dy_packed) & 15))
     return mnb_fail(MNB_E_UNSUPPORTED, "packed BatchNorm backward needs channels %% 8 == 0 and a 16-byte aligned output");
+  if (hw % 32) return mnb_fail(MNB_E_UNSUPPORTED, "packed BatchNorm backward needs H*W %% 32 == 0");
   const int c8n = channels / 8;
-  const int tx = std::min(256, (hw + 31) / 32 * 32), ty = 256 / tx;
-  const int planes = batch * c8n, gy = (planes + ty - 1) / ty;
-  const int bx = std::max(1, std::min((hw + tx - 1) / tx, std::max(1, (MNB_NUM_SMS * 16) / std::max(1, gy))));
-  if (gy > 65535) return mnb_fail(MNB_E_UNSUPPORTED, "bn_sign_bwd_pack: %d (image, octet) planes exceed the grid", planes);
-  pk::bn_sign_bwd_pack_kernel<<<dim3(bx, gy), dim3(tx, ty), 0, (cudaStream_t)stream>>>(
-      g, pass_bits, x, batch, channels, hw, out_shuffle_groups, 1.f / (float)((int64_t)batch * hw), mean, invstd, gamma, dgamma,
-      dbeta, ch_scale, terms, dx, reinterpret_cast<uint4*>(dy_packed), (int64_t)batch * c8n * hw);
+  auto al = [](const void* p, int a) { return p == nullptr || (reinterpret_cast<uintptr_t>(p) & (uintptr_t)(a - 1)) == 0; };
+  const int vec = (hw % 128 == 0 && al(g, 16) && al(x, 16) && al(dx, 16)) ? 4 : ((hw % 64 == 0 && al(g, 8) && al(x, 8) && al(dx, 8)) ? 2 : 1);
+  const int64_t warps = (int64_t)batch * c8n * (hw / (32 * vec));
+  const int blocks = (int)std::min<int64_t>(mnb_ceil_div(warps, 8), (int64_t)MNB_NUM_SMS * 8);
+  const float inv_count = 1.f / (float)((int64_t)batch * hw);
+  uint4* outp = reinterpret_cast<uint4*>(dy_packed);
+  const int64_t plane_vecs = (int64_t)batch * c8n * hw;
+  cudaStream_t st = (cudaStream_t)stream;
+#define MNB_BWD_PACK(V)                                                                                                      \
+  pk::bn_sign_bwd_pack_kernel<V><<<blocks, 256, 0, st>>>(g, pass_bits, x, batch, channels, hw, out_shuffle_groups, inv_count, \
+                                                         mean, invstd, gamma, dgamma, dbeta, ch_scale, terms, dx, outp, plane_vecs)
+  if (vec == 4) MNB_BWD_PACK(4); else if (vec == 2) MNB_BWD_PACK(2); else MNB_BWD_PACK(1);
+#undef MNB_BWD_PACK
   MNB_LAUNCHED(1);
   return 0;
 }

@@ -280,14 +280,19 @@ def channel_sums(x4):
 
 
 
-def xnor_preferred(sh):
-    """MNB_XNOR=auto: take the XNOR-popcount forward for this layer?  Decided from the layer-by-layer measurement of
-    harness/xnor_probe.py on B200 (profiles/r2_xnor_vs_tc.md): rule = the measured winners, nothing extrapolated."""
-    return _XNOR_RULE(sh)
+def xnor_preferred(sh, has_plane):
+    """MNB_XNOR=auto: take the XNOR-popcount forward for this wbwtab inference layer?  Decided from the layer-by-layer
+    measurement of harness/xnor_probe.py on B200 (profiles/r2_xnor_vs_tc.md, NIN-GC layers at batch 256):
 
+    * the two convolution kernels tie (31 - 102 us vs 31 - 99 us; XNOR ahead only on the 3x3 g32 layer, 52 vs 69 us): both are
+      bound by the fp32 output they write, and B200's popc pipe (16 lanes / clk / SM) gives the bit kernel no arithmetic edge
+      over tcgen05 on +-1 operands;
+    * the operand it reads is 16 x smaller (1 bit vs one bf16 per activation): packing it from an fp32 tensor costs 11 - 49 us
+      against 25 - 156 us for the bf16 plane, so a layer that has to pack its own input is 1.3 - 1.7 x faster end to end.
 
-def _XNOR_RULE(sh):
-    return False     # filled from the measurement (see profiles/r2_xnor_vs_tc.md)
+    Hence: XNOR when the layer packs its own operand (no producer-written plane came with x), the tensor-core forward when a
+    fused BatchNorm + binarizer already wrote the bf16 plane (the pack pass is free there)."""
+    return not has_plane
 
 
 def _pk_terms(spec, w_int, pm1=False):
@@ -407,13 +412,14 @@ class QuantConv2dFn(Function):
         done = False
         ctx.pk = False
         if (L.XNOR_MODE != "off" and spec is None and w_int is not None and getattr(x, "_mnb_pm1", False)
-                and not any(ctx.needs_input_grad[:3]) and x.dtype == torch.float32 and not pre_relu):
+                and not (torch.is_grad_enabled() and any(ctx.needs_input_grad[:3])) and x.dtype == torch.float32
+                and not pre_relu):
             # wbwtab inference forward on +-1 activations: bit-packed XNOR-popcount kernel where it was measured to beat the
             # tensor-core forward (north_star; table: profiles/r2_xnor_vs_tc.md).  Same integer sums, same fmaf epilogue:
             # bit-identical to the packed-operand path.  Training steps never come here (their backward multiplies real-valued
             # gradients and wants the bf16 operand plane the forward already read).
             from . import xnor as XN
-            if XN.supported(sh) and (L.XNOR_MODE == "all" or xnor_preferred(sh)):
+            if XN.supported(sh) and (L.XNOR_MODE == "all" or xnor_preferred(sh, getattr(x, "_mnb_pk_pm1", None) is not None)):
                 a_bits = XN.pack_act(x, groups)
                 rc = _timed("fwd_xnor", sh, lambda: XN.conv(sh, a_bits, XN.pack_weight(sh, w_int), y, alpha=w_scale, bias=bias))
                 if rc == 0:
@@ -439,6 +445,12 @@ class QuantConv2dFn(Function):
                 pm1_plane = None
             done = _pk_forward(ctx, x, wq, bias, w_int, w_scale, None, sh, y, ctx.needs_input_grad[0], prepacked=pm1_plane,
                                pm1=True)
+        if (not done and L.PK_MODE != "off" and spec is None and w_int is None and x.dtype == torch.float32
+                and getattr(x, "_mnb_pm1", False) and not pre_relu):
+            # un-quantized conv behind a binarizer (the 10-way head of a wbwtab model, fused.EnginePmConv2d): the +-1 input is
+            # ONE exact bf16 piece - the producer's plane when it wrote one - against exact pieces of the fp32 weights
+            plane = pm1_plane if (pm1_plane is not None and pm1_plane.numel() == x.numel() * 2) else None
+            done = _pk_forward(ctx, x, wq, bias, None, None, None, sh, y, ctx.needs_input_grad[0], prepacked=plane, pm1=True)
         if not done and pre_relu:
             x = torch.relu(x)     # outside the packed-operand cover: the folded ReLU as its own pass
         if not done and packed is not None and spec is None and w_int is not None and packed.numel() == x.numel() \
@@ -596,6 +608,100 @@ class QuantConv2dFn(Function):
 def quant_conv2d(x, wq, bias, w_int, w_scale, spec, stride, padding, dilation, groups, pre_relu=False):
     return QuantConv2dFn.apply(x, wq, bias, w_int, w_scale, spec, tuple(stride), tuple(padding),
                                tuple(dilation), groups, pre_relu)
+
+
+# --------------------------------------------------------------------------
+# transposed convolution (IAO.QuantConvTranspose2d, IAO:510-636)
+# --------------------------------------------------------------------------
+def _pk_plain(sh, mode, a, w, out, T):
+    """fp32 x fp32 convolution (mode 0) / data gradient (mode 1) of shape ``sh`` on the packed-operand tensor-core family:
+    both operands as T exact bf16 pieces.  False when the shape is outside its cover."""
+    from . import pk as PK
+    if L.PK_MODE == "off" or not PK.supported(sh, mode, T, T):
+        return False
+    a_pk, _ = PK.pack_act(a, None, T, phase_split=(mode == 0 and sh.stride_h == 2))
+    w_img = PK.pack_weight(sh, mode, T, T, w_f32=w)
+    rc = _timed("fwd_pk" if mode == 0 else "dgrad_pk", sh, lambda: PK.conv(sh, mode, a_pk, T, w_img, T, out))
+    if rc == L.E_UNSUPPORTED:
+        return False
+    L.check(rc, "pk_conv (plain)")
+    return True
+
+
+class ConvTranspose2dFn(Function):
+    """y = F.conv_transpose2d(x, w, bias, stride, padding, output_padding, groups, dilation) on the engine's convolution
+    kernels.  A transposed convolution IS the data gradient of the convolution S that maps y-space to x-space (w is
+    already stored as S's weight [K = C_in][C_out / g][R][S]):
+
+        forward   y  = dgrad_S(dy := x, w)            backward  dx = fwd_S(gy, w),  dw = wgrad_S(x := gy, dy := x)
+
+    so the three kernels of QuantConv2dFn serve it with the roles swapped: the packed-operand tensor-core family where it
+    has cover (exact bf16 pieces of the fp32 operands), the generic implicit-GEMM kernels elsewhere."""
+
+    @staticmethod
+    def forward(ctx, x, w, bias, stride, padding, output_padding, groups, dilation):
+        L.require_cuda(x, w)
+        L.require_f32(x, w)
+        lib = L.load()
+        x, w = x.contiguous(), w.contiguous()
+        b, cin, h, wd = x.shape
+        if w.shape[0] != cin or cin % groups:
+            raise ValueError("conv_transpose2d: weight must be [C_in, C_out / groups, R, S]")
+        cout = w.shape[1] * groups
+        oh = (h - 1) * stride[0] - 2 * padding[0] + dilation[0] * (w.shape[2] - 1) + output_padding[0] + 1
+        ow = (wd - 1) * stride[1] - 2 * padding[1] + dilation[1] * (w.shape[3] - 1) + output_padding[1] + 1
+        sh = _shape_struct((b, cout, oh, ow), w.shape, stride, padding, dilation, groups)
+        if _out_hw(sh) != (h, wd):
+            raise ValueError("conv_transpose2d: output_padding must be smaller than the stride")
+        y = torch.empty((b, cout, oh, ow), dtype=torch.float32, device=x.device)
+        if not _pk_plain(sh, 1, x, w, y, L.PK_TERMS):
+            L.check(_timed("dgrad", sh, lambda: lib.mnb_conv2d_dgrad(C.byref(sh), x.data_ptr(), w.data_ptr(), None, None,
+                                                                      y.data_ptr(), L.stream())), "conv2d_dgrad")
+        if bias is not None:
+            y += bias.view(1, -1, 1, 1)
+        ctx.save_for_backward(x, w)
+        ctx.sh, ctx.has_bias = sh, bias is not None
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        from . import pk as PK
+        lib = L.load()
+        x, w = ctx.saved_tensors
+        sh = ctx.sh
+        gy = gy.contiguous()
+        gx = gw = gb = None
+        T = min(L.PK_TERMS, L.PK_TERMS_BWD)
+        if ctx.needs_input_grad[0]:
+            gx = torch.empty_like(x)
+            if not _pk_plain(sh, 0, gy, w, gx, T):
+                ops = L.ConvOperands()
+                ops.a_f32, ops.w_f32 = gy.data_ptr(), w.data_ptr()
+                L.check(_timed("fwd", sh, lambda: lib.mnb_conv2d_fwd(C.byref(sh), C.byref(ops), gx.data_ptr(), L.stream())),
+                        "conv2d_fwd")
+        if ctx.needs_input_grad[1]:
+            gw = torch.empty_like(w)
+            done = False
+            if L.PK_MODE != "off" and PK.wgrad_supported(sh, T, T):
+                x_pk, _ = PK.pack_act(x, None, T)                                   # S's output-gradient operand
+                g_pk, _ = PK.pack_act(gy, None, T, phase_split=sh.stride_h == 2)    # S's input operand
+                rc = _timed("wgrad_pk", sh, lambda: PK.wgrad(sh, x_pk, T, g_pk, T, gw))
+                if rc != L.E_UNSUPPORTED:
+                    L.check(rc, "pk_wgrad (transposed conv)")
+                    done = True
+            if not done:
+                ops = L.ConvOperands()
+                ops.a_f32 = gy.data_ptr()
+                ws = torch.empty(max(int(lib.mnb_wgrad_scratch_bytes(C.byref(sh))), 4), dtype=torch.uint8, device=gy.device)
+                L.check(_timed("wgrad", sh, lambda: lib.mnb_conv2d_wgrad(C.byref(sh), x.data_ptr(), C.byref(ops), gw.data_ptr(),
+                                                                         ws.data_ptr(), L.stream())), "conv2d_wgrad")
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            gb = channel_sums(gy)
+        return gx, gw, gb, None, None, None, None, None
+
+
+def conv_transpose2d(x, w, bias, stride, padding, output_padding, groups, dilation):
+    return ConvTranspose2dFn.apply(x, w, bias, tuple(stride), tuple(padding), tuple(output_padding), groups, tuple(dilation))
 
 
 # --------------------------------------------------------------------------

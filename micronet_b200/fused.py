@@ -366,6 +366,23 @@ class EngineFloatConv2d(nn.Conv2d):
         return FloatConvFn.apply(input, self.weight, self.bias, int(self.padding[0]))
 
 
+class EnginePmConv2d(nn.Conv2d):
+    """drop-in for an un-quantized nn.Conv2d that reads a binarizer's +-1 output (wbwtab leaves the last conv of a model in
+    fp32, WB:247-331): on the packed-operand tensor-core family when its input carries the +-1 tag and the shape is inside
+    the family's cover (forward and both gradients), otherwise exactly the stock convolution.  Same parameters / state_dict."""
+
+    def forward(self, input):
+        from . import functional as F_, pk as PK
+        if (getattr(input, "_mnb_pm1", False) and L.PK_MODE != "off" and input.is_cuda and input.dtype == torch.float32
+                and input.dim() == 4 and self.padding_mode == "zeros" and not isinstance(self.padding, str)):
+            sh = F_._shape_struct(input.shape, self.weight.shape, self.stride, self.padding, self.dilation, self.groups)
+            T, Tb = L.PK_TERMS, min(L.PK_TERMS, L.PK_TERMS_BWD)
+            if (PK.supported(sh, 0, 1, T) and PK.supported(sh, 1, Tb, Tb) and PK.wgrad_supported(sh, Tb, 1)):
+                return F_.quant_conv2d(input, self.weight, self.bias, None, None, None, self.stride, self.padding,
+                                       self.dilation, self.groups)
+        return self._conv_forward(input, self.weight, self.bias)
+
+
 def _fuse_pairs(module: nn.Module):
     from .wbwtab import ActivationQuantizer
     prev_name, prev = None, None
@@ -382,6 +399,11 @@ def _fuse_pairs(module: nn.Module):
         elif type(child) is nn.Conv2d and _float_conv_cover(child):
             conv = EngineFloatConv2d(child.in_channels, child.out_channels, child.kernel_size, child.stride, child.padding,
                                      child.dilation, child.groups, child.bias is not None)
+            conv.weight, conv.bias = child.weight, child.bias
+            module._modules[name] = conv
+        elif type(child) is nn.Conv2d and child.in_channels % 8 == 0 and child.in_channels >= 64:
+            conv = EnginePmConv2d(child.in_channels, child.out_channels, child.kernel_size, child.stride, child.padding,
+                                  child.dilation, child.groups, child.bias is not None, child.padding_mode)
             conv.weight, conv.bias = child.weight, child.bias
             module._modules[name] = conv
         elif type(child) is nn.MaxPool2d and _pool_cfg(child) is not None:

@@ -314,6 +314,28 @@ class QuantConv2d(nn.Conv2d):
         return self._quant_conv(input, self.weight, self.bias)
 
 
+class QuantConvTranspose2d(nn.ConvTranspose2d):
+    """IAO:510-636.  Both quantizers observe per layer ("L"), whatever the model-level q_level is (the reference hard-codes
+    them); the transposed convolution runs on the engine's convolution kernels with the roles swapped
+    (functional.ConvTranspose2dFn)."""
+
+    def __init__(self, in_channels, out_channels, kernel_size, stride=1, padding=0, output_padding=0, groups=1, bias=True,
+                 dilation=1, padding_mode="zeros", a_bits=8, w_bits=8, q_type=0, weight_observer=0, quant_inference=False,
+                 qaft=False, ptq=False, percentile=0.9999):
+        super().__init__(in_channels, out_channels, kernel_size, stride, padding, output_padding, groups, bias, dilation,
+                         padding_mode)
+        self.quant_inference = quant_inference
+        self.activation_quantizer = _activation_quantizer(a_bits, q_type, qaft, ptq, percentile)
+        self.weight_quantizer = _weight_quantizer(w_bits, q_type, 1, weight_observer, None, qaft, ptq)
+
+    def forward(self, input):
+        L.require_cuda(input, self.weight)
+        quant_input = self.activation_quantizer(input)
+        quant_weight = self.weight if self.quant_inference else self.weight_quantizer(self.weight)
+        return F_.conv_transpose2d(quant_input, quant_weight, self.bias, self.stride, self.padding, self.output_padding,
+                                   self.groups, self.dilation)
+
+
 def reshape_to_activation(input):
     return input.reshape(1, -1, 1, 1)
 
@@ -560,8 +582,13 @@ def add_quant_op(module, a_bits=8, w_bits=8, q_type=0, q_level=0, weight_observe
                 fused.running_var.copy_(child.running_var)
                 module._modules[conv_name_temp] = fused
                 module._modules[name] = nn.Identity()
-        elif isinstance(child, nn.ConvTranspose2d):
-            raise NotImplementedError("QuantConvTranspose2d is out of scope of the B200 engine (SURVEY §8 f4)")
+        elif isinstance(child, nn.ConvTranspose2d):   # IAO:1606-1640 (never BN-fused in the reference either)
+            module._modules[name] = _adopt(QuantConvTranspose2d(
+                child.in_channels, child.out_channels, child.kernel_size, stride=child.stride, padding=child.padding,
+                output_padding=child.output_padding, groups=child.groups, bias=child.bias is not None,
+                dilation=child.dilation, padding_mode=child.padding_mode, a_bits=a_bits, w_bits=w_bits, q_type=q_type,
+                weight_observer=weight_observer, quant_inference=quant_inference, qaft=qaft, ptq=ptq,
+                percentile=percentile), child)
         elif isinstance(child, nn.Linear):
             module._modules[name] = _adopt(QuantLinear(
                 child.in_features, child.out_features, bias=child.bias is not None,

@@ -430,6 +430,25 @@ class IaoQuantConv2d(nn.Conv2d):
         return F.conv2d(qx, qw, self.bias, self.stride, self.padding, self.dilation, self.groups)
 
 
+class IaoQuantConvTranspose2d(nn.ConvTranspose2d):
+    """IAO:510-636: per-layer ("L") observers for both operands whatever q_level says (the reference hard-codes them)."""
+
+    def __init__(self, in_channels, out_channels, kernel_size, stride=1, padding=0, output_padding=0, groups=1,
+                 bias=True, dilation=1, padding_mode="zeros", a_bits=8, w_bits=8, q_type=0, weight_observer=0,
+                 quant_inference=False, qaft=False, ptq=False, percentile=0.9999):
+        super().__init__(in_channels, out_channels, kernel_size, stride, padding, output_padding, groups, bias, dilation,
+                         padding_mode)
+        self.quant_inference = quant_inference
+        self.activation_quantizer = _iao_act_quantizer(a_bits, q_type, qaft, ptq, percentile)
+        self.weight_quantizer = _iao_weight_quantizer(w_bits, q_type, 1, weight_observer, None, qaft, ptq)
+
+    def forward(self, x):
+        qx = self.activation_quantizer(x)
+        qw = self.weight if self.quant_inference else self.weight_quantizer(self.weight)
+        return F.conv_transpose2d(qx, qw, self.bias, self.stride, self.padding, self.output_padding, self.groups,
+                                  self.dilation)
+
+
 class IaoQuantBNFuseConv2d(IaoQuantConv2d):
     """IAO:652-994."""
 

@@ -63,6 +63,13 @@ LAYER_CASES = [
        (6, 24), 17, train_steps=2),
     _c("iao_linear_asym_pl", "iao", "linear", (24, 10), dict(q_type=1, q_level=1),
        (6, 24), 18, train_steps=2),
+    # ---- IAO transposed conv (IAO:510-636) ---------------------------------------------
+    _c("iao_convT_sym_s2", "iao", "convT", (8, 6, 3), dict(stride=2, padding=1, output_padding=1, q_type=0),
+       (2, 8, 7, 7), 24, train_steps=3),
+    _c("iao_convT_asym_g2_ema", "iao", "convT", (8, 12, 4), dict(stride=2, padding=1, groups=2, q_type=1, weight_observer=1),
+       (2, 8, 6, 6), 25, train_steps=3, x_kind="relu"),
+    _c("iao_convT_s1_nobias", "iao", "convT", (6, 8, 3), dict(padding=1, bias=False, a_bits=4, w_bits=4),
+       (3, 6, 8, 8), 26, train_steps=2),
     # ---- IAO BN-fuse (IAO:652-994) ---------------------------------------------------
     _c("iao_bnfuse_sym_pc", "iao", "bnfuse", (8, 12, 3), dict(padding=1),
        (4, 8, 8, 8), 19, train_steps=3),

@@ -39,6 +39,7 @@ REF_CLASSES = {
     ("iao", "conv"): ref_iao.QuantConv2d,
     ("iao", "bnfuse"): ref_iao.QuantBNFuseConv2d,
     ("iao", "linear"): ref_iao.QuantLinear,
+    ("iao", "convT"): ref_iao.QuantConvTranspose2d,
 }
 
 
@@ -150,11 +151,16 @@ def _narrow_resnet(widths):
 
 def main():
     torch.set_num_threads(1)  # fixed summation order for the fixtures
+    only_new = "--only-new" in sys.argv     # keep the committed fixtures, generate the cases that have none yet
     for case in LAYER_CASES:
+        if only_new and os.path.exists(os.path.join(HERE, f"layer_{case['name']}.npz")):
+            continue
         arrays = run_layer_case(case)
         np.savez_compressed(os.path.join(HERE, f"layer_{case['name']}.npz"), **arrays)
         print("layer", case["name"], sum(a.nbytes for a in arrays.values()) // 1024, "KiB raw")
     for case in MODEL_CASES:
+        if only_new and os.path.exists(os.path.join(HERE, f"model_{case['name']}.npz")):
+            continue
         arrays = run_model_case(case)
         np.savez_compressed(os.path.join(HERE, f"model_{case['name']}.npz"), **arrays)
         print("model", case["name"], sum(a.nbytes for a in arrays.values()) // 1024, "KiB raw")

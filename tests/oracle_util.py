@@ -15,6 +15,7 @@ ORACLE_CLASSES = {
     ("iao", "conv"): O.IaoQuantConv2d,
     ("iao", "bnfuse"): O.IaoQuantBNFuseConv2d,
     ("iao", "linear"): O.IaoQuantLinear,
+    ("iao", "convT"): O.IaoQuantConvTranspose2d,
 }
 
 

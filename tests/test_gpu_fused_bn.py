@@ -292,3 +292,42 @@ def test_wbwtab_layer_between_two_fused_producers_on_the_packed_operand_family(c
     assert rel_err(b["dw"], a["dw"]) <= 1e-5 + 50 * allow, (rel_err(b["dw"], a["dw"]), allow)
     assert b["db"].abs().max().item() <= 1e-4 * a["dw"].abs().max().item() + a["db"].abs().max().item() * 2 + 1e-6
     L.tc_check()
+
+
+@pytest.mark.parametrize("shape", [(8, 1024, 8, 8, 10, 1), (4, 256, 16, 16, 24, 3)], ids=["head1x1", "3x3"])
+def test_unquantized_conv_behind_a_binarizer_runs_on_the_packed_family(shape):
+    """fused.EnginePmConv2d (the fp32 10-way head of a wbwtab model, WB:247-331 leaves it un-quantized): BatchNorm+binarizer
+    -> conv on the packed-operand family (+-1 plane from the producer, exact pieces of the fp32 weights) against ATen in
+    fp64 on the same +-1 tensor; without the +-1 tag the module is exactly the stock convolution."""
+    import torch.nn.functional as TF
+    from micronet_b200 import _lib as L, functional as F_
+    from micronet_b200.fused import BatchNormBinarize2d, EnginePmConv2d
+    B, C, H, W, K, R = shape
+    torch.manual_seed(sum(shape))
+    bn = BatchNormBinarize2d(C).to(DEV).train()
+    conv = EnginePmConv2d(C, K, R, padding=R // 2).to(DEV)
+    x = (torch.randn(B, C, H, W) * 1.5).to(DEV)
+    go = torch.randn(B, K, H, W).to(DEV)
+    F_.TIMER = F_.KernelTimer()
+    try:
+        a = bn(x)
+        a.retain_grad()
+        y = conv(a)
+        y.backward(go)
+        torch.cuda.synchronize()
+        kinds = {k for k, _, _, _ in F_.TIMER.records}
+    finally:
+        F_.TIMER = None
+    L.tc_check()
+    assert {"fwd_pk", "dgrad_pk", "wgrad_pk"} <= kinds, kinds
+    ad = a.detach().double().cpu().requires_grad_(True)
+    wd = conv.weight.detach().double().cpu().requires_grad_(True)
+    bd = conv.bias.detach().double().cpu().requires_grad_(True)
+    yd = TF.conv2d(ad, wd, bd, 1, R // 2)
+    yd.backward(go.double().cpu())
+    assert rel_err(y.detach(), yd.detach()) <= 2e-6
+    assert rel_err(a.grad, ad.grad) <= 1e-5
+    assert rel_err(conv.weight.grad, wd.grad) <= 1e-5
+    assert rel_err(conv.bias.grad, bd.grad) <= 1e-5
+    plain = torch.randn(B, C, H, W, device=DEV)          # no +-1 tag: the stock path, bit for bit
+    assert torch.equal(conv(plain), TF.conv2d(plain, conv.weight, conv.bias, 1, R // 2))

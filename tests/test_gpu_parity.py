@@ -23,6 +23,7 @@ def engine_classes():
         ("dorefa", "conv"): E.dorefa.QuantConv2d, ("dorefa", "linear"): E.dorefa.QuantLinear,
         ("wbwtab", "conv"): E.wbwtab.QuantConv2d, ("iao", "conv"): E.iao.QuantConv2d,
         ("iao", "bnfuse"): E.iao.QuantBNFuseConv2d, ("iao", "linear"): E.iao.QuantLinear,
+        ("iao", "convT"): E.iao.QuantConvTranspose2d,
     }
 
 

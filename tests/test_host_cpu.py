@@ -101,9 +101,11 @@ def test_fuse_pass_rewrites_the_prepared_graph_only():
     moved = sorted(m.out_shuffle_groups for m in fused.modules() if getattr(m, "out_shuffle_groups", 1) > 1)
     assert moved == sorted(m.shuffle_groups for m in plain.modules() if getattr(m, "channel_shuffle_flag", 0))
     assert any(getattr(m, "channel_shuffle_flag", 0) for m in base.modules()), "the user's model is left untouched"
-    # only the covered plain conv (3 -> 256, 5x5) is swapped; the 1024-channel classifier conv stays
+    # the covered plain conv (3 -> 256, 5x5) goes to the fp32 tensor-core kernels; the 1024-channel classifier conv behind
+    # the last binarizer to the packed-operand family (+-1 input), falling back to the stock conv without that tag
+    from micronet_b200.fused import EnginePmConv2d
     assert [n for n, c in fused.named_modules() if isinstance(c, EngineFloatConv2d)] == ["model.0.conv"]
-    assert type(dict(fused.named_modules())["model.10.conv"]) is nn.Conv2d
+    assert type(dict(fused.named_modules())["model.10.conv"]) is EnginePmConv2d
     # A != 2 keeps the ReLU path: nothing to fuse
     relu = E.wbwtab.prepare(base, A=32, W=2, fuse_bn=True)
     assert not any(isinstance(m, BatchNormBinarize2d) for m in relu.modules())
