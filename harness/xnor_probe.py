@@ -25,7 +25,11 @@ LAYERS = [
 ]
 
 
-def timeit(fn, iters=20):
+ITERS = 20
+
+
+def timeit(fn, iters=None):
+    iters = iters or ITERS
     fn(0)
     torch.cuda.synchronize()
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -41,13 +45,19 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--json", default=None)
     ap.add_argument("--batch", type=int, default=256)
+    ap.add_argument("--only", default=None, help="substring of the layer name (ncu target: one layer)")
+    ap.add_argument("--iters", type=int, default=20)
     args = ap.parse_args()
     from micronet_b200 import _lib as L, pk as PK, xnor as X
     dev = torch.device("cuda:0")
     pk_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     hbm = json.load(open(pk_path))["hbm_gbs"] if os.path.exists(pk_path) else 6650.0
     B, nb, rows = args.batch, 4, []
+    global ITERS
+    ITERS = args.iters
     for name, Cc, H, W, K, R, pad, G in LAYERS:
+        if args.only and args.only not in name:
+            continue
         sh = L.ConvShape(B, Cc, H, W, K, R, R, 1, 1, pad, pad, 1, 1, G)
         xs = [torch.where(torch.randn(B, Cc, H, W, device=dev) < 0, -1.0, 1.0) for _ in range(nb)]
         ys = [torch.empty(B, K, H, W, device=dev) for _ in range(nb)]

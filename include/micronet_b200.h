@@ -335,6 +335,14 @@ int mnb_bn_sign_bwd_pack(const float* g, const uint32_t* pass_bits, const float*
                          const float* mean, const float* invstd, const float* gamma, const float* dgamma, const float* dbeta,
                          int32_t out_shuffle_groups, const float* ch_scale, int32_t terms, float* dx, void* dy_packed,
                          mnb_stream_t stream);
+/* The same for a producer with the 2x2 max-pool folded in: second pass of mnb_bn_sign_pool_bwd (call that one with
+ * training = 2 first: reduce pass only, dgamma / dbeta) writing the full-resolution gradient [batch, channels, H, W] as the
+ * producing conv's packed operand.  argmax / pass_bits as written by mnb_bn_sign_pool_fwd; g is the pooled gradient
+ * [batch, channels, H/2, W/2] in the shuffled order.  Needs even H, W % 8 == 0, channels % 8 == 0.                  */
+int mnb_bn_sign_pool_bwd_pack(const float* g, const uint32_t* pass_bits, const uint8_t* argmax, const float* x, int32_t batch,
+                              int32_t channels, int32_t H, int32_t W, const float* mean, const float* invstd,
+                              const float* gamma, const float* dgamma, const float* dbeta, int32_t out_shuffle_groups,
+                              const float* ch_scale, int32_t terms, void* dy_packed, mnb_stream_t stream);
 /* mnb_pk_pack_act with a preceding nn.ReLU folded in (relu != 0: x is clamped at 0 before it is quantized / split) */
 int mnb_pk_pack_act_relu(const float* x, int32_t batch, int32_t channels, int32_t h, int32_t w, const mnb_act_qparams* qp,
                          int32_t terms, const float* ch_scale, int32_t phase_split, int32_t relu, void* out_pk,

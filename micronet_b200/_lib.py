@@ -94,6 +94,7 @@ PROTOTYPES = {
     "mnb_pk_pack_weight": (C.c_int, [_SHAPE, _I, _I, _I, _P, _P, _P, _P, _P]),
     "mnb_pk_conv": (C.c_int, [_SHAPE, _I, _P, _I, _P, _I, _P, _P, C.c_float, _P, _P, C.c_float, _P, _P, _P]),
     "mnb_bn_sign_bwd_pack": (C.c_int, [_P, _P, _P, _I, _I, _I, _P, _P, _P, _P, _P, _I, _P, _I, _P, _P, _P]),
+    "mnb_bn_sign_pool_bwd_pack": (C.c_int, [_P, _P, _P, _P, _I, _I, _I, _I, _P, _P, _P, _P, _P, _I, _P, _I, _P, _P]),
     "mnb_pk_conv_post": (C.c_int, [_SHAPE, _P, _I, _P, _I, _P, _P, C.c_float, _P, _P, C.POINTER(PkPost), _P, _P]),
     "mnb_quant_add_pack_fwd": (C.c_int, [_P, _P, _I, _I, _I, _I, _ACTQ, _I, _P, C.POINTER(PkPost), _P]),
     "mnb_pk_wgrad_scratch_bytes": (_L, [_SHAPE, _I, _I]),
@@ -209,6 +210,10 @@ PK_WBWTAB = os.environ.get("MNB_PK_WBWTAB", "1") == "1"
 # bit-packed XNOR-popcount forward for wbwtab inference (mnb_xnor.cu): "auto" = the layers where it was measured to beat the
 # tensor-core forward (functional.xnor_preferred), "all" = wherever it has cover, "off" = never
 XNOR_MODE = os.environ.get("MNB_XNOR", "auto")
+
+# fused BatchNorm + binarizer producers whose only reader takes the bf16 operand plane skip their fp32 output (fused.py
+# _mark_plane_only); MNB_PLANE_ONLY=0 makes them write it again (e.g. to look at intermediate activations with hooks)
+PLANE_ONLY = os.environ.get("MNB_PLANE_ONLY", "1") == "1"
 
 _scratch = {}
 

@@ -517,6 +517,7 @@ extern "C" int mnb_bn_sign_pool_bwd(const float* g, const uint32_t* pass_bits, c
   bn_sign_pool_bwd_reduce_kernel<<<grid, 256, 0, S(stream)>>>(reinterpret_cast<const float2*>(g),
                                                               reinterpret_cast<const uchar2*>(argmax), bits8, x, batch, gm, mean,
                                                               invstd, dgamma, dbeta, counters, partial);
+  if (training == 2) { MNB_LAUNCHED(1); return 0; }   // reduce pass only: the caller applies (mnb_bn_sign_pool_bwd_pack)
   bn_sign_pool_bwd_apply_kernel<<<grid, 256, 0, S(stream)>>>(reinterpret_cast<const float2*>(g),
                                                              reinterpret_cast<const uchar2*>(argmax), bits8,
                                                              reinterpret_cast<const float4*>(x), batch, gm, 1.f / (float)per, mean,

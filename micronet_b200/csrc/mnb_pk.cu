@@ -575,6 +575,70 @@ __global__ void __launch_bounds__(256) bn_sign_bwd_pack_kernel(const float* __re
   }
 }
 
+// The same for a producer with the 2x2 max-pool folded in (mnb_bn_sign_pool_*): second pass of its backward writing the
+// full-resolution gradient of the producing conv's output as that conv's packed operand.  One lane = two horizontally
+// adjacent pooling windows (4 x 2 pixels) of the 8 channels of one octet: per channel one float2 of the pooled gradient
+// (read in the shuffled order), the two window arg-max bytes, the pass nibbles and two float4 of x; per piece plane two
+// runs of 4 consecutive 16-byte pixels.  Layouts of arg / bits8 as written by bn_sign_pool_fwd_kernel (mnb_fused.cu).
+__global__ void __launch_bounds__(256) bn_sign_pool_bwd_pack_kernel(const float2* __restrict__ g, const uchar2* __restrict__ arg,
+                                                                    const uint8_t* __restrict__ bits8, const float4* __restrict__ x,
+                                                                    int batch, int channels, int H, int W4, int sg, float inv_count,
+                                                                    const float* __restrict__ mean, const float* __restrict__ invstd,
+                                                                    const float* __restrict__ gamma, const float* __restrict__ dgamma,
+                                                                    const float* __restrict__ dbeta, const float* __restrict__ ch_scale,
+                                                                    int terms, uint4* __restrict__ out, int64_t plane_vecs) {
+  const uint32_t OH = (uint32_t)H / 2u, OW2 = (uint32_t)W4, c8n = (uint32_t)channels / 8u, cpg = (uint32_t)channels / (uint32_t)sg;
+  const uint32_t per_plane = OH * OW2;                                       // lane items per (image, channel) plane
+  const int64_t total = (int64_t)batch * c8n * per_plane;
+  for (int64_t it = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; it < total; it += (int64_t)gridDim.x * blockDim.x) {
+    const uint32_t rem = (uint32_t)(it % per_plane);
+    const int64_t pl = it / per_plane;                                      // b * c8n + c8
+    const uint32_t c8 = (uint32_t)(pl % c8n), b = (uint32_t)(pl / c8n);
+    const uint32_t oh = rem / OW2, j = rem - oh * OW2;
+    float v[8][8];                                                            // [pixel e: row (e >> 2), column (e & 3)][channel]
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const uint32_t c = c8 * 8u + q;
+      const uint32_t oc = sg > 1 ? (c % cpg) * (uint32_t)sg + c / cpg : c;
+      const uint32_t plane = b * (uint32_t)channels + c;
+      const float2 gv = __ldg(g + ((size_t)(b * (uint32_t)channels + oc) * OH + oh) * OW2 + j);
+      const uchar2 a = arg[((size_t)plane * OH + oh) * OW2 + j];
+      const uint32_t i0 = (plane * (uint32_t)H + 2u * oh) * (uint32_t)W4 + j, i1 = i0 + (uint32_t)W4;
+      const uint32_t n0 = (bits8[i0 >> 1] >> (4u * (i0 & 1u))) & 15u, n1 = (bits8[i1 >> 1] >> (4u * (i1 & 1u))) & 15u;
+      const float4 r0 = __ldg(x + i0), r1 = __ldg(x + i1);
+      const float mu = __ldg(mean + c), is = __ldg(invstd + c), k = __ldg(gamma + c) * is;
+      const float db = __ldg(dbeta + c) * inv_count, dg = __ldg(dgamma + c) * inv_count;
+      const float sc = ch_scale ? __ldg(ch_scale + c) : 1.f;
+      const uint32_t e0 = (a.x >> 1) * 4u + (a.x & 1u), e1 = (a.y >> 1) * 4u + 2u + (a.y & 1u);
+      const uint32_t nib = n0 | (n1 << 4);
+      const float xs[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        float t = 0.f;
+        if ((uint32_t)e == e0 && ((nib >> e) & 1u)) t = gv.x;
+        if ((uint32_t)e == e1 && ((nib >> e) & 1u)) t = gv.y;
+        t = t - db - ((xs[e] - mu) * is) * dg;
+        t = k * t;
+        v[e][q] = ch_scale ? __fmul_rn(t, sc) : t;
+      }
+    }
+    const int64_t dst0 = (pl * H + 2 * oh) * (int64_t)(4 * W4) + 4 * j;     // pixel (2 oh, 4 j) of this octet plane
+    for (int tm = 0; tm < terms; ++tm) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        uint32_t pk4[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          pk4[q] = pack2(v[e][2 * q], v[e][2 * q + 1]);
+          v[e][2 * q] -= __uint_as_float(pk4[q] << 16);
+          v[e][2 * q + 1] -= __uint_as_float(pk4[q] & 0xffff0000u);
+        }
+        out[(int64_t)tm * plane_vecs + dst0 + (e >> 2) * (int64_t)(4 * W4) + (e & 3)] = make_uint4(pk4[0], pk4[1], pk4[2], pk4[3]);
+      }
+    }
+  }
+}
+
 struct PackWParams {
   Plan pl;
   const int16_t* w_int; const float* w_f32; const float* kzero;   // kzero[k] == 0 -> the weights of channel k read as 0 (dgrad)
@@ -695,10 +759,18 @@ __device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, uint32_t (&r)[16])
       : "r"(taddr));
 }
 
-__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+template <int NEPI>
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(NEPI) : "memory"); }
+
+// Epilogue warps: one warp can only read the 32 TMEM lanes of its own quarter (warp % 4), and a lone warp per scheduler
+// issues its dependent tcgen05.ld -> fma -> st chains at ~0.3 instructions per cycle - ncu r3b: every forward / data-gradient
+// launch of the family sat at 42 - 47 k instructions per epilogue warp in 160 - 173 k cycles, tensor pipe 7 - 9 % busy, DRAM
+// 3.6 TB/s.  The un-segmented kernel therefore runs TWO warps per quarter (warps 4..7 take the even 16-column slots of an
+// item, warps 8..11 the odd ones); the segmented kernel keeps one (its 128 running sums per thread need the registers).
+template <bool SEG> struct ConvCfg { static constexpr int EPIW = SEG ? 4 : 8, THREADS = 128 + 32 * EPIW; };
 
 template <bool SEG>   // SEG: segmented accumulation (split fp32 operands), the epilogue keeps the N tile in registers
-__global__ void __launch_bounds__(NTHREADS, 1)
+__global__ void __launch_bounds__(ConvCfg<SEG>::THREADS, 1)
 pk_conv_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_constant__ CUtensorMap tmap1,
                const __grid_constant__ CUtensorMap tmap2, const __grid_constant__ ConvParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -707,7 +779,7 @@ pk_conv_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_constant_
 
   if (tid == 0) {
     for (int i = 0; i < MAXST; ++i) { tc::mbar_init(&sh.full[i], 1); tc::mbar_init(&sh.empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { tc::mbar_init(&sh.acc_full[i], 1); tc::mbar_init(&sh.acc_empty[i], 128); }
+    for (int i = 0; i < 2; ++i) { tc::mbar_init(&sh.acc_full[i], 1); tc::mbar_init(&sh.acc_empty[i], 32 * ConvCfg<SEG>::EPIW); }
     sh.abort = 0;
     tc::fence_barrier_init();
     tc::prefetch_tmap(&tmap0);
@@ -720,7 +792,7 @@ pk_conv_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_constant_
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
   // rows behind a box that only invalid accumulator rows read must at least be finite
-  for (int i = tid; i < p.smem_bytes / 16; i += NTHREADS) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
+  for (int i = tid; i < p.smem_bytes / 16; i += ConvCfg<SEG>::THREADS) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
   tc::fence_proxy_async_smem();
   tc::tc_fence_before();
   __syncthreads();
@@ -820,7 +892,8 @@ pk_conv_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_constant_
     }
   } else if (warp >= 4) {
     // ================================================================= epilogue: TMEM -> scale/bias or STE -> fp32 NCHW
-    const int q = warp - 4, et = tid - 128;
+    constexpr int NEPI = 32 * ConvCfg<SEG>::EPIW;
+    const int q = (warp - 4) & 3, half = (warp - 4) >> 2, et = tid - 128;   // TMEM lane quarter, slot parity (8 epilogue warps)
     const int m = q * 32 + lane;                     // accumulator row = position of the zero-padded tile raster
     const int tb = m / (p.THH * p.BW);
     const int rem = m - tb * (p.THH * p.BW);
@@ -843,7 +916,7 @@ pk_conv_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_constant_
       const int n_base = g * p.ng + nt * p.Nt;                // first output channel of this N tile
       const int n_cnt = min(p.Nt, p.ng - nt * p.Nt);
       // per-channel constants of this N tile (the previous item's readers are done: barrier at the end of the loop body)
-      for (int n = et; n < p.Nt; n += 128) {
+      for (int n = et; n < p.Nt; n += NEPI) {
         float sc = 1.f, bs = 0.f;
         if (n < n_cnt) {
           sc = p.n_scale ? __fmul_rn(a_sc, __ldg(p.n_scale + n_base + n)) : a_sc;
@@ -851,7 +924,7 @@ pk_conv_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_constant_
         }
         sh.epi_scale[n] = sc; sh.epi_bias[n] = bs;
       }
-      epi_bar_sync();
+      epi_bar_sync<NEPI>();
       const int nseg = SEG ? p.nseg[y] : 1;
       // running sums of the item's accumulator columns (segmented mode only: MT * Nt <= 128 -> 8 slots of 16 columns;
       // slot = mt * (Nt / 16) + column chunk).  The slot loop is fully unrolled so that rs[][] stays in registers.
@@ -963,12 +1036,13 @@ pk_conv_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_constant_
 #pragma unroll 1
           for (int mt = 0, slot = 0; mt < p.MT; ++mt)
 #pragma unroll 1
-            for (int c16 = 0; c16 < nc16; ++c16, ++slot) do_slot(slot, mt, c16, rs[0]);
+            for (int c16 = 0; c16 < nc16; ++c16, ++slot)
+              if (ConvCfg<SEG>::EPIW == 4 || (slot & 1) == half) do_slot(slot, mt, c16, rs[0]);
         }
         tc::tc_fence_before();
         tc::mbar_arrive(&sh.acc_empty[acc]);
       }
-      epi_bar_sync();   // everyone is done with epi_scale / epi_bias of this item
+      epi_bar_sync<NEPI>();   // everyone is done with epi_scale / epi_bias of this item
     }
   }
 done:
@@ -1415,6 +1489,29 @@ extern "C" int mnb_bn_sign_bwd_pack(const float* g, const uint32_t* pass_bits, c
   return 0;
 }
 
+extern "C" int mnb_bn_sign_pool_bwd_pack(const float* g, const uint32_t* pass_bits, const uint8_t* argmax, const float* x,
+                                         int32_t batch, int32_t channels, int32_t H, int32_t W, const float* mean,
+                                         const float* invstd, const float* gamma, const float* dgamma, const float* dbeta,
+                                         int32_t out_shuffle_groups, const float* ch_scale, int32_t terms, void* dy_packed,
+                                         mnb_stream_t stream) {
+  MNB_REQUIRE(g && pass_bits && argmax && x && mean && invstd && gamma && dgamma && dbeta && dy_packed, "NULL bn_sign_pool_bwd_pack pointer");
+  MNB_REQUIRE(batch > 0 && channels > 0 && H > 0 && W > 0 && terms >= 1 && terms <= 3, "bad bn_sign_pool_bwd_pack arguments");
+  MNB_REQUIRE(out_shuffle_groups >= 1 && channels % out_shuffle_groups == 0, "shuffle groups %d do not divide %d channels",
+              out_shuffle_groups, channels);
+  if ((H & 1) || (W & 7) || channels % 8 || (int64_t)batch * channels * H * W >= (1ll << 31) ||
+      ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(dy_packed)) & 15) || (reinterpret_cast<uintptr_t>(g) & 7))
+    return mnb_fail(MNB_E_UNSUPPORTED, "packed pooled BatchNorm backward needs even H, W %% 8 == 0, channels %% 8 == 0, aligned tensors");
+  const int c8n = channels / 8;
+  const int64_t total = (int64_t)batch * c8n * (H / 2) * (W / 4);
+  const int blocks = (int)std::min<int64_t>(mnb_ceil_div(total, 256), (int64_t)MNB_NUM_SMS * 8);
+  pk::bn_sign_pool_bwd_pack_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(
+      reinterpret_cast<const float2*>(g), reinterpret_cast<const uchar2*>(argmax), reinterpret_cast<const uint8_t*>(pass_bits),
+      reinterpret_cast<const float4*>(x), batch, channels, H, W / 4, out_shuffle_groups, 1.f / (float)((int64_t)batch * H * W), mean,
+      invstd, gamma, dgamma, dbeta, ch_scale, terms, reinterpret_cast<uint4*>(dy_packed), (int64_t)batch * c8n * H * W);
+  MNB_LAUNCHED(1);
+  return 0;
+}
+
 extern "C" int mnb_quant_add_pack_fwd(const float* a, const float* b, int32_t batch, int32_t channels, int32_t h, int32_t w,
                                       const mnb_act_qparams* qp, int32_t relu, float* out, const mnb_pk_post* post,
                                       mnb_stream_t stream) {
@@ -1572,10 +1669,10 @@ static int pk_conv_impl(const mnb_conv_shape* s, int32_t mode, const void* a_pk,
   if (pl.segmented) {
     if (pl.MT * pl.Nt > 128) return mnb_fail(MNB_E_ARG, "pk conv: segmented plan with Nt %d, MT %d", pl.Nt, pl.MT);
     if (int e = set_max_smem(pk_conv_kernel<true>, kSmemBudget)) return e;
-    pk_conv_kernel<true><<<dim3(gx, pl.ny), NTHREADS, pl.smem_bytes, (cudaStream_t)stream>>>(tm[0], tm[1], tm[2], p);
+    pk_conv_kernel<true><<<dim3(gx, pl.ny), ConvCfg<true>::THREADS, pl.smem_bytes, (cudaStream_t)stream>>>(tm[0], tm[1], tm[2], p);
   } else {
     if (int e = set_max_smem(pk_conv_kernel<false>, kSmemBudget)) return e;
-    pk_conv_kernel<false><<<dim3(gx, pl.ny), NTHREADS, pl.smem_bytes, (cudaStream_t)stream>>>(tm[0], tm[1], tm[2], p);
+    pk_conv_kernel<false><<<dim3(gx, pl.ny), ConvCfg<false>::THREADS, pl.smem_bytes, (cudaStream_t)stream>>>(tm[0], tm[1], tm[2], p);
   }
   MNB_LAUNCHED(1);
   return 0;

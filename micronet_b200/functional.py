@@ -280,6 +280,17 @@ def channel_sums(x4):
 
 
 
+def materialized(t):
+    """the values of a producer output: ``t`` itself, or - for a plane-only output of a fused BatchNorm + binarizer (its fp32
+    storage was never written) - the +-1 tensor rebuilt from the bf16 operand plane [b][c/8][h][w][8].  Plumbing for tests,
+    hooks and convs outside the packed-operand cover; the training step never calls it."""
+    if not getattr(t, "_mnb_plane_only", False):
+        return t
+    b, c, h, w = t.shape
+    plane = t._mnb_pk_pm1.view(torch.bfloat16).view(b, c // 8, h, w, 8)
+    return plane.permute(0, 1, 4, 2, 3).reshape(b, c, h, w).float()
+
+
 def xnor_preferred(sh, has_plane):
     """MNB_XNOR=auto: take the XNOR-popcount forward for this wbwtab inference layer?  Decided from the layer-by-layer
     measurement of harness/xnor_probe.py on B200 (profiles/r2_xnor_vs_tc.md, NIN-GC layers at batch 256):
@@ -395,7 +406,7 @@ class QuantConv2dFn(Function):
     and the clip-STE fused into dgrad.  ``spec`` None => x is used as fp32 (wbwtab, a_bits=32)."""
 
     @staticmethod
-    def forward(ctx, x, wq, bias, w_int, w_scale, spec, stride, padding, dilation, groups, pre_relu=False):
+    def forward(ctx, x, wq, bias, w_int, w_scale, spec, stride, padding, dilation, groups, pre_relu=False, no_grad=False):
         L.require_cuda(x, wq)
         assert not (pre_relu and any(ctx.needs_input_grad)), "the folded ReLU is an inference-only fusion"
         lib = L.load()
@@ -412,15 +423,14 @@ class QuantConv2dFn(Function):
         done = False
         ctx.pk = False
         if (L.XNOR_MODE != "off" and spec is None and w_int is not None and getattr(x, "_mnb_pm1", False)
-                and not (torch.is_grad_enabled() and any(ctx.needs_input_grad[:3])) and x.dtype == torch.float32
-                and not pre_relu):
+                and (no_grad or not any(ctx.needs_input_grad[:3])) and x.dtype == torch.float32 and not pre_relu):
             # wbwtab inference forward on +-1 activations: bit-packed XNOR-popcount kernel where it was measured to beat the
             # tensor-core forward (north_star; table: profiles/r2_xnor_vs_tc.md).  Same integer sums, same fmaf epilogue:
             # bit-identical to the packed-operand path.  Training steps never come here (their backward multiplies real-valued
             # gradients and wants the bf16 operand plane the forward already read).
             from . import xnor as XN
             if XN.supported(sh) and (L.XNOR_MODE == "all" or xnor_preferred(sh, getattr(x, "_mnb_pk_pm1", None) is not None)):
-                a_bits = XN.pack_act(x, groups)
+                a_bits = XN.pack_act(materialized(x), groups)
                 rc = _timed("fwd_xnor", sh, lambda: XN.conv(sh, a_bits, XN.pack_weight(sh, w_int), y, alpha=w_scale, bias=bias))
                 if rc == 0:
                     done = True
@@ -433,7 +443,8 @@ class QuantConv2dFn(Function):
             done = _pk_forward(ctx, x, wq, bias, w_int, w_scale, spec, sh, y, ctx.needs_input_grad[0], prepacked=pkq[0])
             if not done:
                 raise RuntimeError("micronet_b200: fused producer output in front of a conv outside the packed-operand cover")
-        if not done and L.PK_MODE != "off" and x.dtype == torch.float32 and (L.PK_MODE == "all" or spec is not None):
+        if (not done and L.PK_MODE != "off" and x.dtype == torch.float32 and (L.PK_MODE == "all" or spec is not None)
+                and not getattr(x, "_mnb_plane_only", False)):
             done = _pk_forward(ctx, x, wq, bias, w_int, w_scale, spec, sh, y, ctx.needs_input_grad[0], pre_relu=pre_relu)
         pm1_plane = getattr(x, "_mnb_pk_pm1", None)
         if (not done and L.PK_WBWTAB and L.PK_MODE != "off" and spec is None and w_int is not None and x.dtype == torch.float32
@@ -451,6 +462,8 @@ class QuantConv2dFn(Function):
             # ONE exact bf16 piece - the producer's plane when it wrote one - against exact pieces of the fp32 weights
             plane = pm1_plane if (pm1_plane is not None and pm1_plane.numel() == x.numel() * 2) else None
             done = _pk_forward(ctx, x, wq, bias, None, None, None, sh, y, ctx.needs_input_grad[0], prepacked=plane, pm1=True)
+        if not done and getattr(x, "_mnb_plane_only", False):
+            x = materialized(x)   # outside the packed-operand cover (rare): the kernels below read the fp32 values
         if not done and pre_relu:
             x = torch.relu(x)     # outside the packed-operand cover: the folded ReLU as its own pass
         if not done and packed is not None and spec is None and w_int is not None and packed.numel() == x.numel() \
@@ -541,7 +554,7 @@ class QuantConv2dFn(Function):
             db = presummed if presummed is not None and presummed.numel() == dy.shape[1] else channel_sums(dy)
         if ctx.pk:
             dx, dwq = _pk_backward(ctx, dy)
-            return dx, dwq, db, None, None, None, None, None, None, None, None
+            return dx, dwq, db, None, None, None, None, None, None, None, None, None
         if ctx.needs_input_grad[0]:
             dx = torch.empty((sh.batch, sh.in_c, sh.in_h, sh.in_w), dtype=torch.float32, device=dy.device)
             qp = spec.struct() if spec is not None else None
@@ -602,12 +615,14 @@ class QuantConv2dFn(Function):
                 L.check(_timed("wgrad", sh, lambda: lib.mnb_conv2d_wgrad(
                     C.byref(sh), dy.data_ptr(), C.byref(ops), dwq.data_ptr(), ws.data_ptr(), L.stream())),
                     "conv2d_wgrad")
-        return dx, dwq, db, None, None, None, None, None, None, None, None
+        return dx, dwq, db, None, None, None, None, None, None, None, None, None
 
 
 def quant_conv2d(x, wq, bias, w_int, w_scale, spec, stride, padding, dilation, groups, pre_relu=False):
+    # (autograd runs a Function's forward with grad mode off and needs_input_grad ignores torch.no_grad(): whether this call
+    # will ever be differentiated is only known out here)
     return QuantConv2dFn.apply(x, wq, bias, w_int, w_scale, spec, tuple(stride), tuple(padding),
-                               tuple(dilation), groups, pre_relu)
+                               tuple(dilation), groups, pre_relu, not torch.is_grad_enabled())
 
 
 # --------------------------------------------------------------------------

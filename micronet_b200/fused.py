@@ -33,7 +33,7 @@ class BNSignFn(Function):
     """sign(batch_norm(x)) [-> max_pool2d(2, 2)] [-> channel_shuffle] with the saturate STE"""
 
     @staticmethod
-    def forward(ctx, x, gamma, beta, mean, invstd, training, shuffle_groups, pool):
+    def forward(ctx, x, gamma, beta, mean, invstd, training, shuffle_groups, pool, plane_only=False):
         lib = L.load()
         x = x.contiguous()
         b, c = x.shape[0], x.shape[1]
@@ -54,11 +54,16 @@ class BNSignFn(Function):
                 # the +-1 output also as the operand plane of the consuming conv (packed-operand family): 2 extra bytes per
                 # element here save that conv's 4-byte read and its pack pass
                 plane = torch.empty(x.numel() * 2, dtype=torch.uint8, device=x.device)
+                # plane_only (set by the rewrite pass when the ONLY reader is a conv of the packed-operand family): the fp32
+                # tensor is a shape-carrying placeholder, 4 of the 10 bytes per element this pass moved are never written
+                skip_y = bool(plane_only) and L.PLANE_ONLY
                 rc = lib.mnb_bn_sign_fwd_packed(x.data_ptr(), b, c, hw, mean.data_ptr(), invstd.data_ptr(), gamma.data_ptr(),
-                                                beta.data_ptr(), shuffle_groups, y.data_ptr(), bits.data_ptr(),
-                                                plane.data_ptr(), L.stream())
+                                                beta.data_ptr(), shuffle_groups, None if skip_y else y.data_ptr(),
+                                                bits.data_ptr(), plane.data_ptr(), L.stream())
                 if rc == 0:
                     y._mnb_pk_pm1 = plane
+                    if skip_y:
+                        y._mnb_plane_only = True    # functional.materialized(y) rebuilds the values from the plane
                     packed = False          # done (not the experimental bf16 tensor of MNB_PACKED_OPERANDS)
                 elif rc != L.E_UNSUPPORTED:
                     L.check(rc, "bn_sign_fwd_packed")
@@ -97,7 +102,23 @@ class BNSignFn(Function):
         out = torch.empty(3 * c, dtype=torch.float32, device=x.device)
         dgamma, dbeta, dx_sum = out[:c], out[c:2 * c], out[2 * c:]
         scratch = L.scratch(x.device, c)
-        if ctx.arg is not None:
+        if (ctx.arg is not None and ctx.pk_conv is not None and ctx.training and c % 8 == 0 and x.shape[3] % 8 == 0
+                and x.shape[2] % 2 == 0 and "mnb_bn_sign_pool_bwd_pack" in L.PROTOTYPES):
+            # pooled producer behind a conv of the packed-operand family: reduce pass (dgamma, dbeta), then the apply pass
+            # writes the full-resolution gradient straight as that conv's packed operand (no fp32 dx, no pack pass)
+            w_scale, T = ctx.pk_conv
+            L.check(lib.mnb_bn_sign_pool_bwd(g.data_ptr(), ctx.bits.data_ptr(), ctx.arg.data_ptr(), x.data_ptr(), b, c,
+                                             x.shape[2], x.shape[3], mean.data_ptr(), invstd.data_ptr(), gamma.data_ptr(),
+                                             2, ctx.shuffle_groups, dx.data_ptr(), dgamma.data_ptr(),
+                                             dbeta.data_ptr(), None, scratch.data_ptr(), L.stream()), "bn_sign_pool_bwd (reduce)")
+            dy_pk = torch.empty(T * x.numel() * 2, dtype=torch.uint8, device=x.device)
+            L.check(lib.mnb_bn_sign_pool_bwd_pack(g.data_ptr(), ctx.bits.data_ptr(), ctx.arg.data_ptr(), x.data_ptr(), b, c,
+                                                  x.shape[2], x.shape[3], mean.data_ptr(), invstd.data_ptr(), gamma.data_ptr(),
+                                                  dgamma.data_ptr(), dbeta.data_ptr(), ctx.shuffle_groups, L.ptr(w_scale), T,
+                                                  dy_pk.data_ptr(), L.stream()), "bn_sign_pool_bwd_pack")
+            dx_sum.zero_()
+            dx._mnb_pk_dy = (dy_pk, T, w_scale)     # dx itself is NOT written: its only reader is that conv's backward
+        elif ctx.arg is not None:
             L.check(lib.mnb_bn_sign_pool_bwd(g.data_ptr(), ctx.bits.data_ptr(), ctx.arg.data_ptr(), x.data_ptr(), b, c,
                                              x.shape[2], x.shape[3], mean.data_ptr(), invstd.data_ptr(), gamma.data_ptr(),
                                              1 if ctx.training else 0, ctx.shuffle_groups, dx.data_ptr(), dgamma.data_ptr(),
@@ -126,7 +147,7 @@ class BNSignFn(Function):
                                         scratch.data_ptr(), L.stream()), "bn_sign_bwd")
         # picked up by QuantConv2dFn.backward when this dx is its grad_output (saves its own channel-sum pass)
         dx._mnb_channel_sum = dx_sum
-        return dx, dgamma, dbeta, None, None, None, None, None
+        return dx, dgamma, dbeta, None, None, None, None, None, None
 
 
 class BatchNormBinarize2d(nn.BatchNorm2d):
@@ -136,6 +157,7 @@ class BatchNormBinarize2d(nn.BatchNorm2d):
 
     out_shuffle_groups = 1
     pool2 = False
+    plane_only = False     # set by fuse_wbwtab_blocks: the only reader of the output is a conv that takes the bf16 plane
 
     def forward(self, input):
         L.require_cuda(input, self.weight)
@@ -160,7 +182,8 @@ class BatchNormBinarize2d(nn.BatchNorm2d):
             # plane shape outside the fused pool kernel's cover: the same result in two steps
             y = BNSignFn.apply(input, self.weight, self.bias, mean, invstd, self.training, 1, False)
             return MaxPoolFn.apply(y, 2, 2, 0, sg)
-        return BNSignFn.apply(input, self.weight, self.bias, mean, invstd, self.training, sg, bool(self.pool2))
+        return BNSignFn.apply(input, self.weight, self.bias, mean, invstd, self.training, sg, bool(self.pool2),
+                              bool(self.plane_only) and not self.pool2)
 
     def extra_repr(self):
         return super().extra_repr() + f", pool2={self.pool2}, out_shuffle_groups={self.out_shuffle_groups}"
@@ -380,7 +403,8 @@ class EnginePmConv2d(nn.Conv2d):
             if (PK.supported(sh, 0, 1, T) and PK.supported(sh, 1, Tb, Tb) and PK.wgrad_supported(sh, Tb, 1)):
                 return F_.quant_conv2d(input, self.weight, self.bias, None, None, None, self.stride, self.padding,
                                        self.dilation, self.groups)
-        return self._conv_forward(input, self.weight, self.bias)
+        from . import functional as F2
+        return self._conv_forward(F2.materialized(input), self.weight, self.bias)
 
 
 def _fuse_pairs(module: nn.Module):
@@ -505,12 +529,37 @@ def _fuse_dorefa_producers(module: nn.Module):
         prev._modules[names[-1]] = nn.Identity()
 
 
+def _mark_plane_only(module: nn.Module):
+    """BatchNorm + binarizer whose output is read by exactly one module - the conv that opens the next block of the same
+    nn.Sequential, un-shuffled - and that conv is one that takes the producer's bf16 plane (wbwtab QuantConv2d with binary /
+    ternary weights, or the +-1-input head EnginePmConv2d): the producer then skips its fp32 output."""
+    from .wbwtab import QuantConv2d as WbConv
+    for child in module.children():
+        _mark_plane_only(child)
+    if not isinstance(module, nn.Sequential):
+        return
+    kids = [k for k in module.children() if not isinstance(k, nn.Identity)]
+    for prev, nxt in zip(kids, kids[1:]):
+        prod, conv = _tail_producer(prev), _first_conv(nxt)
+        if not isinstance(prod, BatchNormBinarize2d) or prod.pool2 or conv is None:
+            continue
+        if getattr(nxt, "channel_shuffle_flag", 0) or conv.in_channels % 8:
+            continue
+        if isinstance(conv, WbConv):
+            ok = conv.weight_quantizer.W in (2, 3) and not conv.quant_inference
+        else:
+            ok = isinstance(conv, EnginePmConv2d)
+        if ok:
+            prod.plane_only = True
+
+
 def fuse_wbwtab_blocks(model: nn.Module, fold_shuffle: bool = True) -> nn.Module:
     _fuse_pairs(model)
     _fold_pools(model)
     _fuse_dorefa_producers(model)
     if fold_shuffle:
         _fold_shuffles(model)
+    _mark_plane_only(model)
     return model
 
 

@@ -249,11 +249,13 @@ def test_dorefa_fuse_option_agrees_with_the_unfused_engine():
 
 @pytest.mark.parametrize("cfg", [(8, 256, 256, 32, 1, 2, 2), (8, 256, 512, 16, 3, 16, 1), (4, 512, 512, 16, 1, 4, 4)],
                          ids=["1x1g2", "3x3g16", "1x1g4"])
-def test_wbwtab_layer_between_two_fused_producers_on_the_packed_operand_family(cfg):
+@pytest.mark.parametrize("pool", [False, True], ids=["plain", "pooled"])
+def test_wbwtab_layer_between_two_fused_producers_on_the_packed_operand_family(cfg, pool):
     """BatchNormBinarize2d -> wbwtab QuantConv2d -> BatchNormBinarize2d with both conv operands written by the producers
     (+-1 plane forward: mnb_bn_sign_fwd_packed, gradient pieces backward: mnb_bn_sign_bwd_pack) against the same chain on the
     fused kernels (MNB_PK_WBWTAB=0), which the oracle tests pin: identical +-1 outputs, gradients to 1e-5 (weight gradient:
-    plus the cancellation allowance of tests/test_gpu_parity.py)."""
+    plus the cancellation allowance of tests/test_gpu_parity.py).  ``pool``: the consuming producer has the 2x2 max-pool folded
+    in (mnb_bn_sign_pool_bwd_pack writes the full-resolution gradient pieces)."""
     import micronet_b200 as E
     from micronet_b200 import _lib as L
     from micronet_b200.fused import BatchNormBinarize2d
@@ -261,7 +263,7 @@ def test_wbwtab_layer_between_two_fused_producers_on_the_packed_operand_family(c
     B, C, K, H, R, G, sg = cfg
     torch.manual_seed(sum(cfg))
     x = torch.randn(B, C, H, H) * 1.3
-    go = torch.randn(B, K, H, H)
+    go = torch.randn(B, K, H // 2, H // 2) if pool else torch.randn(B, K, H, H)
     bn0, bn1 = _pair(C, 3), _pair(K, 4)
     conv = E.wbwtab.QuantConv2d(C, K, R, padding=R // 2, groups=G, W=3)
     res = {}
@@ -269,7 +271,7 @@ def test_wbwtab_layer_between_two_fused_producers_on_the_packed_operand_family(c
         L.PK_WBWTAB = mode
         try:
             p0 = BatchNormBinarize2d(C); p0.load_state_dict(bn0.state_dict()); p0.out_shuffle_groups = sg
-            p1 = BatchNormBinarize2d(K); p1.load_state_dict(bn1.state_dict())
+            p1 = BatchNormBinarize2d(K); p1.load_state_dict(bn1.state_dict()); p1.pool2 = pool
             cv = copy.deepcopy(conv)
             net = nn.Sequential(p0, cv, p1).to(DEV).train()
             captured = {}
@@ -331,3 +333,34 @@ def test_unquantized_conv_behind_a_binarizer_runs_on_the_packed_family(shape):
     assert rel_err(conv.bias.grad, bd.grad) <= 1e-5
     plain = torch.randn(B, C, H, W, device=DEV)          # no +-1 tag: the stock path, bit for bit
     assert torch.equal(conv(plain), TF.conv2d(plain, conv.weight, conv.bias, 1, R // 2))
+
+
+@pytest.mark.parametrize("shape", [(4, 256, 32, 32, 256, 1, 2, 2), (4, 512, 8, 8, 1024, 3, 32, 4)], ids=["1x1", "3x3"])
+def test_plane_only_producer_gives_the_same_block(shape):
+    """BatchNormBinarize2d.plane_only (fuse pass: the only reader is a conv of the packed-operand family): the fp32 output is
+    never written, functional.materialized() rebuilds it from the bf16 plane, and conv output / every gradient are
+    bit-identical to the run that writes it."""
+    from micronet_b200 import _lib as L, functional as F_
+    from micronet_b200.fused import BatchNormBinarize2d
+    B, C, H, W, K, R, G, sg = shape
+    torch.manual_seed(sum(shape))
+    x0 = (torch.randn(B, C, H, W) * 1.5).to(DEV)
+    w_int = torch.randint(-1, 2, (K, C // G, R, R), dtype=torch.int16).to(DEV)
+    w_scale = (torch.rand(K) * 0.02 + 0.001).to(DEV)
+    go = torch.randn(B, K, H, W).to(DEV)
+    res = {}
+    for flag in (False, True):
+        torch.manual_seed(5)
+        bn = BatchNormBinarize2d(C).to(DEV).train()
+        bn.out_shuffle_groups, bn.plane_only = sg, flag
+        x = x0.clone().requires_grad_(True)
+        wq = (w_int.float() * w_scale.view(-1, 1, 1, 1)).requires_grad_(True)
+        a = bn(x)
+        assert bool(getattr(a, "_mnb_plane_only", False)) == flag
+        vals = F_.materialized(a).detach().clone()
+        out = F_.quant_conv2d(a, wq, None, w_int, w_scale, None, (1, 1), (R // 2, R // 2), (1, 1), G)
+        out.backward(go)
+        res[flag] = (vals, out.detach(), x.grad, wq.grad, bn.weight.grad, bn.bias.grad)
+    L.tc_check()
+    for a, b in zip(res[True], res[False]):
+        assert torch.equal(a, b)

@@ -521,7 +521,8 @@ def test_fused_headline_graph_blocks_teacher_forced(batch):
         ye = e(xe)
         want = yo.detach() if out_g == 1 else _shuffle(yo.detach(), out_g)
         ok0 = edge0 if out_g == 1 else _shuffle(edge0.float(), out_g) > 0
-        diff = ye.detach().cpu() != want
+        from micronet_b200 import functional as F_
+        diff = F_.materialized(ye).detach().cpu() != want     # (a plane-only producer output: values rebuilt from its bf16 plane)
         # (BatchNorm of a conv of +-1 / ternary operands takes few distinct values per channel: whole clusters of elements
         # can sit at bn ~ 1e-7, so the NUMBER of such elements is a property of the data; what must hold is that no output
         # differs anywhere else)

@@ -106,6 +106,9 @@ def test_fuse_pass_rewrites_the_prepared_graph_only():
     from micronet_b200.fused import EnginePmConv2d
     assert [n for n, c in fused.named_modules() if isinstance(c, EngineFloatConv2d)] == ["model.0.conv"]
     assert type(dict(fused.named_modules())["model.10.conv"]) is EnginePmConv2d
+    # producers whose only reader takes their bf16 plane skip the fp32 output: every un-pooled BatchNorm + binarizer here
+    assert sum(bool(getattr(m, "plane_only", False)) for m in fused.modules()) == 6
+    assert not any(getattr(m, "plane_only", False) and m.pool2 for m in fused.modules() if isinstance(m, BatchNormBinarize2d))
     # A != 2 keeps the ReLU path: nothing to fuse
     relu = E.wbwtab.prepare(base, A=32, W=2, fuse_bn=True)
     assert not any(isinstance(m, BatchNormBinarize2d) for m in relu.modules())
