@@ -289,6 +289,7 @@ def run_engine(workload, steps, warmup, dev, rank, world, detail):
                    "d2h_bytes_per_step": (B * 10 * 4 if inference else 4) * world},
            "gpu_launches": int(launches), "clocks": clocks, "timer": timer,
            "ms_total": ms_detail,   # the eager detail pass the per-kernel events were recorded in (dsteps steps)
+           "detail_steps": dsteps,
            "cuda_graph": {"used": bool(graph_used), "error": getattr(stepper, "graph_error", None),
                           "eager_ms_per_step": ms_detail / dsteps}}
     del stepper, model
@@ -348,7 +349,10 @@ def main():
         return
 
     hbm, tfl, peak_src = _peaks()
-    timer, ms_total = main_res.pop("timer"), main_res.pop("ms_total")
+    timer, ms_total, dsteps = main_res.pop("timer"), main_res.pop("ms_total"), main_res.pop("detail_steps")
+    # kernel time per step (CUDA events of the eager detail pass) over the TIMED step (graph replay): the eager pass itself is
+    # longer than the step it repeats (Python / ctypes issue time between launches), so it is not the denominator
+    step_ms = main_res["ms_per_step"]
     agg, rows = kernel_table(timer, ms_total, args.steps, hbm, tfl)
     if args.kernels_json:
         json.dump({"ms_per_step": main_res["ms_per_step"], "kernels": rows}, open(args.kernels_json, "w"), indent=1)
@@ -376,8 +380,8 @@ def main():
         roof.update({"traffic": traffic, "traffic_source": tsrc, "algorithmic_bytes": nbytes, "algorithmic_flops": flops,
                      "peak_source": peak_src,
                      "kernel": f"conv2d_{dk} shape(B,C,H,W,K,R,S,sh,sw,ph,pw,dh,dw,G)={list(dshape)}",
-                     "avg_launch_us": avg_s * 1e6, "launches_timed": dn, "share_of_step": dtot / ms_total,
-                     "engine_conv_share_of_step": sum(v[0] for v in agg.values()) / ms_total,
+                     "avg_launch_us": avg_s * 1e6, "launches_timed": dn, "share_of_step": dtot / dsteps / step_ms,
+                     "engine_conv_share_of_step": sum(v[0] for v in agg.values()) / dsteps / step_ms,
                      # all engine conv launches of the timed region: sum of their rooflines / sum of their measured times
                      "all_conv_kernels_frac": t_roof_sum * 1e3 / max(1e-9, sum(v[0] for v in agg.values()))})
     line = {"metric": main_res["metric"], "value": main_res["value"], "unit": "img/s", "n_gpus": world, "steps": args.steps,
@@ -394,11 +398,11 @@ def main():
                 continue
             try:
                 r = run_engine(name, 5, 3, dev, rank, world, detail=True)
-                t2, ms2 = r.pop("timer"), r.pop("ms_total")
+                t2, ms2, ds2 = r.pop("timer"), r.pop("ms_total"), r.pop("detail_steps")
                 agg2, _ = kernel_table(t2, ms2, 5, hbm, tfl)
                 r.pop("clocks")
                 r["config"] = config_dict(name, world)["workload"]
-                r["engine_conv_share_of_step"] = sum(v[0] for v in agg2.values()) / ms2 if agg2 else None
+                r["engine_conv_share_of_step"] = sum(v[0] for v in agg2.values()) / ds2 / r["ms_per_step"] if agg2 else None
                 r["conv_kinds"] = sorted({k for k, _ in agg2})
                 extras.append(r)
             except Exception as e:  # an extra must never take the headline line down with it

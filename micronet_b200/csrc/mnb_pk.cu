@@ -767,6 +767,19 @@ __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" 
 // launch of the family sat at 42 - 47 k instructions per epilogue warp in 160 - 173 k cycles, tensor pipe 7 - 9 % busy, DRAM
 // 3.6 TB/s.  The un-segmented kernel therefore runs TWO warps per quarter (warps 4..7 take the even 16-column slots of an
 // item, warps 8..11 the odd ones); the segmented kernel keeps one (its 128 running sums per thread need the registers).
+// n = q * d + r for n < 2^22 through one float multiply (the compiler's 32-bit integer division is a ~25-instruction dependent
+// chain; the TMA-issuing lane ran ~2100 instructions per work item, most of them these, at one instruction every four cycles -
+// as long as a whole 3x3 g16 item takes: ncu r3b, source page).  q from the reciprocal is within +-1: corrected exactly.
+struct FastDiv {
+  uint32_t d; float inv;
+  __device__ __forceinline__ explicit FastDiv(int dd) : d((uint32_t)dd), inv(1.0f / (float)dd) {}
+  __device__ __forceinline__ void divmod(uint32_t n, uint32_t& q, uint32_t& r) const {
+    q = __float2uint_rz(__uint2float_rz(n) * inv);
+    r = n - q * d;
+    if ((int32_t)r < 0) { --q; r += d; } else if (r >= d) { ++q; r -= d; }
+  }
+};
+
 template <bool SEG> struct ConvCfg { static constexpr int EPIW = SEG ? 4 : 8, THREADS = 128 + 32 * EPIW; };
 
 template <bool SEG>   // SEG: segmented accumulation (split fp32 operands), the epilogue keeps the N tile in registers
@@ -804,10 +817,11 @@ pk_conv_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_constant_
     if (lane == 0) {
       const int y = blockIdx.y;
       uint32_t sc = 0;
+      const FastDiv d_nt(p.n_ntiles), d_g(p.G), d_ct(p.col_tiles), d_rt(p.row_tiles);
       for (int it = blockIdx.x; it < p.n_items; it += gridDim.x) {
-        const int nt = it % p.n_ntiles;
-        const int r1 = it / p.n_ntiles;
-        const int g = r1 % p.G, mg = r1 / p.G;
+        uint32_t nt, r1, g, mg;
+        d_nt.divmod((uint32_t)it, r1, nt);
+        d_g.divmod(r1, mg, g);
         const uint8_t* wsrc = p.w_img + (size_t)p.y_off[y] + (size_t)(nt * p.G + g) * (size_t)p.img_bytes[y];
         for (int t = 0; t < p.ntmpl[y]; ++t) {
           const int kph = p.tmpl_kph[y][t];
@@ -822,11 +836,11 @@ pk_conv_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_constant_
             uint8_t* sbase = smem + (size_t)slot * p.stage_bytes;
             const int c8 = kph * p.C8A + g * p.kg8 + cc * p.CC8;
             for (int mt = 0; mt < (ld_a ? p.MT : 0); ++mt) {
-              const int tile = mg * p.MT + mt;
-              const int ct = tile % p.col_tiles;
-              const int r2 = tile / p.col_tiles;
-              const int rt = r2 % p.row_tiles, bt = r2 / p.row_tiles;
-              const int cw = ct * p.Wt - p.wlo, chh = rt * p.TH - p.hlo, cb = bt * p.TB;
+              const uint32_t tile = mg * (uint32_t)p.MT + (uint32_t)mt;
+              uint32_t ct, r2, rt, bt;
+              d_ct.divmod(tile, r2, ct);
+              d_rt.divmod(r2, bt, rt);
+              const int cw = (int)ct * p.Wt - p.wlo, chh = (int)rt * p.TH - p.hlo, cb = (int)bt * p.TB;
               tc::tma_load_4d(sbase + (size_t)(mt * p.TA) * p.a_bytes, &tmap0, &sh.full[slot], 2 * cw, chh, cb, c8);
               if (p.TA > 1) tc::tma_load_4d(sbase + (size_t)(mt * p.TA + 1) * p.a_bytes, &tmap1, &sh.full[slot], 2 * cw, chh, cb, c8);
               if (p.TA > 2) tc::tma_load_4d(sbase + (size_t)(mt * p.TA + 2) * p.a_bytes, &tmap2, &sh.full[slot], 2 * cw, chh, cb, c8);
@@ -909,10 +923,12 @@ pk_conv_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_constant_
       if (p.post_q.mode == MNB_ACT_IAO && p.post_q.zero_point) pzp = __ldg(p.post_q.zero_point);
     }
     uint32_t accq = 0;
+    const FastDiv e_nt(p.n_ntiles), e_g(p.G), e_ct(p.col_tiles), e_rt(p.row_tiles);
     for (int it = blockIdx.x; it < p.n_items; it += gridDim.x) {
-      const int nt = it % p.n_ntiles;
-      const int r1 = it / p.n_ntiles;
-      const int g = r1 % p.G, mg = r1 / p.G;
+      uint32_t nt_u, r1_u, g_u, mg_u;
+      e_nt.divmod((uint32_t)it, r1_u, nt_u);
+      e_g.divmod(r1_u, mg_u, g_u);
+      const int nt = (int)nt_u, g = (int)g_u, mg = (int)mg_u;
       const int n_base = g * p.ng + nt * p.Nt;                // first output channel of this N tile
       const int n_cnt = min(p.Nt, p.ng - nt * p.Nt);
       // per-channel constants of this N tile (the previous item's readers are done: barrier at the end of the loop body)
@@ -948,9 +964,10 @@ pk_conv_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_constant_
           if (mt != mt_cur) {   // output row of this thread in M tile mt
             mt_cur = mt;
             const int tile = mg * p.MT + mt;
-            const int ct = tile % p.col_tiles;
-            const int r2 = tile / p.col_tiles;
-            const int rt = r2 % p.row_tiles, bt = r2 / p.row_tiles;
+            uint32_t ct_u, r2_u, rt_u, bt_u;
+            e_ct.divmod((uint32_t)tile, r2_u, ct_u);
+            e_rt.divmod(r2_u, bt_u, rt_u);
+            const int ct = (int)ct_u, rt = (int)rt_u, bt = (int)bt_u;
             const int b = bt * p.TB + tb, i = rt * p.TH + th, j = ct * p.Wt + wc;
             valid = row_ok && tile < p.n_mtiles && b < p.B && i < p.OHr && j < p.OWr;
             const int oh = i * p.omul + ya, ow = j * p.omul + yb;
@@ -1665,6 +1682,8 @@ static int pk_conv_impl(const mnb_conv_shape* s, int32_t mode, const void* a_pk,
     const int tt = t < pl.TA ? t : 0;
     if (int e = make_pk_tmap(&tm[t], a_pk, plane_bytes, tt, pl.B, C8tot, pl.HA, pl.WA, pl.BW, pl.THH, pl.TB, pl.CC / 8)) return e;
   }
+  if (pl.n_items >= (1 << 22) || pl.n_mtiles >= (1 << 22))     // FastDiv's exact range (fp32 reciprocal + one correction step)
+    return mnb_fail(MNB_E_UNSUPPORTED, "pk conv: %d work items / %d M tiles exceed the index arithmetic of the kernel", pl.n_items, pl.n_mtiles);
   const int gx = std::max(1, std::min(pl.n_items, MNB_NUM_SMS / pl.ny));
   if (pl.segmented) {
     if (pl.MT * pl.Nt > 128) return mnb_fail(MNB_E_ARG, "pk conv: segmented plan with Nt %d, MT %d", pl.Nt, pl.MT);
