@@ -295,11 +295,11 @@ def xnor_preferred(sh, has_plane):
     """MNB_XNOR=auto: take the XNOR-popcount forward for this wbwtab inference layer?  Decided from the layer-by-layer
     measurement of harness/xnor_probe.py on B200 (profiles/r2_xnor_vs_tc.md, NIN-GC layers at batch 256):
 
-    * the two convolution kernels tie (31 - 102 us vs 31 - 99 us; XNOR ahead only on the 3x3 g32 layer, 52 vs 69 us): both are
-      bound by the fp32 output they write, and B200's popc pipe (16 lanes / clk / SM) gives the bit kernel no arithmetic edge
-      over tcgen05 on +-1 operands;
-    * the operand it reads is 16 x smaller (1 bit vs one bf16 per activation): packing it from an fp32 tensor costs 11 - 49 us
-      against 25 - 156 us for the bf16 plane, so a layer that has to pack its own input is 1.3 - 1.7 x faster end to end.
+    * the two convolution kernels tie within ~7 % on the 1x1 layers (29 - 87 us vs 27 - 81 us) and split the 3x3 layers
+      (102 vs 83 us, 56 vs 58 us): both are dominated by the fp32 output they write, and B200's popc pipe (16 lanes / clk /
+      SM) gives the bit kernel no arithmetic edge over tcgen05 on +-1 operands;
+    * the operand it reads is 16 x smaller (1 bit vs one bf16 per activation): packing it from an fp32 tensor costs 11 - 50 us
+      against 25 - 156 us for the bf16 plane, so a layer that has to pack its own input is 1.08 - 1.79 x faster end to end.
 
     Hence: XNOR when the layer packs its own operand (no producer-written plane came with x), the tensor-core forward when a
     fused BatchNorm + binarizer already wrote the bf16 plane (the pack pass is free there)."""
