@@ -746,8 +746,8 @@ struct ConvParams {
 struct alignas(16) ConvShared {
   uint64_t full[MAXST], empty[MAXST], acc_full[2], acc_empty[2];
   uint32_t tmem_slot, abort;
-  alignas(16) float epi_scale[2][256];   // double-buffered per work item (see the epilogue role)
-  alignas(16) float epi_bias[2][256];
+  alignas(16) float epi_scale[256];
+  alignas(16) float epi_bias[256];
 };
 
 __device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, uint32_t (&r)[16]) {
@@ -924,25 +924,6 @@ pk_conv_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_constant_
     }
     uint32_t accq = 0;
     const FastDiv e_nt(p.n_ntiles), e_g(p.G), e_ct(p.col_tiles), e_rt(p.row_tiles);
-    const bool staged = p.n_scale != nullptr || p.bias != nullptr;
-    int buf = 0;
-    if (et < p.Nt) {      // first item's constants (or, un-staged, the constants of every item) before the loop
-      float sc0 = a_sc, bs0 = 0.f;
-      if (staged && (int)blockIdx.x < p.n_items) {
-        uint32_t nt0, r10, g0, mg0;
-        e_nt.divmod(blockIdx.x, r10, nt0);
-        e_g.divmod(r10, mg0, g0);
-        const int nb0 = (int)g0 * p.ng + (int)nt0 * p.Nt, nc0 = min(p.Nt, p.ng - (int)nt0 * p.Nt);
-        sc0 = 1.f;
-        if (et < nc0) {
-          sc0 = p.n_scale ? __fmul_rn(a_sc, __ldg(p.n_scale + nb0 + et)) : a_sc;
-          if (p.bias) bs0 = __ldg(p.bias + nb0 + et);
-        }
-      }
-      sh.epi_scale[0][et] = sc0; sh.epi_bias[0][et] = bs0;
-      if (!staged) { sh.epi_scale[1][et] = sc0; sh.epi_bias[1][et] = bs0; }
-    }
-    if (!staged) epi_bar_sync<NEPI>();
     for (int it = blockIdx.x; it < p.n_items; it += gridDim.x) {
       uint32_t nt_u, r1_u, g_u, mg_u;
       e_nt.divmod((uint32_t)it, r1_u, nt_u);
@@ -950,30 +931,16 @@ pk_conv_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_constant_
       const int nt = (int)nt_u, g = (int)g_u, mg = (int)mg_u;
       const int n_base = g * p.ng + nt * p.Nt;                // first output channel of this N tile
       const int n_cnt = min(p.Nt, p.ng - nt * p.Nt);
-      // Per-channel constants (scale, bias) of the item's N tile sit in shared memory, DOUBLE-BUFFERED over the items: the values
-      // of item i + 1 are fetched into registers at the start of item i (their global-load latency hides behind the item's
-      // slots) and stored after them; ONE barrier per item makes buffer `buf` visible and proves that everyone has left the
-      // previous item, whose buffer is the one about to be overwritten.  Launches without per-channel constants (plain data
-      // gradients) fill both buffers once and run without any barrier.  (r3f: with loads, MMAs, TMEM reads and stores all
-      // switched off the 3x3 g16 forward still took 48 of its 86 us - the fixed per-item cost of this role, two 256-thread
-      // barriers and an exposed global load among it.)
-      float nsc = 1.f, nbs = 0.f;
-      bool stage_next = false;
-      if (staged) {
-        epi_bar_sync<NEPI>();
-        const int itn = it + (int)gridDim.x;
-        if (itn < p.n_items && et < p.Nt) {      // Nt <= NEPI: one constant pair per thread
-          uint32_t ntn, r1n, gn, mgn;
-          e_nt.divmod((uint32_t)itn, r1n, ntn);
-          e_g.divmod(r1n, mgn, gn);
-          const int nb2 = (int)gn * p.ng + (int)ntn * p.Nt, nc2 = min(p.Nt, p.ng - (int)ntn * p.Nt);
-          stage_next = true;
-          if (et < nc2) {
-            nsc = p.n_scale ? __fmul_rn(a_sc, __ldg(p.n_scale + nb2 + et)) : a_sc;
-            if (p.bias) nbs = __ldg(p.bias + nb2 + et);
-          }
+      // per-channel constants of this N tile (the previous item's readers are done: barrier at the end of the loop body)
+      for (int n = et; n < p.Nt; n += NEPI) {
+        float sc = 1.f, bs = 0.f;
+        if (n < n_cnt) {
+          sc = p.n_scale ? __fmul_rn(a_sc, __ldg(p.n_scale + n_base + n)) : a_sc;
+          if (p.bias) bs = __ldg(p.bias + n_base + n);
         }
+        sh.epi_scale[n] = sc; sh.epi_bias[n] = bs;
       }
+      epi_bar_sync<NEPI>();
       const int nseg = SEG ? p.nseg[y] : 1;
       // running sums of the item's accumulator columns (segmented mode only: MT * Nt <= 128 -> 8 slots of 16 columns;
       // slot = mt * (Nt / 16) + column chunk).  The slot loop is fully unrolled so that rs[][] stays in registers.
@@ -1034,8 +1001,8 @@ pk_conv_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_constant_
           float sc[16], bs[16];
 #pragma unroll
           for (int v = 0; v < 4; ++v) {
-            const float4 a = *reinterpret_cast<const float4*>(&sh.epi_scale[buf][n0 + 4 * v]);
-            const float4 c = *reinterpret_cast<const float4*>(&sh.epi_bias[buf][n0 + 4 * v]);
+            const float4 a = *reinterpret_cast<const float4*>(&sh.epi_scale[n0 + 4 * v]);
+            const float4 c = *reinterpret_cast<const float4*>(&sh.epi_bias[n0 + 4 * v]);
             sc[4 * v] = a.x; sc[4 * v + 1] = a.y; sc[4 * v + 2] = a.z; sc[4 * v + 3] = a.w;
             bs[4 * v] = c.x; bs[4 * v + 1] = c.y; bs[4 * v + 2] = c.z; bs[4 * v + 3] = c.w;
           }
@@ -1092,8 +1059,7 @@ pk_conv_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_constant_
         tc::tc_fence_before();
         tc::mbar_arrive(&sh.acc_empty[acc]);
       }
-      if (stage_next) { sh.epi_scale[buf ^ 1][et] = nsc; sh.epi_bias[buf ^ 1][et] = nbs; }
-      buf ^= 1;
+      epi_bar_sync<NEPI>();   // everyone is done with epi_scale / epi_bias of this item
     }
   }
 done:
