@@ -74,6 +74,30 @@ class QuantConv2d(nn.Conv2d):
                                self.dilation, self.groups)
 
 
+class QuantConvTranspose2d(nn.ConvTranspose2d):
+    """DF:125-174.  The reference hands (dilation, groups, bias) POSITIONALLY to ``nn.ConvTranspose2d.__init__``, whose order is
+    (groups, bias, dilation): with current PyTorch its forward raises ``TypeError`` (dilation = (True, True)), so there is no
+    reference behaviour to reproduce beyond the intent - activation quantizer, weight quantizer, ``F.conv_transpose2d`` - which
+    is what this module does, with the constructor arguments taken by name.  The transposed convolution runs on the engine's
+    convolution kernels with the roles swapped (functional.ConvTranspose2dFn)."""
+
+    def __init__(self, in_channels, out_channels, kernel_size, stride=1, padding=0, output_padding=0, dilation=1, groups=1,
+                 bias=True, padding_mode="zeros", a_bits=8, w_bits=8, quant_inference=False):
+        super().__init__(in_channels, out_channels, kernel_size, stride=stride, padding=padding,
+                         output_padding=output_padding, groups=groups, bias=bias, dilation=dilation,
+                         padding_mode=padding_mode)
+        self.quant_inference = quant_inference
+        self.activation_quantizer = ActivationQuantizer(a_bits=a_bits)
+        self.weight_quantizer = WeightQuantizer(w_bits=w_bits)
+
+    def forward(self, input):
+        L.require_cuda(input, self.weight)
+        quant_input = self.activation_quantizer(input)
+        quant_weight = self.weight if self.quant_inference else self.weight_quantizer(self.weight)
+        return F_.conv_transpose2d(quant_input, quant_weight, self.bias, self.stride, self.padding, self.output_padding,
+                                   self.groups, self.dilation)
+
+
 class QuantLinear(nn.Linear):
     def __init__(self, in_features, out_features, bias=True, a_bits=8, w_bits=8, quant_inference=False):
         super().__init__(in_features, out_features, bias)
@@ -110,8 +134,12 @@ def add_quant_op(module, layer_counter, a_bits=8, w_bits=8, quant_inference=Fals
                     w_bits=w_bits, quant_inference=quant_inference), child)
         elif isinstance(child, nn.ConvTranspose2d):
             layer_counter[0] += 1
-            if layer_counter[0] > 1:
-                raise NotImplementedError("QuantConvTranspose2d is out of scope of the B200 engine (SURVEY §8 f4)")
+            if layer_counter[0] > 1:     # DF:236-277
+                module._modules[name] = _adopt(QuantConvTranspose2d(
+                    child.in_channels, child.out_channels, child.kernel_size, stride=child.stride,
+                    padding=child.padding, output_padding=child.output_padding, dilation=child.dilation,
+                    groups=child.groups, bias=child.bias is not None, padding_mode=child.padding_mode, a_bits=a_bits,
+                    w_bits=w_bits, quant_inference=quant_inference), child)
         elif isinstance(child, nn.Linear):
             layer_counter[0] += 1
             if layer_counter[0] > 1:

@@ -65,6 +65,29 @@ class QuantConv2d(nn.Conv2d):
                                self.dilation, self.groups)
 
 
+class QuantConvTranspose2d(nn.ConvTranspose2d):
+    """WB:198-244 (only the weight is quantized; the input is whatever the previous block produced).  Like DF:125-174 the
+    reference passes (dilation, groups, bias) positionally in the wrong order and its forward raises ``TypeError`` under
+    current PyTorch: this module implements the intent - ``F.conv_transpose2d(x, Wq(w), bias, ...)`` - with the constructor
+    arguments taken by name, on the engine's convolution kernels with the roles swapped (functional.ConvTranspose2dFn).
+    The per-channel statistics of the weight quantizer run over dim 0 of the [C_in, C_out / g, R, S] weight, exactly as
+    WB:105-149 would compute them."""
+
+    def __init__(self, in_channels, out_channels, kernel_size, stride=1, padding=0, output_padding=0, dilation=1, groups=1,
+                 bias=True, padding_mode="zeros", W=2, quant_inference=False):
+        super().__init__(in_channels, out_channels, kernel_size, stride=stride, padding=padding,
+                         output_padding=output_padding, groups=groups, bias=bias, dilation=dilation,
+                         padding_mode=padding_mode)
+        self.quant_inference = quant_inference
+        self.weight_quantizer = WeightQuantizer(W=W)
+
+    def forward(self, input):
+        L.require_cuda(input, self.weight)
+        tnn_bin_weight = self.weight if self.quant_inference else self.weight_quantizer(self.weight)
+        return F_.conv_transpose2d(input, tnn_bin_weight, self.bias, self.stride, self.padding, self.output_padding,
+                                   self.groups, self.dilation)
+
+
 def _adopt(dst, src):
     dst.weight.data = src.weight
     if src.bias is not None:
@@ -86,8 +109,12 @@ def add_quant_op(module, layer_counter, layer_num, A=2, W=2, quant_inference=Fal
                     quant_inference=quant_inference), child)
         elif isinstance(child, nn.ConvTranspose2d):
             layer_counter[0] += 1
-            if 1 < layer_counter[0] < layer_num:
-                raise NotImplementedError("QuantConvTranspose2d is out of scope of the B200 engine (SURVEY §8 f4)")
+            if 1 < layer_counter[0] < layer_num:     # WB:280-318
+                module._modules[name] = _adopt(QuantConvTranspose2d(
+                    child.in_channels, child.out_channels, child.kernel_size, stride=child.stride,
+                    padding=child.padding, output_padding=child.output_padding, dilation=child.dilation,
+                    groups=child.groups, bias=child.bias is not None, padding_mode=child.padding_mode, W=W,
+                    quant_inference=quant_inference), child)
         elif isinstance(child, nn.ReLU):
             if 0 < layer_counter[0] < layer_num:
                 module._modules[name] = ActivationQuantizer(A=A)
